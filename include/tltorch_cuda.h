@@ -1,0 +1,135 @@
+/*
+ * tltorch_cuda.h -- C ABI of the B200-native TensorLy-Torch factorized-layer hot path (libtltorch_cuda.so).
+ *
+ * The reference (tensorly/torch 0.5.0) has no FFI layer: its hot path bottoms out in library calls issued from
+ * tltorch/functional/*.py (torch.einsum through tensorly, F.conv{1,2,3}d, torch.matmul).  Each entry point below
+ * replaces one family of those call sites; the reference file:line it stands in for is cited with it.  The
+ * reference-side binding (a ctypes stub) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes and strides in ELEMENTS, no torch types;
+ *   - every function returns 0 on success or a negative tlt_status; tlt_last_error_string() describes the failure
+ *     (thread-local); nothing ever throws across the ABI;
+ *   - the caller allocates every input / output / workspace buffer and owns it; the library keeps no per-call
+ *     state (only immutable caches of kernel attributes and TMA descriptors keyed by shape);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - dtype codes: TLT_F32 / TLT_BF16; accumulation is always fp32.
+ */
+#ifndef TLTORCH_CUDA_H_
+#define TLTORCH_CUDA_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLT_ABI_VERSION 1
+#define TLT_MAX_SUBDIMS 4
+
+typedef enum { TLT_F32 = 0, TLT_BF16 = 1 } tlt_dtype;
+
+typedef enum {
+  TLT_OK = 0,
+  TLT_ERR_INVALID = -1,     /* bad descriptor / unsupported shape          */
+  TLT_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed         */
+  TLT_ERR_WORKSPACE = -3,   /* workspace too small                         */
+  TLT_ERR_UNSUPPORTED = -4  /* valid request the kernel does not implement */
+} tlt_status;
+
+int tlt_version(void);
+const char* tlt_last_error_string(void);
+/* Number of kernel launches issued through this library since load (bench.py's "gpu_launches" evidence). */
+uint64_t tlt_launch_count(void);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * tlt_contract: generic pairwise tensor contraction  C[b,m,n] = alpha * sum_k A[b,m,k] * B[b,k,n] (+ D[b,m,n])
+ *
+ * Each logical index class (batch b, rows m, cols n, reduction k) is a multi-index of up to TLT_MAX_SUBDIMS
+ * sub-dimensions, each with its own stride per operand, so mode-n products and TT / Tucker / CP sweeps run on the
+ * tensors where they lie -- no permute/contiguous copies.  Sub-dimension 0 is the OUTERMOST of its class.
+ * Replaces: every pairwise step of tl.einsum in tltorch/functional/factorized_linear.py:59 and
+ * factorized_tensordot.py:66,102; tenalg.mode_dot / multi_mode_dot (tensor_regression.py:40-42, convolution.py:160,
+ * factorized_layers/tensor_contraction_layers.py:75); tenalg.inner (tensor_regression.py:32-49); the einsum loop of
+ * BlockTT.to_tensor (factorized_tensors/tensorized_matrices.py:382); tl.{cp,tucker,tt}_to_tensor
+ * (factorized_tensors/factorized_tensors.py:130,308,415); F.conv1d(k=1) channel mixing (convolution.py:154,168,207,
+ * 223,262,278,311,340); the lambda scaling x*weights (convolution.py:278,340) and the "+ bias" elementwise adds
+ * (linear.py:32-43).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype_a, dtype_b, dtype_c, dtype_d;           /* tlt_dtype; dtype_d ignored when D == NULL               */
+  int32_t nb, nm, nn, nk;                               /* number of sub-dims per class (0 => class has extent 1)  */
+  int64_t size_b[TLT_MAX_SUBDIMS], size_m[TLT_MAX_SUBDIMS], size_n[TLT_MAX_SUBDIMS], size_k[TLT_MAX_SUBDIMS];
+  int64_t a_b[TLT_MAX_SUBDIMS], a_m[TLT_MAX_SUBDIMS], a_k[TLT_MAX_SUBDIMS];    /* strides of A                      */
+  int64_t b_b[TLT_MAX_SUBDIMS], b_k[TLT_MAX_SUBDIMS], b_n[TLT_MAX_SUBDIMS];    /* strides of B                      */
+  int64_t c_b[TLT_MAX_SUBDIMS], c_m[TLT_MAX_SUBDIMS], c_n[TLT_MAX_SUBDIMS];    /* strides of C                      */
+  int64_t d_b[TLT_MAX_SUBDIMS], d_m[TLT_MAX_SUBDIMS], d_n[TLT_MAX_SUBDIMS];    /* strides of D (0 = broadcast)      */
+  float alpha;
+  int32_t accumulate;                                   /* 1: C += result (C must be fp32)                         */
+  int32_t split_k;                                      /* 0 = library chooses; >1 needs fp32 C or a workspace     */
+} tlt_contract_desc;
+
+/* Bytes of fp32 workspace tlt_contract needs for this descriptor (0 when none). */
+size_t tlt_contract_workspace_size(const tlt_contract_desc* desc);
+int tlt_contract(const tlt_contract_desc* desc, const void* A, const void* B, const void* D, void* C,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * tlt_gemm_bf16_tc: dense bf16 GEMM on the tcgen05 tensor cores (TMA-staged operands, TMEM fp32 accumulators).
+ *   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])      A, B bf16;  C bf16 or fp32, row-major with leading dim ldc.
+ * a_major / b_major: 0 = K-major (element (i,k) at i*ld + k), 1 = MN-major (element (i,k) at k*ld + i).
+ * Requirements: the contiguous extent and ld of A and B are multiples of 8 elements; base pointers 16-byte aligned.
+ * Replaces: F.linear / torch.matmul on reconstructed or dense-regime weights (functional/linear.py:50,
+ * tensor_regression.py:47-49), and the large Tucker-core / TT stage GEMMs inside the einsums cited above.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t M, N, K;
+  int64_t lda, ldb, ldc;
+  int32_t a_major, b_major;
+  int32_t dtype_c;                                      /* TLT_BF16 or TLT_F32                                     */
+  int32_t accumulate;                                   /* 1: C += A*B^T (fp32 C only)                             */
+  int32_t dtype_bias;                                   /* dtype of bias[N] (ignored when bias == NULL)            */
+  float alpha;
+} tlt_gemm_desc;
+
+int tlt_gemm_bf16_tc_supported(const tlt_gemm_desc* desc);      /* 1 if the tensor-core kernel accepts this problem */
+int tlt_gemm_bf16_tc(const tlt_gemm_desc* desc, const void* A, const void* B, const void* bias, void* C, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Convolution building blocks (channels-first, 1 to 3 spatial dims).
+ * Replaces: F.conv{1,2,3}d call sites of tltorch/functional/convolution.py -- :133 (general_conv1d, depthwise for CP
+ * :268-271 and full for TT :213-216), :161 (Tucker core conv), :321-332 (mobilenet depthwise N-D), and their autograd.
+ * Dense (groups == 1) convolutions run as unfold (im2col) + tlt_contract / tlt_gemm_bf16_tc; depthwise
+ * (groups == channels) ones run in the dedicated kernels.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype;
+  int32_t ndim;                                         /* spatial dims, 1..3                                      */
+  int64_t batch, channels;
+  int64_t in_size[3], out_size[3];
+  int32_t kernel[3], stride[3], padding[3], dilation[3];
+} tlt_conv_desc;
+
+/* cols[(b, o...), (c, t...)] = x[b, c, o*stride - pad + t*dil]  (zero outside)  -- row-major (B*prod(out), C*prod(kernel)) */
+int tlt_im2col(const tlt_conv_desc* desc, const void* x, void* cols, void* stream);
+/* dx[b, c, i...] = sum over (o,t) with o*stride - pad + t*dil == i of dcols[(b,o),(c,t)]   (gather form, no atomics) */
+int tlt_col2im(const tlt_conv_desc* desc, const void* dcols, void* dx, void* stream);
+/* depthwise: y[b,c,o] = sum_t x[b,c,o*s-p+t*d] * w[c,t]; w is (channels, prod(kernel)) row-major */
+int tlt_dwconv_fwd(const tlt_conv_desc* desc, const void* x, const void* w, void* y, void* stream);
+int tlt_dwconv_dgrad(const tlt_conv_desc* desc, const void* dy, const void* w, void* dx, void* stream);
+/* dw must be fp32 (channels, prod(kernel)), zero-initialised by the caller; the kernel accumulates into it */
+int tlt_dwconv_wgrad(const tlt_conv_desc* desc, const void* x, const void* dy, float* dw, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Small utilities used by the host side.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* dst[i] = (dst dtype) src[i], n elements */
+int tlt_cast(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, int64_t n, void* stream);
+/* Writes `bytes` bytes of zeros/garbage through L2 (bench.py's L2 flush between timed iterations). */
+int tlt_l2_flush(void* scratch, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TLTORCH_CUDA_H_ */

@@ -1,0 +1,141 @@
+"""TEST-ONLY descriptor emulators.
+
+``torch_b200.ops`` funnels every kernel launch through two functions (``_execute_contract`` and ``_execute_conv``).
+Here they are replaced by CPU interpreters of the *same descriptors* the CUDA kernels receive, so that the host logic
+(index classification, sub-dim merging, stride bookkeeping, spec strings of every functional path and of their autograd
+formulas) is verified on the GPU-less build box.  Nothing in the product imports this file.
+"""
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+from torch_b200 import ops
+
+LOG = []
+
+
+def _view(t, sizes, strides):
+    return torch.as_strided(t, list(sizes), list(strides), storage_offset=t.storage_offset())
+
+
+def emulate_contract(plan, a, b, d, out, alpha):
+    f = plan.desc_fields
+    sb, sm, sn, sk = f["size_b"], f["size_m"], f["size_n"], f["size_k"]
+    for name in ("b", "m", "n", "k"):
+        assert len(f["size_" + name]) <= 4
+    A = _view(a, sb + sm + sk, f["a_b"] + f["a_m"] + f["a_k"])
+    B = _view(b, sb + sk + sn, f["b_b"] + f["b_k"] + f["b_n"])
+    nb, nm, nn, nk = len(sb), len(sm), len(sn), len(sk)
+    L = "abcdefghijklmnopqrstuvwxyz"
+    lb, lm, ln, lk = L[:nb], L[nb:nb + nm], L[nb + nm:nb + nm + nn], L[nb + nm + nn:nb + nm + nn + nk]
+    res = torch.einsum(f"{lb}{lm}{lk},{lb}{lk}{ln}->{lb}{lm}{ln}", A, B) * alpha
+    if d is not None:
+        res = res + _view(d, sb + sm + sn, f["d_b"] + f["d_m"] + f["d_n"])
+    _view(out, sb + sm + sn, f["c_b"] + f["c_m"] + f["c_n"]).copy_(res)
+    LOG.append(("contract", plan.spec, dict(plan.classes), plan.tc is not None))
+
+
+def _geom(desc):
+    n = desc.ndim
+    g = dict(ndim=n, batch=desc.batch, channels=desc.channels)
+    for k in ("in_size", "out_size", "kernel", "stride", "padding", "dilation"):
+        g[k] = [int(getattr(desc, k)[i]) for i in range(n)]
+    return g
+
+
+def _tap_slices(g, taps):
+    sl = [slice(None), slice(None)]
+    for i in range(g["ndim"]):
+        start = taps[i] * g["dilation"][i]
+        sl.append(slice(start, start + (g["out_size"][i] - 1) * g["stride"][i] + 1, g["stride"][i]))
+    return tuple(sl)
+
+
+def _pad_arg(g):
+    pad = []
+    for p in reversed(g["padding"]):
+        pad += [p, p]
+    return pad
+
+
+def _unpad(xp, g):
+    sl = [slice(None), slice(None)]
+    for i in range(g["ndim"]):
+        p = g["padding"][i]
+        sl.append(slice(p, p + g["in_size"][i]))
+    return xp[tuple(sl)]
+
+
+def _all_taps(g):
+    import itertools
+    return itertools.product(*[range(k) for k in g["kernel"]])
+
+
+def _im2col(x, g):
+    n = g["ndim"]
+    B, C = x.shape[0], x.shape[1]
+    xp = F.pad(x, _pad_arg(g))
+    cols = x.new_zeros((B, *g["out_size"], C, *g["kernel"]))
+    for taps in _all_taps(g):
+        patch = xp[_tap_slices(g, taps)]                         # (B, C, *out)
+        cols[(slice(None),) + (slice(None),) * n + (slice(None),) + taps] = patch.movedim(1, -1)
+    return cols.reshape(B * math.prod(g["out_size"]), C * math.prod(g["kernel"]))
+
+
+def _col2im(dcols, g, B, C):
+    n = g["ndim"]
+    padded = [s + 2 * p for s, p in zip(g["in_size"], g["padding"])]
+    dxp = dcols.new_zeros((B, C, *padded))
+    cols = dcols.reshape(B, *g["out_size"], C, *g["kernel"])
+    for taps in _all_taps(g):
+        part = cols[(slice(None),) + (slice(None),) * n + (slice(None),) + taps]      # (B, *out, C)
+        dxp[_tap_slices(g, taps)] += part.movedim(-1, 1)
+    return _unpad(dxp, g)
+
+
+def emulate_conv(which, desc, *tensors):
+    g = _geom(desc)
+    n = g["ndim"]
+    conv = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[n]
+    if which == "tlt_im2col":
+        x, cols = tensors
+        cols.copy_(_im2col(x, g))
+    elif which == "tlt_col2im":
+        dcols, dx = tensors
+        dx.copy_(_col2im(dcols, g, dx.shape[0], dx.shape[1]))
+    elif which == "tlt_dwconv_fwd":
+        x, w, y = tensors
+        y.copy_(conv(x, w.reshape(w.shape[0], 1, *g["kernel"]), stride=g["stride"], padding=g["padding"],
+                     dilation=g["dilation"], groups=x.shape[1]))
+    elif which == "tlt_dwconv_dgrad":
+        dy, w, dx = tensors
+        B, C = dx.shape[0], dx.shape[1]
+        padded = [s + 2 * p for s, p in zip(g["in_size"], g["padding"])]
+        dxp = dy.new_zeros((B, C, *padded))
+        wk = w.reshape(C, *g["kernel"])
+        for taps in _all_taps(g):
+            dxp[_tap_slices(g, taps)] += dy * wk[(slice(None),) + taps].reshape(1, C, *([1] * n))
+        dx.copy_(_unpad(dxp, g))
+    elif which == "tlt_dwconv_wgrad":
+        x, dy, dw = tensors
+        xp = F.pad(x, _pad_arg(g))
+        dwk = dw.reshape(x.shape[1], *g["kernel"])
+        for taps in _all_taps(g):
+            dwk[(slice(None),) + taps] += (xp[_tap_slices(g, taps)] * dy).sum(dim=[0] + list(range(2, 2 + n))).to(dw.dtype)
+    else:
+        raise AssertionError(which)
+    LOG.append((which, g))
+
+
+@contextlib.contextmanager
+def emulated_kernels():
+    """Swap the two launch funnels for the CPU interpreters (tests only)."""
+    saved = ops._execute_contract, ops._execute_conv
+    ops._execute_contract, ops._execute_conv = emulate_contract, emulate_conv
+    del LOG[:]
+    try:
+        yield LOG
+    finally:
+        ops._execute_contract, ops._execute_conv = saved

@@ -1,0 +1,271 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI, against
+  (a) golden fixtures produced by the real reference (tests/golden/*.pt),
+  (b) the CPU oracle on seeded inputs at sizes the oracle finishes in seconds,
+  (c) size-independent properties at BASELINE.json's full sizes.
+Tolerances are north_star's: relative Frobenius error <= 1e-5 (fp32), <= 2e-2 (bf16)."""
+import math
+
+import pytest
+import torch
+
+import _golden as G
+import _cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def q(t, dtype):
+    """values representable in `dtype`, held in fp64 on the CPU (what the oracle consumes)"""
+    return t.to(dtype).double().cpu()
+
+
+# ------------------------------------------------------------------------------------------------- (a) goldens
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name,sub", _cases.all_cases())
+def test_golden_cases(name, sub, dtype):
+    import torch_b200 as tlt
+    g, sub2 = _cases.load_case(name, sub)
+    before = tlt.ops.launch_count()
+    y, grads, ey, eg = _cases.run_case(name, g, dev(), dtype, sub2)
+    assert tlt.ops.launch_count() > before, "no kernel of libtltorch_cuda.so was launched"
+    tol = TOL[dtype] if dtype == torch.float32 else 3e-2   # goldens were computed from un-rounded fp32 inputs
+    assert G.rel_err(y, ey.reshape(y.shape)) < tol
+    for n, gr in grads.items():
+        assert G.rel_err(gr, eg[n]) < tol * (1 if dtype == torch.float32 else 1.5), n
+
+
+def test_golden_reconstruction():
+    allg = G.load("reconstruction")
+    for key, g in allg.items():
+        w, _ = _cases.build_weight(g["kind"], g["params"], dev(), torch.float32, g.get("tensorized_shape"))
+        full = w.to_matrix() if key.startswith("matrix_") else w.to_tensor()
+        assert G.rel_err(full, g["full"]) < 1e-5, key
+
+
+# ------------------------------------------------------------------------------------------------- (b) oracle, seeded
+def _contract_vs_einsum(spec, a_shape, b_shape, dtype, addend=None, a_perm=None, b_perm=None, alpha=1.0):
+    from torch_b200.ops import contract
+    torch.manual_seed(hash(spec) % 1000)
+    a = torch.randn(a_shape, device=dev(), dtype=dtype)
+    b = torch.randn(b_shape, device=dev(), dtype=dtype)
+    if a_perm:
+        a = a.permute(a_perm).contiguous().permute([a_perm.index(i) for i in range(len(a_perm))])
+    if b_perm:
+        b = b.permute(b_perm).contiguous().permute([b_perm.index(i) for i in range(len(b_perm))])
+    want = torch.einsum(spec, a.double().cpu(), b.double().cpu()) * alpha
+    d = None
+    if addend:
+        letters = spec.split("->")[1]
+        d = torch.randn([want.shape[letters.index(l)] for l in addend], device=dev(), dtype=dtype)
+        view = [want.shape[i] if l in addend else 1 for i, l in enumerate(letters)]
+        want = want + d.double().cpu().reshape(view)
+    got = contract(spec, a, b, d, addend or "", alpha)
+    return G.rel_err(got, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_contract_kernel_shapes_and_edges(dtype):
+    tol = TOL[dtype] if dtype == torch.float32 else 1e-2
+    cases = [
+        ("mk,kn->mn", (70, 33), (33, 65), {}),                       # ragged tiles
+        ("mk,nk->mn", (128, 64), (96, 64), {}),                      # both K-major
+        ("km,kn->mn", (40, 130), (40, 17), {}),                      # both MN-major, small N tile
+        ("bmk,bkn->bmn", (3, 20, 7), (3, 7, 9), {}),                 # batched
+        ("abcd,dcef->abef", (4, 3, 5, 6), (6, 5, 2, 7), {}),         # composite K (2 sub-dims, different order)
+        ("abc,bd->adc", (6, 7, 8), (7, 5), {}),                      # mode product writing a middle mode
+        ("ar,br->abr", (5, 16), (7, 16), {}),                        # Khatri-Rao (K empty, batch r)
+        ("a,a->", (1000,), (1000,), {}),                             # full reduction to a scalar
+        ("mk,kn->mn", (3000, 5), (5, 4), {}),                        # tall-skinny (128x16 tile)
+        ("mk,kn->mn", (7, 5), (5, 3000), {}),                        # short-wide (16x128 tile)
+        ("mk,kn->mn", (8, 40000), (40000, 8), {}),                   # split-K + workspace
+        ("mk,kn->mn", (64, 32), (32, 48), dict(addend="n")),         # bias along n
+        ("mk,kn->mn", (64, 32), (32, 48), dict(addend="m", alpha=0.5)),
+        ("mk,kn->nm", (33, 20), (20, 17), {}),                       # transposed output
+        ("mk,kn->mn", (0, 4), (4, 5), {}),                           # empty M
+        ("mk,kn->mn", (4, 0), (0, 5), dict(addend="n")),             # empty K: output is the addend
+        ("abc,bd->adc", (6, 7, 8), (7, 5), dict(a_perm=(2, 0, 1))),  # non-contiguous operand
+    ]
+    for spec, sa, sb, kw in cases:
+        err = _contract_vs_einsum(spec, sa, sb, dtype, **kw)
+        assert err < tol, (spec, sa, sb, kw, err)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 128, 0, 0), (300, 520, 200, 0, 0), (128, 128, 64, 1, 1), (384, 136, 4096, 1, 1),
+                                   (1000, 264, 72, 0, 1), (130, 1024, 256, 1, 0), (2048, 3072, 768, 0, 0)])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_tcgen05_gemm_against_fp64(shape, out_dtype):
+    """tlt_gemm_bf16_tc directly through the C ABI: all four operand-major combinations, ragged M/N/K tails, bias."""
+    import ctypes as C
+    from torch_b200 import _cuda
+    M, N, K, a_mn, b_mn = shape
+    torch.manual_seed(M + N + K)
+    a = torch.randn((K, M) if a_mn else (M, K), device=dev(), dtype=torch.bfloat16)
+    b = torch.randn((K, N) if b_mn else (N, K), device=dev(), dtype=torch.bfloat16)
+    bias = torch.randn(N, device=dev(), dtype=torch.float32)
+    c = torch.full((M, N), float("nan"), device=dev(), dtype=out_dtype)
+    g = _cuda.GemmDesc()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldc = a.shape[1], b.shape[1], N
+    g.a_major, g.b_major = a_mn, b_mn
+    g.dtype_c = _cuda.dtype_code(out_dtype)
+    g.dtype_bias = _cuda.F32
+    g.alpha = 0.5
+    lib = _cuda.lib()
+    assert lib.tlt_gemm_bf16_tc_supported(C.byref(g)) == 1
+    _cuda.check(lib.tlt_gemm_bf16_tc(C.byref(g), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(bias), _cuda.ptr(c),
+                                     _cuda.stream_ptr(c)), "tlt_gemm_bf16_tc")
+    torch.cuda.synchronize()
+    A = (a.t() if a_mn else a).double().cpu()
+    Bm = (b.t() if b_mn else b).double().cpu()
+    want = 0.5 * (A @ Bm.t()) + bias.double().cpu()
+    assert not torch.isnan(c.float()).any()
+    assert G.rel_err(c, want) < (1e-5 if out_dtype == torch.float32 else 4e-3)
+
+
+def test_tcgen05_and_simt_agree_through_contract():
+    from torch_b200 import ops
+    torch.manual_seed(3)
+    x = torch.randn(512, 768, device=dev(), dtype=torch.bfloat16)
+    w = torch.randn(3072, 768, device=dev(), dtype=torch.bfloat16)
+    before = ops.launch_count()
+    y_tc = ops.contract("bi,oi->bo", x, w)
+    ops._FORCE_SIMT = True
+    try:
+        y_simt = ops.contract("bi,oi->bo", x, w)
+    finally:
+        ops._FORCE_SIMT = False
+    assert ops.launch_count() - before == 2
+    assert G.rel_err(y_tc, y_simt.double()) < 1e-2
+    want = x.double().cpu() @ w.double().cpu().t()
+    assert G.rel_err(y_tc, want) < 4e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fact", ["cp", "tucker", "blocktt"])
+def test_factorized_linear_layer_vs_oracle(fact, dtype):
+    """FactorizedLinear module fwd+bwd vs the oracle (fp64, same rounded parameter values)."""
+    import torch_b200 as tlt
+    from oracle import reference_path as rp
+    torch.manual_seed(11)
+    in_ts, out_ts = (4, 8, 4), (8, 4, 8)
+    layer = tlt.FactorizedLinear(in_ts, out_ts, bias=True, factorization=fact, rank=0.3 if fact != "blocktt" else 8,
+                                 device=dev()).to(dtype)
+    if fact == "cp":
+        layer.weight.weights.data.uniform_(0.5, 1.5)
+    x = torch.randn(96, 128, device=dev(), dtype=dtype, requires_grad=True)
+    y = layer(x)
+    gy = torch.randn_like(y)
+    params = dict(layer.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    # oracle
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(len(layer.weight.factors))]
+    if fact == "cp":
+        p = (leaves["weight.weights"], fs)
+    elif fact == "tucker":
+        p = (leaves["weight.core"], fs)
+    else:
+        p = fs
+    yo = rp.factorized_linear(xo, fact, p, (out_ts, in_ts), bias=leaves["bias"], order="sane")
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    tol = TOL[dtype]
+    assert G.rel_err(y, yo) < tol
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < tol * (1 if dtype == torch.float32 else 1.5), n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fact,impl", [("cp", "factorized"), ("cp", "mobilenet"), ("tucker", "factorized"),
+                                       ("tt", "factorized"), ("cp", "reconstructed")])
+def test_factorized_conv_layer_vs_oracle(fact, impl, dtype):
+    import torch_b200 as tlt
+    from oracle import reference_path as rp
+    torch.manual_seed(5)
+    conv = tlt.FactorizedConv(16, 24, 3, order=2, stride=2, padding=1, bias=True, factorization=fact, rank=0.5,
+                              implementation=impl, device=dev())
+    conv.reset_parameters(std=0.3)
+    conv.bias.data.normal_()
+    conv = conv.to(dtype)
+    x = torch.randn(4, 16, 14, 14, device=dev(), dtype=dtype, requires_grad=True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    params = dict(conv.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(len(conv.weight.factors))]
+    kw = dict(bias=leaves["bias"], stride=[2, 2], padding=[1, 1], dilation=[1, 1])
+    if impl == "reconstructed":
+        yo = rp.reconstructed_conv(xo, fact, (leaves["weight.weights"], fs), **kw)
+    elif fact == "cp":
+        yo = (rp.cp_conv if impl == "factorized" else rp.cp_conv_mobilenet)(xo, leaves["weight.weights"], fs, **kw)
+    elif fact == "tucker":
+        yo = rp.tucker_conv(xo, leaves["weight.core"], fs, **kw)
+    else:
+        yo = rp.tt_conv(xo, fs, **kw)
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    tol = TOL[dtype]
+    assert G.rel_err(y, yo) < tol
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < tol * (1 if dtype == torch.float32 else 1.5), n
+
+
+def test_trl_and_dropout_vs_oracle():
+    import torch_b200 as tlt
+    from torch_b200.functional.tensor_regression import trl
+    from oracle import reference_path as rp
+    torch.manual_seed(9)
+    layer = tlt.TRL((32, 7, 7), (10,), bias=True, factorization="tucker", rank=(8, 4, 4, 5), device=dev())
+    x = torch.randn(16, 32, 7, 7, device=dev(), requires_grad=True)
+    y = layer(x)
+    core = layer.weight.core.detach().double().cpu()
+    fs = [f.detach().double().cpu() for f in layer.weight.factors]
+    yo = rp.tucker_trl(x.detach().double().cpu(), core, fs, bias=layer.bias.detach().double().cpu())
+    assert G.rel_err(y, yo) < 1e-5
+    # dropout through the functional (TRL.forward bypasses hooks, App. C.1); same seed -> same kept components
+    tlt.tensor_dropout(layer.weight, p=0.5, min_dim=3)
+    layer.weight.train()
+    torch.manual_seed(77)
+    dropped = layer.weight()
+    torch.manual_seed(77)
+    idx = [rp.sample_keep_indices(r, 0.5, 3, device=dev()).cpu() for r in layer.weight.rank]
+    c2, f2 = rp.tucker_dropout_apply(core, fs, idx, 0.5, training=True)
+    assert dropped.rank == tuple(c2.shape)
+    yd = trl(x, dropped, bias=layer.bias)
+    yo = rp.tucker_trl(x.detach().double().cpu(), c2, f2, bias=layer.bias.detach().double().cpu())
+    assert G.rel_err(yd, yo) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------- (c) full size
+def test_config2_full_size_properties():
+    """BASELINE config 2 (BERT-base FFN, BlockTT rank 16, 64x512 tokens, bf16): linearity in x, agreement of the
+    factorized path with x @ to_matrix().T on a row sample checked in fp64, and gradient identities."""
+    import torch_b200 as tlt
+    torch.manual_seed(2)
+    up = tlt.FactorizedLinear((8, 8, 12), (8, 12, 32), bias=True, factorization="blocktt", rank=16, device=dev()).to(torch.bfloat16)
+    B = 64 * 512
+    x = torch.randn(B, 768, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    y = up(x)
+    assert y.shape == (B, 3072)
+    W = up.weight.to_matrix().double().cpu()
+    rows = torch.randint(0, B, (64,))
+    want = x.detach()[rows.to(dev())].double().cpu() @ W.t() + up.bias.double().cpu()
+    assert G.rel_err(y[rows.to(dev())], want) < 2e-2
+    # linearity: f(2x) - b == 2 (f(x) - b)   (exact scaling by 2 in bf16)
+    y2 = up(2 * x.detach())
+    lhs = (y2.float() - up.bias.float())
+    rhs = 2 * (y.detach().float() - up.bias.float())
+    assert G.rel_err(lhs, rhs.double()) < 2e-2
+    # gradient identities on a column sample: dX = dY W ; dbias = sum_b dY
+    gy = torch.randn_like(y)
+    gx, gb = torch.autograd.grad(y, [x, up.bias], gy)
+    want_gx = gy[rows.to(dev())].double().cpu() @ W
+    assert G.rel_err(gx[rows.to(dev())], want_gx) < 2e-2
+    assert G.rel_err(gb, gy.double().sum(0).cpu()) < 2e-2

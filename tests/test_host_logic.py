@@ -1,0 +1,163 @@
+"""CPU tests of the product's HOST logic with the CUDA kernels replaced by descriptor interpreters
+(tests/_emulator.py): every functional path and its autograd must reproduce the real reference's golden outputs."""
+import pytest
+import torch
+
+import torch_b200 as tlt
+from torch_b200 import ops, tenalg
+import _golden as G
+import _cases
+from _emulator import emulated_kernels
+
+TOL = 1e-10
+D = torch.float64
+
+
+@pytest.mark.parametrize("name,sub", _cases.all_cases())
+def test_functional_paths_match_reference_goldens(name, sub):
+    g, sub2 = _cases.load_case(name, sub)
+    with emulated_kernels() as log:
+        y, grads, ey, eg = _cases.run_case(name, g, "cpu", D, sub2)
+    assert log, "no kernel launch was recorded: the path bypassed the custom ops"
+    assert G.rel_err(y, ey.reshape(y.shape)) < TOL
+    assert set(grads) == set(eg)
+    for n, gr in grads.items():
+        assert gr is not None, n
+        assert G.rel_err(gr, eg[n]) < TOL, n
+
+
+def test_reconstruction_matches_reference():
+    allg = G.load("reconstruction")
+    with emulated_kernels():
+        for key, g in allg.items():
+            w, _ = _cases.build_weight(g["kind"], g["params"], "cpu", D, g.get("tensorized_shape"))
+            full = w.to_matrix() if key.startswith("matrix_") else w.to_tensor()
+            assert tuple(full.shape) == tuple(g["full"].shape), key
+            assert G.rel_err(full, g["full"]) < TOL, key
+
+
+def test_dropout_replays_reference_rng():
+    from torch_b200.tensor_hooks._tensor_dropout import TuckerDropout, CPDropout, TTDropout
+    allg = G.load("dropout")
+    with emulated_kernels():
+        for key, g in allg.items():
+            kind = key.split("_")[0]
+            w, _ = _cases.build_weight(kind, g["params"], "cpu", D)
+            hook = {"tucker": TuckerDropout, "cp": CPDropout, "tt": TTDropout}[kind](g["proba"], min_dim=g["min_dim"],
+                                                                                    min_values=1, drop_test=True)
+            torch.manual_seed(g["seed"])
+            dropped = hook._apply_tensor_dropout(w, training=g["training"])
+            assert G.rel_err(dropped.to_tensor(), g["full"]) < TOL, key
+            exp = g["dropped"]
+            for a, b in zip(dropped.factors, exp["factors"]):
+                assert a.shape == b.shape and G.rel_err(a, b) < 1e-14, key
+
+
+def test_dropout_hook_plumbing():
+    # reference tests: tensor_hooks/tests/test_tensor_dropout.py:8-61 (shapes only)
+    with emulated_kernels():
+        for fact in ("cp", "tucker", "tt"):
+            t = tlt.FactorizedTensor.new((10, 11, 12), rank=8 if fact != "tt" else (1, 8, 8, 1), factorization=fact).normal_()
+            t = tlt.tensor_dropout(t, p=0.999, min_dim=1)
+            t.train()
+            r = t().rank
+            r = (r,) if isinstance(r, int) else tuple(r)
+            assert all(v == 1 for v in (r[1:-1] if fact == "tt" else r)), (fact, r)
+            tlt.remove_tensor_dropout(t)
+            assert not t._forward_hooks
+            t = tlt.tensor_dropout(t, p=0)
+            assert t().rank == t.rank
+    with pytest.raises(KeyError):          # App. C.2: no dropout class for tensorized matrices
+        tlt.tensor_dropout(tlt.TensorizedTensor.new(((2, 2), (2, 2)), rank=2, factorization="cp"), p=0.5)
+
+
+def test_layers_match_dense_equivalents():
+    """The reference's own identities: FactorizedLinear == nn.Linear(to_matrix) (factorized_layers/tests/
+    test_factorized_linear.py:10-31), FactorizedConv == nn.Conv2d(to_tensor) (test_factorized_convolution.py:13-57)."""
+    torch.manual_seed(0)
+    with emulated_kernels():
+        for fact in ("cp", "tucker", "blocktt"):
+            for impl in ("factorized", "reconstructed"):
+                layer = tlt.FactorizedLinear((3, 3), (4, 4), bias=True, factorization=fact, rank=0.5 if fact != "blocktt" else 2,
+                                             implementation=impl, dtype=D)
+                x = torch.randn(2, 9, dtype=D)
+                want = torch.nn.functional.linear(x, layer.weight.to_matrix(), layer.bias)
+                assert G.rel_err(layer(x), want) < TOL, (fact, impl)
+        for fact, impls in (("cp", ("factorized", "reconstructed", "mobilenet")), ("tucker", ("factorized", "reconstructed")),
+                            ("tt", ("factorized", "reconstructed"))):
+            for impl in impls:
+                conv = tlt.FactorizedConv(4, 5, 3, order=2, padding=1, bias=True, factorization=fact, rank=0.5,
+                                          implementation=impl, dtype=D)
+                conv.reset_parameters(std=0.5)
+                conv.bias.data.normal_()
+                x = torch.randn(1, 4, 8, 7, dtype=D)
+                from torch_b200.factorized_layers.factorized_convolution import tensor_to_kernel
+                k = tensor_to_kernel(fact, conv.weight.to_tensor())
+                want = torch.nn.functional.conv2d(x, k, conv.bias, padding=1)
+                assert G.rel_err(conv(x), want) < TOL, (fact, impl)
+        # n_layers > 1: jointly factorized linears / convs index the leading mode in factorized form
+        for fact in ("cp", "tucker", "blocktt"):
+            layer = tlt.FactorizedLinear((3, 3), (4, 4), bias=True, factorization=fact, rank=3, n_layers=2, dtype=D)
+            x = torch.randn(2, 9, dtype=D)
+            full = layer.weight.to_matrix()
+            for i in range(2):
+                want = torch.nn.functional.linear(x, full[i], layer.bias[i])
+                assert G.rel_err(layer(x, i), want) < TOL, fact
+                assert G.rel_err(layer[i](x), want) < TOL, fact
+        # TRL / TCL modules
+        trl = tlt.TRL((3, 4), (2,), bias=True, factorization="tucker", rank=(2, 3, 2), dtype=D)
+        x = torch.randn(5, 3, 4, dtype=D)
+        want = torch.einsum("bij,ijo->bo", x, trl.weight.to_tensor()) + trl.bias
+        assert G.rel_err(trl(x), want) < TOL
+        tcl = tlt.TCL((4, 5, 6), (2, 3, 5), bias=True, dtype=D)
+        x = torch.randn(2, 4, 5, 6, dtype=D)
+        assert tuple(tcl(x).shape) == (2, 2, 3, 5)     # reference test pins the shape only
+        want = torch.einsum("bijk,ri,sj,tk->brst", x, *tcl.factors) + tcl.bias
+        assert G.rel_err(tcl(x), want) < TOL
+
+
+def test_state_dict_keys_match_reference_names():
+    lin = tlt.FactorizedLinear((2, 2), (2, 2), factorization="cp", rank=2)
+    assert set(lin.state_dict()) == {"bias", "weight.weights", "weight.factors.factor_0", "weight.factors.factor_1",
+                                     "weight.factors.factor_2", "weight.factors.factor_3"}
+    conv = tlt.FactorizedConv(3, 4, 3, order=2, factorization="tucker", rank=0.5)
+    assert {"weight.core", "weight.factors.factor_0"} <= set(conv.state_dict())
+    tt = tlt.FactorizedLinear((2, 2), (2, 2), factorization="blocktt", rank=2, bias=False)
+    assert set(tt.state_dict()) == {"weight.factors.factor_0", "weight.factors.factor_1"}
+
+
+def test_planner_merges_and_classifies():
+    # contiguous GEMM: everything merges to one sub-dim per class and is tensor-core eligible
+    p = ops.plan_contract("bi,oi->bo", (64, 32), (32, 1), (16, 32), (32, 1), None, None)
+    assert p.classes == dict(b=[], m=[64], n=[16], k=[32]) and p.tc is not None
+    assert p.tc["a_major"] == 0 and p.tc["b_major"] == 0
+    # dW = dY^T X: both operands MN-major
+    p = ops.plan_contract("bo,bi->oi", (64, 16), (16, 1), (64, 32), (32, 1), None, None)
+    assert p.tc is not None and p.tc["a_major"] == 1 and p.tc["b_major"] == 1 and p.tc["lda"] == 16
+    # TT sweep stage: composite m and k
+    p = ops.plan_contract("abcr,rodq->acodq"[:0] + "abcr,rodq->acodq".replace("d", "b"), (5, 4, 3, 2), (24, 6, 2, 1),
+                          (2, 6, 4, 7), (168, 28, 7, 1), None, None)
+    assert p.classes["k"] and p.tc is None
+    # size-1 dims disappear, batch index detected
+    p = ops.plan_contract("zar,zbr->zab", (3, 4, 1), (4, 1, 1), (3, 5, 1), (5, 1, 1), None, None)
+    assert p.classes["b"] == [3] and p.classes["k"] == []
+    with pytest.raises(ValueError):
+        ops.plan_contract("ab,bc->c", (2, 3), (3, 1), (3, 4), (4, 1), None, None)   # 'a' summed alone
+
+
+def test_blocktt_cost_model_picks_dense_for_bert_ffn():
+    from torch_b200.functional.factorized_linear import blocktt_plan, blocktt_sweep_macs
+    assert blocktt_sweep_macs((8, 8, 12), (8, 12, 32), (1, 16, 16, 1)) == 3047424          # 3.05 M MAC
+    assert blocktt_plan(32768, (8, 8, 12), (8, 12, 32), (1, 16, 16, 1)) == "dense"
+    assert blocktt_plan(32768, (8, 12, 32), (8, 8, 12), (1, 16, 16, 1)) == "dense"
+    assert blocktt_plan(32768, (16, 16, 16), (16, 16, 16), (1, 2, 2, 1)) == "sweep"
+
+
+def test_cpu_tensors_are_rejected_without_fallback():
+    lin = tlt.FactorizedLinear((2, 2), (2, 2), factorization="cp", rank=2)
+    with pytest.raises(NotImplementedError):
+        lin(torch.randn(3, 4))
+    with pytest.raises(AssertionError):
+        tlt.functional.factorized_linear(torch.randn(3, 4), lin.weight, implementation="nope")
+    with pytest.raises(ValueError):
+        tlt.FactorizedTensor.new((2, 2), rank=1, factorization="nope")

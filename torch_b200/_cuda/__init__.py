@@ -1,0 +1,118 @@
+"""ctypes binding of libtltorch_cuda.so (the C ABI declared in include/tltorch_cuda.h).
+
+There is NO CPU fallback: every launcher raises if the tensors are not CUDA tensors, and loading fails loudly if the
+shared library is missing on a box that has a GPU.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtltorch_cuda.so")
+MAX_SUBDIMS = 4
+F32, BF16 = 0, 1
+
+_lib = None
+
+
+class TltError(RuntimeError):
+    pass
+
+
+class ContractDesc(C.Structure):
+    _A = C.c_int64 * MAX_SUBDIMS
+    _fields_ = [("dtype_a", C.c_int32), ("dtype_b", C.c_int32), ("dtype_c", C.c_int32), ("dtype_d", C.c_int32),
+                ("nb", C.c_int32), ("nm", C.c_int32), ("nn", C.c_int32), ("nk", C.c_int32),
+                ("size_b", _A), ("size_m", _A), ("size_n", _A), ("size_k", _A),
+                ("a_b", _A), ("a_m", _A), ("a_k", _A),
+                ("b_b", _A), ("b_k", _A), ("b_n", _A),
+                ("c_b", _A), ("c_m", _A), ("c_n", _A),
+                ("d_b", _A), ("d_m", _A), ("d_n", _A),
+                ("alpha", C.c_float), ("accumulate", C.c_int32), ("split_k", C.c_int32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+                ("a_major", C.c_int32), ("b_major", C.c_int32), ("dtype_c", C.c_int32), ("accumulate", C.c_int32),
+                ("dtype_bias", C.c_int32), ("alpha", C.c_float)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("ndim", C.c_int32), ("batch", C.c_int64), ("channels", C.c_int64),
+                ("in_size", C.c_int64 * 3), ("out_size", C.c_int64 * 3),
+                ("kernel", C.c_int32 * 3), ("stride", C.c_int32 * 3), ("padding", C.c_int32 * 3),
+                ("dilation", C.c_int32 * 3)]
+
+
+# every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
+_vp = C.c_void_p
+SYMBOLS = {
+    "tlt_version": (C.c_int, []),
+    "tlt_last_error_string": (C.c_char_p, []),
+    "tlt_launch_count": (C.c_uint64, []),
+    "tlt_contract_workspace_size": (C.c_size_t, [C.POINTER(ContractDesc)]),
+    "tlt_contract": (C.c_int, [C.POINTER(ContractDesc), _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "tlt_gemm_bf16_tc_supported": (C.c_int, [C.POINTER(GemmDesc)]),
+    "tlt_gemm_bf16_tc": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp]),
+    "tlt_im2col": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "tlt_col2im": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "tlt_dwconv_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwconv_dgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwconv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "tlt_cast": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, _vp]),
+    "tlt_l2_flush": (C.c_int, [_vp, C.c_size_t, _vp]),
+}
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TltError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU or PyTorch fallback for the factorized-layer hot path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.tlt_version() != 1:
+            raise TltError(f"ABI version mismatch: library reports {handle.tlt_version()}")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().tlt_last_error_string()
+        raise TltError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise TypeError(f"the tltorch CUDA path computes in float32 or bfloat16, got {dt}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NotImplementedError(
+                "tltorch-b200 runs the factorized-layer hot path on CUDA (sm_100a) only; got a CPU tensor. "
+                "There is deliberately no CPU fallback (the CPU oracle under oracle/ is test infrastructure).")
+
+
+def stream_ptr(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def launch_count():
+    return int(lib().tlt_launch_count())

@@ -1,0 +1,367 @@
+// tlt_contract: generic strided pairwise contraction  C[b,m,n] = alpha * sum_k A[b,m,k] B[b,k,n] (+ D[b,m,n]).
+//
+// SIMT (FFMA, fp32 accumulate) kernel used for (a) every fp32 path -- north_star's 1e-5 relative-Frobenius bound rules
+// out plain TF32/bf16 tensor-core math for fp32 inputs -- and (b) the skinny / awkwardly-strided stages of the bf16
+// paths that the tcgen05 GEMM (gemm_tc.cu) cannot take.  Every index class (b, m, n, k) is a multi-index with
+// per-operand strides, so TT sweeps, Tucker mode products, Khatri-Rao builds and NCHW channel mixing all run on the
+// tensors where they lie, with no permute / contiguous copies in HBM.
+#include "common.cuh"
+
+namespace tlt {
+
+constexpr int kBK = 16;
+constexpr int kThreads = 256;
+
+struct ContractParams {
+  int nb, nm, nn, nk;
+  int size_b[TLT_MAX_SUBDIMS], size_m[TLT_MAX_SUBDIMS], size_n[TLT_MAX_SUBDIMS], size_k[TLT_MAX_SUBDIMS];
+  long long a_b[TLT_MAX_SUBDIMS], a_m[TLT_MAX_SUBDIMS], a_k[TLT_MAX_SUBDIMS];
+  long long b_b[TLT_MAX_SUBDIMS], b_k[TLT_MAX_SUBDIMS], b_n[TLT_MAX_SUBDIMS];
+  long long c_b[TLT_MAX_SUBDIMS], c_m[TLT_MAX_SUBDIMS], c_n[TLT_MAX_SUBDIMS];
+  long long d_b[TLT_MAX_SUBDIMS], d_m[TLT_MAX_SUBDIMS], d_n[TLT_MAX_SUBDIMS];
+  int M, N, K, Bt;
+  int tiles_m, tiles_n, split_k, k_per_split;
+  float alpha;
+  int accumulate;   // C += (fp32 C)
+  int atomic_out;   // partial sums -> atomicAdd
+  int dense_c;      // C is the dense fp32 workspace [Bt][M][N]
+  int has_d, d_bf16;
+  int a_k_fast, b_n_fast;
+};
+
+// offset of flattened index `idx` of one class: sub-dim 0 is outermost.
+__device__ __forceinline__ long long decomp(int idx, const int* size, const long long* stride, int n) {
+  long long off = 0;
+#pragma unroll
+  for (int d = TLT_MAX_SUBDIMS - 1; d >= 1; --d) {
+    if (d < n) {
+      int s = size[d];
+      int q = idx / s;
+      off += (long long)(idx - q * s) * stride[d];
+      idx = q;
+    }
+  }
+  if (n >= 1) off += (long long)idx * stride[0];
+  return off;
+}
+
+template <typename TA, typename TB, typename TC, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(kThreads) contract_kernel(const ContractParams p, const TA* __restrict__ A,
+                                                            const TB* __restrict__ B, const void* __restrict__ D,
+                                                            TC* __restrict__ C) {
+  static_assert((BM / TM) * (BN / TN) == kThreads, "thread tiling must cover the block tile");
+  constexpr int A_PER_T = BM * kBK / kThreads;   // = BM / 16
+  constexpr int B_PER_T = BN * kBK / kThreads;   // = BN / 16
+  __shared__ __align__(16) float As[kBK][BM + 4];
+  __shared__ __align__(16) float Bs[kBK][BN + 4];
+
+  const int tid = threadIdx.x;
+  // block id -> (z, tile_m, tile_n);  z -> (batch, split)
+  unsigned bid = blockIdx.x;
+  const int tn = bid % p.tiles_n; bid /= p.tiles_n;
+  const int tm = bid % p.tiles_m; bid /= p.tiles_m;
+  const int split = bid % p.split_k;
+  const int bidx = bid / p.split_k;
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int k_begin = split * p.k_per_split;
+  const int k_end = min(p.K, k_begin + p.k_per_split);
+
+  A += decomp(bidx, p.size_b, p.a_b, p.nb);
+  B += decomp(bidx, p.size_b, p.b_b, p.nb);
+
+  // ---- per-thread load coordinates -------------------------------------------------------------------------
+  // A tile (BM x BK): k-fast mapping (kk = tid%16) when the contiguous dim of A is a K dim, else m-fast.
+  int a_mm[A_PER_T], a_kk[A_PER_T];
+  long long a_moff[A_PER_T];
+#pragma unroll
+  for (int j = 0; j < A_PER_T; ++j) {
+    if (p.a_k_fast) { a_kk[j] = tid % kBK; a_mm[j] = tid / kBK + (kThreads / kBK) * j; }
+    else            { a_mm[j] = tid % BM;  a_kk[j] = tid / BM + (kThreads / BM) * j; }
+    int m = m0 + a_mm[j];
+    a_moff[j] = (m < p.M) ? decomp(m, p.size_m, p.a_m, p.nm) : -1;
+  }
+  int b_nn[B_PER_T], b_kk[B_PER_T];
+  long long b_noff[B_PER_T];
+#pragma unroll
+  for (int j = 0; j < B_PER_T; ++j) {
+    if (p.b_n_fast) { b_nn[j] = tid % BN;  b_kk[j] = tid / BN + (kThreads / BN) * j; }
+    else            { b_kk[j] = tid % kBK; b_nn[j] = tid / kBK + (kThreads / kBK) * j; }
+    int n = n0 + b_nn[j];
+    b_noff[j] = (n < p.N) ? decomp(n, p.size_n, p.b_n, p.nn) : -1;
+  }
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  float ra[A_PER_T], rb[B_PER_T];
+
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < A_PER_T; ++j) {
+      int k = k0 + a_kk[j];
+      float v = 0.f;
+      if (a_moff[j] >= 0 && k < k_end) {
+        long long ko = (p.nk == 1) ? (long long)k * p.a_k[0] : decomp(k, p.size_k, p.a_k, p.nk);
+        v = to_f32<TA>(A[a_moff[j] + ko]);
+      }
+      ra[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER_T; ++j) {
+      int k = k0 + b_kk[j];
+      float v = 0.f;
+      if (b_noff[j] >= 0 && k < k_end) {
+        long long ko = (p.nk == 1) ? (long long)k * p.b_k[0] : decomp(k, p.size_k, p.b_k, p.nk);
+        v = to_f32<TB>(B[b_noff[j] + ko]);
+      }
+      rb[j] = v;
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int j = 0; j < A_PER_T; ++j) As[a_kk[j]][a_mm[j]] = ra[j];
+#pragma unroll
+    for (int j = 0; j < B_PER_T; ++j) Bs[b_kk[j]][b_nn[j]] = rb[j];
+  };
+
+  if (k_begin < k_end) {
+    load_tile(k_begin);
+    store_tile();
+    __syncthreads();
+    for (int k0 = k_begin; k0 < k_end; k0 += kBK) {
+      const bool more = (k0 + kBK) < k_end;
+      if (more) load_tile(k0 + kBK);   // global loads in flight while the FMAs below run
+#pragma unroll
+      for (int kk = 0; kk < kBK; ++kk) {
+        float av[TM], bv[TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+      if (more) {
+        store_tile();
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- epilogue ----------------------------------------------------------------------------------------------
+  long long cb = p.dense_c ? (long long)bidx * p.M * p.N : decomp(bidx, p.size_b, p.c_b, p.nb);
+  long long db = (p.has_d && !p.dense_c) ? decomp(bidx, p.size_b, p.d_b, p.nb) : 0;
+  long long cn[TN], dn[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    int n = n0 + tx * TN + j;
+    cn[j] = dn[j] = 0;
+    if (n < p.N) {
+      cn[j] = p.dense_c ? (long long)n : decomp(n, p.size_n, p.c_n, p.nn);
+      if (p.has_d && !p.dense_c) dn[j] = decomp(n, p.size_n, p.d_n, p.nn);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+    long long cm = p.dense_c ? (long long)m * p.N : decomp(m, p.size_m, p.c_m, p.nm);
+    long long dm = (p.has_d && !p.dense_c) ? decomp(m, p.size_m, p.d_m, p.nm) : 0;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= p.N) continue;
+      float v = p.alpha * acc[i][j];
+      if (p.has_d && !p.dense_c && split == 0) {
+        long long doff = db + dm + dn[j];
+        v += p.d_bf16 ? __bfloat162float(((const __nv_bfloat16*)D)[doff]) : ((const float*)D)[doff];
+      }
+      TC* dst = C + cb + cm + cn[j];
+      if constexpr (sizeof(TC) == 4) {
+        if (p.atomic_out) atomicAdd((float*)dst, v);
+        else if (p.accumulate) *dst = from_f32<TC>(to_f32<TC>(*dst) + v);
+        else *dst = from_f32<TC>(v);
+      } else {
+        *dst = from_f32<TC>(v);
+      }
+    }
+  }
+}
+
+// workspace [Bt][M][N] fp32 -> strided C (+D)
+template <typename TC>
+__global__ void contract_finalize_kernel(const ContractParams p, const float* __restrict__ ws,
+                                         const void* __restrict__ D, TC* __restrict__ C) {
+  long long total = (long long)p.Bt * p.M * p.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i % p.N);
+    long long r = i / p.N;
+    int m = (int)(r % p.M);
+    int b = (int)(r / p.M);
+    float v = ws[i];
+    if (p.has_d) {
+      long long doff = decomp(b, p.size_b, p.d_b, p.nb) + decomp(m, p.size_m, p.d_m, p.nm) +
+                       decomp(n, p.size_n, p.d_n, p.nn);
+      v += p.d_bf16 ? __bfloat162float(((const __nv_bfloat16*)D)[doff]) : ((const float*)D)[doff];
+    }
+    long long coff = decomp(b, p.size_b, p.c_b, p.nb) + decomp(m, p.size_m, p.c_m, p.nm) +
+                     decomp(n, p.size_n, p.c_n, p.nn);
+    if (p.accumulate) C[coff] = from_f32<TC>(to_f32<TC>(C[coff]) + v);
+    else C[coff] = from_f32<TC>(v);
+  }
+}
+
+static long long prod(const int64_t* s, int n) {
+  long long r = 1;
+  for (int i = 0; i < n; ++i) r *= s[i];
+  return r;
+}
+
+static int choose_split(const tlt_contract_desc* d, long long M, long long N, long long K, long long Bt, int bm, int bn) {
+  if (d->split_k > 0) return d->split_k;
+  long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Bt;
+  if (tiles >= 148 || K < 1024) return 1;
+  long long want = (2 * 148 + tiles - 1) / tiles;
+  long long max_by_k = K / 256;
+  long long s = want < max_by_k ? want : max_by_k;
+  if (s > 128) s = 128;
+  return s < 1 ? 1 : (int)s;
+}
+
+static void tile_shape(long long M, long long N, int* bm, int* bn) {
+  if (N <= 16 && M > 64) { *bm = 128; *bn = 16; }
+  else if (M <= 16 && N > 64) { *bm = 16; *bn = 128; }
+  else { *bm = 64; *bn = 64; }
+}
+
+static bool needs_workspace(const tlt_contract_desc* d, int split) {
+  // split-K partials are combined with fp32 atomics in a dense fp32 workspace, then written (cast / +D / +=C) by the
+  // finalize kernel, so the caller never has to pre-zero C.
+  (void)d;
+  return split > 1;
+}
+
+template <typename TA, typename TB, typename TC>
+static int launch_typed(const ContractParams& p, int bm, int bn, const void* A, const void* B, const void* D, void* C,
+                        cudaStream_t st) {
+  long long blocks = (long long)p.tiles_m * p.tiles_n * p.split_k * p.Bt;
+  if (blocks <= 0 || blocks > 0x7fffffffLL) {
+    set_error("tlt_contract: grid of %lld blocks is out of range", blocks);
+    return TLT_ERR_INVALID;
+  }
+  dim3 grid((unsigned)blocks), block(kThreads);
+  if (bm == 64) contract_kernel<TA, TB, TC, 64, 64, 4, 4><<<grid, block, 0, st>>>(p, (const TA*)A, (const TB*)B, D, (TC*)C);
+  else if (bm == 128) contract_kernel<TA, TB, TC, 128, 16, 4, 2><<<grid, block, 0, st>>>(p, (const TA*)A, (const TB*)B, D, (TC*)C);
+  else contract_kernel<TA, TB, TC, 16, 128, 2, 4><<<grid, block, 0, st>>>(p, (const TA*)A, (const TB*)B, D, (TC*)C);
+  return check_launch("contract_kernel");
+}
+
+template <typename TC>
+static int launch_ab(const ContractParams& p, int da, int db, int bm, int bn, const void* A, const void* B,
+                     const void* D, void* C, cudaStream_t st) {
+  typedef __nv_bfloat16 bf;
+  if (da == TLT_F32 && db == TLT_F32) return launch_typed<float, float, TC>(p, bm, bn, A, B, D, C, st);
+  if (da == TLT_BF16 && db == TLT_BF16) return launch_typed<bf, bf, TC>(p, bm, bn, A, B, D, C, st);
+  if (da == TLT_F32 && db == TLT_BF16) return launch_typed<float, bf, TC>(p, bm, bn, A, B, D, C, st);
+  return launch_typed<bf, float, TC>(p, bm, bn, A, B, D, C, st);
+}
+
+static int fill_params(const tlt_contract_desc* d, ContractParams* p) {
+  TLT_REQUIRE(d != nullptr, "tlt_contract: null descriptor");
+  TLT_REQUIRE(d->nb >= 0 && d->nb <= TLT_MAX_SUBDIMS && d->nm >= 0 && d->nm <= TLT_MAX_SUBDIMS && d->nn >= 0 &&
+                  d->nn <= TLT_MAX_SUBDIMS && d->nk >= 0 && d->nk <= TLT_MAX_SUBDIMS,
+              "tlt_contract: sub-dimension counts must be in [0, %d]", TLT_MAX_SUBDIMS);
+  long long M = prod(d->size_m, d->nm), N = prod(d->size_n, d->nn), K = prod(d->size_k, d->nk), Bt = prod(d->size_b, d->nb);
+  TLT_REQUIRE(M >= 0 && N >= 0 && K >= 0 && Bt >= 0, "tlt_contract: negative extent");
+  TLT_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31) && Bt < (1LL << 31),
+              "tlt_contract: a flattened index class exceeds 2^31-1");
+  memset(p, 0, sizeof(*p));
+  p->nb = d->nb; p->nm = d->nm; p->nn = d->nn; p->nk = d->nk;
+  for (int i = 0; i < TLT_MAX_SUBDIMS; ++i) {
+    p->size_b[i] = i < d->nb ? (int)d->size_b[i] : 1;
+    p->size_m[i] = i < d->nm ? (int)d->size_m[i] : 1;
+    p->size_n[i] = i < d->nn ? (int)d->size_n[i] : 1;
+    p->size_k[i] = i < d->nk ? (int)d->size_k[i] : 1;
+    p->a_b[i] = d->a_b[i]; p->a_m[i] = d->a_m[i]; p->a_k[i] = d->a_k[i];
+    p->b_b[i] = d->b_b[i]; p->b_k[i] = d->b_k[i]; p->b_n[i] = d->b_n[i];
+    p->c_b[i] = d->c_b[i]; p->c_m[i] = d->c_m[i]; p->c_n[i] = d->c_n[i];
+    p->d_b[i] = d->d_b[i]; p->d_m[i] = d->d_m[i]; p->d_n[i] = d->d_n[i];
+  }
+  p->M = (int)M; p->N = (int)N; p->K = (int)K; p->Bt = (int)Bt;
+  p->alpha = d->alpha;
+  p->accumulate = d->accumulate;
+  // choose the coalescing-friendly load mapping: is the unit-stride dim of A (of B) a K dim?
+  p->a_k_fast = 0;
+  for (int i = 0; i < d->nk; ++i) if (d->a_k[i] == 1 && d->size_k[i] > 1) p->a_k_fast = 1;
+  for (int i = 0; i < d->nm; ++i) if (d->a_m[i] == 1 && d->size_m[i] > 1) p->a_k_fast = 0;
+  p->b_n_fast = 1;
+  for (int i = 0; i < d->nk; ++i) if (d->b_k[i] == 1 && d->size_k[i] > 1) p->b_n_fast = 0;
+  for (int i = 0; i < d->nn; ++i) if (d->b_n[i] == 1 && d->size_n[i] > 1) p->b_n_fast = 1;
+  return TLT_OK;
+}
+
+}  // namespace tlt
+
+using namespace tlt;
+
+extern "C" size_t tlt_contract_workspace_size(const tlt_contract_desc* d) {
+  ContractParams p;
+  if (fill_params(d, &p) != TLT_OK) return 0;
+  if (p.M == 0 || p.N == 0 || p.Bt == 0) return 0;
+  int bm, bn;
+  tile_shape(p.M, p.N, &bm, &bn);
+  int split = choose_split(d, p.M, p.N, p.K, p.Bt, bm, bn);
+  if (!needs_workspace(d, split)) return 0;
+  return (size_t)p.Bt * p.M * p.N * sizeof(float);
+}
+
+extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const void* B, const void* D, void* C,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  ContractParams p;
+  int rc = fill_params(d, &p);
+  if (rc != TLT_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.M == 0 || p.N == 0 || p.Bt == 0) return TLT_OK;   // empty output: nothing to do
+  TLT_REQUIRE(A && B && C, "tlt_contract: null operand pointer");
+  TLT_REQUIRE(!(d->accumulate && d->dtype_c != TLT_F32), "tlt_contract: accumulate needs an fp32 C");
+  int bm, bn;
+  tile_shape(p.M, p.N, &bm, &bn);
+  p.tiles_m = (p.M + bm - 1) / bm;
+  p.tiles_n = (p.N + bn - 1) / bn;
+  p.split_k = choose_split(d, p.M, p.N, p.K, p.Bt, bm, bn);
+  p.k_per_split = ((p.K + p.split_k - 1) / p.split_k + kBK - 1) / kBK * kBK;
+  if (p.k_per_split < kBK) p.k_per_split = kBK;
+  p.has_d = D != nullptr;
+  p.d_bf16 = d->dtype_d == TLT_BF16;
+
+  if (needs_workspace(d, p.split_k)) {
+    size_t need = (size_t)p.Bt * p.M * p.N * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("tlt_contract: split-K needs %zu bytes of workspace, got %zu", need, workspace_bytes);
+      return TLT_ERR_WORKSPACE;
+    }
+    TLT_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    ContractParams q = p;
+    q.dense_c = 1; q.atomic_out = 1; q.accumulate = 0; q.has_d = 0;
+    rc = launch_ab<float>(q, d->dtype_a, d->dtype_b, bm, bn, A, B, nullptr, workspace, st);
+    if (rc != TLT_OK) return rc;
+    long long total = (long long)p.Bt * p.M * p.N;
+    int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+    if (d->dtype_c == TLT_F32) contract_finalize_kernel<float><<<blocks, 256, 0, st>>>(p, (const float*)workspace, D, (float*)C);
+    else contract_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p, (const float*)workspace, D, (__nv_bfloat16*)C);
+    return check_launch("contract_finalize_kernel");
+  }
+  p.split_k = 1;
+  p.k_per_split = (p.K + kBK - 1) / kBK * kBK;
+  if (p.k_per_split < kBK) p.k_per_split = kBK;
+  if (d->dtype_c == TLT_F32) return launch_ab<float>(p, d->dtype_a, d->dtype_b, bm, bn, A, B, D, C, st);
+  return launch_ab<__nv_bfloat16>(p, d->dtype_a, d->dtype_b, bm, bn, A, B, D, C, st);
+}

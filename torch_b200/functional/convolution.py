@@ -1,0 +1,176 @@
+"""Factorized N-D convolutions: B200 counterparts of tltorch/functional/convolution.py.
+
+Every 1x1 channel-mixing stage is an ``ops.contract`` launch on the NCHW tensor where it lies (weights as the row
+operand so stores are coalesced along the spatial dim), depthwise stages run in the dedicated depthwise kernels, and
+dense k x k stages (Tucker core, TT cores, reconstructed kernels) run as unfold + contraction.
+"""
+import math
+
+import torch
+
+from .. import ops, tenalg
+from ..ops import contract
+
+
+def _tuple(v, order):
+    return (v,) * order if isinstance(v, int) else tuple(int(e) for e in v)
+
+
+def _pointwise(x, w_spec, w, bias=None):
+    """1x1 conv: x (B, C, *S), w indexed by ``w_spec`` in {'oc', 'co'} -> (B, O, *S)  (reference: F.conv1d k=1 call sites,
+    convolution.py:154,168,207,223,262,278,311,340)."""
+    b, c = x.shape[0], x.shape[1]
+    x3 = x.reshape(b, c, -1)
+    if bias is not None:
+        y = contract(f"{w_spec},bcs->bos", w, x3, bias, "o")
+    else:
+        y = contract(f"{w_spec},bcs->bos", w, x3)
+    return y.reshape(b, y.shape[1], *x.shape[2:])
+
+
+def _dense_conv(x, w_kmajor, w_spec, kernel, bias, stride, padding, dilation):
+    """Dense conv through unfold: cols[(b,s),(c,taps)] then one contraction writing NCHW directly.
+    ``w_kmajor`` is indexed by ``w_spec`` whose letters are 'q' (out channel), 'c' (in channel) and 't' (flattened taps)."""
+    order = len(kernel)
+    b, c = x.shape[0], x.shape[1]
+    out_size = ops.conv_out_size(list(x.shape[2:]), kernel, stride, padding, dilation)
+    cols = ops.im2col(x, kernel, stride, padding, dilation).reshape(b, math.prod(out_size), c, math.prod(kernel))
+    if bias is not None:
+        y = contract(f"{w_spec},bsct->bqs", w_kmajor, cols, bias, "q")
+    else:
+        y = contract(f"{w_spec},bsct->bqs", w_kmajor, cols)
+    return y.reshape(b, y.shape[1], *out_size)
+
+
+def convolve(x, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """Convolution of any order 1..3 with a dense or factorized (reconstructed on the fly) kernel.
+    reference: functional/convolution.py:16-53."""
+    from ..factorized_tensors import TTTensor
+    if not torch.is_tensor(weight):
+        if isinstance(weight, TTTensor):
+            weight = torch.movedim(weight.to_tensor(), -1, 0)
+        else:
+            weight = weight.to_tensor()
+    order = weight.dim() - 2
+    if order not in (1, 2, 3):
+        raise ValueError(f"Got tensor of order={weight.dim()} but pytorch only supports up to 3rd order (3D) Convs.")
+    stride, padding, dilation = _tuple(stride, order), _tuple(padding, order), _tuple(dilation, order)
+    kernel = list(weight.shape[2:])
+    if groups == 1:
+        w = weight.reshape(weight.shape[0], weight.shape[1], -1)
+        return _dense_conv(x, w, "qct", kernel, bias, stride, padding, dilation)
+    if groups == x.shape[1] and weight.shape[0] == groups and weight.shape[1] == 1:
+        y = ops.dwconv(x, weight.reshape(groups, *kernel), stride, padding, dilation)
+        if bias is not None:
+            one = torch.ones((), dtype=y.dtype, device=y.device)
+            y3 = y.reshape(y.shape[0], y.shape[1], -1)
+            y = contract("bcs,->bcs", y3, one, bias, "c").reshape(y.shape)
+        return y
+    raise NotImplementedError("grouped convolutions other than depthwise are not on the factorized-layer hot path")
+
+
+def general_conv1d(x, kernel, mode, bias=None, stride=1, padding=0, groups=1, dilation=1, verbose=False):
+    """1-D convolution along dimension ``mode`` of x (B, C, S1..SN); kernel (out, in/groups, k).
+    reference: functional/convolution.py:99-137."""
+    if verbose:
+        print(f"Convolving {tuple(x.shape)} with {tuple(kernel.shape)} along mode {mode}, "
+              f"stride={stride}, padding={padding}, groups={groups}")
+    order = x.dim() - 2
+    axis = mode - 2
+    pick = lambda v, other: [v if i == axis else other for i in range(order)]   # noqa: E731
+    kshape = pick(kernel.shape[-1], 1)
+    w = kernel.reshape(kernel.shape[0], kernel.shape[1], *kshape)
+    return convolve(x, w, bias=bias, stride=pick(stride, 1), padding=pick(padding, 0), dilation=pick(dilation, 1),
+                    groups=groups)
+
+
+def _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation):
+    factors = list(cp_tensor.factors)
+    order = len(factors) - 2
+    stride, padding, dilation = _tuple(stride, order), _tuple(padding, order), _tuple(dilation, order)
+    # C_in -> R : z[b,r,s] = sum_c F1[c,r] x[b,c,s]
+    z = _pointwise(x, "co", factors[1])
+    # depthwise over all spatial modes at once: taps[r, k1..kd] = prod_j F_{2+j}[k_j, r]
+    taps = factors[2].t()
+    for f in factors[3:]:
+        taps = tenalg.batched_outer(taps, f.t())
+    z = ops.dwconv(z, taps, stride, padding, dilation)
+    # R -> C_out with lambda folded into the (small) output factor
+    f0 = contract("or,r->or", factors[0], cp_tensor.weights)
+    return _pointwise(z, "oc", f0, bias)
+
+
+def cp_conv(x, cp_tensor, bias=None, stride=1, padding=0, dilation=1):
+    """Factorized CP convolution (reference: functional/convolution.py:231-283).
+
+    The reference chains d depthwise 1-D convs; the product of those separable passes equals one depthwise N-D conv
+    with the rank-1 kernel prod_j F_{2+j}[k_j, r], which is what is launched (one pass over the R-channel tensor
+    instead of d)."""
+    return _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation)
+
+
+def cp_conv_mobilenet(x, cp_tensor, bias=None, stride=1, padding=0, dilation=1):
+    """MobileNet-style CP convolution (reference: functional/convolution.py:286-345)."""
+    return _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation)
+
+
+def tucker_conv(x, tucker_tensor, bias=None, stride=1, padding=0, dilation=1):
+    """Factorized Tucker convolution (reference: functional/convolution.py:140-173)."""
+    core, factors = tucker_tensor.core, list(tucker_tensor.factors)
+    order = core.dim() - 2
+    stride, padding, dilation = _tuple(stride, order), _tuple(padding, order), _tuple(dilation, order)
+    z = _pointwise(x, "co", factors[1])                                           # C_in -> r1
+    w = tenalg.multi_mode_dot(core, factors[2:], modes=list(range(2, core.dim())))  # (r0, r1, k...)
+    kernel = list(w.shape[2:])
+    z = _dense_conv(z, w.reshape(w.shape[0], w.shape[1], -1), "qct", kernel, None, stride, padding, dilation)
+    return _pointwise(z, "oc", factors[0], bias)                                   # r0 -> C_out (+ bias)
+
+
+def tt_conv(x, tt_tensor, bias=None, stride=1, padding=0, dilation=1):
+    """Factorized TT convolution (reference: functional/convolution.py:176-228); cores follow (C_in, k_1..k_d, C_out)."""
+    cores = list(tt_tensor.factors)
+    order = len(cores) - 2
+    stride, padding, dilation = _tuple(stride, order), _tuple(padding, order), _tuple(dilation, order)
+    z = _pointwise(x, "co", cores[0][0])                                           # (C_in, r1)
+    for j in range(order):
+        core = cores[j + 1]                                                        # (r_in, k_j, r_out)
+        pick = lambda v, other: [v if i == j else other for i in range(order)]    # noqa: E731
+        z = _dense_conv(z, core, "ctq", pick(core.shape[1], 1), None, pick(stride[j], 1), pick(padding[j], 0),
+                        pick(dilation[j], 1))
+    return _pointwise(z, "co", cores[-1][:, :, 0], bias)                           # (r, C_out)
+
+
+def _get_factorized_conv(factorization, implementation="factorized"):
+    from ..factorized_tensors import CPTensor, TTTensor, TuckerTensor
+    if implementation == "reconstructed" or factorization == "Dense":
+        return convolve
+    if isinstance(factorization, CPTensor):
+        if implementation == "factorized":
+            return cp_conv
+        if implementation == "mobilenet":
+            return cp_conv_mobilenet
+    elif isinstance(factorization, TuckerTensor):
+        return tucker_conv
+    elif isinstance(factorization, TTTensor):
+        return tt_conv
+    raise ValueError(f"Got unknown type {factorization}")
+
+
+def convNd(x, weight, bias=None, stride=1, padding=0, dilation=1, implementation="factorized"):
+    """reference: functional/convolution.py:363-381."""
+    from ..factorized_tensors import CPTensor, TTTensor, TuckerTensor, DenseTensor
+    if implementation == "reconstructed":
+        weight = weight.to_tensor()
+    if isinstance(weight, DenseTensor):
+        return convolve(x, weight.tensor, bias=bias, stride=stride, padding=padding, dilation=dilation)
+    if torch.is_tensor(weight):
+        return convolve(x, weight, bias=bias, stride=stride, padding=padding, dilation=dilation)
+    if isinstance(weight, CPTensor):
+        if implementation == "factorized":
+            return cp_conv(x, weight, bias=bias, stride=stride, padding=padding, dilation=dilation)
+        if implementation == "mobilenet":
+            return cp_conv_mobilenet(x, weight, bias=bias, stride=stride, padding=padding, dilation=dilation)
+    elif isinstance(weight, TuckerTensor):
+        return tucker_conv(x, weight, bias=bias, stride=stride, padding=padding, dilation=dilation)
+    elif isinstance(weight, TTTensor):
+        return tt_conv(x, weight, bias=bias, stride=stride, padding=padding, dilation=dilation)
