@@ -330,7 +330,7 @@ extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const voi
   if (rc != TLT_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (p.M == 0 || p.N == 0 || p.Bt == 0) return TLT_OK;   // empty output: nothing to do
-  TLT_REQUIRE(A && B && C, "tlt_contract: null operand pointer");
+  TLT_REQUIRE(C && (p.K == 0 || (A && B)), "tlt_contract: null operand pointer");   // empty K: operands are never read
   TLT_REQUIRE(!(d->accumulate && d->dtype_c != TLT_F32), "tlt_contract: accumulate needs an fp32 C");
   int bm, bn;
   tile_shape(p.M, p.N, &bm, &bn);

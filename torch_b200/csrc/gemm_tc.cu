@@ -23,7 +23,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B span
 constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 256;
-constexpr uint32_t kSpinLimit = 200u * 1000u * 1000u;   // bounded mbarrier spin: trap instead of hanging the box
+constexpr uint32_t kSpinLimit = 20u * 1000u * 1000u;   // bounded mbarrier spin: trap instead of hanging the box
 
 // ------------------------------------------------------------------------------------------------------------
 // PTX wrappers

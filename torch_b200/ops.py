@@ -26,7 +26,11 @@ launch_count = _cuda.launch_count
 
 # minimum M*N*K for which a plain bf16 GEMM is routed to the tcgen05 kernel instead of the SIMT contraction kernel
 TC_MIN_WORK = 1 << 21
-_FORCE_SIMT = False      # tests flip this to compare both kernels on the same problem
+import os as _os
+_FORCE_SIMT = _os.environ.get("TLT_FORCE_SIMT", "0") == "1"   # debugging aid: route every contraction to the SIMT kernel
+
+
+PROFILE = None          # set to a list by bench.py to collect (kernel, start_event, end_event, flops, bytes) per launch
 
 
 # =====================================================================================================================
@@ -175,8 +179,15 @@ def _execute_contract(plan, a, b, d, out, alpha):
         g.alpha = alpha
         if (lib.tlt_gemm_bf16_tc_supported(C.byref(g)) and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
                 and out.data_ptr() % 16 == 0):
+            if PROFILE is not None:      # bench.py: CUDA-event pair around this launch, on the launching stream
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             _cuda.check(lib.tlt_gemm_bf16_tc(C.byref(g), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(d), _cuda.ptr(out),
                                              _cuda.stream_ptr(out)), f"tlt_gemm_bf16_tc[{plan.spec}]")
+            if PROFILE is not None:
+                e1.record()
+                PROFILE.append(("gemm_bf16_tc", e0, e1, 2.0 * tc["M"] * tc["N"] * tc["K"],
+                                2.0 * (tc["M"] * tc["K"] + tc["N"] * tc["K"]) + out.element_size() * tc["M"] * tc["N"]))
             return
     desc = _fill_desc(plan, _cuda.dtype_code(a.dtype), _cuda.dtype_code(b.dtype), _cuda.dtype_code(out.dtype), dt_d, alpha)
     ws_bytes = lib.tlt_contract_workspace_size(C.byref(desc))
