@@ -21,6 +21,8 @@ def _view(t, sizes, strides):
 
 
 def emulate_contract(plan, a, b, d, out, alpha):
+    if plan.swap:
+        a, b = b, a
     f = plan.desc_fields
     sb, sm, sn, sk = f["size_b"], f["size_m"], f["size_n"], f["size_k"]
     for name in ("b", "m", "n", "k"):

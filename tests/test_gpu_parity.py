@@ -90,13 +90,17 @@ def test_contract_kernel_shapes_and_edges(dtype):
         ("mk,kn->mn", (0, 4), (4, 5), {}),                           # empty M
         ("mk,kn->mn", (4, 0), (0, 5), dict(addend="n")),             # empty K: output is the addend
         ("abc,bd->adc", (6, 7, 8), (7, 5), dict(a_perm=(2, 0, 1))),  # non-contiguous operand
+        ("ko,k->o", (5000, 300), (5000,), {}),                       # vector-matrix path, matrix contiguous along j
+        ("ok,k->o", (300, 5000), (5000,), dict(addend="o")),         # vector-matrix path, matrix contiguous along k
+        ("bko,bk->bo", (3, 2000, 40), (3, 2000), {}),                # batched vector-matrix
+        ("k,kon->on", (700,), (700, 9, 11), dict(alpha=2.0)),        # vector first, composite j
     ]
     for spec, sa, sb, kw in cases:
         err = _contract_vs_einsum(spec, sa, sb, dtype, **kw)
         assert err < tol, (spec, sa, sb, kw, err)
 
 
-@pytest.mark.parametrize("shape", [(256, 256, 128, 0, 0), (300, 520, 200, 0, 0), (128, 128, 64, 1, 1), (384, 136, 4096, 1, 1),
+@pytest.mark.parametrize("shape", [(256, 256, 128, 0, 0), (512, 512, 64, 0, 0), (4096, 768, 3072, 0, 0), (768, 3072, 4096, 1, 1), (300, 520, 200, 0, 0), (128, 128, 64, 1, 1), (384, 136, 4096, 1, 1),
                                    (1000, 264, 72, 0, 1), (136, 1024, 256, 1, 0), (2048, 3072, 768, 0, 0)])
 @pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
 def test_tcgen05_gemm_against_fp64(shape, out_dtype):

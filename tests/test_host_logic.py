@@ -133,7 +133,10 @@ def test_planner_merges_and_classifies():
     assert p.tc["a_major"] == 0 and p.tc["b_major"] == 0
     # dW = dY^T X: both operands MN-major
     p = ops.plan_contract("bo,bi->oi", (64, 16), (16, 1), (64, 32), (32, 1), None, None)
-    assert p.tc is not None and p.tc["a_major"] == 1 and p.tc["b_major"] == 1 and p.tc["lda"] == 16
+    assert p.tc is not None and p.tc["a_major"] == 1 and p.tc["b_major"] == 1 and p.tc["lda"] == 16 and not p.swap
+    # same product written operand-swapped (what autograd emits for dW): planner swaps roles back -> row-major C
+    p = ops.plan_contract("bi,bo->oi", (64, 32), (32, 1), (64, 16), (16, 1), None, None)
+    assert p.swap and p.tc is not None and p.tc["M"] == 16 and p.tc["N"] == 32 and p.tc["ldc"] == 32
     # TT sweep stage: composite m and k
     p = ops.plan_contract("abcr,rodq->acodq"[:0] + "abcr,rodq->acodq".replace("d", "b"), (5, 4, 3, 2), (24, 6, 2, 1),
                           (2, 6, 4, 7), (168, 28, 7, 1), None, None)

@@ -219,6 +219,88 @@ __global__ void contract_finalize_kernel(const ContractParams p, const float* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vector-matrix special case (M == 1 or N == 1): y[j] = alpha * sum_k v[k] X[k, j].  Bias-gradient reductions
+// (v = stride-0 ones), lambda folds and projections onto rank-1 modes land here.  HBM-bound: every element of X is
+// read once, coalesced, by the variant matching X's contiguous dimension; K is split across blockIdx.y and partial
+// sums meet in the fp32 workspace.
+// ---------------------------------------------------------------------------------------------------------------
+struct MatvecParams {
+  ContractParams p;
+  int vec_is_a, J, k_per_split;
+};
+
+template <typename TV, typename TX, bool J_FAST>
+__global__ void __launch_bounds__(256) matvec_kernel(const MatvecParams q, const TV* __restrict__ vec,
+                                                     const TX* __restrict__ mat, float* __restrict__ ws) {
+  const ContractParams& p = q.p;
+  const int b = blockIdx.z;
+  const int* size_j = q.vec_is_a ? p.size_n : p.size_m;
+  const long long* mat_j = q.vec_is_a ? p.b_n : p.a_m;
+  const int nj = q.vec_is_a ? p.nn : p.nm;
+  const long long* vec_k = q.vec_is_a ? p.a_k : p.b_k;
+  const long long* mat_k = q.vec_is_a ? p.b_k : p.a_k;
+  vec += decomp(b, p.size_b, q.vec_is_a ? p.a_b : p.b_b, p.nb);
+  mat += decomp(b, p.size_b, q.vec_is_a ? p.b_b : p.a_b, p.nb);
+  const int k_begin = blockIdx.y * q.k_per_split;
+  const int k_end = min(p.K, k_begin + q.k_per_split);
+  if (J_FAST) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= q.J) return;
+    const TX* col = mat + decomp(j, size_j, mat_j, nj);
+    float acc = 0.f;
+    if (p.nk == 1) {
+      const long long sv = vec_k[0], sx = mat_k[0];
+      int k = k_begin;
+      for (; k + 8 <= k_end; k += 8) {
+        float xv[8], vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xv[u] = to_f32<TX>(col[(long long)(k + u) * sx]); vv[u] = to_f32<TV>(vec[(long long)(k + u) * sv]); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(xv[u], vv[u], acc);
+      }
+      for (; k < k_end; ++k) acc = fmaf(to_f32<TX>(col[(long long)k * sx]), to_f32<TV>(vec[(long long)k * sv]), acc);
+    } else {
+      for (int k = k_begin; k < k_end; ++k)
+        acc = fmaf(to_f32<TX>(col[decomp(k, p.size_k, mat_k, p.nk)]), to_f32<TV>(vec[decomp(k, p.size_k, vec_k, p.nk)]), acc);
+    }
+    atomicAdd(ws + (long long)b * q.J + j, p.alpha * acc);
+  } else {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= q.J) return;
+    const int lane = threadIdx.x & 31;
+    const TX* col = mat + decomp(j, size_j, mat_j, nj);
+    float acc = 0.f;
+    for (int k = k_begin + lane; k < k_end; k += 32) {
+      long long ox = p.nk == 1 ? (long long)k * mat_k[0] : decomp(k, p.size_k, mat_k, p.nk);
+      long long ov = p.nk == 1 ? (long long)k * vec_k[0] : decomp(k, p.size_k, vec_k, p.nk);
+      acc = fmaf(to_f32<TX>(col[ox]), to_f32<TV>(vec[ov]), acc);
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (lane == 0) atomicAdd(ws + (long long)b * q.J + j, p.alpha * acc);
+  }
+}
+
+template <typename TV, typename TX>
+static int launch_matvec(const MatvecParams& q, bool j_fast, int splits, const void* vec, const void* mat, float* ws, cudaStream_t st) {
+  if (j_fast) {
+    dim3 grid((q.J + 255) / 256, splits, q.p.Bt);
+    matvec_kernel<TV, TX, true><<<grid, 256, 0, st>>>(q, (const TV*)vec, (const TX*)mat, ws);
+  } else {
+    dim3 grid((q.J + 7) / 8, splits, q.p.Bt);
+    matvec_kernel<TV, TX, false><<<grid, 256, 0, st>>>(q, (const TV*)vec, (const TX*)mat, ws);
+  }
+  return check_launch("matvec_kernel");
+}
+
+static bool use_matvec(const ContractParams& p) {
+  if (p.Bt > 65535) return false;
+  long long J = p.M == 1 ? p.N : (p.N == 1 ? p.M : 0);
+  return J > 0 && (long long)p.K * J >= 4096;
+}
+
 static long long prod(const int64_t* s, int n) {
   long long r = 1;
   for (int i = 0; i < n; ++i) r *= s[i];
@@ -316,6 +398,7 @@ extern "C" size_t tlt_contract_workspace_size(const tlt_contract_desc* d) {
   ContractParams p;
   if (fill_params(d, &p) != TLT_OK) return 0;
   if (p.M == 0 || p.N == 0 || p.Bt == 0) return 0;
+  if (use_matvec(p)) return (size_t)p.Bt * p.M * p.N * sizeof(float);
   int bm, bn;
   tile_shape(p.M, p.N, &bm, &bn);
   int split = choose_split(d, p.M, p.N, p.K, p.Bt, bm, bn);
@@ -341,6 +424,51 @@ extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const voi
   if (p.k_per_split < kBK) p.k_per_split = kBK;
   p.has_d = D != nullptr;
   p.d_bf16 = d->dtype_d == TLT_BF16;
+
+  if (use_matvec(p)) {
+    MatvecParams q;
+    q.p = p;
+    q.vec_is_a = p.M == 1;
+    q.J = q.vec_is_a ? p.N : p.M;
+    size_t need = (size_t)p.Bt * q.J * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("tlt_contract: vector-matrix path needs %zu bytes of workspace, got %zu", need, workspace_bytes);
+      return TLT_ERR_WORKSPACE;
+    }
+    TLT_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    // does the matrix operand run contiguously along j (output index) or along k?
+    const int64_t* mj = q.vec_is_a ? d->b_n : d->a_m;
+    const int64_t* sj = q.vec_is_a ? d->size_n : d->size_m;
+    int nj = q.vec_is_a ? d->nn : d->nm;
+    bool j_fast = false;
+    for (int i = 0; i < nj; ++i) if (mj[i] == 1 && sj[i] > 1) j_fast = true;
+    long long blocks_j = j_fast ? (q.J + 255) / 256 : (q.J + 7) / 8;
+    long long want = (148LL * 8 + blocks_j * p.Bt - 1) / (blocks_j * p.Bt);
+    long long max_by_k = p.K / (j_fast ? 64 : 256);
+    long long splits = want < max_by_k ? want : max_by_k;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    q.k_per_split = (int)((p.K + splits - 1) / splits);
+    if (q.k_per_split < 1) q.k_per_split = 1;
+    splits = (p.K + q.k_per_split - 1) / q.k_per_split;
+    if (splits < 1) splits = 1;
+    const void* vec = q.vec_is_a ? A : B;
+    const void* mat = q.vec_is_a ? B : A;
+    int dv = q.vec_is_a ? d->dtype_a : d->dtype_b, dx = q.vec_is_a ? d->dtype_b : d->dtype_a;
+    typedef __nv_bfloat16 bf;
+    if (dv == TLT_F32 && dx == TLT_F32) rc = launch_matvec<float, float>(q, j_fast, (int)splits, vec, mat, (float*)workspace, st);
+    else if (dv == TLT_BF16 && dx == TLT_BF16) rc = launch_matvec<bf, bf>(q, j_fast, (int)splits, vec, mat, (float*)workspace, st);
+    else if (dv == TLT_F32 && dx == TLT_BF16) rc = launch_matvec<float, bf>(q, j_fast, (int)splits, vec, mat, (float*)workspace, st);
+    else rc = launch_matvec<bf, float>(q, j_fast, (int)splits, vec, mat, (float*)workspace, st);
+    if (rc != TLT_OK) return rc;
+    ContractParams f = p;
+    f.alpha = 1.f;
+    long long total = (long long)p.Bt * q.J;
+    int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+    if (d->dtype_c == TLT_F32) contract_finalize_kernel<float><<<blocks, 256, 0, st>>>(f, (const float*)workspace, D, (float*)C);
+    else contract_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(f, (const float*)workspace, D, (__nv_bfloat16*)C);
+    return check_launch("contract_finalize_kernel");
+  }
 
   if (needs_workspace(d, p.split_k)) {
     size_t need = (size_t)p.Bt * p.M * p.N * sizeof(float);

@@ -37,10 +37,11 @@ PROFILE = None          # set to a list by bench.py to collect (kernel, start_ev
 # contraction planning (host logic; pure python, exercised on CPU by tests/test_host_logic.py)
 # =====================================================================================================================
 class ContractPlan:
-    __slots__ = ("out_shape", "classes", "desc_fields", "tc", "spec")
+    __slots__ = ("out_shape", "classes", "desc_fields", "tc", "spec", "swap")
 
     def __init__(self):
         self.tc = None
+        self.swap = False
 
 
 def _parse(spec):
@@ -88,6 +89,16 @@ def plan_contract(spec, a_shape, a_stride, b_shape, b_stride, d_letters, d_strid
     for l in lo:
         if l not in size:
             raise ValueError(f"output index {l!r} of {spec!r} appears in no operand")
+    # The kernels put the column class (indices of the SECOND operand) innermost in their store pattern, and the tensor-
+    # core GEMM needs a row-major C.  If the innermost non-trivial output index belongs to the first operand only,
+    # swap the operand roles (C^T = B^T A^T): same contraction, same output tensor.
+    swap = False
+    inner = next((l for l in reversed(lo) if size[l] != 1), None)
+    if inner is not None and inner in la and inner not in lb:
+        la, lb = lb, la
+        a_shape, b_shape = b_shape, a_shape
+        a_stride, b_stride = b_stride, a_stride
+        swap = True
     sa = dict(zip(la, a_stride))
     sb = dict(zip(lb, b_stride))
     out_shape = tuple(size[l] for l in lo)
@@ -122,6 +133,7 @@ def plan_contract(spec, a_shape, a_stride, b_shape, b_stride, d_letters, d_strid
             raise ValueError(f"{spec!r}: {len(s)} non-mergeable {name} sub-dimensions exceed the kernel limit "
                              f"of {_cuda.MAX_SUBDIMS}; make an operand contiguous first")
     plan = ContractPlan()
+    plan.swap = swap
     plan.spec = spec
     plan.out_shape = out_shape
     plan.classes = dict(b=sz_b, m=sz_m, n=sz_n, k=sz_k)
@@ -164,6 +176,8 @@ def _fill_desc(plan, dt_a, dt_b, dt_c, dt_d, alpha):
 # =====================================================================================================================
 def _execute_contract(plan, a, b, d, out, alpha):
     _cuda.require_cuda(a, b, d, out)
+    if plan.swap:
+        a, b = b, a
     lib = _cuda.lib()
     dt_d = _cuda.dtype_code(d.dtype) if d is not None else 0
     tc = plan.tc
