@@ -218,25 +218,48 @@ def run_ours(args):
         step()
     barrier()
 
+    # One step = ~26 short kernels; issued eagerly the host (Python dispatch, ~45 us per op) is slower than the GPU, so
+    # the step is captured once into a CUDA graph and replayed (torch_b200.graphs.GraphedStep).  --eager disables it.
+    launches0 = ops.launch_count()
+    step()
+    launches_per_step = ops.launch_count() - launches0
+    run_step, mode = step, "eager"
+    if not args.eager:
+        try:
+            from torch_b200.graphs import GraphedStep
+            run_step, mode = GraphedStep(step).replay, "cuda_graph"
+        except Exception as exc:            # e.g. a collective that cannot be captured on this stack
+            if rank == 0:
+                print(f"bench.py: CUDA-graph capture failed ({exc!r}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+    for _ in range(3):
+        run_step()
+    barrier()
+
     # ------------------------------------------------------------------ timed region (device-resident inputs)
     sampler = ClockSampler(local_rank)
-    ops.PROFILE = []
-    launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     e0.record()
     for _ in range(args.steps):
-        step()
+        run_step()
     e1.record()
     barrier()
     clocks = sampler.stop()
-    launches = ops.launch_count() - launches0
-    prof, ops.PROFILE = ops.PROFILE, None
+    launches = launches_per_step * args.steps
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
     value = world * B * args.steps / (ms / 1e3)
+
+    # per-launch CUDA events cannot be recorded inside a graph replay: the dominant kernel is timed launch by launch in
+    # an eager pass over the same steps (kernel durations do not depend on how the launch was issued)
+    ops.PROFILE = []
+    for _ in range(args.steps):
+        step()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
 
     # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration, per launch
     gemm_ms = sum(a.elapsed_time(b) for _, a, b, _, _ in prof)
@@ -253,8 +276,15 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launches": len(prof),
-                "avg_launch_ms": gemm_ms / max(len(prof), 1), "kernel_share_of_step": gemm_ms / ms,
+                "avg_launch_ms": gemm_ms / max(len(prof), 1), "kernel_share_of_step": gemm_ms / ms, "step_mode": mode,
                 "algorithmic_flops_per_step": gemm_flops / max(args.steps, 1)}
+    per_shape = {}
+    for name, a, b, f, _ in prof:
+        t = per_shape.setdefault(name, [0.0, 0, f])
+        t[0] += a.elapsed_time(b)
+        t[1] += 1
+    roofline["per_gemm"] = {k: {"avg_ms": round(v[0] / v[1], 4), "tflops": round(v[2] / (v[0] / v[1] / 1e3) / 1e12, 1)}
+                            for k, v in per_shape.items()}
 
     if args.skip_extras:
         if rank == 0:
@@ -275,7 +305,7 @@ def run_ours(args):
         with torch.no_grad():
             x.copy_(x_h, non_blocking=True)
             gy.copy_(gy_h, non_blocking=True)
-        step()
+        run_step()
         dx_h.copy_(x.grad, non_blocking=True)
         gp_h.copy_(torch.cat([p.grad.reshape(-1) for p in params]), non_blocking=True)
 
@@ -297,7 +327,7 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": _config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "data": "synthetic", "config": _config(world, {"step_mode": mode}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline}
     if rank == 0:
         if world == 1:
@@ -313,6 +343,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--eager", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--skip-extras", action="store_true", help="profiling runs: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":

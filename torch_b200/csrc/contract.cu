@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(kThreads) contract_kernel(const ContractParams
   constexpr int B_PER_T = BN * kBK / kThreads;   // = BN / 16
   __shared__ __align__(16) float As[kBK][BM + 4];
   __shared__ __align__(16) float Bs[kBK][BN + 4];
+  // composite reduction index (nk > 1): offsets of the 16 k's of a tile are decomposed ONCE per tile by 32 threads
+  // into these double-buffered tables instead of once per load by every thread
+  __shared__ long long koffA[2][kBK], koffB[2][kBK];
 
   const int tid = threadIdx.x;
   // block id -> (z, tile_m, tile_n);  z -> (batch, split)
@@ -99,13 +102,18 @@ __global__ void __launch_bounds__(kThreads) contract_kernel(const ContractParams
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   float ra[A_PER_T], rb[B_PER_T];
 
-  auto load_tile = [&](int k0) {
+  const bool ktab = p.nk > 1;
+  auto fill_ktab = [&](int k0, int buf) {
+    if (tid < kBK) { int k = k0 + tid; if (k < k_end) koffA[buf][tid] = decomp(k, p.size_k, p.a_k, p.nk); }
+    else if (tid >= 32 && tid < 32 + kBK) { int k = k0 + tid - 32; if (k < k_end) koffB[buf][tid - 32] = decomp(k, p.size_k, p.b_k, p.nk); }
+  };
+  auto load_tile = [&](int k0, int buf) {
 #pragma unroll
     for (int j = 0; j < A_PER_T; ++j) {
       int k = k0 + a_kk[j];
       float v = 0.f;
       if (a_moff[j] >= 0 && k < k_end) {
-        long long ko = (p.nk == 1) ? (long long)k * p.a_k[0] : decomp(k, p.size_k, p.a_k, p.nk);
+        long long ko = ktab ? koffA[buf][a_kk[j]] : (long long)k * p.a_k[0];
         v = to_f32<TA>(A[a_moff[j] + ko]);
       }
       ra[j] = v;
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(kThreads) contract_kernel(const ContractParams
       int k = k0 + b_kk[j];
       float v = 0.f;
       if (b_noff[j] >= 0 && k < k_end) {
-        long long ko = (p.nk == 1) ? (long long)k * p.b_k[0] : decomp(k, p.size_k, p.b_k, p.nk);
+        long long ko = ktab ? koffB[buf][b_kk[j]] : (long long)k * p.b_k[0];
         v = to_f32<TB>(B[b_noff[j] + ko]);
       }
       rb[j] = v;
@@ -129,12 +137,19 @@ __global__ void __launch_bounds__(kThreads) contract_kernel(const ContractParams
   };
 
   if (k_begin < k_end) {
-    load_tile(k_begin);
+    if (ktab) {
+      fill_ktab(k_begin, 0);
+      fill_ktab(k_begin + kBK, 1);
+      __syncthreads();
+    }
+    load_tile(k_begin, 0);
     store_tile();
     __syncthreads();
-    for (int k0 = k_begin; k0 < k_end; k0 += kBK) {
+    int it = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += kBK, ++it) {
       const bool more = (k0 + kBK) < k_end;
-      if (more) load_tile(k0 + kBK);   // global loads in flight while the FMAs below run
+      if (more) load_tile(k0 + kBK, (it + 1) & 1);   // global loads in flight while the FMAs below run
+      if (ktab && k0 + 2 * kBK < k_end) fill_ktab(k0 + 2 * kBK, it & 1);   // table of tile it+2 (buffer last read for tile it)
 #pragma unroll
       for (int kk = 0; kk < kBK; ++kk) {
         float av[TM], bv[TN];
@@ -283,6 +298,62 @@ __global__ void __launch_bounds__(256) matvec_kernel(const MatvecParams q, const
   }
 }
 
+// Vectorised j-fast variant: the matrix is unit-stride along a single j dim; each thread owns VEC adjacent outputs and
+// reads them with one 16-byte load per k (bias-gradient column sums run at HBM speed through this path).
+template <typename TV, typename TX, int VEC>
+__global__ void __launch_bounds__(256) matvec_vec_kernel(const MatvecParams q, const TV* __restrict__ vec,
+                                                         const TX* __restrict__ mat, float* __restrict__ ws) {
+  const ContractParams& p = q.p;
+  const int b = blockIdx.z;
+  const long long* vec_k = q.vec_is_a ? p.a_k : p.b_k;
+  const long long* mat_k = q.vec_is_a ? p.b_k : p.a_k;
+  vec += decomp(b, p.size_b, q.vec_is_a ? p.a_b : p.b_b, p.nb);
+  mat += decomp(b, p.size_b, q.vec_is_a ? p.b_b : p.a_b, p.nb);
+  const int k_begin = blockIdx.y * q.k_per_split;
+  const int k_end = min(p.K, k_begin + q.k_per_split);
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (j >= q.J) return;
+  const long long sv = vec_k[0], sx = mat_k[0];
+  float acc[VEC];
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) acc[u] = 0.f;
+  const TX* col = mat + j;
+  constexpr int UNROLL = 4;
+  int k = k_begin;
+  for (; k + UNROLL <= k_end; k += UNROLL) {
+    uint4 raw[UNROLL];
+    float vv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      raw[u] = *(const uint4*)(col + (long long)(k + u) * sx);
+      vv[u] = to_f32<TV>(vec[(long long)(k + u) * sv]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const TX* e = (const TX*)&raw[u];
+#pragma unroll
+      for (int w = 0; w < VEC; ++w) acc[w] = fmaf(to_f32<TX>(e[w]), vv[u], acc[w]);
+    }
+  }
+  for (; k < k_end; ++k) {
+    uint4 raw = *(const uint4*)(col + (long long)k * sx);
+    float vv = to_f32<TV>(vec[(long long)k * sv]);
+    const TX* e = (const TX*)&raw;
+#pragma unroll
+    for (int w = 0; w < VEC; ++w) acc[w] = fmaf(to_f32<TX>(e[w]), vv, acc[w]);
+  }
+#pragma unroll
+  for (int w = 0; w < VEC; ++w) atomicAdd(ws + (long long)b * q.J + j + w, p.alpha * acc[w]);
+}
+
+template <typename TV, typename TX>
+static int launch_matvec_vec(const MatvecParams& q, int splits, const void* vec, const void* mat, float* ws, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(TX);
+  dim3 grid((q.J / VEC + 127) / 128, splits, q.p.Bt);
+  matvec_vec_kernel<TV, TX, VEC><<<grid, 128, 0, st>>>(q, (const TV*)vec, (const TX*)mat, ws);
+  return check_launch("matvec_vec_kernel");
+}
+
 template <typename TV, typename TX>
 static int launch_matvec(const MatvecParams& q, bool j_fast, int splits, const void* vec, const void* mat, float* ws, cudaStream_t st) {
   if (j_fast) {
@@ -310,9 +381,9 @@ static long long prod(const int64_t* s, int n) {
 static int choose_split(const tlt_contract_desc* d, long long M, long long N, long long K, long long Bt, int bm, int bn) {
   if (d->split_k > 0) return d->split_k;
   long long tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * Bt;
-  if (tiles >= 148 || K < 1024) return 1;
-  long long want = (2 * 148 + tiles - 1) / tiles;
-  long long max_by_k = K / 256;
+  if (tiles >= 2 * 148 || K < 128) return 1;
+  long long want = (2 * 148 + tiles - 1) / tiles;       // aim at ~2 blocks per SM
+  long long max_by_k = K / 64;                          // but keep >= 4 k-tiles per split
   long long s = want < max_by_k ? want : max_by_k;
   if (s > 128) s = 128;
   return s < 1 ? 1 : (int)s;
@@ -442,6 +513,40 @@ extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const voi
     int nj = q.vec_is_a ? d->nn : d->nm;
     bool j_fast = false;
     for (int i = 0; i < nj; ++i) if (mj[i] == 1 && sj[i] > 1) j_fast = true;
+    // 16-byte vector path: single unit-stride j dim, single k dim, everything 16-byte aligned
+    {
+      int dxm = q.vec_is_a ? d->dtype_b : d->dtype_a;
+      int vecw = dxm == TLT_BF16 ? 8 : 4;
+      const int64_t* mk = q.vec_is_a ? d->b_k : d->a_k;
+      const void* matp = q.vec_is_a ? B : A;
+      bool ok = nj == 1 && mj[0] == 1 && d->nk == 1 && d->nb == 0 && q.J % vecw == 0 && mk[0] % vecw == 0 &&
+                ((uintptr_t)matp % 16) == 0 && q.J >= vecw * 128;
+      if (ok) {
+        long long blocks_jv = (q.J / vecw + 127) / 128;
+        long long want = (148LL * 16 + blocks_jv - 1) / blocks_jv;
+        long long max_by_k = p.K / 32;
+        long long sp = want < max_by_k ? want : max_by_k;
+        if (sp < 1) sp = 1;
+        if (sp > 65535) sp = 65535;
+        q.k_per_split = (int)((p.K + sp - 1) / sp);
+        sp = (p.K + q.k_per_split - 1) / q.k_per_split;
+        const void* vecp = q.vec_is_a ? A : B;
+        int dvv = q.vec_is_a ? d->dtype_a : d->dtype_b;
+        typedef __nv_bfloat16 bf;
+        if (dvv == TLT_F32 && dxm == TLT_F32) rc = launch_matvec_vec<float, float>(q, (int)sp, vecp, matp, (float*)workspace, st);
+        else if (dvv == TLT_BF16 && dxm == TLT_BF16) rc = launch_matvec_vec<bf, bf>(q, (int)sp, vecp, matp, (float*)workspace, st);
+        else if (dvv == TLT_F32 && dxm == TLT_BF16) rc = launch_matvec_vec<float, bf>(q, (int)sp, vecp, matp, (float*)workspace, st);
+        else rc = launch_matvec_vec<bf, float>(q, (int)sp, vecp, matp, (float*)workspace, st);
+        if (rc != TLT_OK) return rc;
+        ContractParams f = p;
+        f.alpha = 1.f;
+        long long total = (long long)q.J;
+        int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+        if (d->dtype_c == TLT_F32) contract_finalize_kernel<float><<<blocks, 256, 0, st>>>(f, (const float*)workspace, D, (float*)C);
+        else contract_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(f, (const float*)workspace, D, (__nv_bfloat16*)C);
+        return check_launch("contract_finalize_kernel");
+      }
+    }
     long long blocks_j = j_fast ? (q.J + 255) / 256 : (q.J + 7) / 8;
     long long want = (148LL * 8 + blocks_j * p.Bt - 1) / (blocks_j * p.Bt);
     long long max_by_k = p.K / (j_fast ? 64 : 256);

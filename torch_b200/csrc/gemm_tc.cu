@@ -157,7 +157,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta_r
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into the executing CTA's smem that signals the mbarrier of the pair's LEADER CTA (bit 24 of a
 // shared::cluster address is the CTA rank inside a 2-CTA cluster; clearing it selects rank 0).
@@ -300,7 +300,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     tma_prefetch_desc(&map_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
     fence_barrier_init();
   }
@@ -317,15 +317,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===================================== TMA producer (both CTAs) =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t leader_full0 = mapa_u32(full_bar(0), 0);
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile / p.tiles_n) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
         const int n0 = (tile % p.tiles_n) * BN + (int)cta_rank * HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);      // bytes of both CTAs land on the leader's barrier
-          else mbar_arrive_cluster(leader_full0 + 8u * stage);
+          // Bytes of BOTH CTAs complete_tx on the leader's barrier; the leader's single arrive.expect_tx covers them all
+          // (the tx-count may go transiently negative if the peer's bytes land first -- the phase cannot complete until
+          // the leader's arrival).  No remote arrive on this path: a cluster-scope release would cost a MEMBAR per stage.
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn) {
             tma_load_2d_2sm(sa, &map_a, full_bar(stage), k0, m0);

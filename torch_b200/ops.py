@@ -200,7 +200,8 @@ def _execute_contract(plan, a, b, d, out, alpha):
                                              _cuda.stream_ptr(out)), f"tlt_gemm_bf16_tc[{plan.spec}]")
             if PROFILE is not None:
                 e1.record()
-                PROFILE.append(("gemm_bf16_tc", e0, e1, 2.0 * tc["M"] * tc["N"] * tc["K"],
+                PROFILE.append((f"gemm_bf16_tc M{tc['M']} N{tc['N']} K{tc['K']} a{tc['a_major']}b{tc['b_major']}", e0, e1,
+                                2.0 * tc["M"] * tc["N"] * tc["K"],
                                 2.0 * (tc["M"] * tc["K"] + tc["N"] * tc["K"]) + out.element_size() * tc["M"] * tc["N"]))
             return
     desc = _fill_desc(plan, _cuda.dtype_code(a.dtype), _cuda.dtype_code(b.dtype), _cuda.dtype_code(out.dtype), dt_d, alpha)
