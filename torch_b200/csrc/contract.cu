@@ -303,54 +303,67 @@ __global__ void __launch_bounds__(256) matvec_kernel(const MatvecParams q, const
 template <typename TV, typename TX, int VEC>
 __global__ void __launch_bounds__(256) matvec_vec_kernel(const MatvecParams q, const TV* __restrict__ vec,
                                                          const TX* __restrict__ mat, float* __restrict__ ws) {
+  // block = 32 j-vectors (32*VEC adjacent outputs: one 512-byte row segment per warp load) x 8 k-lanes;
+  // k-lanes meet in shared memory, then ONE atomic per output per block (few-way contention only).
   const ContractParams& p = q.p;
-  const int b = blockIdx.z;
   const long long* vec_k = q.vec_is_a ? p.a_k : p.b_k;
   const long long* mat_k = q.vec_is_a ? p.b_k : p.a_k;
-  vec += decomp(b, p.size_b, q.vec_is_a ? p.a_b : p.b_b, p.nb);
-  mat += decomp(b, p.size_b, q.vec_is_a ? p.b_b : p.a_b, p.nb);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k_begin = blockIdx.y * q.k_per_split;
   const int k_end = min(p.K, k_begin + q.k_per_split);
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-  if (j >= q.J) return;
+  const int j = (blockIdx.x * 32 + tx) * VEC;
+  const bool active = j < q.J;
   const long long sv = vec_k[0], sx = mat_k[0];
   float acc[VEC];
 #pragma unroll
   for (int u = 0; u < VEC; ++u) acc[u] = 0.f;
-  const TX* col = mat + j;
-  constexpr int UNROLL = 4;
-  int k = k_begin;
-  for (; k + UNROLL <= k_end; k += UNROLL) {
-    uint4 raw[UNROLL];
-    float vv[UNROLL];
+  if (active) {
+    const TX* col = mat + j;
+    constexpr int UNROLL = 4;
+    int k = k_begin + ty;
+    for (; k + 8 * (UNROLL - 1) < k_end; k += 8 * UNROLL) {
+      uint4 raw[UNROLL];
+      float vv[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      raw[u] = *(const uint4*)(col + (long long)(k + u) * sx);
-      vv[u] = to_f32<TV>(vec[(long long)(k + u) * sv]);
+      for (int u = 0; u < UNROLL; ++u) {
+        raw[u] = *(const uint4*)(col + (long long)(k + 8 * u) * sx);
+        vv[u] = to_f32<TV>(vec[(long long)(k + 8 * u) * sv]);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const TX* e = (const TX*)&raw[u];
+#pragma unroll
+        for (int w = 0; w < VEC; ++w) acc[w] = fmaf(to_f32<TX>(e[w]), vv[u], acc[w]);
+      }
     }
+    for (; k < k_end; k += 8) {
+      uint4 raw = *(const uint4*)(col + (long long)k * sx);
+      float vv = to_f32<TV>(vec[(long long)k * sv]);
+      const TX* e = (const TX*)&raw;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const TX* e = (const TX*)&raw[u];
-#pragma unroll
-      for (int w = 0; w < VEC; ++w) acc[w] = fmaf(to_f32<TX>(e[w]), vv[u], acc[w]);
+      for (int w = 0; w < VEC; ++w) acc[w] = fmaf(to_f32<TX>(e[w]), vv, acc[w]);
     }
   }
-  for (; k < k_end; ++k) {
-    uint4 raw = *(const uint4*)(col + (long long)k * sx);
-    float vv = to_f32<TV>(vec[(long long)k * sv]);
-    const TX* e = (const TX*)&raw;
+  __shared__ float red[8][32 * VEC + 1];
 #pragma unroll
-    for (int w = 0; w < VEC; ++w) acc[w] = fmaf(to_f32<TX>(e[w]), vv, acc[w]);
+  for (int w = 0; w < VEC; ++w) red[ty][tx * VEC + w] = acc[w];
+  __syncthreads();
+  for (int o = threadIdx.x; o < 32 * VEC; o += 256) {
+    const int jj = blockIdx.x * 32 * VEC + o;
+    if (jj < q.J) {
+      float sum = 0.f;
+#pragma unroll
+      for (int l = 0; l < 8; ++l) sum += red[l][o];
+      atomicAdd(ws + jj, p.alpha * sum);
+    }
   }
-#pragma unroll
-  for (int w = 0; w < VEC; ++w) atomicAdd(ws + (long long)b * q.J + j + w, p.alpha * acc[w]);
 }
 
 template <typename TV, typename TX>
 static int launch_matvec_vec(const MatvecParams& q, int splits, const void* vec, const void* mat, float* ws, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(TX);
-  dim3 grid((q.J / VEC + 127) / 128, splits, q.p.Bt);
-  matvec_vec_kernel<TV, TX, VEC><<<grid, 128, 0, st>>>(q, (const TV*)vec, (const TX*)mat, ws);
+  dim3 grid((q.J + 32 * VEC - 1) / (32 * VEC), splits, 1);
+  matvec_vec_kernel<TV, TX, VEC><<<grid, 256, 0, st>>>(q, (const TV*)vec, (const TX*)mat, ws);
   return check_launch("matvec_vec_kernel");
 }
 
@@ -520,11 +533,11 @@ extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const voi
       const int64_t* mk = q.vec_is_a ? d->b_k : d->a_k;
       const void* matp = q.vec_is_a ? B : A;
       bool ok = nj == 1 && mj[0] == 1 && d->nk == 1 && d->nb == 0 && q.J % vecw == 0 && mk[0] % vecw == 0 &&
-                ((uintptr_t)matp % 16) == 0 && q.J >= vecw * 128;
+                ((uintptr_t)matp % 16) == 0 && q.J >= vecw * 32;
       if (ok) {
-        long long blocks_jv = (q.J / vecw + 127) / 128;
-        long long want = (148LL * 16 + blocks_jv - 1) / blocks_jv;
-        long long max_by_k = p.K / 32;
+        long long blocks_jv = (q.J + 32 * vecw - 1) / (32 * vecw);
+        long long want = (148LL * 4 + blocks_jv - 1) / blocks_jv;
+        long long max_by_k = p.K / 64;
         long long sp = want < max_by_k ? want : max_by_k;
         if (sp < 1) sp = 1;
         if (sp > 65535) sp = 65535;
