@@ -91,10 +91,36 @@ typedef struct {
   int32_t accumulate;                                   /* 1: C += A*B^T (fp32 C only)                             */
   int32_t dtype_bias;                                   /* dtype of bias[N] (ignored when bias == NULL)            */
   float alpha;
+  int32_t split_k;                                      /* 0 = library chooses; > 1 only honoured for fp32 C (partials
+                                                           meet in C through TMA reduce-add; C is zeroed by the call
+                                                           unless accumulate)                                       */
 } tlt_gemm_desc;
 
 int tlt_gemm_bf16_tc_supported(const tlt_gemm_desc* desc);      /* 1 if the tensor-core kernel accepts this problem */
 int tlt_gemm_bf16_tc(const tlt_gemm_desc* desc, const void* A, const void* B, const void* bias, void* C, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Fused 3-core BlockTT (TT-matrix) kernels.
+ *   W[(r1,r2,r3),(c1,c2,c3)] = sum_{a,b} C1[0,r1,c1,a] * C2[a,r2,c2,b] * C3[b,r3,c3,0]      W row-major (prod rows, prod cols)
+ * cores are contiguous (rank_k, rows_k, cols_k, rank_{k+1}) tensors of dtype `dtype`; accumulation is fp32.
+ * Replaces: BlockTT.to_tensor / to_matrix (tltorch/factorized_tensors/tensorized_matrices.py:354-384, core.py:536-543)
+ * -- the pairwise einsum loop 'adeb,bfgc->adfegc' + permute -- in ONE launch with the rank-indexed intermediate kept in
+ * shared memory, and its autograd (tlt_blocktt3_core_grads: the dense-matrix gradient contracted back onto the cores).
+ * Returns TLT_ERR_UNSUPPORTED when the intermediate does not fit shared memory (callers fall back to tlt_contract).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype;                                        /* dtype of the cores and of W / the core gradients        */
+  int32_t rows[3], cols[3];                             /* tensorized shape of the matrix                          */
+  int32_t rank1, rank2;                                 /* interior TT ranks (boundary ranks are 1)                */
+} tlt_blocktt3_desc;
+
+int tlt_blocktt3_reconstruct(const tlt_blocktt3_desc* desc, const void* c1, const void* c2, const void* c3, void* W,
+                             void* stream);
+size_t tlt_blocktt3_core_grads_workspace_size(const tlt_blocktt3_desc* desc);
+/* dW: fp32 (prod rows, prod cols) row-major, 16-byte aligned; d1..d3: gradients of the cores, dtype `dtype` */
+int tlt_blocktt3_core_grads(const tlt_blocktt3_desc* desc, const void* c1, const void* c2, const void* c3,
+                            const float* dW, void* d1, void* d2, void* d3, void* workspace, size_t workspace_bytes,
+                            void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * Convolution building blocks (channels-first, 1 to 3 spatial dims).

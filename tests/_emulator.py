@@ -131,13 +131,47 @@ def emulate_conv(which, desc, *tensors):
     LOG.append((which, g))
 
 
+def emulate_btt3_reconstruct(c1, c2, c3, W, rows, cols, r1, r2):
+    assert list(c1.shape) == [1, rows[0], cols[0], r1] and list(c2.shape) == [r1, rows[1], cols[1], r2]
+    assert list(c3.shape) == [r2, rows[2], cols[2], 1]
+    W.copy_(torch.einsum("aoib,bpjc,cqkd->opqijk", c1, c2, c3).reshape(W.shape))
+    LOG.append(("blocktt3_reconstruct", tuple(rows), tuple(cols), r1, r2))
+
+
+def emulate_btt3_core_grads(c1, c2, c3, dW32, d1, d2, d3, rows, cols, r1, r2):
+    # autograd is unavailable inside a custom-op body: write the three chain-rule contractions out
+    g6 = dW32.double().reshape(*rows, *cols)                                   # (o, p, q, i, j, k)
+    C1, C2, C3 = c1.double(), c2.double(), c3.double()
+    g = (torch.einsum("opqijk,bpjc,cqkd->oib", g6, C2, C3).unsqueeze(0),
+         torch.einsum("opqijk,aoib,cqkd->bpjc", g6, C1, C3),
+         torch.einsum("opqijk,aoib,bpjc->cqk", g6, C1, C2).unsqueeze(-1))
+    for dst, src in zip((d1, d2, d3), g):
+        dst.copy_(src.to(dst.dtype))
+    LOG.append(("blocktt3_core_grads", tuple(rows), tuple(cols), r1, r2))
+
+
+def emulate_gemm(a, b, bias, out, M, N, K, lda, ldb, a_major, b_major, alpha=1.0, split_k=0):
+    A = torch.as_strided(a, (M, K), (1, lda) if a_major else (lda, 1), a.storage_offset())
+    Bm = torch.as_strided(b, (N, K), (1, ldb) if b_major else (ldb, 1), b.storage_offset())
+    res = alpha * (A.double() @ Bm.double().t())
+    if bias is not None:
+        res = res + bias.double()
+    out.copy_(res.to(out.dtype))
+    LOG.append(("gemm", M, N, K, a_major, b_major))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
-    """Swap the two launch funnels for the CPU interpreters (tests only)."""
+    """Swap the launch funnels for the CPU interpreters (tests only)."""
+    from torch_b200 import blocktt_ops as bo
     saved = ops._execute_contract, ops._execute_conv
+    saved_b = bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm
     ops._execute_contract, ops._execute_conv = emulate_contract, emulate_conv
+    bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = (
+        emulate_btt3_reconstruct, emulate_btt3_core_grads, emulate_gemm)
     del LOG[:]
     try:
         yield LOG
     finally:
         ops._execute_contract, ops._execute_conv = saved
+        bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b

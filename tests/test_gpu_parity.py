@@ -132,6 +132,103 @@ def test_tcgen05_gemm_against_fp64(shape, out_dtype):
     assert G.rel_err(c, want) < (1e-5 if out_dtype == torch.float32 else 4e-3)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(768, 3072, 8192, 1, 1, 0), (768, 3072, 8192, 1, 1, 4), (300, 520, 4104, 0, 0, 3),
+                                   (512, 264, 2048, 1, 0, 16), (256, 256, 1024, 0, 1, 2)])
+@pytest.mark.parametrize("accumulate", [0, 1])
+def test_tcgen05_gemm_split_k(shape, accumulate):
+    """Split-K work units: fp32 partials meet in C through TMA reduce-add (C zeroed by the call unless accumulate)."""
+    import ctypes as C
+    from torch_b200 import _cuda
+    M, N, K, a_mn, b_mn, split = shape
+    torch.manual_seed(M + N + K + split)
+    a = torch.randn((K, M) if a_mn else (M, K), device=dev(), dtype=torch.bfloat16)
+    b = torch.randn((K, N) if b_mn else (N, K), device=dev(), dtype=torch.bfloat16)
+    bias = torch.randn(N, device=dev(), dtype=torch.float32)
+    c0 = torch.randn(M, N, device=dev(), dtype=torch.float32)
+    c = c0.clone() if accumulate else torch.full((M, N), float("nan"), device=dev(), dtype=torch.float32)
+    g = _cuda.GemmDesc()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldc = a.shape[1], b.shape[1], N
+    g.a_major, g.b_major = a_mn, b_mn
+    g.dtype_c = _cuda.F32
+    g.dtype_bias = _cuda.F32
+    g.alpha = 0.25
+    g.accumulate = accumulate
+    g.split_k = split
+    lib = _cuda.lib()
+    _cuda.check(lib.tlt_gemm_bf16_tc(C.byref(g), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(bias), _cuda.ptr(c),
+                                     _cuda.stream_ptr(c)), "tlt_gemm_bf16_tc")
+    torch.cuda.synchronize()
+    A = (a.t() if a_mn else a).double().cpu()
+    Bm = (b.t() if b_mn else b).double().cpu()
+    want = 0.25 * (A @ Bm.t()) + bias.double().cpu()
+    if accumulate:
+        want = want + c0.double().cpu()
+    assert not torch.isnan(c).any()
+    assert G.rel_err(c, want) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols,r1,r2", [((8, 12, 32), (8, 8, 12), 16, 16), ((8, 8, 12), (8, 12, 32), 16, 16),
+                                             ((3, 5, 7), (2, 6, 5), 4, 9), ((4, 4, 4), (4, 4, 4), 1, 1),
+                                             ((2, 3, 50), (3, 2, 3), 8, 5)])
+def test_blocktt3_fused_kernels_vs_fp64(rows, cols, r1, r2, dtype):
+    """tlt_blocktt3_reconstruct / tlt_blocktt3_core_grads (one fused launch / two) against the fp64 einsum definition
+    of BlockTT.to_tensor (tensorized_matrices.py:354-384) and its autograd, incl. ragged o3 groups."""
+    from torch_b200 import blocktt_ops
+    torch.manual_seed(sum(rows) + sum(cols) + r1 + r2)
+    shapes = [(1, rows[0], cols[0], r1), (r1, rows[1], cols[1], r2), (r2, rows[2], cols[2], 1)]
+    cores = [(torch.randn(s, device=dev()) * 0.5).to(dtype).requires_grad_(True) for s in shapes]
+    W = blocktt_ops.blocktt3_to_matrix(*cores)
+    gW = torch.randn_like(W)
+    grads = torch.autograd.grad(W, cores, gW)
+    ref = [c.detach().double().cpu().requires_grad_(True) for c in cores]
+    Wr = torch.einsum("aoib,bpjc,cqkd->opqijk", *ref).reshape(W.shape)
+    gr = torch.autograd.grad(Wr, ref, gW.double().cpu())
+    tol = TOL[dtype]
+    assert G.rel_err(W, Wr) < tol
+    for a, b in zip(grads, gr):
+        assert G.rel_err(a, b) < tol
+
+
+@pytest.mark.parametrize("transpose", [True, False])
+def test_blocktt3_fused_linear_vs_oracle(transpose):
+    """The fused dense-regime route (reconstruct + tcgen05 GEMMs + split-K dW + fused core grads) vs the oracle's
+    restatement of linear_blocktt (functional/factorized_linear.py:39-60), fwd and every gradient, bf16."""
+    from oracle import reference_path as rp
+    from torch_b200 import blocktt_ops
+    torch.manual_seed(11)
+    rows, cols = (8, 12, 32), (8, 8, 12)
+    shapes = [(1, rows[0], cols[0], 16), (16, rows[1], cols[1], 16), (16, rows[2], cols[2], 1)]
+    cores = [(torch.randn(s, device=dev()) * 0.3).bfloat16().requires_grad_(True) for s in shapes]
+    fin, fout = (768, 3072) if transpose else (3072, 768)
+    x = torch.randn(1000, fin, device=dev()).bfloat16().requires_grad_(True)
+    bias = torch.randn(fout, device=dev()).bfloat16().requires_grad_(True)
+    assert blocktt_ops.linear_eligible(x, cores, bias, transpose)
+    before = tlt_launches()
+    y = blocktt_ops.blocktt3_linear(x, *cores, bias, transpose)
+    gy = torch.randn_like(y)
+    got = torch.autograd.grad(y, [x, bias] + cores, gy)
+    assert tlt_launches() - before >= 7
+    xo = x.detach().double().cpu().requires_grad_(True)
+    bo = bias.detach().double().cpu().requires_grad_(True)
+    co = [c.detach().double().cpu().requires_grad_(True) for c in cores]
+    Wo = torch.einsum("aoib,bpjc,cqkd->opqijk", *co).reshape(3072, 768)
+    yo = (xo @ Wo.t() if transpose else xo @ Wo) + bo
+    if transpose:
+        assert G.rel_err(yo, rp.blocktt_linear(xo, co, cols) + bo) < 1e-12        # the oracle agrees with the definition
+    want = torch.autograd.grad(yo, [xo, bo] + co, gy.double().cpu())
+    assert G.rel_err(y, yo) < 2e-2
+    for a, b in zip(got, want):
+        assert G.rel_err(a, b) < 2e-2
+
+
+def tlt_launches():
+    from torch_b200 import ops
+    return ops.launch_count()
+
+
 def test_tcgen05_and_simt_agree_through_contract():
     from torch_b200 import ops
     torch.manual_seed(3)

@@ -36,7 +36,7 @@ class GemmDesc(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
                 ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
                 ("a_major", C.c_int32), ("b_major", C.c_int32), ("dtype_c", C.c_int32), ("accumulate", C.c_int32),
-                ("dtype_bias", C.c_int32), ("alpha", C.c_float)]
+                ("dtype_bias", C.c_int32), ("alpha", C.c_float), ("split_k", C.c_int32)]
 
 
 class ConvDesc(C.Structure):
@@ -44,6 +44,11 @@ class ConvDesc(C.Structure):
                 ("in_size", C.c_int64 * 3), ("out_size", C.c_int64 * 3),
                 ("kernel", C.c_int32 * 3), ("stride", C.c_int32 * 3), ("padding", C.c_int32 * 3),
                 ("dilation", C.c_int32 * 3)]
+
+
+class BlockTT3Desc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("rows", C.c_int32 * 3), ("cols", C.c_int32 * 3),
+                ("rank1", C.c_int32), ("rank2", C.c_int32)]
 
 
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
@@ -56,6 +61,9 @@ SYMBOLS = {
     "tlt_contract": (C.c_int, [C.POINTER(ContractDesc), _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "tlt_gemm_bf16_tc_supported": (C.c_int, [C.POINTER(GemmDesc)]),
     "tlt_gemm_bf16_tc": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp]),
+    "tlt_blocktt3_reconstruct": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp]),
+    "tlt_blocktt3_core_grads_workspace_size": (C.c_size_t, [C.POINTER(BlockTT3Desc)]),
+    "tlt_blocktt3_core_grads": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "tlt_im2col": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
     "tlt_col2im": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
     "tlt_dwconv_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),

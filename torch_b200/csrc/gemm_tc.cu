@@ -138,6 +138,7 @@ struct GemmParams {
   int c_f32, accumulate, has_bias, bias_bf16;
   float alpha;
   int tiles_m, tiles_n;
+  int splits, kb_per_split, c_reduce;
 };
 
 
@@ -416,25 +417,56 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
 }
 
+
+// =====================================================================================================================
+// v3: the CTA-pair mainloop of v2 with (a) a shared-memory-staged epilogue -- TMEM -> registers -> SWIZZLE_128B smem
+// -> cp.async.bulk.tensor store (full 128-byte lines, OOB rows/columns clipped by the TMA unit) instead of per-thread
+// 16-byte global stores, which kept l1tex 72 % busy and the tensor pipe 44 % active on the N=3072 / K=768 launches
+// (profiles/r01_gemm_tc2_full.md) -- and (b) split-K work units whose fp32 partials meet in C through
+// cp.reduce.async.bulk.tensor (.add), so the K = tokens weight-gradient GEMMs (36 output tiles) fill all 74 SM pairs.
+//   warp 0: TMA producer   warp 1: MMA issuer (leader CTA only)   warp 2: TMEM alloc   warps 4-11: epilogue
+// =====================================================================================================================
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&h;
+}
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiBufBytes = 4096;          // 32 rows x 128 bytes per epilogue warp
+
 template <int BN, int kStages>
-struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;           // 32 KB @ BN=256
+struct SmemLayout3 {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;       // this CTA's half of the N extent
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;      // barriers + tmem slot + alignment slack
+  static constexpr int EPI_OFFSET = kStages * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + kEpiWarps * kEpiBufBytes;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
 template <int BN, int kStages>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const GemmParams p, const void* __restrict__ bias, void* __restrict__ Cout) {
-  using L = SmemLayout<BN, kStages>;
-  constexpr uint32_t TMEM_COLS = 2 * BN;                     // two accumulator buffers (power of two: 256 / 512)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+gemm_bf16_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_c, const GemmParams p, const void* __restrict__ bias) {
+  using L = SmemLayout3<BN, kStages>;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int HALF_N = BN / 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-
   const uint32_t bar_base = smem_base + L::BAR_OFFSET;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -444,51 +476,58 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_units = p.tiles_m * p.tiles_n * p.splits;
   const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer (both CTAs) =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.tiles_n) * BLOCK_M, n0 = (tile % p.tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const int tile = u / p.splits, split = u - tile * p.splits;
+        const int m0 = (tile / p.tiles_n) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+        const int n0 = (tile % p.tiles_n) * BN + (int)cta_rank * HALF_N;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn) {
-            tma_load_2d(sa, &map_a, full_bar(stage), k0, m0);                       // box {64 k, 128 m}
+            tma_load_2d_2sm(sa, &map_a, full_bar(stage), k0, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)                                   // box {64 m, 64 k} per chunk
-              tma_load_2d(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0);
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d_2sm(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0);
           }
           if (!p.b_mn) {
-            tma_load_2d(sb, &map_b, full_bar(stage), k0, n0);                       // box {64 k, BN n}
+            tma_load_2d_2sm(sb, &map_b, full_bar(stage), k0, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (BLOCK_K * 128), &map_b, full_bar(stage), n0 + 64 * c, k0);
+            for (int c = 0; c < HALF_N / 64; ++c)
+              tma_load_2d_2sm(sb + c * (BLOCK_K * 128), &map_b, full_bar(stage), n0 + 64 * c, k0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -496,19 +535,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_M, BN, p.a_mn, p.b_mn);
+    // ===================================== MMA issuer (leader CTA) ======================================
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc(2 * BLOCK_M, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? BLOCK_K * 128 : 16, b_lbo = p.b_mn ? BLOCK_K * 128 : 16;
-      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);               // bytes per UMMA_K step
+      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);
       const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const int tile = u / p.splits, split = u - tile * p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
@@ -516,10 +557,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));            // frees this smem stage once the MMAs above have read it
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          umma_commit_2sm(empty_bar(stage));
+          if (kb == kb1 - 1) umma_commit_2sm(tfull_bar(acc));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -527,71 +568,83 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================== epilogue =========================================
-    const int ew = warp - 4;                       // == warp % 4 -> TMEM lanes [32*ew, 32*ew + 32)
+    // ===================================== epilogue (both CTAs, 8 warps) ================================
+    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
+    const int col_half = (warp - 4) >> 2;          // columns [HALF_N*col_half, +HALF_N)
+    const uint32_t leader_tempty0 = mapa_u32(tempty_bar(0), 0);
+    const uint32_t ebuf = smem_base + L::EPI_OFFSET + (warp - 4) * kEpiBufBytes;
+    const uint32_t erow = ebuf + lane * 128;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const int chunk_cols = p.c_f32 ? 32 : 64;      // 128 bytes of C per row per TMA store box
+    const int n_chunks = HALF_N / chunk_cols;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.tiles_n) * BLOCK_M, n0 = (tile % p.tiles_n) * BN;
+    for (int u = cluster_id; u < num_units; u += num_clusters) {
+      const int tile = u / p.splits, split = u - tile * p.splits;
+      const int m0 = (tile / p.tiles_n) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M + quarter * 32;
+      const int n0 = (tile % p.tiles_n) * BN + col_half * HALF_N;
+      const bool add_bias = p.has_bias && split == 0;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + ew * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_half * HALF_N);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          float f[32];
+      for (int c = 0; c < n_chunks; ++c) {
+        const int col0 = n0 + c * chunk_cols;
+        uint32_t w[32];                              // the 128 output bytes of this thread's row
+        if (p.c_f32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          float bv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = p.alpha * __uint_as_float(v[i]);
-          if (p.has_bias) {
+          for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+          if (add_bias && col0 < p.N) load_bias32(bias, p.bias_bf16, col0, p.N, bv);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.N)
-                f[i] += p.bias_bf16 ? __bfloat162float(((const __nv_bfloat16*)bias)[col0 + i]) : __ldg((const float*)bias + col0 + i);
-          }
-          if (p.c_f32) {
-            float* dst = (float*)Cout + (long long)row * p.ldc + col0;
-            if (col0 + 32 <= p.N) {
+          for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(fmaf(p.alpha, __uint_as_float(v[i]), bv[i]));
+        } else {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                if (p.accumulate) { float4 q = *(float4*)(dst + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-                *(float4*)(dst + i) = o;
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) dst[i] = p.accumulate ? dst[i] + f[i] : f[i];
-            }
-          } else {
-            __nv_bfloat16* dst = (__nv_bfloat16*)Cout + (long long)row * p.ldc + col0;
-            if (col0 + 32 <= p.N) {
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c * 64 + h * 32, v);
+            float bv[32];
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 o;
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[i], f[i + 1]), h1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]), h3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-                o.x = *(uint32_t*)&h0; o.y = *(uint32_t*)&h1; o.z = *(uint32_t*)&h2; o.w = *(uint32_t*)&h3;
-                *(uint4*)(dst + i) = o;
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) dst[i] = __float2bfloat16_rn(f[i]);
-            }
+            for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+            if (add_bias && col0 + 32 * h < p.N) load_bias32(bias, p.bias_bf16, col0 + 32 * h, p.N, bv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              w[16 * h + i] = pack_bf16x2(fmaf(p.alpha, __uint_as_float(v[2 * i]), bv[2 * i]),
+                                          fmaf(p.alpha, __uint_as_float(v[2 * i + 1]), bv[2 * i + 1]));
           }
         }
+        if (c == n_chunks - 1) {                      // accumulator fully read: hand the TMEM buffer back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+        }
+        if (lane == 0) bulk_wait_read0();             // the previous store of this warp has finished reading ebuf
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(erow + ((((uint32_t)j) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && m0 < p.M && col0 < p.N) {
+          if (p.c_reduce) tma_reduce_add_2d(&map_c, ebuf, col0, m0);
+          else tma_store_2d(&map_c, ebuf, col0, m0);
+          bulk_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();          // both CTAs are done with TMEM and with each other's shared memory
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -615,15 +668,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner (contiguous) extent d0, outer extent d1 with row pitch ld elements.
-static int make_map(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1, int64_t ld, int box0, int box1) {
+// 2-D tensor map (bf16, or fp32 when f32 != 0): inner (contiguous) extent d0, outer extent d1, row pitch ld elements.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1, int64_t ld, int box0, int box1, int f32 = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)"); return TLT_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -644,37 +697,6 @@ static int num_sms() {
   }
   return n;
 }
-
-template <int BN, int kStages>
-static int launch_gemm(const tlt_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, cudaStream_t st) {
-  using L = SmemLayout<BN, kStages>;
-  CUtensorMap ma, mb;
-  int rc;
-  if (!d->a_major) rc = make_map(&ma, A, d->K, d->M, d->lda, BLOCK_K, BLOCK_M);
-  else rc = make_map(&ma, A, d->M, d->K, d->lda, 64, BLOCK_K);
-  if (rc) return rc;
-  if (!d->b_major) rc = make_map(&mb, B, d->K, d->N, d->ldb, BLOCK_K, BN);
-  else rc = make_map(&mb, B, d->N, d->K, d->ldb, 64, BLOCK_K);
-  if (rc) return rc;
-
-  GemmParams p;
-  p.M = (int)d->M; p.N = (int)d->N; p.K = (int)d->K; p.ldc = d->ldc;
-  p.a_mn = d->a_major; p.b_mn = d->b_major;
-  p.c_f32 = d->dtype_c == TLT_F32; p.accumulate = d->accumulate; p.has_bias = bias != nullptr; p.bias_bf16 = d->dtype_bias == TLT_BF16;
-  p.alpha = d->alpha;
-  p.tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
-  p.tiles_n = (p.N + BN - 1) / BN;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
-  int tiles = p.tiles_m * p.tiles_n;
-  int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tc_kernel<BN, kStages><<<grid, kGemmThreads, L::TOTAL, st>>>(ma, mb, p, bias, C);
-  return check_launch("gemm_bf16_tc_kernel");
-}
-
 
 template <int BN, int kStages>
 static int launch_gemm2(const tlt_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, cudaStream_t st) {
@@ -706,13 +728,81 @@ static int launch_gemm2(const tlt_gemm_desc* d, const void* A, const void* B, co
   return check_launch("gemm_bf16_tc2_kernel");
 }
 
+template <int BN, int kStages>
+static int launch_gemm3(const tlt_gemm_desc* d, int splits, const void* A, const void* B, const void* bias, void* C, cudaStream_t st) {
+  using L = SmemLayout3<BN, kStages>;
+  CUtensorMap ma, mb, mc;
+  int rc;
+  if (!d->a_major) rc = make_map(&ma, A, d->K, d->M, d->lda, BLOCK_K, BLOCK_M);
+  else rc = make_map(&ma, A, d->M, d->K, d->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!d->b_major) rc = make_map(&mb, B, d->K, d->N, d->ldb, BLOCK_K, BN / 2);
+  else rc = make_map(&mb, B, d->N, d->K, d->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  const int c_f32 = d->dtype_c == TLT_F32;
+  rc = make_map(&mc, C, d->N, d->M, d->ldc, c_f32 ? 32 : 64, 32, c_f32);     // 128-byte x 32-row store boxes
+  if (rc) return rc;
+  GemmParams p;
+  p.M = (int)d->M; p.N = (int)d->N; p.K = (int)d->K; p.ldc = d->ldc;
+  p.a_mn = d->a_major; p.b_mn = d->b_major;
+  p.c_f32 = c_f32; p.accumulate = d->accumulate; p.has_bias = bias != nullptr; p.bias_bf16 = d->dtype_bias == TLT_BF16;
+  p.alpha = d->alpha;
+  p.tiles_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  p.tiles_n = (p.N + BN - 1) / BN;
+  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;          // every split owns >= 1 k-block
+  p.c_reduce = (p.accumulate || p.splits > 1) ? 1 : 0;
+  if (p.splits > 1 && !p.accumulate)                                   // split-K partials are reduce-added into zeros
+    TLT_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc3_kernel<BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  int units = p.tiles_m * p.tiles_n * p.splits;
+  int pairs = num_sms() / 2;
+  int clusters = units < pairs ? units : pairs;
+  gemm_bf16_tc3_kernel<BN, kStages><<<2 * clusters, kGemm2Threads, L::TOTAL, st>>>(ma, mb, mc, p, bias);
+  return check_launch("gemm_bf16_tc3_kernel");
+}
+
 static int gemm_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TLT_GEMM_IMPL");
-    v = (e && e[0] == '1') ? 1 : 2;
+    v = (e && e[0] == '2') ? 2 : 3;
   }
   return v;
+}
+
+// Tile width and split-K factor by a small cost model: units are dealt round-robin to the 74 SM pairs; a unit costs its
+// k-blocks (a 128-wide tile moves 1.5x the operand bytes per FLOP of a 256-wide one, so it runs at ~0.6 of the time of a
+// 256-wide tile rather than 0.5) plus a fixed pipeline-fill / epilogue term.
+static void choose_tiling(const tlt_gemm_desc* d, int* bn_out, int* splits_out) {
+  const int pairs = num_sms() / 2;
+  const long long tm = (d->M + 255) / 256;
+  const long long num_kb = (d->K + BLOCK_K - 1) / BLOCK_K;
+  const bool can_split = d->dtype_c == TLT_F32;
+  double best = 1e300;
+  int best_bn = 256, best_s = 1;
+  const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  for (int bn = 256; bn >= 128; bn -= 128) {
+    if (bn == 256 && d->N <= 128) continue;
+    const long long tiles = tm * ((d->N + bn - 1) / bn);
+    for (int s : cand_s) {
+      if (s > 1 && (!can_split || num_kb / s < 8)) continue;
+      const long long units = tiles * s;
+      const long long waves = (units + pairs - 1) / pairs;
+      const double unit_cost = (double)((num_kb + s - 1) / s) * (bn == 256 ? 1.0 : 0.6) + 4.0;
+      const double cost = (double)waves * unit_cost + (s > 1 ? 2.0 : 0.0);
+      if (cost < best) { best = cost; best_bn = bn; best_s = s; }
+    }
+  }
+  *bn_out = best_bn;
+  *splits_out = best_s;
 }
 
 }  // namespace tlt
@@ -742,7 +832,7 @@ extern "C" int tlt_gemm_bf16_tc(const tlt_gemm_desc* d, const void* A, const voi
               "tlt_gemm_bf16_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (gemm_impl() == 2) {
-    // CTA-pair kernel: 256 x 256 tiles unless 256 x 128 tiles fill the 74 SM pairs markedly better
+    // previous CTA-pair kernel (per-thread global stores in the epilogue), kept for A/B comparison: TLT_GEMM_IMPL=2
     int pairs = num_sms() / 2;
     long long tm = (d->M + 255) / 256;
     long long t256 = tm * ((d->N + 255) / 256), t128 = tm * ((d->N + 127) / 128);
@@ -751,12 +841,9 @@ extern "C" int tlt_gemm_bf16_tc(const tlt_gemm_desc* d, const void* A, const voi
     if (n256) return launch_gemm2<256, 6>(d, A, B, bias, C, st);
     return launch_gemm2<128, 8>(d, A, B, bias, C, st);
   }
-  // Tile choice: 128x256 tiles halve the smem traffic per FLOP, 128x128 tiles fill the 148 SMs better on small outputs.
-  long long t256 = ((d->M + 127) / 128) * ((d->N + 255) / 256);
-  long long t128 = ((d->M + 127) / 128) * ((d->N + 127) / 128);
-  int sms = num_sms();
-  auto waves_eff = [&](long long tiles) { long long w = (tiles + sms - 1) / sms; return (double)tiles / (double)(w * sms); };
-  bool use256 = d->N > 128 && (waves_eff(t256) >= 0.8 * waves_eff(t128));
-  if (use256) return launch_gemm<256, 4>(d, A, B, bias, C, st);
-  return launch_gemm<128, 6>(d, A, B, bias, C, st);
+  int bn, splits;
+  choose_tiling(d, &bn, &splits);
+  if (d->split_k > 0) splits = d->dtype_c == TLT_F32 ? d->split_k : 1;
+  if (bn == 256) return launch_gemm3<256, 6>(d, splits, A, B, bias, C, st);
+  return launch_gemm3<128, 8>(d, splits, A, B, bias, C, st);
 }

@@ -3,6 +3,7 @@ import math
 
 from ..ops import contract
 from .. import tenalg
+from .. import blocktt_ops
 from .factorized_tensordot import tensor_dot_tucker, tensor_dot_cp
 
 _L = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
@@ -74,6 +75,10 @@ def linear_blocktt(tensor, tt_matrix, transpose=True, plan=None, bias=None):
     if plan is None:
         plan = blocktt_plan(batch, in_shape, out_shape, rank)
     if plan == "dense":
+        x2 = x.reshape(batch, -1)
+        if blocktt_ops.linear_eligible(x2, cores, bias, transpose):
+            # rebuild W (1 launch) + tcgen05 GEMM with the bias in its epilogue; fused core-gradient kernels in backward
+            return blocktt_ops.blocktt3_linear(x2, cores[0], cores[1], cores[2], bias, transpose)
         w = tenalg.blocktt_to_tensor(cores, tt_matrix.tensorized_shape).reshape(tt_matrix.shape)     # (rows, cols)
         x2 = x.reshape(batch, -1)
         spec = "bi,oi->bo" if transpose else "bi,io->bo"

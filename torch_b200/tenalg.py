@@ -129,6 +129,13 @@ def blocktt_to_tensor(cores, tensorized_shape):
     (entry-major, core-minor) index order, so no reshuffling pass over the reconstructed weight is ever needed."""
     cores = list(cores)
     n_entries = len(tensorized_shape)
+    if (len(cores) == 3 and n_entries == 2 and all(c.dim() == 4 for c in cores)
+            and not any(isinstance(s, int) for s in tensorized_shape) and cores[0].shape[0] == 1 and cores[2].shape[3] == 1):
+        from . import blocktt_ops
+        rows, cols = [c.shape[1] for c in cores], [c.shape[2] for c in cores]
+        if blocktt_ops.blocktt3_fits(rows, cols, cores[0].shape[3], cores[1].shape[3], True):
+            # one fused launch: the rank-indexed intermediate stays in shared memory (csrc/blocktt.cu)
+            return blocktt_ops.blocktt3_to_matrix(*cores).reshape(rows + cols)
     shared = {j: _L[j] for j, s in enumerate(tensorized_shape) if isinstance(s, int)}
     nxt = n_entries
 
