@@ -75,6 +75,14 @@ size_t tlt_contract_workspace_size(const tlt_contract_desc* desc);
 int tlt_contract(const tlt_contract_desc* desc, const void* A, const void* B, const void* D, void* C,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Bridge to the tensor cores for contractions whose operands are strided or break TMA's 16-byte pitch rule:
+ *   tlt_contract_pack   copies operand A (operand = 0: rows = the m class) or B (operand = 1: rows = the n class), read
+ *                       through the descriptor's strides, into a dense K-major bf16 matrix rows x K with pitch dst_ld;
+ *   tlt_contract_unpack writes a dense M x N result of dtype_c (pitch ldc) (+ the strided addend D) to the strided output.
+ * Used as pack -> tlt_gemm_bf16_tc -> unpack; only for descriptors with nb == 0.  Same reference call sites as tlt_contract. */
+int tlt_contract_pack(const tlt_contract_desc* desc, int32_t operand, const void* src, void* dst, int64_t dst_ld, void* stream);
+int tlt_contract_unpack(const tlt_contract_desc* desc, const void* Cp, int64_t ldc, const void* D, void* C, void* stream);
+
 /* --------------------------------------------------------------------------------------------------------------
  * tlt_gemm_bf16_tc: dense bf16 GEMM on the tcgen05 tensor cores (TMA-staged operands, TMEM fp32 accumulators).
  *   C[M,N] = A[M,K] * B[N,K]^T (+ bias[N])      A, B bf16;  C bf16 or fp32, row-major with leading dim ldc.
@@ -121,6 +129,29 @@ size_t tlt_blocktt3_core_grads_workspace_size(const tlt_blocktt3_desc* desc);
 int tlt_blocktt3_core_grads(const tlt_blocktt3_desc* desc, const void* c1, const void* c2, const void* c3,
                             const float* dW, void* d1, void* d2, void* d3, void* workspace, size_t workspace_bytes,
                             void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Pointwise (1x1) channel mixing of channels-first bf16 activations on the tcgen05 tensor cores, from NCHW memory.
+ *   tlt_pointwise_tc       : y[b, n, s] = sum_k wt[n, k] * x[b, k, s] (+ bias[n])      x (batch, in, spatial), y (batch, out, spatial)
+ *   tlt_pointwise_wgrad_tc : dw[n, k]   = sum_{b, s} dy[b, n, s] * x[b, k, s]          dw fp32, row pitch w_ld
+ * wt is a K-major (out_channels, w_ld) bf16 matrix (tlt_pack_kmajor builds it from any strided view; the columns past
+ * in_channels are zero).  spatial must be a multiple of 8 (TMA pitch): tlt_pointwise_tc_supported() tells; other shapes
+ * stay on tlt_contract.  The data gradient is the same call with the transposed weight.
+ * Replaces: F.conv1d(kernel_size=1) in tltorch/functional/convolution.py (:154,168 tucker_conv, :207,223 tt_conv,
+ * :262,278 cp_conv, :311,340 cp_conv_mobilenet) and its autograd.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t batch, in_channels, out_channels, spatial;
+  int64_t w_ld;                                         /* pitch (elements) of wt (bf16) / of dw (fp32)             */
+  int32_t dtype_bias;                                   /* tlt_dtype of bias[out_channels] (ignored when NULL)      */
+} tlt_pointwise_desc;
+
+int tlt_pointwise_tc_supported(const tlt_pointwise_desc* desc);
+int tlt_pointwise_tc(const tlt_pointwise_desc* desc, const void* x, const void* wt, const void* bias, void* y, void* stream);
+int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* desc, const void* dy, const void* x, float* dw, void* stream);
+/* dst[r, c] = (bf16) src[r * row_stride + c * col_stride] for c < cols, 0 for cols <= c < dst_ld   (rows x dst_ld, bf16) */
+int tlt_pack_kmajor(const void* src, int32_t dtype_src, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+                    void* dst, int64_t dst_ld, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * Convolution building blocks (channels-first, 1 to 3 spatial dims).

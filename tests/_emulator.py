@@ -160,10 +160,27 @@ def emulate_gemm(a, b, bias, out, M, N, K, lda, ldb, a_major, b_major, alpha=1.0
     LOG.append(("gemm", M, N, K, a_major, b_major))
 
 
+def emulate_pointwise(x3, w_nk, bias, y):
+    res = torch.einsum("nk,bks->bns", w_nk.double(), x3.double())
+    if bias is not None:
+        res = res + bias.double()[None, :, None]
+    y.copy_(res.to(y.dtype))
+    LOG.append(("pointwise_tc", tuple(x3.shape), tuple(w_nk.shape), tuple(w_nk.stride())))
+
+
+def emulate_pointwise_wgrad(gy3, x3, dw32):
+    K = x3.shape[1]
+    dw32[:, :K].copy_(torch.einsum("bns,bks->nk", gy3.double(), x3.double()).to(dw32.dtype))
+    LOG.append(("pointwise_wgrad_tc", tuple(gy3.shape), tuple(x3.shape)))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
     """Swap the launch funnels for the CPU interpreters (tests only)."""
     from torch_b200 import blocktt_ops as bo
+    from torch_b200 import pointwise_ops as po
+    saved_p = po._execute_pointwise, po._execute_pointwise_wgrad
+    po._execute_pointwise, po._execute_pointwise_wgrad = emulate_pointwise, emulate_pointwise_wgrad
     saved = ops._execute_contract, ops._execute_conv
     saved_b = bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm
     ops._execute_contract, ops._execute_conv = emulate_contract, emulate_conv
@@ -175,3 +192,4 @@ def emulated_kernels():
     finally:
         ops._execute_contract, ops._execute_conv = saved
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
+        po._execute_pointwise, po._execute_pointwise_wgrad = saved_p

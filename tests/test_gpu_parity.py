@@ -224,6 +224,60 @@ def test_blocktt3_fused_linear_vs_oracle(transpose):
         assert G.rel_err(a, b) < 2e-2
 
 
+@pytest.mark.parametrize("B,K,N,S", [(3, 64, 69, 3136), (2, 69, 64, 784), (5, 130, 300, 64), (2, 512, 573, 200), (1, 8, 8, 8),
+                                     (4, 93, 128, 784)])
+def test_pointwise_tc_kernels_vs_fp64(B, K, N, S):
+    """tlt_pointwise_tc (fwd / dgrad) and tlt_pointwise_wgrad_tc straight from NCHW memory, ragged channel counts and
+    partial position tiles, against fp64 einsum (the F.conv1d(k=1) stages of functional/convolution.py)."""
+    from torch_b200 import pointwise_ops
+    torch.manual_seed(B + K + N + S)
+    x = torch.randn(B, K, S, device=dev()).bfloat16().requires_grad_(True)
+    w_kn = (torch.randn(K, N, device=dev()) / math.sqrt(K)).bfloat16().requires_grad_(True)    # stored (in, out): w_nk is a strided view
+    bias = torch.randn(N, device=dev()).bfloat16().requires_grad_(True)
+    y = pointwise_ops.pointwise_tc(x, w_kn.t(), bias)
+    gy = torch.randn_like(y)
+    gx, gw, gb = torch.autograd.grad(y, [x, w_kn, bias], gy)
+    xr, wr, br = (t.detach().double().cpu().requires_grad_(True) for t in (x, w_kn, bias))
+    yr = torch.einsum("kn,bks->bns", wr, xr) + br[None, :, None]
+    want = torch.autograd.grad(yr, [xr, wr, br], gy.double().cpu())
+    assert G.rel_err(y, yr) < 1e-2
+    for a, b in zip((gx, gw, gb), want):
+        assert G.rel_err(a, b) < 1e-2
+
+
+@pytest.mark.parametrize("spec,sa,sb,bias_letters", [
+    ("mk,nk->mn", (1024, 3375), (3375, 3375), None),                 # Tucker core GEMM of config 5: K, N not multiples of 8
+    ("bijk,ri->brjk", (256, 64, 16, 16), (60, 64), None),            # mode product along a middle mode
+    ("oc,bcs->bos", (388, 512), (64, 512, 49), "o"),                 # 1x1 conv on 7x7 maps (S = 49 breaks the TMA pitch rule) + bias
+    ("bsct,qct->bqs", (32, 49, 388, 9), (388, 388, 9), None),        # unfolded Tucker core conv, K = 388 * 9
+    ("bk,kn->bn", (4096, 1000), (1000, 264), "n"),
+])
+def test_packed_tensor_core_contract(spec, sa, sb, bias_letters):
+    """Strided / TMA-misaligned bf16 contractions take pack -> tcgen05 GEMM -> unpack; result against fp64 einsum."""
+    from torch_b200 import ops
+    torch.manual_seed(len(spec) + sum(sa))
+    a = (torch.randn(sa, device=dev()) * 0.5).bfloat16()
+    b = (torch.randn(sb, device=dev()) * 0.5).bfloat16()
+    lo = spec.split("->")[1]
+    size = dict(zip(spec.split("->")[0].split(",")[0], sa))
+    size.update(zip(spec.split("->")[0].split(",")[1], sb))
+    bias = torch.randn([size[l] for l in bias_letters], device=dev()).bfloat16() if bias_letters else None
+    ops.PROFILE = []
+    try:
+        y = ops.contract(spec, a, b, bias, bias_letters) if bias is not None else ops.contract(spec, a, b)
+        torch.cuda.synchronize()
+        took_tc = any("gemm_bf16_tc" in e[0] for e in ops.PROFILE)
+    finally:
+        ops.PROFILE = None
+    assert took_tc, "the contraction did not reach the tensor cores"
+    want = torch.einsum(spec, a.double().cpu(), b.double().cpu())
+    if bias is not None:
+        shape = [size[l] if l in bias_letters else 1 for l in lo]
+        want = want + bias.double().cpu().reshape(shape)
+    assert tuple(y.shape) == tuple(want.shape)
+    assert G.rel_err(y, want) < 1e-2
+
+
 def tlt_launches():
     from torch_b200 import ops
     return ops.launch_count()

@@ -164,3 +164,37 @@ def test_cpu_tensors_are_rejected_without_fallback():
         tlt.functional.factorized_linear(torch.randn(3, 4), lin.weight, implementation="nope")
     with pytest.raises(ValueError):
         tlt.FactorizedTensor.new((2, 2), rank=1, factorization="nope")
+
+
+def test_tensor_core_routes_host_logic_bf16():
+    """bf16 inputs take the tcgen05 routes (fused BlockTT linear, NCHW pointwise); with the launch funnels emulated on the
+    CPU the op plumbing (operand majors, transposed weight views, gradient shapes) must reproduce fp64 autograd."""
+    from torch_b200.functional.convolution import cp_conv, tucker_conv
+    torch.manual_seed(5)
+    bf = torch.bfloat16
+    with emulated_kernels() as log:
+        # CP conv 16 -> 24 channels on 8x8 maps (S = 64, a multiple of 8 -> pointwise_tc eligible once work is large enough)
+        from torch_b200 import pointwise_ops
+        old = pointwise_ops.MIN_WORK
+        pointwise_ops.MIN_WORK = 1
+        try:
+            w = tlt.FactorizedTensor.new((24, 16, 3, 3), rank=5, factorization="cp").normal_(0, 0.3).to(bf)
+            x = torch.randn(3, 16, 8, 8).to(bf).requires_grad_(True)
+            bias = torch.randn(24).to(bf).requires_grad_(True)
+            y = cp_conv(x, w, bias=bias, stride=1, padding=1)
+            leaves = [x, bias, w.weights] + list(w.factors)
+            gy = torch.randn_like(y)
+            got = torch.autograd.grad(y, leaves, gy)
+            assert any(e[0] == "pointwise_tc" for e in log) and any(e[0] == "pointwise_wgrad_tc" for e in log)
+        finally:
+            pointwise_ops.MIN_WORK = old
+    # fp64 reference with torch's own conv on the reconstructed kernel
+    ref_leaves = [t.detach().double().requires_grad_(True) for t in leaves]
+    xr, br, lam = ref_leaves[0], ref_leaves[1], ref_leaves[2]
+    f = ref_leaves[3:]
+    kern = torch.einsum("r,or,cr,hr,wr->ochw", lam, f[0], f[1], f[2], f[3])
+    yr = torch.nn.functional.conv2d(xr, kern, br, stride=1, padding=1)
+    want = torch.autograd.grad(yr, ref_leaves, gy.double())
+    assert G.rel_err(y, yr) < 3e-2
+    for a, b in zip(got, want):
+        assert G.rel_err(a, b) < 3e-2

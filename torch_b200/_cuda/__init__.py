@@ -51,6 +51,11 @@ class BlockTT3Desc(C.Structure):
                 ("rank1", C.c_int32), ("rank2", C.c_int32)]
 
 
+class PointwiseDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("in_channels", C.c_int64), ("out_channels", C.c_int64), ("spatial", C.c_int64),
+                ("w_ld", C.c_int64), ("dtype_bias", C.c_int32)]
+
+
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -59,11 +64,17 @@ SYMBOLS = {
     "tlt_launch_count": (C.c_uint64, []),
     "tlt_contract_workspace_size": (C.c_size_t, [C.POINTER(ContractDesc)]),
     "tlt_contract": (C.c_int, [C.POINTER(ContractDesc), _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "tlt_contract_pack": (C.c_int, [C.POINTER(ContractDesc), C.c_int32, _vp, _vp, C.c_int64, _vp]),
+    "tlt_contract_unpack": (C.c_int, [C.POINTER(ContractDesc), _vp, C.c_int64, _vp, _vp, _vp]),
     "tlt_gemm_bf16_tc_supported": (C.c_int, [C.POINTER(GemmDesc)]),
     "tlt_gemm_bf16_tc": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_blocktt3_reconstruct": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_blocktt3_core_grads_workspace_size": (C.c_size_t, [C.POINTER(BlockTT3Desc)]),
     "tlt_blocktt3_core_grads": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "tlt_pointwise_tc_supported": (C.c_int, [C.POINTER(PointwiseDesc)]),
+    "tlt_pointwise_tc": (C.c_int, [C.POINTER(PointwiseDesc), _vp, _vp, _vp, _vp, _vp]),
+    "tlt_pointwise_wgrad_tc": (C.c_int, [C.POINTER(PointwiseDesc), _vp, _vp, _vp, _vp]),
+    "tlt_pack_kmajor": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64, _vp]),
     "tlt_im2col": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
     "tlt_col2im": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
     "tlt_dwconv_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),

@@ -611,3 +611,186 @@ extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const voi
   if (d->dtype_c == TLT_F32) return launch_ab<float>(p, d->dtype_a, d->dtype_b, bm, bn, A, B, D, C, st);
   return launch_ab<__nv_bfloat16>(p, d->dtype_a, d->dtype_b, bm, bn, A, B, D, C, st);
 }
+
+// =====================================================================================================================
+// Pack / unpack: the bridge that lets ANY large bf16 contraction run on the tcgen05 GEMM (gemm_tc.cu).
+//
+//   tlt_contract_pack   : operand (read through the descriptor's multi-index strides) -> dense K-major bf16 matrix
+//                         rows x K with pitch ld (rows = the m class for operand A, the n class for operand B)
+//   tlt_contract_unpack : dense M x N result (+ strided addend D) -> the strided output tensor of the descriptor
+//
+// Mode products whose reduction index is not contiguous, ranks such as 15 / 69 / 388 that break TMA's 16-byte pitch rule,
+// unfolded convolutions with K = 9 * 388 ... all ran on the SIMT kernel at 7-15 TFLOP/s.  Two extra streaming passes
+// (tile-transposed through shared memory so that both the strided side and the dense side are coalesced) cost a few
+// microseconds per 10 MB and buy a 50-100x faster inner product.
+// =====================================================================================================================
+namespace tlt {
+
+struct PackParams {
+  int nr, nk;
+  int size_r[TLT_MAX_SUBDIMS], size_k[TLT_MAX_SUBDIMS];
+  long long stride_r[TLT_MAX_SUBDIMS], stride_k[TLT_MAX_SUBDIMS];
+  long long dstride_r[TLT_MAX_SUBDIMS], dstride_k[TLT_MAX_SUBDIMS];   // unpack: strides of the addend D
+  int R, K;
+  long long ld;
+  int fast_is_k;       // the strided tensor's unit-stride index belongs to the column (k / n) class
+  int has_d, d_bf16;
+};
+
+constexpr int kPT = 64;   // tile edge
+
+// dst[r][k] = (bf16) src[off_r(r) + off_k(k)]
+template <typename TS>
+__global__ void __launch_bounds__(256) pack_kernel(const PackParams p, const TS* __restrict__ src, __nv_bfloat16* __restrict__ dst) {
+  __shared__ __nv_bfloat16 tile[kPT][kPT + 2];
+  __shared__ long long roff[kPT], koff[kPT];
+  const int r0 = blockIdx.y * kPT, k0 = blockIdx.x * kPT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x < kPT) {
+    const int r = r0 + threadIdx.x;
+    roff[threadIdx.x] = r < p.R ? decomp(r, p.size_r, p.stride_r, p.nr) : -1;
+  } else if (threadIdx.x < 2 * kPT) {
+    const int k = k0 + threadIdx.x - kPT;
+    koff[threadIdx.x - kPT] = k < p.K ? decomp(k, p.size_k, p.stride_k, p.nk) : -1;
+  }
+  __syncthreads();
+  if (p.fast_is_k) {
+    for (int rr = ty; rr < kPT; rr += 8)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int kk = tx + 32 * h;
+        const long long ro = roff[rr], ko = koff[kk];
+        tile[rr][kk] = (ro >= 0 && ko >= 0) ? __float2bfloat16_rn(to_f32<TS>(src[ro + ko])) : __float2bfloat16_rn(0.f);
+      }
+  } else {
+    for (int kk = ty; kk < kPT; kk += 8)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int rr = tx + 32 * h;
+        const long long ro = roff[rr], ko = koff[kk];
+        tile[rr][kk] = (ro >= 0 && ko >= 0) ? __float2bfloat16_rn(to_f32<TS>(src[ro + ko])) : __float2bfloat16_rn(0.f);
+      }
+  }
+  __syncthreads();
+  // dense side: 4-byte stores, 128 bytes per warp (ld and k0 are even)
+  for (int rr = ty; rr < kPT; rr += 8) {
+    const int r = r0 + rr, k = k0 + 2 * tx;
+    if (r < p.R && k < p.ld) {
+      __nv_bfloat162 v;
+      v.x = tile[rr][2 * tx];
+      v.y = tile[rr][2 * tx + 1];
+      *(__nv_bfloat162*)(dst + (long long)r * p.ld + k) = v;
+    }
+  }
+}
+
+// C[off_m(m) + off_n(n)] = Cp[m][n] (+ D[doff_m(m) + doff_n(n)])        Cp, C of type TC
+template <typename TC>
+__global__ void __launch_bounds__(256) unpack_kernel(const PackParams p, const TC* __restrict__ Cp, const void* __restrict__ D,
+                                                     TC* __restrict__ C) {
+  __shared__ float tile[kPT][kPT + 1];
+  __shared__ long long roff[kPT], koff[kPT], droff[kPT], dkoff[kPT];
+  const int r0 = blockIdx.y * kPT, k0 = blockIdx.x * kPT;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x < kPT) {
+    const int r = r0 + threadIdx.x;
+    roff[threadIdx.x] = r < p.R ? decomp(r, p.size_r, p.stride_r, p.nr) : -1;
+    droff[threadIdx.x] = (r < p.R && p.has_d) ? decomp(r, p.size_r, p.dstride_r, p.nr) : 0;
+  } else if (threadIdx.x < 2 * kPT) {
+    const int k = k0 + threadIdx.x - kPT;
+    koff[threadIdx.x - kPT] = k < p.K ? decomp(k, p.size_k, p.stride_k, p.nk) : -1;
+    dkoff[threadIdx.x - kPT] = (k < p.K && p.has_d) ? decomp(k, p.size_k, p.dstride_k, p.nk) : 0;
+  }
+  for (int rr = ty; rr < kPT; rr += 8)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = tx + 32 * h;
+      const int r = r0 + rr, k = k0 + kk;
+      tile[rr][kk] = (r < p.R && k < p.K) ? to_f32<TC>(Cp[(long long)r * p.ld + k]) : 0.f;
+    }
+  __syncthreads();
+  auto emit = [&](int rr, int kk) {
+    const long long ro = roff[rr], ko = koff[kk];
+    if (ro < 0 || ko < 0) return;
+    float v = tile[rr][kk];
+    if (p.has_d) {
+      const long long doff = droff[rr] + dkoff[kk];
+      v += p.d_bf16 ? __bfloat162float(((const __nv_bfloat16*)D)[doff]) : ((const float*)D)[doff];
+    }
+    C[ro + ko] = from_f32<TC>(v);
+  };
+  if (p.fast_is_k) {
+    for (int rr = ty; rr < kPT; rr += 8) { emit(rr, tx); emit(rr, tx + 32); }
+  } else {
+    for (int kk = ty; kk < kPT; kk += 8) { emit(tx, kk); emit(tx + 32, kk); }
+  }
+}
+
+static long long min_abs_stride(const int64_t* sizes, const int64_t* strides, int n) {
+  long long best = (1LL << 62);
+  for (int i = 0; i < n; ++i)
+    if (sizes[i] > 1) { long long s = strides[i] < 0 ? -strides[i] : strides[i]; if (s < best) best = s; }
+  return best;
+}
+
+static int fill_pack(PackParams* p, int nr, const int64_t* size_r, const int64_t* stride_r, int nk, const int64_t* size_k,
+                     const int64_t* stride_k, long long ld) {
+  TLT_REQUIRE(nr >= 0 && nr <= TLT_MAX_SUBDIMS && nk >= 0 && nk <= TLT_MAX_SUBDIMS, "pack: bad sub-dim counts");
+  long long R = 1, K = 1;
+  p->nr = nr; p->nk = nk;
+  for (int i = 0; i < TLT_MAX_SUBDIMS; ++i) {
+    p->size_r[i] = i < nr ? (int)size_r[i] : 1; p->stride_r[i] = i < nr ? stride_r[i] : 0;
+    p->size_k[i] = i < nk ? (int)size_k[i] : 1; p->stride_k[i] = i < nk ? stride_k[i] : 0;
+    p->dstride_r[i] = 0; p->dstride_k[i] = 0;
+    if (i < nr) R *= size_r[i];
+    if (i < nk) K *= size_k[i];
+  }
+  TLT_REQUIRE(R >= 1 && K >= 1 && R < (1LL << 31) && K < (1LL << 31), "pack: extents out of range");
+  p->R = (int)R; p->K = (int)K; p->ld = ld;
+  p->fast_is_k = min_abs_stride(size_k, stride_k, nk) <= min_abs_stride(size_r, stride_r, nr);
+  p->has_d = 0; p->d_bf16 = 0;
+  return TLT_OK;
+}
+
+}  // namespace tlt
+
+extern "C" int tlt_contract_pack(const tlt_contract_desc* d, int32_t operand, const void* src, void* dst, int64_t dst_ld,
+                                 void* stream) {
+  TLT_REQUIRE(d && src && dst, "tlt_contract_pack: null argument");
+  TLT_REQUIRE(operand == 0 || operand == 1, "tlt_contract_pack: operand must be 0 (A) or 1 (B)");
+  TLT_REQUIRE(d->nb == 0, "tlt_contract_pack: batched contractions are not packed");
+  TLT_REQUIRE(dst_ld % 2 == 0, "tlt_contract_pack: dst_ld must be even");
+  PackParams p;
+  int rc = operand == 0 ? fill_pack(&p, d->nm, d->size_m, d->a_m, d->nk, d->size_k, d->a_k, dst_ld)
+                        : fill_pack(&p, d->nn, d->size_n, d->b_n, d->nk, d->size_k, d->b_k, dst_ld);
+  if (rc) return rc;
+  TLT_REQUIRE(dst_ld >= p.K, "tlt_contract_pack: dst_ld smaller than the reduction extent");
+  const int dt = operand == 0 ? d->dtype_a : d->dtype_b;
+  dim3 grid((unsigned)((dst_ld + kPT - 1) / kPT), (unsigned)((p.R + kPT - 1) / kPT));
+  TLT_REQUIRE(grid.y <= 65535, "tlt_contract_pack: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == TLT_BF16) pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst);
+  else if (dt == TLT_F32) pack_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)src, (__nv_bfloat16*)dst);
+  else { set_error("tlt_contract_pack: unknown dtype"); return TLT_ERR_INVALID; }
+  return check_launch("pack_kernel");
+}
+
+extern "C" int tlt_contract_unpack(const tlt_contract_desc* d, const void* Cp, int64_t ldc, const void* D, void* C, void* stream) {
+  TLT_REQUIRE(d && Cp && C, "tlt_contract_unpack: null argument");
+  TLT_REQUIRE(d->nb == 0, "tlt_contract_unpack: batched contractions are not packed");
+  PackParams p;
+  int rc = fill_pack(&p, d->nm, d->size_m, d->c_m, d->nn, d->size_n, d->c_n, ldc);
+  if (rc) return rc;
+  if (D) {
+    p.has_d = 1; p.d_bf16 = d->dtype_d == TLT_BF16;
+    for (int i = 0; i < d->nm; ++i) p.dstride_r[i] = d->d_m[i];
+    for (int i = 0; i < d->nn; ++i) p.dstride_k[i] = d->d_n[i];
+  }
+  dim3 grid((unsigned)((p.K + kPT - 1) / kPT), (unsigned)((p.R + kPT - 1) / kPT));
+  TLT_REQUIRE(grid.y <= 65535, "tlt_contract_unpack: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->dtype_c == TLT_BF16) unpack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)Cp, D, (__nv_bfloat16*)C);
+  else if (d->dtype_c == TLT_F32) unpack_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)Cp, D, (float*)C);
+  else { set_error("tlt_contract_unpack: unknown dtype"); return TLT_ERR_INVALID; }
+  return check_launch("unpack_kernel");
+}

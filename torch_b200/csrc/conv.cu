@@ -4,6 +4,11 @@
 
 namespace tlt {
 
+// element-wise fallbacks of the depthwise entry points (dwconv.cu dispatches to them when a plane does not fit smem)
+int dwconv_fwd_generic(const tlt_conv_desc* d, const void* x, const void* w, void* y, void* stream);
+int dwconv_dgrad_generic(const tlt_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);
+int dwconv_wgrad_generic(const tlt_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+
 struct ConvParams {
   int ndim;
   long long batch, channels;
@@ -247,7 +252,7 @@ extern "C" int tlt_col2im(const tlt_conv_desc* d, const void* dcols, void* dx, v
   return check_launch("col2im_kernel");
 }
 
-extern "C" int tlt_dwconv_fwd(const tlt_conv_desc* d, const void* x, const void* w, void* y, void* stream) {
+int tlt::dwconv_fwd_generic(const tlt_conv_desc* d, const void* x, const void* w, void* y, void* stream) {
   ConvParams p; int rc = fill_conv(d, &p); if (rc) return rc;
   long long total = p.batch * p.channels * p.out_sp;
   if (total == 0) return TLT_OK;
@@ -257,7 +262,7 @@ extern "C" int tlt_dwconv_fwd(const tlt_conv_desc* d, const void* x, const void*
   return check_launch("dwconv_fwd_kernel");
 }
 
-extern "C" int tlt_dwconv_dgrad(const tlt_conv_desc* d, const void* dy, const void* w, void* dx, void* stream) {
+int tlt::dwconv_dgrad_generic(const tlt_conv_desc* d, const void* dy, const void* w, void* dx, void* stream) {
   ConvParams p; int rc = fill_conv(d, &p); if (rc) return rc;
   long long total = p.batch * p.channels * p.in_sp;
   if (total == 0) return TLT_OK;
@@ -267,7 +272,7 @@ extern "C" int tlt_dwconv_dgrad(const tlt_conv_desc* d, const void* dy, const vo
   return check_launch("dwconv_dgrad_kernel");
 }
 
-extern "C" int tlt_dwconv_wgrad(const tlt_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+int tlt::dwconv_wgrad_generic(const tlt_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
   ConvParams p; int rc = fill_conv(d, &p); if (rc) return rc;
   if (p.batch == 0 || p.channels == 0 || p.out_sp == 0) return TLT_OK;
   cudaStream_t st = (cudaStream_t)stream;

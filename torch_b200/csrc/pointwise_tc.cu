@@ -1,0 +1,362 @@
+// Pointwise (1x1) channel mixing of channels-first activations on the tcgen05 tensor cores, straight from NCHW memory.
+//
+//   forward / data-gradient :  Y[b, n, s] = sum_k Wt[n, k] * X[b, k, s] (+ bias[n])          X (B, K, S), Y (B, N, S) bf16
+//   weight gradient         :  dW[n, k]  = sum_{b, s} dY[b, n, s] * X[b, k, s]                dW fp32 (N, K)
+//
+// Replaces the F.conv1d(kernel_size=1) calls of tltorch/functional/convolution.py (:154,168 tucker_conv, :207,223 tt_conv,
+// :262,278 cp_conv, :311,340 cp_conv_mobilenet) and their autograd.  The generic strided contraction (SIMT FFMA) ran these
+// at ~7 TFLOP/s -- 1 ms for a 214 MB pass at ResNet 56x56 shapes whose HBM floor is 33 us -- because the spatial index, not
+// the channel, is the contiguous one.  Here the activation tile is the MN-MAJOR A operand of the MMA (rows = spatial
+// positions, exactly as they lie in memory): 3-D TMA boxes {64 s, 64 channels, 1 image} land in SWIZZLE_128B shared
+// memory, tcgen05.mma.cta_group::2 (M = 256 positions per CTA pair) accumulates in TMEM, and the epilogue transposes each
+// 32 x 32 block through shared memory so that a 3-D TMA store writes Y rows that are contiguous in s.  Out-of-range
+// rows / channels / positions are zero-filled on load and clipped on store by the TMA unit, so ranks such as 69 or 573 need
+// no padding passes over the activations (only the tiny weight matrix is repacked K-major by the caller).
+// The weight gradient is the same pipeline with the reduction running over (image, position) blocks, split across all
+// SM pairs, partial sums meeting in dW through TMA reduce-add.
+// Requirement: S % 8 == 0 (TMA global strides are multiples of 16 bytes); other shapes stay on tlt_contract.
+#include "tc_common.cuh"
+
+namespace tlt {
+
+constexpr int kPwThreads = 384;
+constexpr int kPwEpiWarps = 8;
+constexpr int kPwEpiBuf = 4096;
+
+struct PwParams {
+  int S, K, N, batch;            // positions per image, input channels, output channels, images
+  int tiles_m, tiles_n;          // fwd: position tiles per image / channel tiles;  wgrad: N tiles / K tiles
+  int kpi;                       // wgrad: 64-position blocks per image
+  int splits, kb_per_split;      // wgrad
+  int has_bias, bias_bf16;
+  int c_reduce;
+};
+
+template <int BN, int kStages>
+struct PwSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_OFFSET = kStages * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + kPwEpiWarps * kPwEpiBuf;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BN, int kStages, bool WGRAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1)
+pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const PwParams p, const void* __restrict__ bias) {
+  using L = PwSmem<BN, kStages>;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int HALF_N = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_units = WGRAD ? p.tiles_m * p.tiles_n * p.splits : p.batch * p.tiles_m * p.tiles_n;
+  const int kb_total = WGRAD ? p.batch * p.kpi : (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  // unit -> (image / split, row tile, column tile) and its k-block range
+  auto decode = [&](int u, int& z, int& tm, int& tn, int& kb0, int& kb1) {
+    if (WGRAD) {
+      const int tile = u / p.splits;
+      z = u - tile * p.splits;
+      tm = tile / p.tiles_n; tn = tile - tm * p.tiles_n;
+      kb0 = z * p.kb_per_split; kb1 = min(kb_total, kb0 + p.kb_per_split);
+    } else {
+      tn = u % p.tiles_n;
+      const int r = u / p.tiles_n;
+      tm = r % p.tiles_m; z = r / p.tiles_m;
+      kb0 = 0; kb1 = kb_total;
+    }
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kPwEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        int z, tm, tn, kb0, kb1;
+        decode(u, z, tm, tn, kb0, kb1);
+        const int m0 = tm * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+        const int n0 = tn * BN + (int)cta_rank * HALF_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+          if (WGRAD) {
+            const int img = kb / p.kpi, s0 = (kb - img * p.kpi) * BLOCK_K;
+            tma_load_3d_2sm(sa, &map_a, full_bar(stage), s0, m0, img);            // dY: {64 s, 128 out-channels}
+            tma_load_3d_2sm(sb, &map_b, full_bar(stage), s0, n0, img);            // X : {64 s, BN/2 in-channels}
+          } else {
+            const int k0 = kb * BLOCK_K;
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)                                 // X^T: {64 s, 64 channels} per 64-row chunk
+              tma_load_3d_2sm(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0, z);
+            tma_load_2d_2sm(sb, &map_b, full_bar(stage), k0, n0);                  // Wt: {64 k, BN/2 n}
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA) ======================================
+    if (leader && lane == 0) {
+      constexpr int a_mn = WGRAD ? 0 : 1;
+      const uint32_t idesc = make_idesc(2 * BLOCK_M, BN, a_mn, 0);
+      const uint32_t a_lbo = a_mn ? BLOCK_K * 128 : 16;
+      const uint32_t a_kstep = a_mn ? (UMMA_K * 128) : (UMMA_K * 2);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        int z, tm, tn, kb0, kb1;
+        decode(u, z, tm, tn, kb0, kb1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(empty_bar(stage));
+          if (kb == kb1 - 1) umma_commit_2sm(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================== epilogue (both CTAs, 8 warps) ================================
+    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
+    const int col_half = (warp - 4) >> 2;          // accumulator columns [HALF_N*col_half, +HALF_N)
+    const uint32_t leader_tempty0 = mapa_u32(tempty_bar(0), 0);
+    const uint32_t ebuf = smem_base + L::EPI_OFFSET + (warp - 4) * kPwEpiBuf;
+    constexpr int n_chunks = HALF_N / 32;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = cluster_id; u < num_units; u += num_clusters) {
+      int z, tm, tn, kb0, kb1;
+      decode(u, z, tm, tn, kb0, kb1);
+      const int m0 = tm * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M + quarter * 32;     // first accumulator row of this warp
+      const int n0 = tn * BN + col_half * HALF_N;
+      const int m_lim = WGRAD ? p.N : p.S, n_lim = WGRAD ? p.K : p.N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_half * HALF_N);
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        const int col0 = n0 + c * 32;
+        const bool live = m0 < m_lim && col0 < n_lim;            // warp-uniform
+        uint32_t v[32];
+        if (live) {
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+        }
+        if (c == n_chunks - 1) {                                  // accumulator fully read: hand the TMEM buffer back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+        }
+        if (!live) continue;
+        if (lane == 0) bulk_wait_read0();                         // previous store of this warp has finished reading ebuf
+        __syncwarp();
+        if (WGRAD) {
+          // fp32 [32 rows][32 cols] block, SWIZZLE_128B, reduce-added into dW
+          const uint32_t erow = ebuf + lane * 128;
+          const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(erow + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.c_reduce) tma_reduce_add_2d(&map_c, ebuf, col0, m0);
+            else tma_store_2d(&map_c, ebuf, col0, m0);
+            bulk_commit();
+          }
+        } else {
+          // transpose: lane holds position s = m0 + lane, v[i] is channel col0 + i  ->  smem [32 channels][32 positions] bf16
+          float bv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+          if (p.has_bias) load_bias32(bias, p.bias_bf16, col0, p.N, bv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(v[i]) + bv[i]);
+            st_shared_b16(ebuf + i * 64 + lane * 2, *(const uint16_t*)&h);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_c, ebuf, m0, col0, z);
+            bulk_commit();
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int kStages, bool WGRAD>
+static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const PwParams& p, const void* bias,
+                     int units, cudaStream_t st) {
+  using L = PwSmem<BN, kStages>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tc_kernel<BN, kStages, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int pairs = num_sms() / 2;
+  const int clusters = units < pairs ? units : pairs;
+  pointwise_tc_kernel<BN, kStages, WGRAD><<<2 * clusters, kPwThreads, L::TOTAL, st>>>(ma, mb, mc, p, bias);
+  return check_launch("pointwise_tc_kernel");
+}
+
+template <typename T>
+__global__ void pack_kmajor_kernel(const T* __restrict__ src, long long rows, long long cols, long long rs, long long cs,
+                                   __nv_bfloat16* __restrict__ dst, long long ld) {
+  const long long total = rows * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld, c = i - r * ld;
+    dst[i] = c < cols ? __float2bfloat16_rn(to_f32<T>(src[r * rs + c * cs])) : __float2bfloat16_rn(0.f);
+  }
+}
+
+static int pw_check(const tlt_pointwise_desc* d, const char* who) {
+  TLT_REQUIRE(d != nullptr, "%s: null descriptor", who);
+  TLT_REQUIRE(d->batch >= 1 && d->in_channels >= 1 && d->out_channels >= 1 && d->spatial >= 1, "%s: sizes must be >= 1", who);
+  TLT_REQUIRE(d->batch < (1LL << 24) && d->in_channels < (1LL << 24) && d->out_channels < (1LL << 24) && d->spatial < (1LL << 28),
+              "%s: sizes too large", who);
+  if (d->spatial % 8) {
+    set_error("%s: spatial size %lld is not a multiple of 8 (TMA pitch); use tlt_contract", who, (long long)d->spatial);
+    return TLT_ERR_UNSUPPORTED;
+  }
+  return TLT_OK;
+}
+
+}  // namespace tlt
+
+using namespace tlt;
+
+extern "C" int tlt_pointwise_tc_supported(const tlt_pointwise_desc* d) {
+  return d && d->batch >= 1 && d->in_channels >= 1 && d->out_channels >= 1 && d->spatial >= 8 && d->spatial % 8 == 0 &&
+         d->w_ld % 8 == 0 && d->w_ld >= d->in_channels;
+}
+
+extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, const void* wt, const void* bias, void* y, void* stream) {
+  int rc = pw_check(d, "tlt_pointwise_tc");
+  if (rc) return rc;
+  TLT_REQUIRE(x && wt && y, "tlt_pointwise_tc: null pointer");
+  TLT_REQUIRE(d->w_ld % 8 == 0 && d->w_ld >= d->in_channels, "tlt_pointwise_tc: w_ld must be a multiple of 8 and >= in_channels");
+  TLT_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)wt % 16) == 0 && ((uintptr_t)y % 16) == 0, "tlt_pointwise_tc: operands must be 16-byte aligned");
+  const int64_t S = d->spatial, K = d->in_channels, N = d->out_channels, B = d->batch;
+  CUtensorMap ma, mb, mc;
+  if ((rc = make_map3d(&ma, x, S, K, B, S, K * S, 64, BLOCK_K, true))) return rc;               // X^T chunks {64 s, 64 k}
+  const bool wide = N > 128;
+  if ((rc = make_map(&mb, wt, K, N, d->w_ld, BLOCK_K, wide ? 128 : 64))) return rc;             // Wt {64 k, BN/2 n}
+  if ((rc = make_map3d(&mc, y, S, N, B, S, N * S, 32, 32, false))) return rc;                   // Y {32 s, 32 n}
+  PwParams p{};
+  p.S = (int)S; p.K = (int)K; p.N = (int)N; p.batch = (int)B;
+  p.tiles_m = (int)((S + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+  p.tiles_n = (int)((N + (wide ? 256 : 128) - 1) / (wide ? 256 : 128));
+  p.has_bias = bias != nullptr; p.bias_bf16 = d->dtype_bias == TLT_BF16;
+  const long long units = (long long)p.batch * p.tiles_m * p.tiles_n;
+  TLT_REQUIRE(units < (1LL << 31), "tlt_pointwise_tc: too many tiles");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wide) return pw_launch<256, 6, false>(ma, mb, mc, p, bias, (int)units, st);
+  return pw_launch<128, 8, false>(ma, mb, mc, p, bias, (int)units, st);
+}
+
+extern "C" int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* d, const void* dy, const void* x, float* dw, void* stream) {
+  int rc = pw_check(d, "tlt_pointwise_wgrad_tc");
+  if (rc) return rc;
+  TLT_REQUIRE(dy && x && dw, "tlt_pointwise_wgrad_tc: null pointer");
+  TLT_REQUIRE(d->w_ld % 4 == 0 && d->w_ld >= d->in_channels, "tlt_pointwise_wgrad_tc: w_ld (pitch of dW) must be a multiple of 4 and >= in_channels");
+  TLT_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dw % 16) == 0, "tlt_pointwise_wgrad_tc: operands must be 16-byte aligned");
+  const int64_t S = d->spatial, K = d->in_channels, N = d->out_channels, B = d->batch;
+  CUtensorMap ma, mb, mc;
+  const bool wide = K > 128;
+  if ((rc = make_map3d(&ma, dy, S, N, B, S, N * S, BLOCK_K, BLOCK_M, true))) return rc;          // dY {64 s, 128 n}
+  if ((rc = make_map3d(&mb, x, S, K, B, S, K * S, BLOCK_K, wide ? 128 : 64, true))) return rc;   // X  {64 s, BN/2 k}
+  if ((rc = make_map(&mc, dw, K, N, d->w_ld, 32, 32, 1))) return rc;                              // dW fp32 {32 k, 32 n}
+  PwParams p{};
+  p.S = (int)S; p.K = (int)K; p.N = (int)N; p.batch = (int)B;
+  p.tiles_m = (int)((N + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
+  p.tiles_n = (int)((K + (wide ? 256 : 128) - 1) / (wide ? 256 : 128));
+  p.kpi = (int)((S + BLOCK_K - 1) / BLOCK_K);
+  const long long kb_total = (long long)p.batch * p.kpi;
+  TLT_REQUIRE(kb_total < (1LL << 31), "tlt_pointwise_wgrad_tc: reduction too long");
+  const int pairs = num_sms() / 2;
+  long long splits = pairs / ((long long)p.tiles_m * p.tiles_n);
+  if (splits < 1) splits = 1;
+  if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+  p.kb_per_split = (int)((kb_total + splits - 1) / splits);
+  p.splits = (int)((kb_total + p.kb_per_split - 1) / p.kb_per_split);
+  p.c_reduce = p.splits > 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.c_reduce) TLT_CHECK_CUDA(cudaMemset2DAsync(dw, (size_t)d->w_ld * 4, 0, (size_t)K * 4, (size_t)N, st));
+  const int units = p.tiles_m * p.tiles_n * p.splits;
+  if (wide) return pw_launch<256, 6, true>(ma, mb, mc, p, nullptr, units, st);
+  return pw_launch<128, 8, true>(ma, mb, mc, p, nullptr, units, st);
+}
+
+extern "C" int tlt_pack_kmajor(const void* src, int32_t dtype_src, int64_t rows, int64_t cols, int64_t row_stride,
+                               int64_t col_stride, void* dst, int64_t dst_ld, void* stream) {
+  TLT_REQUIRE(src && dst && rows >= 1 && cols >= 1 && dst_ld >= cols, "tlt_pack_kmajor: bad arguments");
+  const long long total = rows * dst_ld;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_src == TLT_BF16)
+    pack_kmajor_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, rows, cols, row_stride, col_stride, (__nv_bfloat16*)dst, dst_ld);
+  else if (dtype_src == TLT_F32)
+    pack_kmajor_kernel<float><<<blocks, 256, 0, st>>>((const float*)src, rows, cols, row_stride, col_stride, (__nv_bfloat16*)dst, dst_ld);
+  else { set_error("tlt_pack_kmajor: unknown dtype"); return TLT_ERR_INVALID; }
+  return check_launch("pack_kmajor_kernel");
+}

@@ -8,7 +8,7 @@ import math
 
 import torch
 
-from .. import ops, tenalg
+from .. import ops, tenalg, pointwise_ops
 from ..ops import contract
 
 
@@ -21,7 +21,11 @@ def _pointwise(x, w_spec, w, bias=None):
     convolution.py:154,168,207,223,262,278,311,340)."""
     b, c = x.shape[0], x.shape[1]
     x3 = x.reshape(b, c, -1)
-    if bias is not None:
+    w_nk = w if w_spec == "oc" else w.t()
+    if pointwise_ops.eligible(x3, w_nk, bias):
+        # tcgen05 path: the NCHW tile is the MN-major MMA operand (3-D TMA), output transposed back in the epilogue
+        y = pointwise_ops.pointwise_tc(x3, w_nk, bias)
+    elif bias is not None:
         y = contract(f"{w_spec},bcs->bos", w, x3, bias, "o")
     else:
         y = contract(f"{w_spec},bcs->bos", w, x3)

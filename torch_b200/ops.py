@@ -205,10 +205,82 @@ def _execute_contract(plan, a, b, d, out, alpha):
                                 2.0 * (tc["M"] * tc["K"] + tc["N"] * tc["K"]) + out.element_size() * tc["M"] * tc["N"]))
             return
     desc = _fill_desc(plan, _cuda.dtype_code(a.dtype), _cuda.dtype_code(b.dtype), _cuda.dtype_code(out.dtype), dt_d, alpha)
+    if (not _FORCE_SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+            and _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib)):
+        return
     ws_bytes = lib.tlt_contract_workspace_size(C.byref(desc))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device) if ws_bytes else None
     _cuda.check(lib.tlt_contract(C.byref(desc), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(d), _cuda.ptr(out),
                                  _cuda.ptr(ws), ws_bytes, _cuda.stream_ptr(out)), f"tlt_contract[{plan.spec}]")
+
+
+# large bf16 contractions whose operands are strided / misaligned for TMA: pack -> tcgen05 GEMM -> unpack
+PACK_MIN_WORK = 1 << 26
+
+
+def _direct_matrix(sizes_r, strides_r, sizes_k, strides_k, t):
+    """(major, ld) if the operand already is a TMA-friendly matrix (single row dim, single reduction dim), else None."""
+    if len(sizes_r) != 1 or len(sizes_k) != 1 or t.data_ptr() % 16:
+        return None
+    sr, sk = strides_r[0], strides_k[0]
+    if sk == 1 and sr % 8 == 0 and sr >= sizes_k[0]:
+        return 0, sr
+    if sr == 1 and sk % 8 == 0 and sk >= sizes_r[0]:
+        return 1, sk
+    return None
+
+
+def _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib):
+    f = plan.desc_fields
+    if f["nb"] != 0 or not f["size_m"] or not f["size_n"] or not f["size_k"]:
+        return False
+    M, N, K = math.prod(f["size_m"]), math.prod(f["size_n"]), math.prod(f["size_k"])
+    if M * N * K < PACK_MIN_WORK or K < 8 or max(M, N) < 128:
+        return False
+    st = _cuda.stream_ptr(out)
+    kp = (K + 7) // 8 * 8
+    g = _cuda.GemmDesc()
+    g.M, g.N, g.K = M, N, K
+    keep = []
+    da = _direct_matrix(f["size_m"], f["a_m"], f["size_k"], f["a_k"], a)
+    if da is None:
+        ap = torch.empty((M, kp), dtype=torch.bfloat16, device=out.device)
+        _cuda.check(lib.tlt_contract_pack(C.byref(desc), 0, _cuda.ptr(a), _cuda.ptr(ap), kp, st), "tlt_contract_pack[A]")
+        keep.append(ap)
+        a_ptr, g.a_major, g.lda = _cuda.ptr(ap), 0, kp
+    else:
+        a_ptr, (g.a_major, g.lda) = _cuda.ptr(a), da
+    db = _direct_matrix(f["size_n"], f["b_n"], f["size_k"], f["b_k"], b)
+    if db is None:
+        bp = torch.empty((N, kp), dtype=torch.bfloat16, device=out.device)
+        _cuda.check(lib.tlt_contract_pack(C.byref(desc), 1, _cuda.ptr(b), _cuda.ptr(bp), kp, st), "tlt_contract_pack[B]")
+        keep.append(bp)
+        b_ptr, g.b_major, g.ldb = _cuda.ptr(bp), 0, kp
+    else:
+        b_ptr, (g.b_major, g.ldb) = _cuda.ptr(b), db
+    direct_c = (d is None and len(f["size_m"]) == 1 and len(f["size_n"]) == 1 and f["c_n"][0] == 1 and f["c_m"][0] % 8 == 0
+                and out.data_ptr() % 16 == 0)
+    if direct_c:
+        cp, g.ldc = out, f["c_m"][0]
+    else:
+        np_ = (N + 7) // 8 * 8
+        cp = torch.empty((M, np_), dtype=out.dtype, device=out.device)
+        g.ldc = np_
+    g.dtype_c = _cuda.dtype_code(out.dtype)
+    g.accumulate, g.dtype_bias, g.alpha, g.split_k = 0, 0, alpha, 0
+    if not lib.tlt_gemm_bf16_tc_supported(C.byref(g)):
+        return False
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _cuda.check(lib.tlt_gemm_bf16_tc(C.byref(g), a_ptr, b_ptr, None, _cuda.ptr(cp), st), f"tlt_gemm_bf16_tc[packed {plan.spec}]")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append((f"gemm_bf16_tc(packed) M{M} N{N} K{K}", e0, e1, 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)))
+    if not direct_c:
+        _cuda.check(lib.tlt_contract_unpack(C.byref(desc), _cuda.ptr(cp), g.ldc, _cuda.ptr(d), _cuda.ptr(out), st),
+                    "tlt_contract_unpack")
+    return True
 
 
 def _conv_desc(dtype, batch, channels, in_size, out_size, kernel, stride, padding, dilation):
