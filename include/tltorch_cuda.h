@@ -78,10 +78,12 @@ int tlt_contract(const tlt_contract_desc* desc, const void* A, const void* B, co
 /* Bridge to the tensor cores for contractions whose operands are strided or break TMA's 16-byte pitch rule:
  *   tlt_contract_pack   copies operand A (operand = 0: rows = the m class) or B (operand = 1: rows = the n class), read
  *                       through the descriptor's strides, into a dense K-major bf16 matrix rows x K with pitch dst_ld;
- *   tlt_contract_unpack writes a dense M x N result of dtype_c (pitch ldc) (+ the strided addend D) to the strided output.
+ *   tlt_contract_unpack writes a dense M x N result of dtype_cp (pitch ldc; fp32 when the GEMM ran split-K) (+ the strided
+ *                       addend D) to the strided output of dtype_c.
  * Used as pack -> tlt_gemm_bf16_tc -> unpack; only for descriptors with nb == 0.  Same reference call sites as tlt_contract. */
 int tlt_contract_pack(const tlt_contract_desc* desc, int32_t operand, const void* src, void* dst, int64_t dst_ld, void* stream);
-int tlt_contract_unpack(const tlt_contract_desc* desc, const void* Cp, int64_t ldc, const void* D, void* C, void* stream);
+int tlt_contract_unpack(const tlt_contract_desc* desc, const void* Cp, int32_t dtype_cp, int64_t ldc, const void* D, void* C,
+                        void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * tlt_gemm_bf16_tc: dense bf16 GEMM on the tcgen05 tensor cores (TMA-staged operands, TMEM fp32 accumulators).

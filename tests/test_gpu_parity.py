@@ -251,6 +251,7 @@ def test_pointwise_tc_kernels_vs_fp64(B, K, N, S):
     ("oc,bcs->bos", (388, 512), (64, 512, 49), "o"),                 # 1x1 conv on 7x7 maps (S = 49 breaks the TMA pitch rule) + bias
     ("bsct,qct->bqs", (32, 49, 388, 9), (388, 388, 9), None),        # unfolded Tucker core conv, K = 388 * 9
     ("bk,kn->bn", (4096, 1000), (1000, 264), "n"),
+    ("bijk,brjk->ir", (512, 16, 16, 16), (512, 15, 16, 16), None),   # factor gradient of a mode product: 16 x 15 output, K = 131072
 ])
 def test_packed_tensor_core_contract(spec, sa, sb, bias_letters):
     """Strided / TMA-misaligned bf16 contractions take pack -> tcgen05 GEMM -> unpack; result against fp64 einsum."""

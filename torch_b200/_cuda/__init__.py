@@ -65,7 +65,7 @@ SYMBOLS = {
     "tlt_contract_workspace_size": (C.c_size_t, [C.POINTER(ContractDesc)]),
     "tlt_contract": (C.c_int, [C.POINTER(ContractDesc), _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "tlt_contract_pack": (C.c_int, [C.POINTER(ContractDesc), C.c_int32, _vp, _vp, C.c_int64, _vp]),
-    "tlt_contract_unpack": (C.c_int, [C.POINTER(ContractDesc), _vp, C.c_int64, _vp, _vp, _vp]),
+    "tlt_contract_unpack": (C.c_int, [C.POINTER(ContractDesc), _vp, C.c_int32, C.c_int64, _vp, _vp, _vp]),
     "tlt_gemm_bf16_tc_supported": (C.c_int, [C.POINTER(GemmDesc)]),
     "tlt_gemm_bf16_tc": (C.c_int, [C.POINTER(GemmDesc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_blocktt3_reconstruct": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp]),

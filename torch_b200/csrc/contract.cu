@@ -684,9 +684,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p, const TS*
   }
 }
 
-// C[off_m(m) + off_n(n)] = Cp[m][n] (+ D[doff_m(m) + doff_n(n)])        Cp, C of type TC
-template <typename TC>
-__global__ void __launch_bounds__(256) unpack_kernel(const PackParams p, const TC* __restrict__ Cp, const void* __restrict__ D,
+// C[off_m(m) + off_n(n)] = Cp[m][n] (+ D[doff_m(m) + doff_n(n)])        Cp of type TP (fp32 for split-K results), C of type TC
+template <typename TP, typename TC>
+__global__ void __launch_bounds__(256) unpack_kernel(const PackParams p, const TP* __restrict__ Cp, const void* __restrict__ D,
                                                      TC* __restrict__ C) {
   __shared__ float tile[kPT][kPT + 1];
   __shared__ long long roff[kPT], koff[kPT], droff[kPT], dkoff[kPT];
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const PackParams p, const T
     for (int h = 0; h < 2; ++h) {
       const int kk = tx + 32 * h;
       const int r = r0 + rr, k = k0 + kk;
-      tile[rr][kk] = (r < p.R && k < p.K) ? to_f32<TC>(Cp[(long long)r * p.ld + k]) : 0.f;
+      tile[rr][kk] = (r < p.R && k < p.K) ? to_f32<TP>(Cp[(long long)r * p.ld + k]) : 0.f;
     }
   __syncthreads();
   auto emit = [&](int rr, int kk) {
@@ -775,7 +775,8 @@ extern "C" int tlt_contract_pack(const tlt_contract_desc* d, int32_t operand, co
   return check_launch("pack_kernel");
 }
 
-extern "C" int tlt_contract_unpack(const tlt_contract_desc* d, const void* Cp, int64_t ldc, const void* D, void* C, void* stream) {
+extern "C" int tlt_contract_unpack(const tlt_contract_desc* d, const void* Cp, int32_t dtype_cp, int64_t ldc, const void* D,
+                                   void* C, void* stream) {
   TLT_REQUIRE(d && Cp && C, "tlt_contract_unpack: null argument");
   TLT_REQUIRE(d->nb == 0, "tlt_contract_unpack: batched contractions are not packed");
   PackParams p;
@@ -789,8 +790,10 @@ extern "C" int tlt_contract_unpack(const tlt_contract_desc* d, const void* Cp, i
   dim3 grid((unsigned)((p.K + kPT - 1) / kPT), (unsigned)((p.R + kPT - 1) / kPT));
   TLT_REQUIRE(grid.y <= 65535, "tlt_contract_unpack: too many rows");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->dtype_c == TLT_BF16) unpack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)Cp, D, (__nv_bfloat16*)C);
-  else if (d->dtype_c == TLT_F32) unpack_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)Cp, D, (float*)C);
-  else { set_error("tlt_contract_unpack: unknown dtype"); return TLT_ERR_INVALID; }
+  typedef __nv_bfloat16 bf;
+  if (d->dtype_c == TLT_BF16 && dtype_cp == TLT_BF16) unpack_kernel<bf, bf><<<grid, 256, 0, st>>>(p, (const bf*)Cp, D, (bf*)C);
+  else if (d->dtype_c == TLT_BF16 && dtype_cp == TLT_F32) unpack_kernel<float, bf><<<grid, 256, 0, st>>>(p, (const float*)Cp, D, (bf*)C);
+  else if (d->dtype_c == TLT_F32 && dtype_cp == TLT_F32) unpack_kernel<float, float><<<grid, 256, 0, st>>>(p, (const float*)Cp, D, (float*)C);
+  else { set_error("tlt_contract_unpack: unsupported dtype combination"); return TLT_ERR_INVALID; }
   return check_launch("unpack_kernel");
 }

@@ -8,6 +8,8 @@ namespace tlt {
 int dwconv_fwd_generic(const tlt_conv_desc* d, const void* x, const void* w, void* y, void* stream);
 int dwconv_dgrad_generic(const tlt_conv_desc* d, const void* dy, const void* w, void* dx, void* stream);
 int dwconv_wgrad_generic(const tlt_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);
+int im2col_generic(const tlt_conv_desc* d, const void* x, void* cols, void* stream);
+int col2im_generic(const tlt_conv_desc* d, const void* dcols, void* dx, void* stream);
 
 struct ConvParams {
   int ndim;
@@ -232,7 +234,7 @@ using namespace tlt;
     else { set_error("unknown dtype %d", (int)(dt)); return TLT_ERR_INVALID; } \
   } while (0)
 
-extern "C" int tlt_im2col(const tlt_conv_desc* d, const void* x, void* cols, void* stream) {
+int tlt::im2col_generic(const tlt_conv_desc* d, const void* x, void* cols, void* stream) {
   ConvParams p; int rc = fill_conv(d, &p); if (rc) return rc;
   long long total = p.batch * p.out_sp * p.channels * p.taps;
   if (total == 0) return TLT_OK;
@@ -242,7 +244,7 @@ extern "C" int tlt_im2col(const tlt_conv_desc* d, const void* x, void* cols, voi
   return check_launch("im2col_kernel");
 }
 
-extern "C" int tlt_col2im(const tlt_conv_desc* d, const void* dcols, void* dx, void* stream) {
+int tlt::col2im_generic(const tlt_conv_desc* d, const void* dcols, void* dx, void* stream) {
   ConvParams p; int rc = fill_conv(d, &p); if (rc) return rc;
   long long total = p.batch * p.channels * p.in_sp;
   if (total == 0) return TLT_OK;

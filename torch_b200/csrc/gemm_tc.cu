@@ -536,7 +536,7 @@ static void choose_tiling(const tlt_gemm_desc* d, int* bn_out, int* splits_out) 
   const bool can_split = d->dtype_c == TLT_F32;
   double best = 1e300;
   int best_bn = 256, best_s = 1;
-  const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 37, 74, 148};
   for (int bn = 256; bn >= 128; bn -= 128) {
     if (bn == 256 && d->N <= 128) continue;
     const long long tiles = tm * ((d->N + bn - 1) / bn);

@@ -235,7 +235,10 @@ def _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib):
     if f["nb"] != 0 or not f["size_m"] or not f["size_n"] or not f["size_k"]:
         return False
     M, N, K = math.prod(f["size_m"]), math.prod(f["size_n"]), math.prod(f["size_k"])
-    if M * N * K < PACK_MIN_WORK or K < 8 or max(M, N) < 128:
+    # skinny outputs with a very long reduction (factor / weight gradients): still worth the tensor cores when the K
+    # blocks can be split over all SM pairs (fp32 partials met by TMA reduce-add)
+    long_k = K >= 16384 and M * N <= 512 * 512
+    if M * N * K < PACK_MIN_WORK or K < 8 or (max(M, N) < 128 and not long_k):
         return False
     st = _cuda.stream_ptr(out)
     kp = (K + 7) // 8 * 8
@@ -258,15 +261,15 @@ def _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib):
         b_ptr, g.b_major, g.ldb = _cuda.ptr(bp), 0, kp
     else:
         b_ptr, (g.b_major, g.ldb) = _cuda.ptr(b), db
-    direct_c = (d is None and len(f["size_m"]) == 1 and len(f["size_n"]) == 1 and f["c_n"][0] == 1 and f["c_m"][0] % 8 == 0
-                and out.data_ptr() % 16 == 0)
+    direct_c = (d is None and not long_k and len(f["size_m"]) == 1 and len(f["size_n"]) == 1 and f["c_n"][0] == 1
+                and f["c_m"][0] % 8 == 0 and out.data_ptr() % 16 == 0)
     if direct_c:
         cp, g.ldc = out, f["c_m"][0]
     else:
         np_ = (N + 7) // 8 * 8
-        cp = torch.empty((M, np_), dtype=out.dtype, device=out.device)
+        cp = torch.empty((M, np_), dtype=torch.float32 if long_k else out.dtype, device=out.device)
         g.ldc = np_
-    g.dtype_c = _cuda.dtype_code(out.dtype)
+    g.dtype_c = _cuda.dtype_code(cp.dtype)
     g.accumulate, g.dtype_bias, g.alpha, g.split_k = 0, 0, alpha, 0
     if not lib.tlt_gemm_bf16_tc_supported(C.byref(g)):
         return False
@@ -278,7 +281,8 @@ def _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib):
         e1.record()
         PROFILE.append((f"gemm_bf16_tc(packed) M{M} N{N} K{K}", e0, e1, 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N)))
     if not direct_c:
-        _cuda.check(lib.tlt_contract_unpack(C.byref(desc), _cuda.ptr(cp), g.ldc, _cuda.ptr(d), _cuda.ptr(out), st),
+        _cuda.check(lib.tlt_contract_unpack(C.byref(desc), _cuda.ptr(cp), _cuda.dtype_code(cp.dtype), g.ldc, _cuda.ptr(d),
+                                            _cuda.ptr(out), st),
                     "tlt_contract_unpack")
     return True
 
