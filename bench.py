@@ -168,6 +168,21 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def _finish(world):
+    """Multi-rank exit: every rank has printed / synchronised; leave without tearing the NCCL communicator down.
+    (destroy_process_group() with captured CUDA graphs that hold NCCL kernels still alive was seen to hang a 2-GPU run for
+    the whole box timeout after the JSON line had been printed.)"""
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -289,9 +304,9 @@ def run_ours(args):
     if args.skip_extras:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "roofline": roofline, "clocks": clocks}))
-        if world > 1:
-            dist.destroy_process_group()
+                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "roofline": roofline, "clocks": clocks}),
+                  flush=True)
+        _finish(world)
         return
 
     # ------------------------------------------------------------------ e2e: host (pinned) inputs, copies inside the timed region
@@ -336,9 +351,8 @@ def run_ours(args):
     if rank == 0:
         if world == 1:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    _finish(world)
 
 
 def main():

@@ -238,7 +238,7 @@ def _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib):
     # skinny outputs with a very long reduction (factor / weight gradients): still worth the tensor cores when the K
     # blocks can be split over all SM pairs (fp32 partials met by TMA reduce-add)
     long_k = K >= 16384 and M * N <= 512 * 512
-    if M * N * K < PACK_MIN_WORK or K < 8 or (max(M, N) < 128 and not long_k):
+    if M * N * K < (PACK_MIN_WORK >> 2 if long_k else PACK_MIN_WORK) or K < 8 or (max(M, N) < 128 and not long_k):
         return False
     st = _cuda.stream_ptr(out)
     kp = (K + 7) // 8 * 8

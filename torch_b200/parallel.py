@@ -28,27 +28,54 @@ class GradientBucket:
             off += p.numel()
 
     def pack(self):
-        for v, p in zip(self.views, self.params):
-            if p.grad is None:
-                v.zero_()
+        """gradients -> flat fp32 bucket.  Grouped by dtype: one concatenation + one cast per group, not one copy per tensor."""
+        groups = {}
+        for i, p in enumerate(self.params):
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            groups.setdefault(g.dtype, []).append((i, g))
+        offs = self._offsets()
+        for dtype, items in groups.items():
+            contiguous_run = all(items[k + 1][0] == items[k][0] + 1 for k in range(len(items) - 1))
+            if contiguous_run and len(items) > 1:
+                lo = offs[items[0][0]]
+                hi = offs[items[-1][0]] + self.params[items[-1][0]].numel()
+                self.flat[lo:hi].copy_(torch.cat([g.reshape(-1) for _, g in items]))
             else:
-                v.copy_(p.grad)
+                for i, g in items:
+                    self.views[i].copy_(g)
+
+    def _offsets(self):
+        offs, off = [], 0
+        for p in self.params:
+            offs.append(off)
+            off += p.numel()
+        return offs
 
     def unpack(self, scale: float = 1.0):
+        if scale != 1.0:
+            self.flat.mul_(scale)
+        have = [p for p in self.params if p.grad is not None]
+        if len(have) == len(self.params):
+            torch._foreach_copy_([p.grad for p in self.params], self.views)      # one fused launch per dtype group
+            return
         for v, p in zip(self.views, self.params):
-            g = v if scale == 1.0 else v * scale
             if p.grad is None:
-                p.grad = g.to(p.dtype).clone()
+                p.grad = v.to(p.dtype).clone()
             else:
-                p.grad.copy_(g)
+                p.grad.copy_(v)
 
     def allreduce(self, group: Optional[dist.ProcessGroup] = None, average: bool = True):
         """grads <- sum (or mean) over ranks.  No-op without an initialised process group."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         self.pack()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.unpack(1.0 / dist.get_world_size(group) if average else 1.0)
+        world = dist.get_world_size(group)
+        if average and dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)       # the mean is taken inside the collective
+            self.unpack(1.0)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.unpack(1.0 / world if average else 1.0)
 
 
 def shard_batch(total: int, rank: int, world_size: int):
