@@ -279,6 +279,37 @@ def test_packed_tensor_core_contract(spec, sa, sb, bias_letters):
     assert G.rel_err(y, want) < 1e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C,H,W,k,stride,pad,dil", [
+    (3, 5, 56, 56, (3, 3), (1, 1), (1, 1), (1, 1)),      # fast path, 16-byte staging
+    (2, 7, 28, 28, (3, 3), (1, 1), (1, 1), (1, 1)),      # fast path, 8-byte staging (bf16)
+    (4, 6, 14, 14, (3, 3), (1, 1), (1, 1), (1, 1)),      # fast path, ragged last strip
+    (5, 9, 7, 7, (3, 3), (1, 1), (1, 1), (1, 1)),        # fast path, scalar staging
+    (2, 4, 10, 13, (3, 3), (1, 1), (1, 1), (1, 1)),
+    (3, 5, 56, 56, (3, 3), (2, 2), (1, 1), (1, 1)),      # generic staged path: stride 2
+    (2, 3, 17, 9, (3, 1), (1, 1), (1, 0), (1, 1)),       # 1-D taps along H
+    (2, 3, 12, 11, (2, 3), (1, 2), (0, 2), (2, 1)),      # dilation, asymmetric everything
+])
+def test_depthwise_conv_kernels_vs_torch(B, C, H, W, k, stride, pad, dil, dtype):
+    """tlt_dwconv_{fwd,dgrad,wgrad} (3x3 fast path and generic smem-staged path) against fp64 F.conv2d(groups=C) autograd --
+    the depthwise stages of cp_conv / cp_conv_mobilenet (functional/convolution.py:268-271, 321-332)."""
+    from torch_b200 import ops
+    torch.manual_seed(B * C + H + W)
+    x = torch.randn(B, C, H, W, device=dev()).to(dtype).requires_grad_(True)
+    w = (torch.randn(C, *k, device=dev()) * 0.5).to(dtype).requires_grad_(True)
+    y = ops.dwconv(x, w, list(stride), list(pad), list(dil))
+    gy = torch.randn_like(y)
+    gx, gw = torch.autograd.grad(y, [x, w], gy)
+    xr, wr = x.detach().double().cpu().requires_grad_(True), w.detach().double().cpu().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr.unsqueeze(1), stride=stride, padding=pad, dilation=dil, groups=C)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy.double().cpu())
+    tol = TOL[dtype]
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert G.rel_err(y, yr) < tol
+    assert G.rel_err(gx, gxr) < tol
+    assert G.rel_err(gw, gwr) < tol
+
+
 def tlt_launches():
     from torch_b200 import ops
     return ops.launch_count()

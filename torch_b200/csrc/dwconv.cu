@@ -12,6 +12,7 @@
 // Planes that do not fit shared memory fall back to the element-wise kernels in conv.cu.
 #include "common.cuh"
 #include <mutex>
+#include <unordered_map>
 
 namespace tlt {
 
@@ -290,6 +291,193 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_staged(const DwParams p, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Fast path: 2-D 3x3 taps, stride 1, padding 1, dilation 1 (every stride-1 3x3 conv of a ResNet -- 13 of the 16 CP layers of
+// BASELINE config 3 -- and, with the taps reversed, its data gradient).  The generic staged kernels above spend ~80
+// instructions per output (runtime tap loops, per-element index decoding while staging); here
+//   * planes are staged with 16-/8-byte loads into rows of pitch RP whose interior starts at float offset 4, so the halo
+//     column sits at offset 3 and every 4-output strip reads one aligned float4 plus two scalars per input row;
+//   * a thread owns a strip of 4 consecutive outputs: 3 rows x 6 inputs in registers feed 36 FMAs with compile-time taps;
+//   * consecutive lanes own consecutive strips: float4 reads of a quarter-warp cover 128 contiguous bytes (no conflicts),
+//     and the 8-byte bf16 stores of a warp cover 256 contiguous bytes.
+// ~17 instructions per output, i.e. within reach of the HBM roofline of these 4-bytes-per-output passes.
+//   FLIP = false: y = corr(x, w)            FLIP = true : dx = corr(dy, reversed w)   (the adjoint at stride 1, pad 1)
+//   smem: xs [PB][H + 2][RP] | ws [PB][12]
+// ---------------------------------------------------------------------------------------------------------------------
+struct Fast3Params {
+  int H, W, RP, PB, strips;        // rows, cols, row pitch (floats), planes per block, strips per row
+  int channels;
+  long long planes;
+  FastDivU f_spp, f_strips, f_rowv, f_rowsv;   // strips per plane, strips per row, vectors per row, vectors per plane
+};
+
+// stages npl planes whose starts are `plane_stride` elements apart (H*W for consecutive planes, channels*H*W for the
+// planes of one channel across images)
+template <typename T, int V>
+__device__ __forceinline__ void fast3_stage(float* xs, const T* __restrict__ src, int npl, long long plane_stride,
+                                            const Fast3Params& q) {
+  // zero the halo rows / columns (interior is fully overwritten below); plane = (H + 2) rows of RP floats
+  const int plane = (q.H + 2) * q.RP;
+  for (int e = threadIdx.x; e < npl * (q.H + 2); e += blockDim.x) {      // one staged row per thread
+    const int j = e / (q.H + 2), row = e - j * (q.H + 2);
+    float* rp = xs + j * plane + row * q.RP;
+    if (row == 0 || row == q.H + 1) {
+      for (int c = 0; c < q.RP; c += 4) *(float4*)(rp + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      *(float4*)rp = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 4 + q.W; c < q.RP; ++c) rp[c] = 0.f;
+    }
+  }
+  const int vec_per_row = q.W / V, vec_per_plane = q.H * vec_per_row;
+  const int total = npl * vec_per_plane;
+#pragma unroll 2
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int j, r, row, cv;
+    q.f_rowsv.divmod(e, j, r);
+    q.f_rowv.divmod(r, row, cv);
+    float* dst = xs + j * plane + (row + 1) * q.RP + 4 + cv * V;
+    const T* sp = src + (long long)j * plane_stride + row * q.W + cv * V;
+    if (V == 1) {
+      dst[0] = to_f32<T>(sp[0]);
+    } else if (sizeof(T) == 2) {
+      if (V == 8) {
+        const uint4 raw = __ldg((const uint4*)sp);
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+        const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]), c = __bfloat1622float2(h[2]), d = __bfloat1622float2(h[3]);
+        *(float4*)dst = make_float4(a.x, a.y, b.x, b.y);
+        *(float4*)(dst + 4) = make_float4(c.x, c.y, d.x, d.y);
+      } else {
+        const uint2 raw = __ldg((const uint2*)sp);
+        const __nv_bfloat162* h = (const __nv_bfloat162*)&raw;
+        const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+        *(float4*)dst = make_float4(a.x, a.y, b.x, b.y);
+      }
+    } else {
+      *(float4*)dst = __ldg((const float4*)sp);
+      if (V == 8) *(float4*)(dst + 4) = __ldg((const float4*)sp + 1);
+    }
+  }
+}
+
+template <typename T, int V, bool FLIP>
+__global__ void __launch_bounds__(256) dwconv3x3_fast(const Fast3Params q, const T* __restrict__ x, const T* __restrict__ w,
+                                                      T* __restrict__ y) {
+  extern __shared__ __align__(16) float dsm[];
+  const int plane = (q.H + 2) * q.RP;
+  const long long bc0 = (long long)blockIdx.x * q.PB;
+  const int npl = (int)min((long long)q.PB, q.planes - bc0);
+  float* xs = dsm;
+  float* ws = dsm + q.PB * plane;
+  for (int e = threadIdx.x; e < npl * 9; e += blockDim.x) {
+    const int j = e / 9, t = e - j * 9;
+    const int c = (int)((bc0 + j) % q.channels);
+    ws[j * 12 + (FLIP ? 8 - t : t)] = to_f32<T>(w[(long long)c * 9 + t]);
+  }
+  fast3_stage<T, V>(xs, x + bc0 * q.H * q.W, npl, (long long)q.H * q.W, q);
+  __syncthreads();
+  const int spp = q.H * q.strips;
+  const int total = npl * spp;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    int j, r, row, sg;
+    q.f_spp.divmod(e, j, r);
+    q.f_strips.divmod(r, row, sg);
+    const float* xr = xs + j * plane + row * q.RP + 4 + 4 * sg;      // output row `row` reads staged rows row .. row+2
+    const float* wp = ws + j * 12;
+    float wk[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t] = wp[t];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t1 = 0; t1 < 3; ++t1) {
+      const float* rr = xr + t1 * q.RP;
+      const float4 mid = *(const float4*)rr;
+      const float in[6] = {rr[-1], mid.x, mid.y, mid.z, mid.w, rr[4]};
+#pragma unroll
+      for (int t2 = 0; t2 < 3; ++t2)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = fmaf(in[o + t2], wk[t1 * 3 + t2], acc[o]);
+    }
+    T* dst = y + (bc0 + j) * (long long)q.H * q.W + row * q.W + 4 * sg;
+    const int nv = min(4, q.W - 4 * sg);
+    if (nv == 4 && (((uintptr_t)dst) & (sizeof(T) * 4 - 1)) == 0) {
+      if (sizeof(T) == 2) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(acc[0], acc[1]), b = __floats2bfloat162_rn(acc[2], acc[3]);
+        uint2 o; o.x = *(uint32_t*)&a; o.y = *(uint32_t*)&b;
+        *(uint2*)dst = o;
+      } else {
+        *(float4*)dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    } else {
+      for (int o = 0; o < nv; ++o) dst[o] = from_f32<T>(acc[o]);
+    }
+  }
+}
+
+// weight gradient of the same configuration:  dw[c, t1, t2] += sum_{b, h, w} dy[b,c,h,w] * x[b,c,h + t1 - 1, w + t2 - 1]
+// grid = (channels, batch chunks); smem: xs [PBW][H + 2][RP] | dys [PBW][H + 2][RP] (same pitched layout) | red [9][8]
+template <typename T, int V>
+__global__ void __launch_bounds__(256) dwconv3x3_wgrad_fast(const Fast3Params q, int batch, int batch_per_block, int PBW,
+                                                            const T* __restrict__ x, const T* __restrict__ dy,
+                                                            float* __restrict__ dw) {
+  extern __shared__ __align__(16) float dsm[];
+  const int plane = (q.H + 2) * q.RP;
+  float* xs = dsm;
+  float* gs = xs + PBW * plane;
+  float* red = gs + PBW * plane;
+  const int c = blockIdx.x;
+  const int b_begin = blockIdx.y * batch_per_block;
+  const int b_end = min(batch, b_begin + batch_per_block);
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  const int spp = q.H * q.strips;
+  const long long psz = (long long)q.H * q.W;
+  for (int b0 = b_begin; b0 < b_end; b0 += PBW) {
+    const int npl = min(PBW, b_end - b0);
+    __syncthreads();
+    {
+      const long long first = ((long long)b0 * q.channels + c) * psz;
+      fast3_stage<T, V>(xs, x + first, npl, (long long)q.channels * psz, q);
+      fast3_stage<T, V>(gs, dy + first, npl, (long long)q.channels * psz, q);
+    }
+    __syncthreads();
+    const int total = npl * spp;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      int j, r, row, sg;
+      q.f_spp.divmod(e, j, r);
+      q.f_strips.divmod(r, row, sg);
+      const float4 g4 = *(const float4*)(gs + j * plane + (row + 1) * q.RP + 4 + 4 * sg);
+      const int nv = q.W - 4 * sg;                                     // strips past the row end carry staged garbage: mask
+      const float g[4] = {g4.x, nv > 1 ? g4.y : 0.f, nv > 2 ? g4.z : 0.f, nv > 3 ? g4.w : 0.f};
+      const float* xr = xs + j * plane + row * q.RP + 4 + 4 * sg;
+#pragma unroll
+      for (int t1 = 0; t1 < 3; ++t1) {
+        const float* rr = xr + t1 * q.RP;
+        const float4 mid = *(const float4*)rr;
+        const float in[6] = {rr[-1], mid.x, mid.y, mid.z, mid.w, rr[4]};
+#pragma unroll
+        for (int t2 = 0; t2 < 3; ++t2)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[t1 * 3 + t2] = fmaf(in[o + t2], g[o], acc[t1 * 3 + t2]);
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float v = acc[t];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[t * 8 + warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float v = 0.f;
+    for (int wv = 0; wv < 8; ++wv) v += red[threadIdx.x * 8 + wv];
+    atomicAdd(dw + (long long)c * 9 + threadIdx.x, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Unfold for dense (non-grouped) convolutions:  cols[(b, o), (c, t)] = x[b, c, o*s - p + t*d]   (zero outside)
 // and its adjoint  dx[b, c, i] = sum_{(o,t) -> i} dcols[(b, o), (c, t)].
 // Replaces the unfold half of F.conv{1,2,3}d for the Tucker core conv (functional/convolution.py:161) and the TT per-mode
@@ -427,15 +615,18 @@ static int choose_pb(const DwParams& p, int plane_floats, int items_per_plane) {
   return (int)pb;
 }
 
+// opt in to > 48 KB of dynamic shared memory, once per (kernel, high-water mark).  Keyed by the function POINTER: kernels
+// with identical signatures (fwd / dgrad, FLIP = false / true) share one template instantiation of this helper.
 template <typename K>
 static int dw_set_smem(K kernel, size_t bytes) {
   static std::mutex mu;
-  static size_t high = 0;            // one instance per kernel type K
+  static std::unordered_map<const void*, size_t> high;
   if (bytes <= 48 * 1024) return TLT_OK;
   std::lock_guard<std::mutex> lock(mu);
-  if (bytes > high) {
+  size_t& h = high[(const void*)kernel];
+  if (bytes > h) {
     TLT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    high = bytes;
+    h = bytes;
   }
   return TLT_OK;
 }
@@ -489,6 +680,100 @@ static int launch_wgrad(const DwParams& p, int batch, const void* x, const void*
   if (p.taps <= 3) return launch_wgrad_t<T, 3>(p, batch, x, dy, dw, st);
   if (p.taps <= 9) return launch_wgrad_t<T, 9>(p, batch, x, dy, dw, st);
   return launch_wgrad_t<T, kMaxTaps>(p, batch, x, dy, dw, st);
+}
+
+static bool fast3_applicable(const DwParams& p) {
+  return p.in[0] == 1 && p.ker[0] == 1 && p.ker[1] == 3 && p.ker[2] == 3 && p.stride[1] == 1 && p.stride[2] == 1 &&
+         p.pad[1] == 1 && p.pad[2] == 1 && p.dil[1] == 1 && p.dil[2] == 1 && p.out[1] == p.in[1] && p.out[2] == p.in[2] &&
+         p.in[2] >= 4;
+}
+
+static void fast3_fill(const DwParams& p, Fast3Params* q, int planes_needed_per_item) {
+  q->H = p.in[1]; q->W = p.in[2];
+  q->strips = (q->W + 3) / 4;
+  q->RP = ((4 + 4 * q->strips + 1) + 3) & ~3;                 // 4 lead floats, interior rounded to strips, >= 1 trailing halo
+  q->channels = p.channels; q->planes = p.planes;
+  q->f_spp = FastDivU(q->H * q->strips); q->f_strips = FastDivU(q->strips);
+  (void)planes_needed_per_item;
+}
+
+template <typename T, bool FLIP>
+static int launch_fast3(const DwParams& p, const void* x, const void* w, void* y, cudaStream_t st) {
+  Fast3Params q;
+  fast3_fill(p, &q, 1);
+  const int plane = (q.H + 2) * q.RP;
+  long long pb = (8 * 256 + q.H * q.strips - 1) / (q.H * q.strips);       // ~8 strips per thread per block
+  const long long by_smem = (long long)(kDwSmemLimit / 4) / (plane + 12);
+  if (pb > by_smem) pb = by_smem;
+  const long long by_grid = p.planes / (2 * 148);
+  if (by_grid >= 1 && pb > by_grid) pb = by_grid;
+  if (pb < 1) pb = 1;
+  q.PB = (int)pb;
+  const size_t smem = (size_t)q.PB * (plane + 12) * 4;
+  const unsigned blocks = (unsigned)((p.planes + q.PB - 1) / q.PB);
+  const bool a16 = (((uintptr_t)x) & 15) == 0;
+  const int esz = (int)sizeof(T);
+  int V = 1;
+  if (a16 && q.W % (16 / esz) == 0) V = 8 / (esz / 2) / 1;               // bf16: 8 elements, fp32: 4 elements (16 bytes)
+  else if (a16 && esz == 2 && q.W % 4 == 0) V = 4;                        // bf16: 8-byte loads
+  // for fp32 the 16-byte vector holds 4 elements: reuse the V == 4 code path (one float4)
+  int rc;
+  if (esz == 4 && V == 4) {
+    q.f_rowv = FastDivU(q.W / 4); q.f_rowsv = FastDivU(q.H * (q.W / 4));
+    if ((rc = dw_set_smem(dwconv3x3_fast<T, 4, FLIP>, smem))) return rc;
+    dwconv3x3_fast<T, 4, FLIP><<<blocks, 256, smem, st>>>(q, (const T*)x, (const T*)w, (T*)y);
+  } else if (esz == 2 && V == 8) {
+    q.f_rowv = FastDivU(q.W / 8); q.f_rowsv = FastDivU(q.H * (q.W / 8));
+    if ((rc = dw_set_smem(dwconv3x3_fast<T, 8, FLIP>, smem))) return rc;
+    dwconv3x3_fast<T, 8, FLIP><<<blocks, 256, smem, st>>>(q, (const T*)x, (const T*)w, (T*)y);
+  } else if (esz == 2 && V == 4) {
+    q.f_rowv = FastDivU(q.W / 4); q.f_rowsv = FastDivU(q.H * (q.W / 4));
+    if ((rc = dw_set_smem(dwconv3x3_fast<T, 4, FLIP>, smem))) return rc;
+    dwconv3x3_fast<T, 4, FLIP><<<blocks, 256, smem, st>>>(q, (const T*)x, (const T*)w, (T*)y);
+  } else {
+    q.f_rowv = FastDivU(q.W); q.f_rowsv = FastDivU(q.H * q.W);
+    if ((rc = dw_set_smem(dwconv3x3_fast<T, 1, FLIP>, smem))) return rc;
+    dwconv3x3_fast<T, 1, FLIP><<<blocks, 256, smem, st>>>(q, (const T*)x, (const T*)w, (T*)y);
+  }
+  return check_launch("dwconv3x3_fast");
+}
+
+template <typename T>
+static int launch_fast3_wgrad(const DwParams& p, int batch, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  Fast3Params q;
+  fast3_fill(p, &q, 2);
+  const int plane = (q.H + 2) * q.RP;
+  long long chunks = (148LL * 8 + p.channels - 1) / p.channels;
+  if (chunks > batch) chunks = batch;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  const int bpb = (int)((batch + chunks - 1) / chunks);
+  chunks = (batch + bpb - 1) / bpb;
+  long long pbw = (4 * 256 + q.H * q.strips - 1) / (q.H * q.strips);
+  const long long by_smem = (long long)((64 * 1024 - 4 * 72) / 4) / (2 * plane) > 0 ? (long long)((64 * 1024 - 4 * 72) / 4) / (2 * plane) : 1;
+  if (pbw > by_smem) pbw = by_smem;
+  if (pbw > bpb) pbw = bpb;
+  if (pbw < 1) pbw = 1;
+  q.PB = (int)pbw;
+  const size_t smem = ((size_t)pbw * 2 * plane + 72) * 4;
+  dim3 grid((unsigned)p.channels, (unsigned)chunks);
+  const int esz = (int)sizeof(T);
+  const bool a16 = (((uintptr_t)x) & 15) == 0 && (((uintptr_t)dy) & 15) == 0 && ((long long)q.H * q.W * esz) % 16 == 0;
+  int rc;
+  if (a16 && esz == 2 && q.W % 8 == 0) {
+    q.f_rowv = FastDivU(q.W / 8); q.f_rowsv = FastDivU(q.H * (q.W / 8));
+    if ((rc = dw_set_smem(dwconv3x3_wgrad_fast<T, 8>, smem))) return rc;
+    dwconv3x3_wgrad_fast<T, 8><<<grid, 256, smem, st>>>(q, batch, bpb, (int)pbw, (const T*)x, (const T*)dy, dw);
+  } else if (a16 && q.W % 4 == 0 && ((long long)q.H * q.W * esz) % 16 == 0) {
+    q.f_rowv = FastDivU(q.W / 4); q.f_rowsv = FastDivU(q.H * (q.W / 4));
+    if ((rc = dw_set_smem(dwconv3x3_wgrad_fast<T, 4>, smem))) return rc;
+    dwconv3x3_wgrad_fast<T, 4><<<grid, 256, smem, st>>>(q, batch, bpb, (int)pbw, (const T*)x, (const T*)dy, dw);
+  } else {
+    q.f_rowv = FastDivU(q.W); q.f_rowsv = FastDivU(q.H * q.W);
+    if ((rc = dw_set_smem(dwconv3x3_wgrad_fast<T, 1>, smem))) return rc;
+    dwconv3x3_wgrad_fast<T, 1><<<grid, 256, smem, st>>>(q, batch, bpb, (int)pbw, (const T*)x, (const T*)dy, dw);
+  }
+  return check_launch("dwconv3x3_wgrad_fast");
 }
 
 int im2col_generic(const tlt_conv_desc* d, const void* x, void* cols, void* stream);
@@ -566,6 +851,10 @@ extern "C" int tlt_dwconv_fwd(const tlt_conv_desc* d, const void* x, const void*
     TLT_REQUIRE(expect == d->out_size[i], "conv: out_size[%d]=%lld inconsistent (expected %lld)", i, (long long)d->out_size[i], expect);
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (fast3_applicable(p)) {
+    if (d->dtype == TLT_BF16) return launch_fast3<__nv_bfloat16, false>(p, x, w, y, st);
+    return launch_fast3<float, false>(p, x, w, y, st);
+  }
   if (d->dtype == TLT_BF16) return launch_fwd<__nv_bfloat16>(p, x, w, y, st);
   return launch_fwd<float>(p, x, w, y, st);
 }
@@ -576,6 +865,10 @@ extern "C" int tlt_dwconv_dgrad(const tlt_conv_desc* d, const void* dy, const vo
     return dwconv_dgrad_generic(d, dy, w, dx, stream);
   TLT_REQUIRE(dy && w && dx, "tlt_dwconv_dgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (fast3_applicable(p)) {                       // stride 1, pad 1: the adjoint is the same correlation with reversed taps
+    if (d->dtype == TLT_BF16) return launch_fast3<__nv_bfloat16, true>(p, dy, w, dx, st);
+    return launch_fast3<float, true>(p, dy, w, dx, st);
+  }
   if (d->dtype == TLT_BF16) return launch_dgrad<__nv_bfloat16>(p, dy, w, dx, st);
   return launch_dgrad<float>(p, dy, w, dx, st);
 }
@@ -587,6 +880,10 @@ extern "C" int tlt_dwconv_wgrad(const tlt_conv_desc* d, const void* x, const voi
     return dwconv_wgrad_generic(d, x, dy, dw, stream);
   TLT_REQUIRE(x && dy && dw, "tlt_dwconv_wgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (fast3_applicable(p)) {
+    if (d->dtype == TLT_BF16) return launch_fast3_wgrad<__nv_bfloat16>(p, (int)d->batch, x, dy, dw, st);
+    return launch_fast3_wgrad<float>(p, (int)d->batch, x, dy, dw, st);
+  }
   if (d->dtype == TLT_BF16) return launch_wgrad<__nv_bfloat16>(p, (int)d->batch, x, dy, dw, st);
   return launch_wgrad<float>(p, (int)d->batch, x, dy, dw, st);
 }
