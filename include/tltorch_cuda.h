@@ -133,6 +133,27 @@ int tlt_blocktt3_core_grads(const tlt_blocktt3_desc* desc, const void* c1, const
                             void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Fused chain of mode products on the trailing (up to) three modes of a contiguous tensor, intermediates in shared memory:
+ *   x (batch, d0, d1, d2) -> y (batch, r0, r1, r2),  y[b] = x[b] x_0 M0 x_1 M1 x_2 M2
+ * M_k is (r_k, d_k) row-major, or (d_k, r_k) when transpose[k] != 0 (multiply by M_k^T); a NULL matrix leaves its mode
+ * untouched (in_dims[k] == out_dims[k]).  Tensors with fewer modes pad LEADING modes with size 1 and NULL matrices.
+ * Returns TLT_ERR_UNSUPPORTED when one sample does not fit shared memory (callers fall back to per-mode tlt_contract).
+ * Replaces: tenalg.multi_mode_dot chains -- TCL.forward (factorized_layers/tensor_contraction_layers.py:75), the input
+ * projection of tucker_trl (functional/tensor_regression.py:40) and the project / expand stages of linear_tucker
+ * (functional/factorized_tensordot.py:10-66) -- and their data gradients (same call, transposed matrices).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dtype;
+  int64_t batch;
+  int32_t in_dims[3], out_dims[3];
+  int32_t transpose[3];
+} tlt_mmd_desc;
+
+/* addend: optional (r0, r1, r2) tensor of the same dtype added to every sample (a bias), or NULL */
+int tlt_multi_mode_dot(const tlt_mmd_desc* desc, const void* x, const void* m0, const void* m1, const void* m2,
+                       const void* addend, void* y, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Pointwise (1x1) channel mixing of channels-first bf16 activations on the tcgen05 tensor cores, from NCHW memory.
  *   tlt_pointwise_tc       : y[b, n, s] = sum_k wt[n, k] * x[b, k, s] (+ bias[n])      x (batch, in, spatial), y (batch, out, spatial)
  *   tlt_pointwise_wgrad_tc : dw[n, k]   = sum_{b, s} dy[b, n, s] * x[b, k, s]          dw fp32, row pitch w_ld

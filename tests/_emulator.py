@@ -174,11 +174,28 @@ def emulate_pointwise_wgrad(gy3, x3, dw32):
     LOG.append(("pointwise_wgrad_tc", tuple(gy3.shape), tuple(x3.shape)))
 
 
+def emulate_mmd(x4, mats, flags, addend, y4):
+    res = x4.double()
+    for k in range(3):
+        if mats[k] is None:
+            continue
+        m = mats[k].double()
+        m = m.t() if flags[k] else m                      # (r, d)
+        res = torch.movedim(torch.tensordot(res, m, dims=([1 + k], [1])), -1, 1 + k)
+    if addend is not None:
+        res = res + addend.double()
+    y4.copy_(res.to(y4.dtype))
+    LOG.append(("multi_mode_dot", tuple(x4.shape), tuple(y4.shape), list(flags)))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
     """Swap the launch funnels for the CPU interpreters (tests only)."""
     from torch_b200 import blocktt_ops as bo
     from torch_b200 import pointwise_ops as po
+    from torch_b200 import modedot_ops as mo
+    saved_m = mo._execute_mmd
+    mo._execute_mmd = emulate_mmd
     saved_p = po._execute_pointwise, po._execute_pointwise_wgrad
     po._execute_pointwise, po._execute_pointwise_wgrad = emulate_pointwise, emulate_pointwise_wgrad
     saved = ops._execute_contract, ops._execute_conv
@@ -193,3 +210,4 @@ def emulated_kernels():
         ops._execute_contract, ops._execute_conv = saved
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p
+        mo._execute_mmd = saved_m

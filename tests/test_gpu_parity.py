@@ -310,6 +310,50 @@ def test_depthwise_conv_kernels_vs_torch(B, C, H, W, k, stride, pad, dil, dtype)
     assert G.rel_err(gw, gwr) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,ranks,modes,transpose,with_bias", [
+    ((512, 16, 16, 16), (15, 15, 15), [1, 2, 3], True, False),       # config 5 Tucker projection (per token 16^3 -> 15^3)
+    ((512, 15, 15, 15), (16, 16, 16), [1, 2, 3], False, True),       # ... and the expansion, with the bias fused
+    ((256, 40, 7, 7), (24, 4, 4), [1, 2, 3], False, True),           # TCL on (C, H, W)
+    ((300, 3, 9, 5), (4, 7), [2, 3], True, False),                   # only two trailing modes, an untouched middle dim ahead
+    ((128, 33), (70,), [1], False, False),                           # a single mode with r > 64 (several register tiles)
+    ((200, 5, 6, 7), (3, 2), [1, 3], False, False),                  # a skipped mode in the middle
+])
+def test_fused_multi_mode_dot_vs_fp64(shape, ranks, modes, transpose, with_bias, dtype):
+    """tlt_multi_mode_dot (one launch, intermediates in shared memory) and its autograd against fp64 tensordot chains --
+    tenalg.multi_mode_dot of TCL / tucker_trl / linear_tucker (tensor_contraction_layers.py:75, tensor_regression.py:40)."""
+    from torch_b200 import tenalg, ops, modedot_ops
+    monkey = modedot_ops.MIN_SAMPLE_ELEMS
+    modedot_ops.MIN_SAMPLE_ELEMS = 1
+    torch.manual_seed(sum(shape) + len(modes))
+    x = torch.randn(shape, device=dev()).to(dtype).requires_grad_(True)
+    mats = [(torch.randn((shape[m], r) if transpose else (r, shape[m]), device=dev()) / math.sqrt(shape[m])).to(dtype).requires_grad_(True)
+            for r, m in zip(ranks, modes)]
+    out_tail = list(shape[min(modes):])
+    for r, m in zip(ranks, modes):
+        out_tail[m - min(modes)] = r
+    bias = torch.randn(out_tail, device=dev()).to(dtype).requires_grad_(True) if with_bias else None
+    before = ops.launch_count()
+    y = tenalg.multi_mode_dot(x, mats, modes, transpose=transpose, addend=bias)
+    assert ops.launch_count() - before == 1, "expected ONE fused launch"
+    gy = torch.randn_like(y)
+    leaves = [x] + mats + ([bias] if with_bias else [])
+    got = torch.autograd.grad(y, leaves, gy)
+    modedot_ops.MIN_SAMPLE_ELEMS = monkey
+    ref_leaves = [t.detach().double().cpu().requires_grad_(True) for t in leaves]
+    ref = ref_leaves[0]
+    for m, mode in zip(ref_leaves[1:1 + len(mats)], modes):
+        mm = m.t() if transpose else m
+        ref = torch.movedim(torch.tensordot(ref, mm, dims=([mode], [1])), -1, mode)
+    if with_bias:
+        ref = ref + ref_leaves[-1]
+    want = torch.autograd.grad(ref, ref_leaves, gy.double().cpu())
+    tol = TOL[dtype]
+    assert G.rel_err(y, ref) < tol
+    for a, b in zip(got, want):
+        assert G.rel_err(a, b) < tol
+
+
 def tlt_launches():
     from torch_b200 import ops
     return ops.launch_count()

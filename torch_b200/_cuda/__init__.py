@@ -56,6 +56,11 @@ class PointwiseDesc(C.Structure):
                 ("w_ld", C.c_int64), ("dtype_bias", C.c_int32)]
 
 
+class MmdDesc(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("batch", C.c_int64), ("in_dims", C.c_int32 * 3), ("out_dims", C.c_int32 * 3),
+                ("transpose", C.c_int32 * 3)]
+
+
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -71,6 +76,7 @@ SYMBOLS = {
     "tlt_blocktt3_reconstruct": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_blocktt3_core_grads_workspace_size": (C.c_size_t, [C.POINTER(BlockTT3Desc)]),
     "tlt_blocktt3_core_grads": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "tlt_multi_mode_dot": (C.c_int, [C.POINTER(MmdDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_pointwise_tc_supported": (C.c_int, [C.POINTER(PointwiseDesc)]),
     "tlt_pointwise_tc": (C.c_int, [C.POINTER(PointwiseDesc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_pointwise_wgrad_tc": (C.c_int, [C.POINTER(PointwiseDesc), _vp, _vp, _vp, _vp]),

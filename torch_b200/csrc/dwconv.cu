@@ -540,8 +540,10 @@ __global__ void __launch_bounds__(256) col2im_staged(const UnfoldParams u, const
   }
   __syncthreads();
   T* dst = dx + ((long long)b * p.channels + c0) * p.in_sp;
+  const bool unit = p.stride[0] == 1 && p.stride[1] == 1 && p.stride[2] == 1;
   for (int e = threadIdx.x; e < cn * p.in_sp; e += blockDim.x) {
-    const int c = e / p.in_sp, sp = e - c * p.in_sp;
+    int c, sp;
+    p.f_insp.divmod(e, c, sp);
     int i0, r, i1, i2;
     u.f_i12.divmod(sp, i0, r);
     u.f_i2.divmod(r, i1, i2);
@@ -549,16 +551,16 @@ __global__ void __launch_bounds__(256) col2im_staged(const UnfoldParams u, const
     int t = 0;
     for (int t0 = 0; t0 < p.ker[0]; ++t0) {
       const int n0 = i0 + p.pad[0] - t0 * p.dil[0];
-      const int o0 = n0 / p.stride[0];
-      const bool ok0 = n0 >= 0 && n0 == o0 * p.stride[0] && o0 < p.out[0];
+      const int o0 = unit ? n0 : n0 / p.stride[0];
+      const bool ok0 = n0 >= 0 && (unit || n0 == o0 * p.stride[0]) && o0 < p.out[0];
       for (int t1 = 0; t1 < p.ker[1]; ++t1) {
         const int n1 = i1 + p.pad[1] - t1 * p.dil[1];
-        const int o1 = n1 / p.stride[1];
-        const bool ok1 = ok0 && n1 >= 0 && n1 == o1 * p.stride[1] && o1 < p.out[1];
+        const int o1 = unit ? n1 : n1 / p.stride[1];
+        const bool ok1 = ok0 && n1 >= 0 && (unit || n1 == o1 * p.stride[1]) && o1 < p.out[1];
         for (int t2 = 0; t2 < p.ker[2]; ++t2, ++t) {
           const int n2 = i2 + p.pad[2] - t2 * p.dil[2];
-          const int o2 = n2 / p.stride[2];
-          if (ok1 && n2 >= 0 && n2 == o2 * p.stride[2] && o2 < p.out[2])
+          const int o2 = unit ? n2 : n2 / p.stride[2];
+          if (ok1 && n2 >= 0 && (unit || n2 == o2 * p.stride[2]) && o2 < p.out[2])
             acc += dsm[((o0 * p.out[1] + o1) * p.out[2] + o2) * run + c * p.taps + t];
         }
       }

@@ -35,16 +35,8 @@ class TCL(nn.Module):
         return [getattr(self, f"factor_{i}") for i in range(self.order)]
 
     def forward(self, x):
-        factors = self.factors
-        if self.bias is None:
-            return tenalg.multi_mode_dot(x, factors, modes=self.contraction_modes)
-        # all but the last mode product, then the last one with the bias fused into its epilogue
-        y = tenalg.multi_mode_dot(x, factors[:-1], modes=self.contraction_modes[:-1])
-        nd = y.dim()
-        t = "abcdefghijklmnopqrstuvwxyz"[:nd]
-        new = "abcdefghijklmnopqrstuvwxyz"[nd]
-        out = t[:nd - 1] + new
-        return contract(f"{t},{new}{t[nd - 1]}->{out}", y, factors[-1], self.bias, out[1:])
+        # one fused launch when a sample fits shared memory (bias added in the same kernel), else a per-mode chain
+        return tenalg.multi_mode_dot(x, self.factors, modes=self.contraction_modes, addend=self.bias)
 
     def reset_parameters(self):
         for i in range(self.order):

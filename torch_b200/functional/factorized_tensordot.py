@@ -39,9 +39,7 @@ def tensor_dot_tucker(tensor, tucker, modes, batched_modes=(), addend=None):
     modes_tensor, modes_tucker = _validate_contraction_modes(tuple(tensor.shape), tuple(tucker.tensor_shape), modes)
     core, factors = tucker.core, list(tucker.factors)
     # 1. project the contracted modes of the dense tensor onto the rank space, in place (mode stays where it is)
-    res = tensor
-    for mt, mk in zip(modes_tensor, modes_tucker):
-        res = tenalg.mode_dot(res, factors[mk], mt, transpose=True)
+    res = tenalg.multi_mode_dot(tensor, [factors[mk] for mk in modes_tucker], modes_tensor, transpose=True)
     # 2. contract with the core: kept tensor modes, then free core modes
     nt = tensor.dim()
     t_letters = list(_L[:nt])
@@ -53,16 +51,9 @@ def tensor_dot_tucker(tensor, tucker, modes, batched_modes=(), addend=None):
     res = contract(f"{''.join(t_letters)},{''.join(core_letters)}->{''.join(kept + free)}", res, core)
     # 3. expand the free modes onto their factors
     free_modes = [i for i in range(core.dim()) if i not in modes_tucker]
-    for pos, mk in enumerate(free_modes):
-        last = pos == len(free_modes) - 1
-        if last and addend is not None:
-            nd = res.dim()
-            t = _L[:nd]
-            mode = len(kept) + pos
-            out = t[:mode] + _L[nd] + t[mode + 1:]
-            res = contract(f"{t},{_L[nd]}{t[mode]}->{out}", res, factors[mk], addend, out[len(kept):])
-        else:
-            res = tenalg.mode_dot(res, factors[mk], len(kept) + pos)
+    if free_modes:
+        res = tenalg.multi_mode_dot(res, [factors[mk] for mk in free_modes], [len(kept) + pos for pos in range(len(free_modes))],
+                                    addend=addend)
     if addend is not None and not free_modes:
         raise ValueError("addend needs at least one free mode")
     return res

@@ -27,7 +27,9 @@ launch_count = _cuda.launch_count
 # minimum M*N*K for which a plain bf16 GEMM is routed to the tcgen05 kernel instead of the SIMT contraction kernel
 TC_MIN_WORK = 1 << 21
 import os as _os
-_FORCE_SIMT = _os.environ.get("TLT_FORCE_SIMT", "0") == "1"   # debugging aid: route every contraction to the SIMT kernel
+_FORCE_SIMT = _os.environ.get("TLT_FORCE_SIMT", "0") == "1"
+_LOG_SIMT = _os.environ.get("TLT_LOG_SIMT", "0") == "1"     # debugging aid: report large contractions that stay on the SIMT kernel
+import sys as _sys   # debugging aid: route every contraction to the SIMT kernel
 
 
 PROFILE = None          # set to a list by bench.py to collect (kernel, start_event, end_event, flops, bytes) per launch
@@ -208,6 +210,12 @@ def _execute_contract(plan, a, b, d, out, alpha):
     if (not _FORCE_SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
             and _packed_tensor_core_contract(plan, desc, a, b, d, out, alpha, lib)):
         return
+    if _LOG_SIMT:
+        f = plan.desc_fields
+        work = math.prod(f["size_b"] or [1]) * math.prod(f["size_m"] or [1]) * math.prod(f["size_n"] or [1]) * math.prod(f["size_k"] or [1])
+        if work >= (1 << 22):
+            print(f"[tlt simt] {plan.spec} {a.dtype} b{f['size_b']} m{f['size_m']} n{f['size_n']} k{f['size_k']} macs={work:.3g}",
+                  file=_sys.stderr)
     ws_bytes = lib.tlt_contract_workspace_size(C.byref(desc))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=out.device) if ws_bytes else None
     _cuda.check(lib.tlt_contract(C.byref(desc), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(d), _cuda.ptr(out),
@@ -375,6 +383,11 @@ def reduce_to(t: torch.Tensor, letters: str, keep: str) -> torch.Tensor:
     if not drop:
         perm = [letters.index(l) for l in keep]
         return t.permute(perm)
+    if len(drop) > 1 and letters[-1] in drop and t.is_contiguous() and t.shape[-1] >= 8:
+        # e.g. the bias gradient of an NCHW conv ("bos" -> "o"): first the contiguous innermost index (row sums, coalesced),
+        # then the rest (a vector-matrix reduction) -- instead of one composite-k reduction on the generic kernel
+        inner = reduce_to(t, letters, letters[:-1])
+        return reduce_to(inner, letters[:-1], keep)
     sizes = [t.shape[letters.index(l)] for l in drop]
     ones = torch.ones((), dtype=t.dtype, device=t.device).expand(sizes)
     return contract(f"{letters},{drop}->{keep}", t, ones)

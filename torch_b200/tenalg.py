@@ -40,9 +40,32 @@ def mode_dot(tensor, matrix_or_vector, mode, transpose=False):
     raise ValueError("Can only take n_mode_product with a vector or a matrix.")
 
 
-def multi_mode_dot(tensor, matrix_or_vec_list, modes=None, skip=None, transpose=False):
+def multi_mode_dot(tensor, matrix_or_vec_list, modes=None, skip=None, transpose=False, addend=None):
+    """tensorly.tenalg.multi_mode_dot.  When the touched modes are the trailing (<= 3) dims of a contiguous tensor with
+    enough leading samples, the whole chain runs as ONE fused launch with the intermediates in shared memory
+    (modedot_ops / csrc/modedot.cu); otherwise mode by mode.  ``addend`` (shaped like the trailing output modes, e.g. a
+    bias) is added in the last launch."""
     if modes is None:
         modes = range(len(matrix_or_vec_list))
+    modes = list(modes)
+    pairs = [(m, mode) for i, (m, mode) in enumerate(zip(matrix_or_vec_list, modes)) if skip is None or i != skip]
+    if pairs and all(m.dim() == 2 for m, _ in pairs):
+        from . import modedot_ops
+        p = modedot_ops.plan(tensor, [m for m, _ in pairs], [mode for _, mode in pairs], transpose)
+        if p is not None and (addend is None or _addend_matches(tensor, p, addend)):
+            return modedot_ops.fused_multi_mode_dot(tensor, *p, addend=addend)
+    if addend is not None:
+        # unfused chain: all but the last product, then the last one with the addend in its epilogue
+        res = multi_mode_dot(tensor, [m for m, _ in pairs[:-1]], [mode for _, mode in pairs[:-1]], transpose=transpose) if len(pairs) > 1 else tensor
+        m, mode = pairs[-1]
+        nd = res.dim()
+        mode = mode + nd if mode < 0 else mode
+        t = _L[:nd]
+        new = _L[nd]
+        out = t[:mode] + new + t[mode + 1:]
+        mspec = (t[mode] + new) if transpose else (new + t[mode])
+        letters = out[nd - addend.dim():]
+        return contract(f"{t},{mspec}->{out}", res, m, addend, letters)
     removed = 0
     res = tensor
     for i, (m, mode) in enumerate(zip(matrix_or_vec_list, modes)):
@@ -52,6 +75,12 @@ def multi_mode_dot(tensor, matrix_or_vec_list, modes=None, skip=None, transpose=
         if m.dim() == 1:
             removed += 1
     return res
+
+
+def _addend_matches(tensor, plan, addend):
+    lead, d, r, mats, flags = plan
+    n_tail = tensor.dim() - len(lead)
+    return list(addend.shape) == list(r[3 - n_tail:])
 
 
 def inner(a, b, n_modes=None, bias=None):
