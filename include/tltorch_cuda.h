@@ -154,6 +154,32 @@ int tlt_multi_mode_dot(const tlt_mmd_desc* desc, const void* x, const void* m0, 
                        const void* addend, void* y, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Tensor-core variant of the fused mode-product chain for bf16 samples whose three modes are all <= 16 (tensorized
+ * linear layers: 4096 = 16^3, Tucker ranks 15^3, ...).  One warp keeps one sample on chip as a 16x16x16 tile; every mode
+ * product is an m16n8k16 HMMA fed by ldmatrix; no block-level barriers.
+ *   tlt_mmd16_fwd : y[b] = x[b] x_0 M0 x_1 M1 x_2 M2 (+ addend)       x (batch, in_dims) pitch ld_in -> y (batch, out_dims) pitch ld_out
+ *   tlt_mmd16_bwd : du[b] = g[b] x_0 M0^T x_1 M1^T x_2 M2^T  and  dM[k][j][i] += d<g, y>/dM_k[j][i]   in one pass over (u, g);
+ *                   dM is fp32 [3][16][16] (j = out index, i = in index), accumulated into (the caller zeroes it); du or dM
+ *                   may be NULL to skip that half.
+ * M_k is (out_dims[k], in_dims[k]) row-major, or (in_dims[k], out_dims[k]) when transpose[k] != 0; NULL = identity.
+ * Sample pitches are in elements, multiples of 8, >= round8(prod dims); the pad elements [prod, round8(prod)) of every
+ * written sample are set to zero, so the tensors can feed tlt_gemm_bf16_tc as K-major operands directly.
+ * Replaces: the project-in / expand-out multi_mode_dot chains of linear_tucker (tltorch/functional/factorized_linear.py:7-21,
+ * factorized_tensordot.py:10-66) and their autograd (data gradient + all three factor gradients in one launch).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t batch;
+  int32_t in_dims[3], out_dims[3];
+  int32_t transpose[3];
+  int64_t ld_in, ld_out;
+} tlt_mmd16_desc;
+
+int tlt_mmd16_fwd(const tlt_mmd16_desc* desc, const void* x, const void* m0, const void* m1, const void* m2,
+                  const void* addend, void* y, void* stream);
+int tlt_mmd16_bwd(const tlt_mmd16_desc* desc, const void* u, const void* g, const void* m0, const void* m1, const void* m2,
+                  void* du, float* dM, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Pointwise (1x1) channel mixing of channels-first bf16 activations on the tcgen05 tensor cores, from NCHW memory.
  *   tlt_pointwise_tc       : y[b, n, s] = sum_k wt[n, k] * x[b, k, s] (+ bias[n])      x (batch, in, spatial), y (batch, out, spatial)
  *   tlt_pointwise_wgrad_tc : dw[n, k]   = sum_{b, s} dy[b, n, s] * x[b, k, s]          dw fp32, row pitch w_ld

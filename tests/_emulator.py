@@ -156,7 +156,7 @@ def emulate_gemm(a, b, bias, out, M, N, K, lda, ldb, a_major, b_major, alpha=1.0
     res = alpha * (A.double() @ Bm.double().t())
     if bias is not None:
         res = res + bias.double()
-    out.copy_(res.to(out.dtype))
+    torch.as_strided(out, (M, N), (out.stride(0), 1), out.storage_offset()).copy_(res.to(out.dtype))   # ldc = out.stride(0)
     LOG.append(("gemm", M, N, K, a_major, b_major))
 
 
@@ -188,14 +188,65 @@ def emulate_mmd(x4, mats, flags, addend, y4):
     LOG.append(("multi_mode_dot", tuple(x4.shape), tuple(y4.shape), list(flags)))
 
 
+def _mmd16_chain(x, dims_in, mats, flags):
+    res = x
+    for k in range(3):
+        if mats[k] is None:
+            continue
+        m = mats[k].double()
+        m = m.t() if flags[k] else m                      # (r, d)
+        res = torch.movedim(torch.tensordot(res, m, dims=([1 + k], [1])), -1, 1 + k)
+    return res
+
+
+def emulate_mmd16_fwd(x2, dims_in, dims_out, mats, flags, addend, y2):
+    B, n_in, n_out = x2.shape[0], math.prod(dims_in), math.prod(dims_out)
+    assert x2.stride(0) % 8 == 0 and y2.stride(0) % 8 == 0 and max(*dims_in, *dims_out) <= 16
+    res = _mmd16_chain(x2[:, :n_in].double().reshape(B, *dims_in), dims_in, mats, flags).reshape(B, n_out)
+    if addend is not None:
+        res = res + addend.double().reshape(-1)
+    y2.zero_()
+    y2[:, :n_out].copy_(res.to(y2.dtype))
+    LOG.append(("mmd16_fwd", tuple(dims_in), tuple(dims_out), list(flags)))
+
+
+def emulate_mmd16_bwd(u2, g2, dims_in, dims_out, mats, flags, du2, dM):
+    B, n_in, n_out = g2.shape[0], math.prod(dims_in), math.prod(dims_out)
+    g = g2[:, :n_out].double().reshape(B, *dims_out)
+    if du2 is not None:
+        gu = _mmd16_chain(g, dims_out, mats, [not f for f in flags])          # multiply by the transposed matrices
+        du2.zero_()
+        du2[:, :n_in].copy_(gu.reshape(B, n_in).to(du2.dtype))
+    if dM is not None:
+        u = u2[:, :n_in].double().reshape(B, *dims_in)
+        letters = "pqr"
+        for k in range(3):
+            if mats[k] is None:
+                continue
+            others = [m if j != k else None for j, m in enumerate(mats)]
+            z = _mmd16_chain(u, dims_in, others, flags)                       # every mode but k projected
+            gm = torch.einsum("b" + letters.replace(letters[k], "j") + ",b" + letters.replace(letters[k], "i") + "->ji", g, z)
+            dM[k, :dims_out[k], :dims_in[k]] += gm.to(dM.dtype)
+    LOG.append(("mmd16_bwd", tuple(dims_in), tuple(dims_out), list(flags)))
+
+
+def emulate_pack_kmajor(src2, dst):
+    dst.zero_()
+    dst[:, :src2.shape[1]].copy_(src2.to(dst.dtype))
+    LOG.append(("pack_kmajor", tuple(src2.shape), dst.stride(0)))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
     """Swap the launch funnels for the CPU interpreters (tests only)."""
     from torch_b200 import blocktt_ops as bo
     from torch_b200 import pointwise_ops as po
     from torch_b200 import modedot_ops as mo
+    from torch_b200 import tucker_ops as to
     saved_m = mo._execute_mmd
     mo._execute_mmd = emulate_mmd
+    saved_t = to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor
+    to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = emulate_mmd16_fwd, emulate_mmd16_bwd, emulate_pack_kmajor
     saved_p = po._execute_pointwise, po._execute_pointwise_wgrad
     po._execute_pointwise, po._execute_pointwise_wgrad = emulate_pointwise, emulate_pointwise_wgrad
     saved = ops._execute_contract, ops._execute_conv
@@ -211,3 +262,4 @@ def emulated_kernels():
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p
         mo._execute_mmd = saved_m
+        to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

@@ -500,3 +500,90 @@ def test_config2_full_size_properties():
     want_gx = gy[rows.to(dev())].double().cpu() @ W
     assert G.rel_err(gx[rows.to(dev())], want_gx) < 2e-2
     assert G.rel_err(gb, gy.double().sum(0).cpu()) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------- mmd16 / Tucker linear
+def _mmd_ref(x, mats, flags):
+    res = x
+    for k in range(3):
+        if mats[k] is None:
+            continue
+        m = mats[k].t() if flags[k] else mats[k]
+        res = torch.movedim(torch.tensordot(res, m, dims=([1 + k], [1])), -1, 1 + k)
+    return res
+
+
+@pytest.mark.parametrize("B,dims_in,dims_out,flags,with_bias,skip", [
+    (301, (16, 16, 16), (15, 15, 15), (True, True, True), False, None),       # config 5 project
+    (301, (15, 15, 15), (16, 16, 16), (False, False, False), True, None),     # config 5 expand + bias (staged loads)
+    (130, (8, 12, 16), (7, 5, 16), (True, False, True), True, None),          # ragged outer modes, full innermost
+    (67, (16, 9, 11), (12, 16, 13), (False, True, False), False, None),       # ragged innermost on both sides
+    (5, (16, 16, 16), (16, 16, 16), (False, False, False), False, 1),         # fewer samples than warps; identity mode
+    (1000, (4, 16, 16), (16, 4, 16), (True, True, False), True, None),
+])
+def test_mmd16_kernels_vs_fp64(B, dims_in, dims_out, flags, with_bias, skip):
+    """tlt_mmd16_fwd / tlt_mmd16_bwd (HMMA mode-product chain, one warp per sample) against an fp64 chain."""
+    from torch_b200 import tucker_ops as to
+    torch.manual_seed(B)
+    dims_in, dims_out = list(dims_in), list(dims_out)
+    if skip is not None:
+        dims_out[skip] = dims_in[skip]
+    n_in, n_out = math.prod(dims_in), math.prod(dims_out)
+    ld = (n_in + 7) & ~7
+    xbuf = torch.randn(B, ld, device=dev(), dtype=torch.bfloat16)
+    xbuf[:, n_in:] = float("nan")                                             # pad columns must never be consumed
+    x = xbuf.detach().requires_grad_(True)
+    mats = []
+    for k in range(3):
+        if skip == k:
+            mats.append(None)
+            continue
+        shape = (dims_in[k], dims_out[k]) if flags[k] else (dims_out[k], dims_in[k])
+        mats.append((torch.randn(shape, device=dev()) / math.sqrt(dims_in[k])).to(torch.bfloat16).requires_grad_(True))
+    bias = torch.randn(n_out, device=dev(), dtype=torch.bfloat16, requires_grad=True) if with_bias else None
+    y = to.mmd16(x, dims_in, dims_out, mats, list(flags), bias)
+    assert y.shape == (B, (n_out + 7) & ~7)
+    assert bool((y[:, n_out:] == 0).all())
+    gy = torch.randn_like(y)
+    leaves = [x] + [m for m in mats if m is not None] + ([bias] if with_bias else [])
+    grads = torch.autograd.grad(y, leaves, gy)
+    # fp64 reference on the same bf16 values
+    xo = xbuf[:, :n_in].double().cpu().reshape(B, *dims_in).requires_grad_(True)
+    mo = [None if m is None else m.detach().double().cpu().requires_grad_(True) for m in mats]
+    yo = _mmd_ref(xo, mo, flags).reshape(B, n_out)
+    bo = None
+    if with_bias:
+        bo = bias.detach().double().cpu().requires_grad_(True)
+        yo = yo + bo
+    lo = [xo] + [m for m in mo if m is not None] + ([bo] if with_bias else [])
+    go = torch.autograd.grad(yo, lo, gy[:, :n_out].double().cpu())
+    assert G.rel_err(y[:, :n_out], yo) < 1e-2
+    assert G.rel_err(grads[0][:, :n_in], go[0].reshape(B, n_in)) < 1.5e-2
+    for a, b in zip(grads[1:], go[1:]):
+        assert G.rel_err(a, b) < 1.5e-2
+
+
+def test_tucker3_fused_linear_vs_oracle():
+    """FactorizedLinear (Tucker, 16^3 -> 16^3, ranks 15^6 like config 5 at a reduced batch) through the fused route
+    (mmd16 -> tcgen05 GEMM at pitch 3376 -> mmd16) vs the fp64 oracle."""
+    import torch_b200 as tlt
+    from torch_b200 import tucker_ops as to
+    from oracle import reference_path as rp
+    torch.manual_seed(5)
+    ts = (16, 16, 16)
+    layer = tlt.FactorizedLinear(ts, ts, bias=True, factorization="tucker", rank=0.75, device=dev()).to(torch.bfloat16)
+    assert tuple(layer.weight.core.shape) == (15,) * 6
+    x = torch.randn(520, 4096, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    assert to.tucker3_eligible(x, layer.weight.core, list(layer.weight.factors), layer.bias, list(ts), list(ts))
+    y = layer(x)
+    gy = torch.randn_like(y)
+    params = dict(layer.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(6)]
+    yo = rp.factorized_linear(xo, "tucker", (leaves["weight.core"], fs), (ts, ts), bias=leaves["bias"], order="sane")
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    assert G.rel_err(y, yo) < 2e-2
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < 3e-2, n

@@ -61,6 +61,11 @@ class MmdDesc(C.Structure):
                 ("transpose", C.c_int32 * 3)]
 
 
+class Mmd16Desc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("in_dims", C.c_int32 * 3), ("out_dims", C.c_int32 * 3), ("transpose", C.c_int32 * 3),
+                ("ld_in", C.c_int64), ("ld_out", C.c_int64)]
+
+
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -77,6 +82,8 @@ SYMBOLS = {
     "tlt_blocktt3_core_grads_workspace_size": (C.c_size_t, [C.POINTER(BlockTT3Desc)]),
     "tlt_blocktt3_core_grads": (C.c_int, [C.POINTER(BlockTT3Desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "tlt_multi_mode_dot": (C.c_int, [C.POINTER(MmdDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_mmd16_fwd": (C.c_int, [C.POINTER(Mmd16Desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_mmd16_bwd": (C.c_int, [C.POINTER(Mmd16Desc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_pointwise_tc_supported": (C.c_int, [C.POINTER(PointwiseDesc)]),
     "tlt_pointwise_tc": (C.c_int, [C.POINTER(PointwiseDesc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_pointwise_wgrad_tc": (C.c_int, [C.POINTER(PointwiseDesc), _vp, _vp, _vp, _vp]),

@@ -4,6 +4,7 @@ import math
 from ..ops import contract
 from .. import tenalg
 from .. import blocktt_ops
+from .. import tucker_ops
 from .factorized_tensordot import tensor_dot_tucker, tensor_dot_cp
 
 _L = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
@@ -13,6 +14,14 @@ def linear_tucker(tensor, tucker_matrix, transpose=True, channels_first=True, bi
     """reference: functional/factorized_linear.py:7-21 (``channels_first`` is unused there as well)."""
     axis = 1 if transpose else 0
     n = len(tucker_matrix.tensorized_shape[axis])
+    if transpose:
+        in_shape, out_shape = list(tucker_matrix.tensorized_shape[1]), list(tucker_matrix.tensorized_shape[0])
+        x2 = tensor.reshape(-1, math.prod(in_shape))
+        factors = list(tucker_matrix.factors)
+        if tucker_ops.tucker3_eligible(x2, tucker_matrix.core, factors, bias, in_shape, out_shape):
+            # project (1 launch, on chip) -> core GEMM on tcgen05 -> expand + bias (1 launch); backward: one launch per
+            # mode-product chain gives the data gradient and all three factor gradients (tucker_ops.py)
+            return tucker_ops.tucker3_linear(x2, tucker_matrix.core, factors, bias, in_shape, out_shape)
     tensor = tensor.reshape(-1, *tucker_matrix.tensorized_shape[axis])
     modes_tensor = list(range(tensor.dim() - n, tensor.dim()))
     modes_tucker = list(range(n, tucker_matrix.order)) if transpose else list(range(n))
