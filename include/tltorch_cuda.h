@@ -228,6 +228,34 @@ int tlt_dwconv_dgrad(const tlt_conv_desc* desc, const void* dy, const void* w, v
 int tlt_dwconv_wgrad(const tlt_conv_desc* desc, const void* x, const void* dy, float* dw, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Channels-last ("rows") staging of bf16 activations for dense k x k convolutions on tlt_gemm_bf16_tc.
+ *   tlt_nchw_to_rows : rows[(b, s), c] = x[b, c, s], c in [channels, ld) zero-filled       rows (batch * spatial, ld)
+ *   tlt_rows_to_nchw : y[b, c, s] = rows[(b, s), c]
+ *   tlt_im2col_rows  : cols[(b, o...), (t..., c)] = z[(b, o*stride - pad + t*dil), c] (zero outside); desc->channels is the
+ *                      row length (a multiple of 8) of z (batch * prod(in_size), channels); cols is
+ *                      (batch * prod(out_size), prod(kernel) * channels) -- 16-byte chunks, coalesced on both sides
+ *   tlt_col2im_rows  : dz[(b, i...), c] = sum over (o, t) with o*stride - pad + t*dil == i of dcols[(b, o), (t, c)]   (gather)
+ * Replaces: the unfold / fold halves of F.conv{1,2,3}d with a dense kernel (tltorch/functional/convolution.py:161 Tucker
+ * core conv, :213-216 TT cores, :16-53 reconstructed weights) when the surrounding 1x1 stages run as row GEMMs.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_nchw_to_rows(const void* x, int64_t batch, int64_t channels, int64_t spatial, void* rows, int64_t ld, void* stream);
+int tlt_rows_to_nchw(const void* rows, int64_t batch, int64_t channels, int64_t spatial, int64_t ld, void* y, void* stream);
+int tlt_im2col_rows(const tlt_conv_desc* desc, const void* z, void* cols, void* stream);
+int tlt_col2im_rows(const tlt_conv_desc* desc, const void* dcols, void* dz, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * Skinny row transform for many rows and tiny extents (I, J <= 32): the core expansion of the factorized convolutions.
+ *   tlt_skinny_fwd : y[r, j] = sum_i a[r, i] k[j, i]                     a (rows, I), k (J, I), y (rows, J), dtype f32 / bf16
+ *   tlt_skinny_bwd : da[r, i] = sum_j g[r, j] k[j, i];  dk[j, i] += sum_r g[r, j] a[r, i]   (dk fp32, caller zeroes; da or dk
+ *                    may be NULL)
+ * Replaces: tenalg.multi_mode_dot(core, factors[2:]) of tucker_conv (tltorch/functional/convolution.py:160) with k the
+ * Kronecker product of the kernel-mode factors, and its autograd.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_skinny_fwd(int32_t dtype, int64_t rows, int32_t I, int32_t J, const void* a, const void* k, void* y, void* stream);
+int tlt_skinny_bwd(int32_t dtype, int64_t rows, int32_t I, int32_t J, const void* a, const void* g, const void* k, void* da,
+                   float* dk, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Small utilities used by the host side.
  * ------------------------------------------------------------------------------------------------------------ */
 /* dst[i] = (dst dtype) src[i], n elements */

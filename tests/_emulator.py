@@ -236,6 +236,56 @@ def emulate_pack_kmajor(src2, dst):
     LOG.append(("pack_kmajor", tuple(src2.shape), dst.stride(0)))
 
 
+def emulate_nchw_to_rows(x3, rows):
+    b, c, sp = x3.shape
+    rows.zero_()
+    rows[:, :c].copy_(x3.permute(0, 2, 1).reshape(b * sp, c))
+    LOG.append(("nchw_to_rows", tuple(x3.shape), rows.stride(0)))
+
+
+def emulate_rows_to_nchw(rows, y3):
+    b, c, sp = y3.shape
+    y3.copy_(rows[:, :c].reshape(b, sp, c).permute(0, 2, 1))
+    LOG.append(("rows_to_nchw", tuple(y3.shape), rows.stride(0)))
+
+
+def emulate_unfold_rows(z, cols, batch, in_size, out_size, kernel, stride, padding, dilation, fold):
+    nd, ld = len(in_size), z.shape[1]
+    taps = math.prod(kernel)
+    fn = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[nd]
+    # unfold as a conv with a one-hot kernel per tap: (taps, 1, *kernel) applied per channel
+    eye = torch.eye(taps, dtype=torch.float64).reshape(taps, 1, *kernel)
+
+    def unfold(zz):
+        img = zz.double().reshape(batch, *in_size, ld).movedim(-1, 1).reshape(batch * ld, 1, *in_size)
+        out = fn(img, eye, None, stride, padding, dilation)                       # (B ld, taps, *out)
+        out = out.reshape(batch, ld, taps, math.prod(out_size)).permute(0, 3, 2, 1)
+        return out.reshape(batch * math.prod(out_size), taps * ld)
+
+    if not fold:
+        cols.copy_(unfold(z).to(cols.dtype))
+    else:
+        with torch.enable_grad():
+            zz = torch.zeros(z.shape, dtype=torch.float64)
+            # fold = transpose of unfold: use the linear map explicitly
+            basis = torch.func.vjp(unfold, zz)[1](cols.double())[0]
+        z.copy_(basis.to(z.dtype))
+    LOG.append(("col2im_rows" if fold else "im2col_rows", tuple(in_size), tuple(kernel), tuple(stride), tuple(padding), tuple(dilation)))
+
+
+def emulate_skinny_fwd(a2, k2, y2):
+    y2.copy_((a2.double() @ k2.double().t()).to(y2.dtype))
+    LOG.append(("skinny_fwd", tuple(a2.shape), tuple(k2.shape)))
+
+
+def emulate_skinny_bwd(a2, g2, k2, da2, dk32):
+    if da2 is not None:
+        da2.copy_((g2.double() @ k2.double()).to(da2.dtype))
+    if dk32 is not None:
+        dk32 += (g2.double().t() @ a2.double()).to(dk32.dtype)
+    LOG.append(("skinny_bwd", tuple(g2.shape), tuple(k2.shape)))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
     """Swap the launch funnels for the CPU interpreters (tests only)."""
@@ -243,6 +293,11 @@ def emulated_kernels():
     from torch_b200 import pointwise_ops as po
     from torch_b200 import modedot_ops as mo
     from torch_b200 import tucker_ops as to
+    from torch_b200 import rows_ops as ro
+    saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
+    saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd
+    ro._execute_skinny_fwd, ro._execute_skinny_bwd = emulate_skinny_fwd, emulate_skinny_bwd
+    ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = emulate_nchw_to_rows, emulate_rows_to_nchw, emulate_unfold_rows
     saved_m = mo._execute_mmd
     mo._execute_mmd = emulate_mmd
     saved_t = to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor
@@ -262,4 +317,6 @@ def emulated_kernels():
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p
         mo._execute_mmd = saved_m
+        ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
+        ro._execute_skinny_fwd, ro._execute_skinny_bwd = saved_s
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

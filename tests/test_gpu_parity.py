@@ -587,3 +587,78 @@ def test_tucker3_fused_linear_vs_oracle():
     assert G.rel_err(y, yo) < 2e-2
     for n, a, b in zip(["x"] + list(params), grads, go):
         assert G.rel_err(a, b) < 3e-2, n
+
+
+# ------------------------------------------------------------------------------------------------- rows (channels-last) conv path
+@pytest.mark.parametrize("B,C,spatial,kernel,stride,padding,dilation", [
+    (3, 40, (7, 7), (3, 3), (1, 1), (1, 1), (1, 1)),
+    (2, 70, (14, 9), (3, 3), (2, 2), (1, 1), (1, 1)),
+    (2, 64, (9, 11), (3, 2), (1, 2), (2, 0), (2, 1)),
+    (4, 33, (19,), (5,), (2,), (2,), (1,)),
+    (2, 16, (5, 6, 7), (3, 3, 3), (1, 2, 1), (1, 1, 1), (1, 1, 1)),
+])
+def test_rows_layout_and_unfold_kernels_vs_torch(B, C, spatial, kernel, stride, padding, dilation):
+    """tlt_nchw_to_rows / rows_to_nchw / im2col_rows / col2im_rows against permute + F.unfold-style references (exact)."""
+    import torch.nn.functional as F
+    from torch_b200 import rows_ops as ro
+    from torch_b200 import ops
+    torch.manual_seed(C)
+    x = torch.randn(B, C, *spatial, device=dev(), dtype=torch.bfloat16)
+    rows = ro.nchw_to_rows(x)
+    ld = (C + 7) & ~7
+    S = math.prod(spatial)
+    assert rows.shape == (B * S, ld)
+    want = x.reshape(B, C, S).permute(0, 2, 1).reshape(B * S, C)
+    assert torch.equal(rows[:, :C], want) and bool((rows[:, C:] == 0).all())
+    assert torch.equal(ro.rows_to_nchw(rows, B, C, list(spatial)), x)
+    # unfold: reference = conv with one-hot taps on every channel, in fp64 (values are copies: exact)
+    nd = len(spatial)
+    fn = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[nd]
+    taps = math.prod(kernel)
+    out_size = ops.conv_out_size(list(spatial), list(kernel), list(stride), list(padding), list(dilation))
+    So = math.prod(out_size)
+    cols = ro.im2col_rows(rows, B, spatial, kernel, stride, padding, dilation)
+    assert cols.shape == (B * So, taps * ld)
+    eye = torch.eye(taps, dtype=torch.float64).reshape(taps, 1, *kernel)
+    img = rows.double().cpu().reshape(B, *spatial, ld).movedim(-1, 1).reshape(B * ld, 1, *spatial)
+    ref = fn(img, eye, None, stride, padding, dilation).reshape(B, ld, taps, So).permute(0, 3, 2, 1).reshape(B * So, taps * ld)
+    assert torch.equal(cols.double().cpu(), ref)
+    # fold = adjoint of unfold: compare with the autograd transpose of the fp64 reference unfold
+    c = torch.randn_like(cols)
+    back = ro._fold_op(c, B, ld, list(spatial), list(kernel), list(stride), list(padding), list(dilation))
+    img = img.requires_grad_(True)
+    ref = fn(img, eye, None, stride, padding, dilation).reshape(B, ld, taps, So).permute(0, 3, 2, 1).reshape(B * So, taps * ld)
+    (gimg,) = torch.autograd.grad(ref, img, c.double().cpu())
+    want_back = gimg.reshape(B, ld, S).permute(0, 2, 1).reshape(B * S, ld)
+    assert G.rel_err(back, want_back) < 5e-3
+
+
+@pytest.mark.parametrize("cin,cout,hw,stride,padding,dilation,rank", [
+    (64, 96, 7, 1, 1, 1, 0.5), (48, 64, 9, 2, 1, 1, 0.8), (96, 64, 8, 1, 2, 2, 0.6),
+])
+def test_tucker_conv_rows_path_vs_oracle(cin, cout, hw, stride, padding, dilation, rank):
+    """Tucker FactorizedConv (bf16) through the channels-last row-GEMM route vs the fp64 oracle."""
+    import torch_b200 as tlt
+    from torch_b200 import rows_ops as ro
+    from oracle import reference_path as rp
+    torch.manual_seed(cin)
+    conv = tlt.FactorizedConv(cin, cout, 3, order=2, stride=stride, padding=padding, dilation=dilation, bias=True,
+                              factorization="tucker", rank=rank, device=dev())
+    conv.reset_parameters(std=0.3)
+    conv.bias.data.normal_()
+    conv = conv.to(torch.bfloat16)
+    assert min(cin, cout, *conv.weight.core.shape[:2]) >= ro.MIN_CHANNELS
+    x = torch.randn(5, cin, hw, hw + 1, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    params = dict(conv.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(4)]
+    yo = rp.tucker_conv(xo, leaves["weight.core"], fs, bias=leaves["bias"], stride=[stride] * 2, padding=[padding] * 2,
+                        dilation=[dilation] * 2)
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    assert G.rel_err(y, yo) < 2e-2
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < 3e-2, n

@@ -93,6 +93,12 @@ SYMBOLS = {
     "tlt_dwconv_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "tlt_dwconv_dgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "tlt_dwconv_wgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "tlt_nchw_to_rows": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64, _vp]),
+    "tlt_rows_to_nchw": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp]),
+    "tlt_im2col_rows": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "tlt_col2im_rows": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "tlt_skinny_fwd": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
+    "tlt_skinny_bwd": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_cast": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, _vp]),
     "tlt_l2_flush": (C.c_int, [_vp, C.c_size_t, _vp]),
 }

@@ -8,7 +8,7 @@ import math
 
 import torch
 
-from .. import ops, tenalg, pointwise_ops
+from .. import ops, tenalg, pointwise_ops, rows_ops
 from ..ops import contract
 
 
@@ -123,8 +123,13 @@ def tucker_conv(x, tucker_tensor, bias=None, stride=1, padding=0, dilation=1):
     core, factors = tucker_tensor.core, list(tucker_tensor.factors)
     order = core.dim() - 2
     stride, padding, dilation = _tuple(stride, order), _tuple(padding, order), _tuple(dilation, order)
+    w = rows_ops.expand_core(core, factors[2:])                                    # (r0, r1, k...) in one launch
+    if w is None:
+        w = tenalg.multi_mode_dot(core, factors[2:], modes=list(range(2, core.dim())))  # (r0, r1, k...)
+    if rows_ops.rows_eligible(x, [core, bias] + factors, order) and min(x.shape[1], factors[0].shape[0], *w.shape[:2]) >= rows_ops.MIN_CHANNELS:
+        # channels-last rows: 1x1 -> unfold -> core GEMM over (tap, channel) -> 1x1 (+ bias), all on the tcgen05 GEMM
+        return rows_ops.tucker_conv_rows(x, w, factors[1], factors[0], bias, stride, padding, dilation)
     z = _pointwise(x, "co", factors[1])                                           # C_in -> r1
-    w = tenalg.multi_mode_dot(core, factors[2:], modes=list(range(2, core.dim())))  # (r0, r1, k...)
     kernel = list(w.shape[2:])
     z = _dense_conv(z, w.reshape(w.shape[0], w.shape[1], -1), "qct", kernel, None, stride, padding, dilation)
     return _pointwise(z, "oc", factors[0], bias)                                   # r0 -> C_out (+ bias)

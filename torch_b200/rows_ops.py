@@ -1,0 +1,282 @@
+"""Custom ops (with autograd) for dense k x k convolutions as row GEMMs -- BASELINE config 4's Tucker convolution.
+
+  tltorch::nchw_to_rows / rows_to_nchw   (B, C, *S) <-> (B * prod(S), round8(C)) channels-last rows (each other's backward)
+  tltorch::im2col_rows / col2im_rows     unfold / fold of rows in 16-byte channel chunks (each other's backward)
+
+``dense_conv_rows`` chains them with ``tucker_ops.padded_linear`` (tcgen05 GEMM on zero-padded pitches):
+  x -> rows -> [1x1: GEMM] -> unfold -> [k x k core: GEMM over (tap, channel)] -> [1x1: GEMM + bias] -> NCHW.
+Reference: tucker_conv (tltorch/functional/convolution.py:140-173); the same building blocks serve tt_conv (:176-228) and
+reconstructed kernels (:16-53).  CPU tensors raise NotImplementedError (no fallback); tests/_emulator.py swaps the funnels.
+"""
+import ctypes as C
+from typing import List
+
+import torch
+import torch.nn.functional as F
+
+from . import _cuda
+from . import ops
+from .tucker_ops import padded_linear, _r8, _prod
+
+__all__ = ["nchw_to_rows", "rows_to_nchw", "im2col_rows", "tucker_conv_rows", "rows_eligible"]
+
+
+def _conv_desc(batch, ld, in_size, out_size, kernel, stride, padding, dilation):
+    d = _cuda.ConvDesc()
+    d.dtype = _cuda.BF16
+    d.ndim = len(in_size)
+    d.batch, d.channels = batch, ld
+    for i in range(len(in_size)):
+        d.in_size[i], d.out_size[i] = in_size[i], out_size[i]
+        d.kernel[i], d.stride[i], d.padding[i], d.dilation[i] = kernel[i], stride[i], padding[i], dilation[i]
+    return d
+
+
+# =====================================================================================================================
+# launch funnels
+# =====================================================================================================================
+def _execute_nchw_to_rows(x3, rows):
+    _cuda.require_cuda(x3, rows)
+    b, c, s = x3.shape
+    _cuda.check(_cuda.lib().tlt_nchw_to_rows(_cuda.ptr(x3), b, c, s, _cuda.ptr(rows), rows.stride(0), _cuda.stream_ptr(x3)),
+                "tlt_nchw_to_rows")
+
+
+def _execute_rows_to_nchw(rows, y3):
+    _cuda.require_cuda(rows, y3)
+    b, c, s = y3.shape
+    _cuda.check(_cuda.lib().tlt_rows_to_nchw(_cuda.ptr(rows), b, c, s, rows.stride(0), _cuda.ptr(y3), _cuda.stream_ptr(y3)),
+                "tlt_rows_to_nchw")
+
+
+def _execute_unfold_rows(z, cols, batch, in_size, out_size, kernel, stride, padding, dilation, fold):
+    """fold=False: cols <- unfold(z);  fold=True: z <- fold(cols)."""
+    _cuda.require_cuda(z, cols)
+    d = _conv_desc(batch, z.shape[1], in_size, out_size, kernel, stride, padding, dilation)
+    lib = _cuda.lib()
+    if fold:
+        _cuda.check(lib.tlt_col2im_rows(C.byref(d), _cuda.ptr(cols), _cuda.ptr(z), _cuda.stream_ptr(z)), "tlt_col2im_rows")
+    else:
+        _cuda.check(lib.tlt_im2col_rows(C.byref(d), _cuda.ptr(z), _cuda.ptr(cols), _cuda.stream_ptr(z)), "tlt_im2col_rows")
+
+
+# =====================================================================================================================
+# layout ops
+# =====================================================================================================================
+@torch.library.custom_op("tltorch::nchw_to_rows", mutates_args=())
+def _to_rows_op(x: torch.Tensor) -> torch.Tensor:
+    b, c = x.shape[0], x.shape[1]
+    x3 = x.contiguous().reshape(b, c, -1)
+    rows = torch.empty((b * x3.shape[2], _r8(c)), dtype=x.dtype, device=x.device)
+    if rows.numel():
+        _execute_nchw_to_rows(x3, rows)
+    return rows
+
+
+@_to_rows_op.register_fake
+def _(x):
+    return x.new_empty((x.shape[0] * _prod(x.shape[2:]), _r8(x.shape[1])))
+
+
+@torch.library.custom_op("tltorch::rows_to_nchw", mutates_args=())
+def _to_nchw_op(rows: torch.Tensor, batch: int, channels: int, spatial: List[int]) -> torch.Tensor:
+    y = torch.empty((batch, channels, *spatial), dtype=rows.dtype, device=rows.device)
+    if y.numel():
+        _execute_rows_to_nchw(rows.contiguous(), y.reshape(batch, channels, -1))
+    return y
+
+
+@_to_nchw_op.register_fake
+def _(rows, batch, channels, spatial):
+    return rows.new_empty((batch, channels, *spatial))
+
+
+def _to_rows_setup(ctx, inputs, output):
+    ctx.shape = tuple(inputs[0].shape)
+
+
+def _to_rows_backward(ctx, g):
+    return _to_nchw_op(g, ctx.shape[0], ctx.shape[1], list(ctx.shape[2:]))
+
+
+def _to_nchw_setup(ctx, inputs, output):
+    pass
+
+
+def _to_nchw_backward(ctx, gy):
+    return _to_rows_op(gy), None, None, None
+
+
+_to_rows_op.register_autograd(_to_rows_backward, setup_context=_to_rows_setup)
+_to_nchw_op.register_autograd(_to_nchw_backward, setup_context=_to_nchw_setup)
+
+
+def nchw_to_rows(x):
+    """(B, C, *S) bf16 -> (B * prod(S), round8(C)); pad channels are zero."""
+    return _to_rows_op(x)
+
+
+def rows_to_nchw(rows, batch, channels, spatial):
+    return _to_nchw_op(rows, batch, channels, list(spatial))
+
+
+@torch.library.custom_op("tltorch::im2col_rows", mutates_args=())
+def _unfold_op(z: torch.Tensor, batch: int, in_size: List[int], kernel: List[int], stride: List[int], padding: List[int],
+               dilation: List[int]) -> torch.Tensor:
+    out_size = ops.conv_out_size(in_size, kernel, stride, padding, dilation)
+    cols = torch.empty((batch * _prod(out_size), _prod(kernel) * z.shape[1]), dtype=z.dtype, device=z.device)
+    if cols.numel():
+        _execute_unfold_rows(z.contiguous(), cols, batch, in_size, out_size, kernel, stride, padding, dilation, False)
+    return cols
+
+
+@_unfold_op.register_fake
+def _(z, batch, in_size, kernel, stride, padding, dilation):
+    out_size = ops.conv_out_size(in_size, kernel, stride, padding, dilation)
+    return z.new_empty((batch * _prod(out_size), _prod(kernel) * z.shape[1]))
+
+
+@torch.library.custom_op("tltorch::col2im_rows", mutates_args=())
+def _fold_op(cols: torch.Tensor, batch: int, channels: int, in_size: List[int], kernel: List[int], stride: List[int],
+             padding: List[int], dilation: List[int]) -> torch.Tensor:
+    out_size = ops.conv_out_size(in_size, kernel, stride, padding, dilation)
+    z = torch.empty((batch * _prod(in_size), channels), dtype=cols.dtype, device=cols.device)
+    if z.numel():
+        _execute_unfold_rows(z, cols.contiguous(), batch, in_size, out_size, kernel, stride, padding, dilation, True)
+    return z
+
+
+@_fold_op.register_fake
+def _(cols, batch, channels, in_size, kernel, stride, padding, dilation):
+    return cols.new_empty((batch * _prod(in_size), channels))
+
+
+def _unfold_setup(ctx, inputs, output):
+    z, ctx.batch, ctx.in_size, ctx.kernel, ctx.stride, ctx.padding, ctx.dilation = inputs
+    ctx.channels = z.shape[1]
+
+
+def _unfold_backward(ctx, gcols):
+    return (_fold_op(gcols, ctx.batch, ctx.channels, ctx.in_size, ctx.kernel, ctx.stride, ctx.padding, ctx.dilation),
+            None, None, None, None, None, None)
+
+
+def _fold_setup(ctx, inputs, output):
+    _, ctx.batch, ctx.channels, ctx.in_size, ctx.kernel, ctx.stride, ctx.padding, ctx.dilation = inputs
+
+
+def _fold_backward(ctx, gz):
+    return (_unfold_op(gz, ctx.batch, ctx.in_size, ctx.kernel, ctx.stride, ctx.padding, ctx.dilation),
+            None, None, None, None, None, None, None)
+
+
+_unfold_op.register_autograd(_unfold_backward, setup_context=_unfold_setup)
+_fold_op.register_autograd(_fold_backward, setup_context=_fold_setup)
+
+
+def im2col_rows(z, batch, in_size, kernel, stride, padding, dilation):
+    """z (B * prod(in_size), Cp) -> cols (B * prod(out_size), prod(kernel) * Cp), taps outer / channels inner."""
+    return _unfold_op(z, batch, list(in_size), list(kernel), list(stride), list(padding), list(dilation))
+
+
+# =====================================================================================================================
+# Tucker convolution on rows
+# =====================================================================================================================
+MIN_CHANNELS = 32
+
+
+def rows_eligible(x, tensors, order):
+    if x.dtype != torch.bfloat16 or any(t is not None and t.dtype != torch.bfloat16 for t in tensors):
+        return False
+    return 1 <= order <= 3 and 1 <= x.shape[0] <= 65535 and x.numel() > 0
+
+
+def tucker_conv_rows(x, w, f_in, f_out, bias, stride, padding, dilation):
+    """x (B, C_in, *S) bf16; w (r0, r1, *k) the core already expanded over its kernel modes; f_in (C_in, r1); f_out (C_out, r0)."""
+    b, spatial = x.shape[0], list(x.shape[2:])
+    r0, r1 = w.shape[0], w.shape[1]
+    kernel = list(w.shape[2:])
+    taps = _prod(kernel)
+    out_size = ops.conv_out_size(spatial, kernel, list(stride), list(padding), list(dilation))
+    xt = nchw_to_rows(x)                                                       # (B S, round8(C_in))
+    z = padded_linear(xt, f_in.t(), None, True)                                # (B S, round8(r1)), pad columns zero
+    cols = im2col_rows(z, b, spatial, kernel, stride, padding, dilation)       # (B S', taps * round8(r1))
+    wc = F.pad(w.reshape(r0, r1, taps).permute(0, 2, 1), (0, _r8(r1) - r1))    # (r0, taps, round8(r1)): K index = (tap, channel)
+    h = padded_linear(cols, wc.reshape(r0, taps * _r8(r1)), None, True)        # (B S', round8(r0))
+    yt = padded_linear(h, f_out, bias, True)                                   # (B S', round8(C_out))
+    return rows_to_nchw(yt, b, f_out.shape[0], out_size)
+
+
+# =====================================================================================================================
+# tltorch::skinny_linear -- core expansion  w[r, :] = K a[r, :]  for tiny K (prod(kernel) x prod(kernel ranks))
+# =====================================================================================================================
+def _execute_skinny_fwd(a2, k2, y2):
+    _cuda.require_cuda(a2, k2, y2)
+    _cuda.check(_cuda.lib().tlt_skinny_fwd(_cuda.dtype_code(a2.dtype), a2.shape[0], a2.shape[1], k2.shape[0], _cuda.ptr(a2),
+                                           _cuda.ptr(k2), _cuda.ptr(y2), _cuda.stream_ptr(a2)), "tlt_skinny_fwd")
+
+
+def _execute_skinny_bwd(a2, g2, k2, da2, dk32):
+    _cuda.require_cuda(a2, g2, k2, da2, dk32)
+    _cuda.check(_cuda.lib().tlt_skinny_bwd(_cuda.dtype_code(g2.dtype), g2.shape[0], k2.shape[1], k2.shape[0], _cuda.ptr(a2),
+                                           _cuda.ptr(g2), _cuda.ptr(k2), _cuda.ptr(da2), _cuda.ptr(dk32), _cuda.stream_ptr(g2)),
+                "tlt_skinny_bwd")
+
+
+@torch.library.custom_op("tltorch::skinny_linear", mutates_args=())
+def _skinny_op(a2: torch.Tensor, k2: torch.Tensor) -> torch.Tensor:
+    y2 = torch.empty((a2.shape[0], k2.shape[0]), dtype=a2.dtype, device=a2.device)
+    if y2.numel():
+        _execute_skinny_fwd(a2.contiguous(), k2.contiguous(), y2)
+    return y2
+
+
+@_skinny_op.register_fake
+def _(a2, k2):
+    return a2.new_empty((a2.shape[0], k2.shape[0]))
+
+
+@torch.library.custom_op("tltorch::skinny_linear_bwd", mutates_args=())
+def _skinny_bwd_op(a2: torch.Tensor, g2: torch.Tensor, k2: torch.Tensor, need_da: bool, need_dk: bool) -> List[torch.Tensor]:
+    da = torch.empty_like(a2) if need_da else a2.new_empty(0)
+    dk = torch.zeros(k2.shape, dtype=torch.float32, device=a2.device) if need_dk else a2.new_empty(0, dtype=torch.float32)
+    if a2.shape[0] and (need_da or need_dk):
+        _execute_skinny_bwd(a2.contiguous(), g2.contiguous(), k2.contiguous(), da if need_da else None, dk if need_dk else None)
+    return [da, dk]
+
+
+@_skinny_bwd_op.register_fake
+def _(a2, g2, k2, need_da, need_dk):
+    return [torch.empty_like(a2) if need_da else a2.new_empty(0),
+            a2.new_empty(k2.shape, dtype=torch.float32) if need_dk else a2.new_empty(0, dtype=torch.float32)]
+
+
+def _skinny_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _skinny_backward(ctx, g):
+    a2, k2 = ctx.saved_tensors
+    need_da, need_dk = ctx.needs_input_grad
+    da, dk = _skinny_bwd_op(a2, g, k2, need_da, need_dk)
+    return (da if need_da else None), (dk.to(k2.dtype) if need_dk else None)
+
+
+_skinny_op.register_autograd(_skinny_backward, setup_context=_skinny_setup)
+
+SKINNY_MAX = 32
+
+
+def expand_core(core, kernel_factors):
+    """core (r0, r1, q_1..q_d) x_2 F_1 ... x_{d+1} F_d with F_j (k_j, q_j)  ->  (r0, r1, k_1..k_d) in ONE launch:
+    rows (r0 r1) times the Kronecker product of the factors (reference: tenalg.multi_mode_dot(core, factors[2:]),
+    tltorch/functional/convolution.py:160).  None when the extents exceed the skinny kernel."""
+    q = [f.shape[1] for f in kernel_factors]
+    k = [f.shape[0] for f in kernel_factors]
+    if _prod(q) > SKINNY_MAX or _prod(k) > SKINNY_MAX or core.dtype not in (torch.float32, torch.bfloat16):
+        return None
+    kron = kernel_factors[0]
+    for f in kernel_factors[1:]:                                             # (K, Q) (x) (k, q) -> (K k, Q q), tiny
+        kron = ops.contract("ac,bd->abcd", kron, f).reshape(kron.shape[0] * f.shape[0], kron.shape[1] * f.shape[1])
+    r0, r1 = core.shape[0], core.shape[1]
+    return _skinny_op(core.reshape(r0 * r1, _prod(q)), kron).reshape(r0, r1, *k)

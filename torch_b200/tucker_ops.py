@@ -163,35 +163,47 @@ def mmd16(x2, dims_in, dims_out, mats, flags, addend=None):
 # tltorch::padded_linear
 # =====================================================================================================================
 @torch.library.custom_op("tltorch::padded_linear", mutates_args=())
-def _plinear_op(xp: torch.Tensor, w2: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """xp (B, round8(K)) bf16, w2 (N, K) bf16 (any strides) -> yp (B, round8(N)), wp (N, round8(K)) the re-pitched weight."""
+def _plinear_op(xp: torch.Tensor, w2: torch.Tensor, bias: Optional[torch.Tensor], full_pad: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """xp (B, round8(K)) bf16, w2 (N, K) bf16 (any strides) -> yp (B, round8(N)), wp the re-pitched weight.
+
+    full_pad=False: wp is (N, round8(K)); the GEMM runs with the true extents (TMA zero-fills / clips the ragged edge) and
+    the pad columns of yp are left unwritten.  full_pad=True: wp is (round8(N), round8(K)) with zero pad rows / columns
+    and the GEMM runs on the padded extents, so the pad columns of yp are exact zeros (xp's pad columns must be finite)."""
     N, K = w2.shape
     B = xp.shape[0]
-    wp = torch.empty((N, _r8(K)), dtype=torch.bfloat16, device=xp.device)
-    _execute_pack_kmajor(w2, wp)
-    yp = torch.empty((B, _r8(N)), dtype=torch.bfloat16, device=xp.device)
+    Np, Kp = _r8(N), _r8(K)
+    wp = torch.empty((Np if full_pad else N, Kp), dtype=torch.bfloat16, device=xp.device)
+    _execute_pack_kmajor(w2, wp[:N])
+    if full_pad and Np != N:
+        wp[N:].zero_()
+    yp = torch.empty((B, Np), dtype=torch.bfloat16, device=xp.device)
+    if bias is not None and full_pad and Np != N:
+        bias = torch.cat([bias, bias.new_zeros(Np - N)])
     if B:
-        _bo._execute_gemm(xp, wp, None, yp, M=B, N=N, K=K, lda=xp.stride(0), ldb=wp.stride(0), a_major=0, b_major=0)
+        n, k = (Np, Kp) if full_pad else (N, K)
+        _bo._execute_gemm(xp, wp, bias, yp, M=B, N=n, K=k, lda=xp.stride(0), ldb=wp.stride(0), a_major=0, b_major=0)
     return yp, wp
 
 
 @_plinear_op.register_fake
-def _(xp, w2):
+def _(xp, w2, bias, full_pad):
     N, K = w2.shape
-    return xp.new_empty((xp.shape[0], _r8(N))), xp.new_empty((N, _r8(K)))
+    return xp.new_empty((xp.shape[0], _r8(N))), xp.new_empty((_r8(N) if full_pad else N, _r8(K)))
 
 
 @torch.library.custom_op("tltorch::padded_linear_bwd", mutates_args=())
-def _plinear_bwd_op(gyp: torch.Tensor, xp: torch.Tensor, wp: torch.Tensor, K: int, need_dx: bool,
+def _plinear_bwd_op(gyp: torch.Tensor, xp: torch.Tensor, wp: torch.Tensor, N: int, K: int, full_pad: bool, need_dx: bool,
                     need_dw: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-    N = wp.shape[0]
     B = xp.shape[0]
+    n, k = (wp.shape[0], wp.shape[1]) if full_pad else (N, K)
     dxp = torch.empty_like(xp) if need_dx else xp.new_empty(0)
     if need_dx and B:
         # dx[b, i] = sum_o gy[b, o] W[o, i]:  B operand (n = i, k = o) at wp[o * ld + i] -> MN-major
-        _bo._execute_gemm(gyp, wp, None, dxp, M=B, N=K, K=N, lda=gyp.stride(0), ldb=wp.stride(0), a_major=0, b_major=1)
+        _bo._execute_gemm(gyp, wp, None, dxp, M=B, N=k, K=n, lda=gyp.stride(0), ldb=wp.stride(0), a_major=0, b_major=1)
     if need_dw:
-        dwp = torch.empty((N, _r8(K)), dtype=torch.bfloat16, device=xp.device)
+        # few output tiles (skinny weights): fp32 output so that the GEMM may split K across all SM pairs (TMA reduce-add)
+        few_tiles = ((N + 255) // 256) * ((K + 255) // 256) < 74
+        dwp = torch.empty((N, _r8(K)), dtype=torch.float32 if few_tiles else torch.bfloat16, device=xp.device)
         if B:
             # dW[o, i] = sum_b gy[b, o] x[b, i]: both operands MN-major
             _bo._execute_gemm(gyp, xp, None, dwp, M=N, N=K, K=B, lda=gyp.stride(0), ldb=xp.stride(0), a_major=1, b_major=1)
@@ -203,36 +215,42 @@ def _plinear_bwd_op(gyp: torch.Tensor, xp: torch.Tensor, wp: torch.Tensor, K: in
 
 
 @_plinear_bwd_op.register_fake
-def _(gyp, xp, wp, K, need_dx, need_dw):
+def _(gyp, xp, wp, N, K, full_pad, need_dx, need_dw):
     return (torch.empty_like(xp) if need_dx else xp.new_empty(0),
-            xp.new_empty((wp.shape[0], _r8(K))) if need_dw else xp.new_empty(0))
+            xp.new_empty((N, _r8(K))) if need_dw else xp.new_empty(0))
 
 
 def _plinear_setup(ctx, inputs, output):
-    xp, w2 = inputs
+    xp, w2, bias, full_pad = inputs
     _, wp = output
     ctx.save_for_backward(xp, wp)
-    ctx.K = w2.shape[1]
+    ctx.N, ctx.K = w2.shape
     ctx.w_dtype = w2.dtype
+    ctx.full_pad = full_pad
+    ctx.has_bias = bias is not None
     ctx.set_materialize_grads(False)
 
 
 def _plinear_backward(ctx, gyp, gwp_unused):
     if gyp is None:
-        return None, None
+        return None, None, None, None
     xp, wp = ctx.saved_tensors
-    need_dx, need_dw = ctx.needs_input_grad
-    dxp, dwp = _plinear_bwd_op(gyp.contiguous(), xp, wp, ctx.K, need_dx, need_dw)
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    gyp = gyp.contiguous()
+    dxp, dwp = _plinear_bwd_op(gyp, xp, wp, ctx.N, ctx.K, ctx.full_pad, need_dx, need_dw)
     dw = dwp[:, :ctx.K].to(ctx.w_dtype) if need_dw else None
-    return (dxp if need_dx else None), dw
+    db = None
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        db = ops.reduce_to(gyp, "bo", "o")[:ctx.N]
+    return (dxp if need_dx else None), dw, db, None
 
 
 _plinear_op.register_autograd(_plinear_backward, setup_context=_plinear_setup)
 
 
-def padded_linear(xp, w2):
-    """yp[:, :N] = xp[:, :K] . w2^T with every operand on the tcgen05 GEMM; see the module docstring for the pitches."""
-    yp, _ = _plinear_op(xp, w2)
+def padded_linear(xp, w2, bias=None, full_pad=False):
+    """yp[:, :N] = xp[:, :K] . w2^T (+ bias) with every operand on the tcgen05 GEMM; see ``_plinear_op`` for the pitches."""
+    yp, _ = _plinear_op(xp, w2, bias, full_pad)
     return yp
 
 
