@@ -662,3 +662,58 @@ def test_tucker_conv_rows_path_vs_oracle(cin, cout, hw, stride, padding, dilatio
     assert G.rel_err(y, yo) < 2e-2
     for n, a, b in zip(["x"] + list(params), grads, go):
         assert G.rel_err(a, b) < 3e-2, n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,I,J", [(150544, 4, 9), (1000, 49, 16), (77, 16, 49), (129, 64, 64), (5, 1, 3), (4096, 27, 8)])
+def test_skinny_kernels_vs_fp64(rows, I, J, dtype):
+    """tlt_skinny_fwd / tlt_skinny_bwd (core expansion, spatial-first TRL projection) vs fp64 matmuls."""
+    from torch_b200 import rows_ops as ro
+    torch.manual_seed(rows + I)
+    a = torch.randn(rows, I, device=dev(), dtype=dtype, requires_grad=True)
+    k = (torch.randn(J, I, device=dev()) / math.sqrt(I)).to(dtype).requires_grad_(True)
+    y = ro.skinny_linear(a, k)
+    gy = torch.randn_like(y)
+    ga, gk = torch.autograd.grad(y, [a, k], gy)
+    ad, kd, gd = a.detach().double().cpu(), k.detach().double().cpu(), gy.double().cpu()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert G.rel_err(y, ad @ kd.t()) < tol
+    assert G.rel_err(ga, gd @ kd) < tol
+    assert G.rel_err(gk, gd.t() @ ad) < tol
+
+
+def test_trl_rows_projection_vs_oracle():
+    """Tucker TRL on (B, 2048, 7, 7) maps (config 4 shape, reduced batch / classes): map -> channels-last rows, channel
+    mode as one tcgen05 GEMM, spatial modes on the 32x smaller result, then the regression GEMM -- against the fp64 einsum
+    of the reconstructed weight."""
+    import torch_b200 as tlt
+    torch.manual_seed(3)
+    trl = tlt.TRL((2048, 7, 7), (200,), bias=True, factorization="tucker", rank=(64, 4, 4, 10), device=dev())
+    with torch.no_grad():
+        for p in trl.parameters():
+            p.mul_(0.3)
+    trl = trl.to(torch.bfloat16)
+    x = torch.randn(48, 2048, 7, 7, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    y = trl(x)
+    gy = torch.randn_like(y)
+    params = dict(trl.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(4)]
+    W = torch.einsum("abcd,ia,jb,kc,ld->ijkl", leaves["weight.core"], *fs)
+    yo = torch.einsum("bijk,ijkl->bl", xo, W) + leaves["bias"]
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    assert G.rel_err(y, yo) < 2e-2
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < 3e-2, n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_contract_small_output_long_reduction(dtype):
+    """tlt_contract's tiny-output path (M, N <= 8, K >= 8192): factor gradients of small spatial matrices."""
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert _contract_vs_einsum("bpqr,bpir->qi", (96, 4, 4, 64), (96, 4, 7, 64), dtype) < tol
+    assert _contract_vs_einsum("bqpr,bipr->qi", (64, 7, 5, 40), (64, 3, 5, 40), dtype) < tol
+    assert _contract_vs_einsum("km,kn->mn", (20000, 8), (20000, 8), dtype) < tol
+    assert _contract_vs_einsum("mk,kn->mn", (2, 9000), (9000, 3), dtype, alpha=0.5) < tol

@@ -379,6 +379,62 @@ static int launch_matvec(const MatvecParams& q, bool j_fast, int splits, const v
   return check_launch("matvec_kernel");
 }
 
+// Tiny output, long reduction (M, N <= 8, no batch): factor gradients of the small spatial / kernel-mode matrices, e.g.
+// dM[q, i] = sum_{b,p,r} g[b,p,q,r] z[b,p,i,r] -- 4 x 7 outputs over 229 376 terms in tucker_trl's backward.  On the tiled
+// kernel a 64 x 64 tile holds 28 useful outputs and the split-K grid is 128 blocks (120-130 us).  Here a thread walks the
+// reduction index (consecutive threads on consecutive k), keeps the whole M x N outer-product sum in registers, and the
+// block leaves one atomicAdd per output.
+constexpr int kSmallOut = 8;
+static bool use_small_out(const ContractParams& p) {
+  return p.Bt == 1 && p.M > 1 && p.N > 1 && p.M <= kSmallOut && p.N <= kSmallOut && p.K >= 8192;
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) small_out_kernel(const ContractParams p, const TA* __restrict__ A, const TB* __restrict__ B,
+                                                        float* __restrict__ ws) {
+  __shared__ float red[kSmallOut * kSmallOut];
+  long long moff[kSmallOut], noff[kSmallOut];
+#pragma unroll
+  for (int m = 0; m < kSmallOut; ++m) moff[m] = m < p.M ? decomp(m, p.size_m, p.a_m, p.nm) : 0;
+#pragma unroll
+  for (int n = 0; n < kSmallOut; ++n) noff[n] = n < p.N ? decomp(n, p.size_n, p.b_n, p.nn) : 0;
+  float acc[kSmallOut][kSmallOut];
+#pragma unroll
+  for (int m = 0; m < kSmallOut; ++m)
+#pragma unroll
+    for (int n = 0; n < kSmallOut; ++n) acc[m][n] = 0.f;
+  if (threadIdx.x < kSmallOut * kSmallOut) red[threadIdx.x] = 0.f;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < p.K; k += (long long)gridDim.x * blockDim.x) {
+    const long long ao = decomp((int)k, p.size_k, p.a_k, p.nk), bo = decomp((int)k, p.size_k, p.b_k, p.nk);
+    float av[kSmallOut], bv[kSmallOut];
+#pragma unroll
+    for (int m = 0; m < kSmallOut; ++m) av[m] = m < p.M ? to_f32<TA>(A[ao + moff[m]]) : 0.f;
+#pragma unroll
+    for (int n = 0; n < kSmallOut; ++n) bv[n] = n < p.N ? to_f32<TB>(B[bo + noff[n]]) : 0.f;
+#pragma unroll
+    for (int m = 0; m < kSmallOut; ++m)
+#pragma unroll
+      for (int n = 0; n < kSmallOut; ++n) acc[m][n] = fmaf(av[m], bv[n], acc[m][n]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < kSmallOut; ++m)
+#pragma unroll
+    for (int n = 0; n < kSmallOut; ++n) {
+      if (m < p.M && n < p.N) {
+        float v = acc[m][n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(red + m * kSmallOut + n, v);
+      }
+    }
+  __syncthreads();
+  if (threadIdx.x < kSmallOut * kSmallOut) {
+    const int m = threadIdx.x / kSmallOut, n = threadIdx.x % kSmallOut;
+    if (m < p.M && n < p.N) atomicAdd(ws + m * p.N + n, p.alpha * red[threadIdx.x]);
+  }
+}
+
 static bool use_matvec(const ContractParams& p) {
   if (p.Bt > 65535) return false;
   long long J = p.M == 1 ? p.N : (p.N == 1 ? p.M : 0);
@@ -482,7 +538,7 @@ extern "C" size_t tlt_contract_workspace_size(const tlt_contract_desc* d) {
   ContractParams p;
   if (fill_params(d, &p) != TLT_OK) return 0;
   if (p.M == 0 || p.N == 0 || p.Bt == 0) return 0;
-  if (use_matvec(p)) return (size_t)p.Bt * p.M * p.N * sizeof(float);
+  if (use_matvec(p) || use_small_out(p)) return (size_t)p.Bt * p.M * p.N * sizeof(float);
   int bm, bn;
   tile_shape(p.M, p.N, &bm, &bn);
   int split = choose_split(d, p.M, p.N, p.K, p.Bt, bm, bn);
@@ -585,6 +641,30 @@ extern "C" int tlt_contract(const tlt_contract_desc* d, const void* A, const voi
     int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
     if (d->dtype_c == TLT_F32) contract_finalize_kernel<float><<<blocks, 256, 0, st>>>(f, (const float*)workspace, D, (float*)C);
     else contract_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(f, (const float*)workspace, D, (__nv_bfloat16*)C);
+    return check_launch("contract_finalize_kernel");
+  }
+
+  if (use_small_out(p)) {
+    const size_t need = (size_t)p.M * p.N * sizeof(float);
+    if (!workspace || workspace_bytes < need) {
+      set_error("tlt_contract: small-output path needs %zu bytes of workspace, got %zu", need, workspace_bytes);
+      return TLT_ERR_WORKSPACE;
+    }
+    TLT_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
+    long long blocks = (p.K + 255) / 256 / 4;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148LL * 4) blocks = 148LL * 4;
+    typedef __nv_bfloat16 bf;
+    if (d->dtype_a == TLT_F32 && d->dtype_b == TLT_F32) small_out_kernel<float, float><<<(unsigned)blocks, 256, 0, st>>>(p, (const float*)A, (const float*)B, (float*)workspace);
+    else if (d->dtype_a == TLT_BF16 && d->dtype_b == TLT_BF16) small_out_kernel<bf, bf><<<(unsigned)blocks, 256, 0, st>>>(p, (const bf*)A, (const bf*)B, (float*)workspace);
+    else if (d->dtype_a == TLT_F32) small_out_kernel<float, bf><<<(unsigned)blocks, 256, 0, st>>>(p, (const float*)A, (const bf*)B, (float*)workspace);
+    else small_out_kernel<bf, float><<<(unsigned)blocks, 256, 0, st>>>(p, (const bf*)A, (const float*)B, (float*)workspace);
+    rc = check_launch("small_out_kernel");
+    if (rc != TLT_OK) return rc;
+    ContractParams f = p;
+    f.alpha = 1.f;
+    if (d->dtype_c == TLT_F32) contract_finalize_kernel<float><<<1, 64, 0, st>>>(f, (const float*)workspace, D, (float*)C);
+    else contract_finalize_kernel<__nv_bfloat16><<<1, 64, 0, st>>>(f, (const float*)workspace, D, (__nv_bfloat16*)C);
     return check_launch("contract_finalize_kernel");
   }
 

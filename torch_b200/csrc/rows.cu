@@ -18,7 +18,7 @@
 
 namespace tlt {
 
-// block (32, 8): tile of 64 channels x 32 positions of one image
+// General tiles: block (32, 8) moves 64 channels x 32 positions of one image through shared memory.
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const __nv_bfloat16* __restrict__ x, long long C, long long S, long long ld,
                                                            __nv_bfloat16* __restrict__ rows) {
   __shared__ unsigned short tile[64][34];
@@ -68,6 +68,55 @@ __global__ void __launch_bounds__(256) rows_to_nchw_kernel(const __nv_bfloat16* 
     const int c = ty + 8 * i;
     if (c0 + c < C && s0 + tx < S) ys[(b * C + c0 + c) * S + s0 + tx] = tile[c][tx];
   }
+}
+
+// Small feature maps (S <= 256, C % 64 == 0, 64 * S * 2 bytes a multiple of 16): the 64 channels x S positions of one
+// image are ONE contiguous span of NCHW memory.  It moves as 16-byte chunks on the NCHW side and as 128-byte row segments
+// (a warp = 64 channels of one position, 4 bytes per lane) on the rows side; shared memory holds the span linearly.
+constexpr int kSpanMaxS = 256;
+__global__ void __launch_bounds__(256) nchw_to_rows_span_kernel(const __nv_bfloat16* __restrict__ x, int C, int S, long long ld,
+                                                                __nv_bfloat16* __restrict__ rows, long long n_units) {
+  extern __shared__ __align__(16) unsigned char span_smem[];
+  unsigned short* sp = reinterpret_cast<unsigned short*>(span_smem);           // [64][S]
+  const int cblocks = C >> 6, n16 = (64 * S * 2) >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const long long b = unit / cblocks;
+    const int c0 = (int)(unit - b * cblocks) << 6;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (b * C + c0) * (long long)S);
+    __syncthreads();
+    for (int v = threadIdx.x; v < n16; v += 256) reinterpret_cast<uint4*>(sp)[v] = src[v];
+    __syncthreads();
+    for (int s = warp; s < S; s += 8) {
+      const uint32_t v = (uint32_t)sp[(2 * lane) * S + s] | ((uint32_t)sp[(2 * lane + 1) * S + s] << 16);
+      *reinterpret_cast<uint32_t*>(rows + (b * S + s) * ld + c0 + 2 * lane) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) rows_to_nchw_span_kernel(const __nv_bfloat16* __restrict__ rows, int C, int S, long long ld,
+                                                                __nv_bfloat16* __restrict__ y, long long n_units) {
+  extern __shared__ __align__(16) unsigned char span_smem[];
+  unsigned short* sp = reinterpret_cast<unsigned short*>(span_smem);           // [64][S]
+  const int cblocks = C >> 6, n16 = (64 * S * 2) >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const long long b = unit / cblocks;
+    const int c0 = (int)(unit - b * cblocks) << 6;
+    __syncthreads();
+    for (int s = warp; s < S; s += 8) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(rows + (b * S + s) * ld + c0 + 2 * lane);
+      sp[(2 * lane) * S + s] = (unsigned short)(v & 0xffffu);
+      sp[(2 * lane + 1) * S + s] = (unsigned short)(v >> 16);
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(y + (b * C + c0) * (long long)S);
+    for (int v = threadIdx.x; v < n16; v += 256) dst[v] = reinterpret_cast<const uint4*>(sp)[v];
+  }
+}
+
+static bool span_ok(long long C, long long S, long long ld, const void* nchw) {
+  return S <= kSpanMaxS && C % 64 == 0 && ld == C && (64 * S * 2) % 16 == 0 && ((uintptr_t)nchw % 16) == 0;
 }
 
 struct RowsGeom {
@@ -196,6 +245,13 @@ using namespace tlt;
 extern "C" int tlt_nchw_to_rows(const void* x, int64_t batch, int64_t channels, int64_t spatial, void* rows, int64_t ld, void* stream) {
   TLT_REQUIRE(x && rows && batch >= 1 && channels >= 1 && spatial >= 1, "tlt_nchw_to_rows: bad arguments");
   TLT_REQUIRE(ld >= channels && ld % 2 == 0 && batch <= 65535, "tlt_nchw_to_rows: ld must be even and >= channels; batch <= 65535");
+  if (span_ok(channels, spatial, ld, x)) {
+    const long long units = batch * (channels >> 6);
+    const unsigned blocks = (unsigned)(units < 148LL * 8 ? units : 148LL * 8);
+    nchw_to_rows_span_kernel<<<blocks, 256, (size_t)64 * spatial * 2, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (int)channels, (int)spatial, ld,
+                                                                                            (__nv_bfloat16*)rows, units);
+    return check_launch("nchw_to_rows_span_kernel");
+  }
   dim3 grid((unsigned)((spatial + 31) / 32), (unsigned)((ld + 63) / 64), (unsigned)batch);
   nchw_to_rows_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, channels, spatial, ld, (__nv_bfloat16*)rows);
   return check_launch("nchw_to_rows_kernel");
@@ -204,6 +260,13 @@ extern "C" int tlt_nchw_to_rows(const void* x, int64_t batch, int64_t channels, 
 extern "C" int tlt_rows_to_nchw(const void* rows, int64_t batch, int64_t channels, int64_t spatial, int64_t ld, void* y, void* stream) {
   TLT_REQUIRE(y && rows && batch >= 1 && channels >= 1 && spatial >= 1, "tlt_rows_to_nchw: bad arguments");
   TLT_REQUIRE(ld >= channels && ld % 2 == 0 && batch <= 65535, "tlt_rows_to_nchw: ld must be even and >= channels; batch <= 65535");
+  if (span_ok(channels, spatial, ld, y)) {
+    const long long units = batch * (channels >> 6);
+    const unsigned blocks = (unsigned)(units < 148LL * 8 ? units : 148LL * 8);
+    rows_to_nchw_span_kernel<<<blocks, 256, (size_t)64 * spatial * 2, (cudaStream_t)stream>>>((const __nv_bfloat16*)rows, (int)channels, (int)spatial, ld,
+                                                                                            (__nv_bfloat16*)y, units);
+    return check_launch("rows_to_nchw_span_kernel");
+  }
   dim3 grid((unsigned)((spatial + 31) / 32), (unsigned)((channels + 63) / 64), (unsigned)batch);
   rows_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)rows, channels, spatial, ld, (__nv_bfloat16*)y);
   return check_launch("rows_to_nchw_kernel");

@@ -254,9 +254,16 @@ inline int make_map(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1, i
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // a thread that has issued no runtime call yet (e.g. an autograd worker whose first op is this GEMM) has no current
+    // context for the driver API: bind the primary context through the runtime and try again
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for dims {%lld,%lld} ld %lld box {%d,%d}", (int)r, (long long)d0,
               (long long)d1, (long long)ld, box0, box1);
@@ -274,9 +281,14 @@ inline int make_map3d(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1,
   cuuint64_t strides[2] = {(cuuint64_t)ld1 * 2, (cuuint64_t)ld2 * 2};
   cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;       // see make_map
+    cudaFree(0);
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d) failed (%d) for dims {%lld,%lld,%lld} pitches {%lld,%lld} box {%d,%d,1}", (int)r,
               (long long)d0, (long long)d1, (long long)d2, (long long)ld1, (long long)ld2, box0, box1);

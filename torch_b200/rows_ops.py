@@ -18,7 +18,7 @@ from . import _cuda
 from . import ops
 from .tucker_ops import padded_linear, _r8, _prod
 
-__all__ = ["nchw_to_rows", "rows_to_nchw", "im2col_rows", "tucker_conv_rows", "rows_eligible"]
+__all__ = ["nchw_to_rows", "rows_to_nchw", "im2col_rows", "tucker_conv_rows", "rows_eligible", "skinny_linear", "expand_core"]
 
 
 def _conv_desc(batch, ld, in_size, out_size, kernel, stride, padding, dilation):
@@ -264,7 +264,12 @@ def _skinny_backward(ctx, g):
 
 _skinny_op.register_autograd(_skinny_backward, setup_context=_skinny_setup)
 
-SKINNY_MAX = 32
+SKINNY_MAX = 64
+
+
+def skinny_linear(a2, k2):
+    """a2 (rows, I) x k2 (J, I)^T -> (rows, J) for I, J <= SKINNY_MAX; differentiable in both."""
+    return _skinny_op(a2, k2)
 
 
 def expand_core(core, kernel_factors):

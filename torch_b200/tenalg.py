@@ -54,6 +54,10 @@ def multi_mode_dot(tensor, matrix_or_vec_list, modes=None, skip=None, transpose=
         p = modedot_ops.plan(tensor, [m for m, _ in pairs], [mode for _, mode in pairs], transpose)
         if p is not None and (addend is None or _addend_matches(tensor, p, addend)):
             return modedot_ops.fused_multi_mode_dot(tensor, *p, addend=addend)
+        if p is None and addend is None:
+            res = _trailing_modes_first(tensor, pairs, transpose)
+            if res is not None:
+                return res
     if addend is not None:
         # unfused chain: all but the last product, then the last one with the addend in its epilogue
         res = multi_mode_dot(tensor, [m for m, _ in pairs[:-1]], [mode for _, mode in pairs[:-1]], transpose=transpose) if len(pairs) > 1 else tensor
@@ -75,6 +79,37 @@ def multi_mode_dot(tensor, matrix_or_vec_list, modes=None, skip=None, transpose=
         if m.dim() == 1:
             removed += 1
     return res
+
+
+def _trailing_modes_first(tensor, pairs, transpose):
+    """(batch, C, s_1..s_n) x_1 M_0 x_2 M_1 ... with a LARGE channel mode and a small odd-sized map -- tucker_trl's input
+    projection on (B, 2048, 7, 7) feature maps (functional/tensor_regression.py:40), TCL on the same maps.
+
+    The channel mode is the expensive one (it reads the whole activation) and its natural GEMM needs rows of contiguous
+    channels: the map is transposed once to channels-last rows (rows_ops), the channel mode runs as ONE K-major tcgen05
+    GEMM (batch * spatial, C) x (C, r_0), and the spatial modes then act on the r_0-channel result, which is C / r_0
+    times smaller.  Returns None when the shapes do not fit this plan."""
+    import torch
+    from . import rows_ops
+    from .tucker_ops import padded_linear
+    nd = tensor.dim()
+    if nd < 3 or not tensor.is_contiguous() or tensor.dtype != torch.bfloat16:
+        return None
+    if [mode + nd if mode < 0 else mode for _, mode in pairs] != list(range(1, nd)):
+        return None
+    if any(m.dtype != tensor.dtype or m.dim() != 2 for m, _ in pairs):
+        return None
+    mats = [m for m, _ in pairs]
+    b, c, spatial = tensor.shape[0], tensor.shape[1], list(tensor.shape[2:])
+    m0 = mats[0].t() if transpose else mats[0]                                   # (r_0, C)
+    r0 = m0.shape[0]
+    if c < 256 or r0 * 4 > c or b * math.prod(spatial) < 1024 or b > 65535:
+        return None
+    rows = rows_ops.nchw_to_rows(tensor)                                         # (B S, round8(C))
+    z = padded_linear(rows, m0, None, True)                                      # (B S, round8(r_0)), pad columns zero
+    z = z.reshape(b, *spatial, z.shape[1])
+    z = multi_mode_dot(z, mats[1:], modes=list(range(1, nd - 1)), transpose=transpose)     # small: (B, q_1.., round8(r_0))
+    return z[..., :r0].movedim(-1, 1)                                            # (B, r_0, q_1, ...), a strided view
 
 
 def _addend_matches(tensor, plan, addend):
