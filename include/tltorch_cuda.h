@@ -256,6 +256,16 @@ int tlt_skinny_bwd(int32_t dtype, int64_t rows, int32_t I, int32_t J, const void
                    float* dk, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * tlt_scale_modes: y[i_0..i_{n-1}] = alpha * prod_k s_k[i_k] * x[i_0..i_{n-1}]  for a contiguous tensor of 1..6 modes;
+ * scales[k] is a vector of dims[k] elements of the same dtype, or NULL to leave mode k untouched.
+ * Replaces: the mask application of tensor dropout (tltorch/tensor_hooks/_tensor_dropout.py:56-142) in fixed-shape form:
+ * the 0/1 keep vectors of the dropped rank modes and the 1/(1-p) rescale multiplied into the core / weights / TT cores
+ * in one pass, so no index vector reaches the host and the training step stays CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_scale_modes(int32_t dtype, int32_t ndim, const int64_t* dims, const void* x, const void* const* scales, float alpha,
+                    void* y, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Small utilities used by the host side.
  * ------------------------------------------------------------------------------------------------------------ */
 /* dst[i] = (dst dtype) src[i], n elements */

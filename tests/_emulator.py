@@ -286,6 +286,17 @@ def emulate_skinny_bwd(a2, g2, k2, da2, dk32):
     LOG.append(("skinny_bwd", tuple(g2.shape), tuple(k2.shape)))
 
 
+def emulate_scale_modes(x, masks, alpha, y):
+    res = x.double() * alpha
+    for k, m in enumerate(masks):
+        if m is not None:
+            shape = [1] * x.dim()
+            shape[k] = -1
+            res = res * m.double().reshape(shape)
+    y.copy_(res.to(y.dtype))
+    LOG.append(("scale_modes", tuple(x.shape), [m is not None for m in masks], alpha))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
     """Swap the launch funnels for the CPU interpreters (tests only)."""
@@ -295,8 +306,8 @@ def emulated_kernels():
     from torch_b200 import tucker_ops as to
     from torch_b200 import rows_ops as ro
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
-    saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd
-    ro._execute_skinny_fwd, ro._execute_skinny_bwd = emulate_skinny_fwd, emulate_skinny_bwd
+    saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes
+    ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes = emulate_skinny_fwd, emulate_skinny_bwd, emulate_scale_modes
     ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = emulate_nchw_to_rows, emulate_rows_to_nchw, emulate_unfold_rows
     saved_m = mo._execute_mmd
     mo._execute_mmd = emulate_mmd
@@ -318,5 +329,5 @@ def emulated_kernels():
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p
         mo._execute_mmd = saved_m
         ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
-        ro._execute_skinny_fwd, ro._execute_skinny_bwd = saved_s
+        ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes = saved_s
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

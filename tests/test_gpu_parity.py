@@ -717,3 +717,39 @@ def test_contract_small_output_long_reduction(dtype):
     assert _contract_vs_einsum("bqpr,bipr->qi", (64, 7, 5, 40), (64, 3, 5, 40), dtype) < tol
     assert _contract_vs_einsum("km,kn->mn", (20000, 8), (20000, 8), dtype) < tol
     assert _contract_vs_einsum("mk,kn->mn", (2, 9000), (9000, 3), dtype, alpha=0.5) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scale_modes_and_fixed_shape_dropout(dtype):
+    """tlt_scale_modes vs broadcasting in fp64, and Tucker tensor dropout in its fixed-shape (sync-free) form vs the
+    reference's gather form on the same RNG draws, through a Tucker convolution."""
+    import torch_b200 as tlt
+    from torch_b200 import rows_ops as ro
+    from torch_b200.tensor_hooks import _tensor_dropout as td
+    torch.manual_seed(1)
+    x = torch.randn(37, 5, 3, 9, device=dev(), dtype=dtype, requires_grad=True)
+    m0 = (torch.rand(37, device=dev()) > 0.3).to(dtype)
+    m3 = torch.randn(9, device=dev()).to(dtype)
+    y = ro.scale_modes(x, [m0, None, None, m3], 1.7)
+    want = 1.7 * x.detach().double().cpu() * m0.double().cpu()[:, None, None, None] * m3.double().cpu()
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert G.rel_err(y, want) < tol
+    (gx,) = torch.autograd.grad(y, x, torch.ones_like(y))
+    assert G.rel_err(gx, want / x.detach().double().cpu()) < tol
+    conv = tlt.FactorizedConv(64, 64, 3, order=2, padding=1, factorization="tucker", rank=0.7, bias=False, device=dev())
+    conv.reset_parameters(std=0.3)
+    conv = conv.to(dtype)
+    assert min(conv.weight.rank[:2]) >= 40
+    conv.weight = tlt.tensor_dropout(conv.weight, p=0.15, min_dim=3)
+    conv.train()
+    xin = torch.randn(3, 64, 8, 8, device=dev(), dtype=dtype)
+    torch.manual_seed(11)
+    y_fixed = conv(xin)
+    saved = td._empty_draw_impossible
+    td._empty_draw_impossible = lambda r, p: False
+    try:
+        torch.manual_seed(11)
+        y_gather = conv(xin)
+    finally:
+        td._empty_draw_impossible = saved
+    assert G.rel_err(y_fixed, y_gather.double().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)

@@ -53,6 +53,33 @@ def test_dropout_replays_reference_rng():
                 assert a.shape == b.shape and G.rel_err(a, b) < 1e-14, key
 
 
+def test_dropout_fixed_shape_form_equals_gather_form():
+    """Large ranks (p ** rank < 1e-30) take the sync-free fixed-shape form: same RNG draws, same reconstructed tensor as
+    the reference's gather form (reference: tensor_hooks/_tensor_dropout.py:56-142)."""
+    import torch_b200 as tlt
+    from torch_b200.tensor_hooks import _tensor_dropout as td
+    with emulated_kernels():
+        for kind, shape, rank in (("tucker", (40, 36, 3, 3), (34, 33, 2, 2)), ("cp", (12, 10, 9), 70), ("tt", (9, 40, 40), (1, 36, 37, 1))):
+            torch.manual_seed(0)
+            w = tlt.FactorizedTensor.new(shape, rank=rank, factorization=kind, dtype=D)
+            w.normal_(0, 0.5)
+            hook = {"tucker": td.TuckerDropout, "cp": td.CPDropout, "tt": td.TTDropout}[kind](0.12, min_dim=3, min_values=1)
+            for training in (True, False):
+                hook.drop_test = True
+                torch.manual_seed(7)
+                fixed = hook._apply_tensor_dropout(w, training=training)
+                assert [tuple(f.shape) for f in fixed.factors] == [tuple(f.shape) for f in w.factors]      # shapes unchanged
+                saved = td._empty_draw_impossible
+                td._empty_draw_impossible = lambda r, p: False                                               # force the gather form
+                try:
+                    torch.manual_seed(7)
+                    gathered = hook._apply_tensor_dropout(w, training=training)
+                finally:
+                    td._empty_draw_impossible = saved
+                assert any(a.shape != b.shape for a, b in zip(gathered.factors, w.factors))                  # something was dropped
+                assert G.rel_err(fixed.to_tensor(), gathered.to_tensor()) < TOL, (kind, training)
+
+
 def test_dropout_hook_plumbing():
     # reference tests: tensor_hooks/tests/test_tensor_dropout.py:8-61 (shapes only)
     with emulated_kernels():

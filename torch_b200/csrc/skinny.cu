@@ -198,3 +198,54 @@ extern "C" int tlt_skinny_bwd(int32_t dtype, int64_t rows, int32_t I, int32_t J,
   if (dk) rc = dtype == TLT_BF16 ? launch_skinny_dk<__nv_bfloat16>(a, g, dk, rows, I, J, st) : launch_skinny_dk<float>(a, g, dk, rows, I, J, st);
   return rc;
 }
+
+// =====================================================================================================================
+// tlt_scale_modes: y[i_0..i_{n-1}] = alpha * prod_k s_k[i_k] * x[i_0..i_{n-1}]   (s_k == NULL: mode untouched)
+// The mask application of tensor dropout in its fixed-shape form (tltorch/tensor_hooks/_tensor_dropout.py:56-142: the 0/1
+// keep vectors of the dropped rank modes and the 1/(1-p)^ndim rescale, multiplied into the Tucker core / CP weights / TT
+// cores in ONE pass instead of index_select gathers).
+// =====================================================================================================================
+namespace tlt {
+struct ScaleModesParams {
+  int ndim;
+  int dims[6];
+  const void* s[6];
+  float alpha;
+  long long total;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_modes_kernel(const ScaleModesParams p, const T* __restrict__ x, T* __restrict__ y) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < p.total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    float f = p.alpha;
+#pragma unroll
+    for (int d = 5; d >= 0; --d) {
+      if (d < p.ndim) {
+        const int i = (int)(r % p.dims[d]);
+        r /= p.dims[d];
+        if (p.s[d] != nullptr) f *= to_f32<T>(static_cast<const T*>(p.s[d])[i]);
+      }
+    }
+    y[e] = from_f32<T>(f * to_f32<T>(x[e]));
+  }
+}
+}  // namespace tlt
+
+extern "C" int tlt_scale_modes(int32_t dtype, int32_t ndim, const int64_t* dims, const void* x, const void* const* scales, float alpha,
+                               void* y, void* stream) {
+  TLT_REQUIRE(x && y && dims && scales && ndim >= 1 && ndim <= 6, "tlt_scale_modes: bad arguments (1..6 modes)");
+  ScaleModesParams p{};
+  p.ndim = ndim; p.alpha = alpha; p.total = 1;
+  for (int k = 0; k < ndim; ++k) {
+    TLT_REQUIRE(dims[k] >= 1 && dims[k] < (1LL << 31), "tlt_scale_modes: bad extent");
+    p.dims[k] = (int)dims[k]; p.s[k] = scales[k]; p.total *= dims[k];
+  }
+  const long long blocks = (p.total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148LL * 8 ? blocks : 148LL * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TLT_BF16) scale_modes_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  else if (dtype == TLT_F32) scale_modes_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)x, (float*)y);
+  else { set_error("tlt_scale_modes: unknown dtype"); return TLT_ERR_INVALID; }
+  return check_launch("scale_modes_kernel");
+}

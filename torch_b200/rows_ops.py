@@ -285,3 +285,54 @@ def expand_core(core, kernel_factors):
         kron = ops.contract("ac,bd->abcd", kron, f).reshape(kron.shape[0] * f.shape[0], kron.shape[1] * f.shape[1])
     r0, r1 = core.shape[0], core.shape[1]
     return _skinny_op(core.reshape(r0 * r1, _prod(q)), kron).reshape(r0, r1, *k)
+
+
+# =====================================================================================================================
+# tltorch::scale_modes -- tensor dropout's mask application in fixed-shape form
+# =====================================================================================================================
+def _execute_scale_modes(x, masks, alpha, y):
+    _cuda.require_cuda(x, y, *masks)
+    nd = x.dim()
+    dims = (C.c_int64 * nd)(*x.shape)
+    ptrs = (C.c_void_p * nd)(*[None if m is None else m.data_ptr() for m in masks])
+    _cuda.check(_cuda.lib().tlt_scale_modes(_cuda.dtype_code(x.dtype), nd, dims, _cuda.ptr(x), ptrs, float(alpha), _cuda.ptr(y),
+                                            _cuda.stream_ptr(x)), "tlt_scale_modes")
+
+
+@torch.library.custom_op("tltorch::scale_modes", mutates_args=())
+def _scale_modes_op(x: torch.Tensor, masks: List[torch.Tensor], modes: List[int], alpha: float) -> torch.Tensor:
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    if x.numel():
+        per_mode = [None] * x.dim()
+        for m, mode in zip(masks, modes):
+            per_mode[mode] = m.contiguous()
+        _execute_scale_modes(x, per_mode, alpha, y)
+    return y
+
+
+@_scale_modes_op.register_fake
+def _(x, masks, modes, alpha):
+    return torch.empty_like(x)
+
+
+def _scale_modes_setup(ctx, inputs, output):
+    _, masks, ctx.modes, ctx.alpha = inputs
+    ctx.save_for_backward(*masks)
+
+
+def _scale_modes_backward(ctx, g):
+    masks = list(ctx.saved_tensors)
+    return _scale_modes_op(g, masks, ctx.modes, ctx.alpha), [None] * len(masks), None, None
+
+
+_scale_modes_op.register_autograd(_scale_modes_backward, setup_context=_scale_modes_setup)
+
+
+def scale_modes(x, masks, alpha=1.0):
+    """x * alpha * prod_k masks[k][i_k] in one launch; ``masks`` has one entry per mode of x (None = untouched).  The masks
+    are constants for autograd (dropout keep vectors)."""
+    if x.dim() > 6 or x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("scale_modes: 1..6 modes, float32 / bfloat16")
+    modes = [k for k, m in enumerate(masks) if m is not None]
+    return _scale_modes_op(x, [masks[k].to(x.dtype) for k in modes], modes, float(alpha))

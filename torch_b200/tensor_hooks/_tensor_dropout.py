@@ -2,10 +2,15 @@
 module (reference: tltorch/tensor_hooks/_tensor_dropout.py:12-196).
 
 Mask GENERATION replays the reference's torch RNG calls in the same order (one ``torch.bernoulli`` per rank mode, a
-``torch.randint`` fallback when nothing survives), so a seeded run drops the same components.  Mask APPLICATION -- the
-gathers of factor columns / core sub-blocks and the 1/(1-p) rescaling -- is one ``torch.index_select`` chain on tiny
-tensors followed by a contraction-kernel scale, and produces a fresh (smaller) factorized tensor that the contraction
-kernels then consume unchanged.
+``torch.randint`` fallback when nothing survives), so a seeded run drops the same components.
+
+Mask APPLICATION has two forms that give the same tensor:
+  * fixed shape (default whenever an empty draw is impossible in practice, p ** rank < 1e-30): the 0/1 keep vectors and
+    the 1/(1-p) factor are MULTIPLIED into the core / weights / cores by the contraction kernel (dropped components
+    contribute exact zeros), the factors are used as they are.  No index vector ever reaches the host, shapes never
+    change, so the whole training step -- mask draw included -- is CUDA-graph capturable;
+  * gather (small ranks, where the reference's ``len(idx) == 0`` fallback can actually fire and has to be checked on the
+    host): ``index_select`` of factor columns / core sub-blocks like the reference.
 """
 import torch
 
@@ -23,6 +28,36 @@ def _sample(rank, proba, min_dim, min_values, device):
         if len(idx) == 0:
             idx = torch.randint(0, rank, size=(min_values,), device=device, dtype=torch.int64)
     return idx
+
+
+def _empty_draw_impossible(rank, proba):
+    return proba == 0 or rank * (-__import__("math").log10(proba)) > 30
+
+
+def _keep_mask(rank, proba, dtype, device):
+    """0/1 keep vector drawn with the SAME RNG call as ``_sample`` (the reference's torch.bernoulli, :64-73)."""
+    keep = torch.bernoulli(torch.ones(rank, device=device) * (1 - proba),
+                           out=torch.empty(rank, device=device, dtype=torch.bool))
+    return keep.to(dtype)
+
+
+def _mask_mode(t, mode, mask, alpha=1.0):
+    """t * mask along ``mode`` (* alpha) through the contraction kernel."""
+    letters = "abcdefghijklmnopqrstuvwxyz"[:t.dim()]
+    return contract(f"{letters},{letters[mode]}->{letters}", t, mask, alpha=float(alpha))
+
+
+def _apply_masks(t, masks, alpha):
+    """t * alpha * prod_k masks[k][i_k] in ONE launch (tlt_scale_modes); wider / exotic tensors go mode by mode."""
+    from ..rows_ops import scale_modes
+    if t.dim() <= 6 and t.dtype in (torch.float32, torch.bfloat16):
+        return scale_modes(t, masks, alpha)
+    out, first = t, True
+    for mode, m in enumerate(masks):
+        if m is not None:
+            out = _mask_mode(out, mode, m, alpha if first else 1.0)
+            first = False
+    return _scale(out, alpha) if first else out
 
 
 def _scale(t, factor):
@@ -76,6 +111,12 @@ class TuckerDropout(TensorDropout, factorization=TuckerTensor):
         if self._inactive(training):
             return tucker_tensor
         core, factors = tucker_tensor.core, list(tucker_tensor.factors)
+        dropped = [r > self.min_dim for r in tucker_tensor.rank]
+        if all(_empty_draw_impossible(r, self.proba) for r, d in zip(tucker_tensor.rank, dropped) if d):
+            # fixed-shape form: core * (m_0 x m_1 x ...) / (1-p)^ndim, factors untouched
+            scale = 1 / ((1 - self.proba) ** core.dim()) if training else 1.0
+            masks = [_keep_mask(r, self.proba, core.dtype, core.device) if d else None for r, d in zip(tucker_tensor.rank, dropped)]
+            return TuckerTensor(_apply_masks(core, masks, scale), factors)
         kept = [_sample(r, self.proba, self.min_dim, self.min_values, core.device) for r in tucker_tensor.rank]
         sub = core
         for mode, idx in enumerate(kept):
@@ -94,6 +135,10 @@ class CPDropout(TensorDropout, factorization=CPTensor):
             # the reference leaves `weights` / `factors` unbound here and crashes with UnboundLocalError (App. C.3);
             # returning the tensor untouched is the evident intent
             return cp_tensor
+        if _empty_draw_impossible(rank, self.proba):
+            w = cp_tensor.weights
+            mask = _keep_mask(rank, self.proba, w.dtype, w.device)
+            return CPTensor(_apply_masks(w, [mask], 1 / (1 - self.proba) if training else 1.0), list(cp_tensor.factors))
         idx = _sample(rank, self.proba, self.min_dim, self.min_values, cp_tensor.factors[0].device)
         weights = cp_tensor.weights.index_select(0, idx)
         if training:
@@ -106,6 +151,17 @@ class TTDropout(TensorDropout, factorization=TTTensor):
         if self._inactive(training):
             return tt_tensor
         device = tt_tensor.factors[0].device
+        inner = list(tt_tensor.rank[1:-1])
+        if all(r > self.min_dim and _empty_draw_impossible(r, self.proba) for r in inner) and tt_tensor.rank[-1] <= self.min_dim:
+            # fixed-shape form: every core but the last is masked along its right rank (which zeroes the matching left
+            # slice of the next core's contribution) and rescaled by 1/(1-p)
+            scaling = 1 / (1 - self.proba) if training else 1.0
+            out = []
+            for i, f in enumerate(tt_tensor.factors):
+                if i < tt_tensor.order - 1:
+                    f = _apply_masks(f, [None, None, _keep_mask(f.shape[2], self.proba, f.dtype, device)], scaling)
+                out.append(f)
+            return TTTensor(out)
         kept = [_sample(r, self.proba, self.min_dim, self.min_values, device) for r in tt_tensor.rank[1:]]
         scaling = 1 / (1 - self.proba) if training else 1
         out = []
