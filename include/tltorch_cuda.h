@@ -244,6 +244,17 @@ int tlt_im2col_rows(const tlt_conv_desc* desc, const void* z, void* cols, void* 
 int tlt_col2im_rows(const tlt_conv_desc* desc, const void* dcols, void* dz, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Depthwise convolution on channels-last rows (bf16; desc->channels = row length, a multiple of 8; 1..3 spatial dims).
+ * w is taps-major: (prod(kernel), channels) bf16.  dw is fp32 (prod(kernel), channels), accumulated into (caller zeroes);
+ * the weight gradient supports up to 9 taps (TLT_ERR_UNSUPPORTED otherwise).
+ * Replaces: the depthwise F.conv1d chain of cp_conv (tltorch/functional/convolution.py:268-271; merged into one N-D
+ * depthwise conv like cp_conv_mobilenet :321-332) and its autograd, when the surrounding 1x1 stages run as row GEMMs.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_dwconv_rows_fwd(const tlt_conv_desc* desc, const void* z, const void* w, void* y, void* stream);
+int tlt_dwconv_rows_dgrad(const tlt_conv_desc* desc, const void* gy, const void* w, void* dz, void* stream);
+int tlt_dwconv_rows_wgrad(const tlt_conv_desc* desc, const void* z, const void* gy, float* dw, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Skinny row transform for many rows and tiny extents (I, J <= 32): the core expansion of the factorized convolutions.
  *   tlt_skinny_fwd : y[r, j] = sum_i a[r, i] k[j, i]                     a (rows, I), k (J, I), y (rows, J), dtype f32 / bf16
  *   tlt_skinny_bwd : da[r, i] = sum_j g[r, j] k[j, i];  dk[j, i] += sum_r g[r, j] a[r, i]   (dk fp32, caller zeroes; da or dk

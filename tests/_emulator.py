@@ -286,6 +286,36 @@ def emulate_skinny_bwd(a2, g2, k2, da2, dk32):
     LOG.append(("skinny_bwd", tuple(g2.shape), tuple(k2.shape)))
 
 
+def emulate_dwconv_rows(kind, a, b, out, batch, in_size, out_size, kernel, stride, padding, dilation):
+    nd, ld = len(in_size), a.shape[1]
+    fn = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[nd]
+
+    def img(rows, size):
+        return rows.double().reshape(batch, *size, ld).movedim(-1, 1)
+
+    def rows_of(t):
+        return t.movedim(1, -1).reshape(-1, ld)
+
+    if kind == "fwd":
+        w = b.double().t().reshape(ld, 1, *kernel)
+        out.copy_(rows_of(fn(img(a, in_size), w, None, stride, padding, dilation, ld)).to(out.dtype))
+    else:
+        with torch.enable_grad():
+            if kind == "dgrad":
+                zz = torch.zeros((batch, ld, *in_size), dtype=torch.float64)
+                w = b.double().t().reshape(ld, 1, *kernel)
+                f = lambda t: fn(t, w, None, stride, padding, dilation, ld)
+                res = torch.func.vjp(f, zz)[1](img(a, out_size).contiguous())[0]
+                out.copy_(rows_of(res).to(out.dtype))
+            else:
+                zz = img(a, in_size).contiguous()
+                w0 = torch.zeros((ld, 1, *kernel), dtype=torch.float64)
+                f = lambda w: fn(zz, w, None, stride, padding, dilation, ld)
+                res = torch.func.vjp(f, w0)[1](img(b, out_size).contiguous())[0]
+                out += res.reshape(ld, -1).t().to(out.dtype)
+    LOG.append(("dwconv_rows_" + kind, tuple(in_size), tuple(kernel), tuple(stride), tuple(padding), tuple(dilation)))
+
+
 def emulate_scale_modes(x, masks, alpha, y):
     res = x.double() * alpha
     for k, m in enumerate(masks):
@@ -306,8 +336,9 @@ def emulated_kernels():
     from torch_b200 import tucker_ops as to
     from torch_b200 import rows_ops as ro
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
-    saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes
-    ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes = emulate_skinny_fwd, emulate_skinny_bwd, emulate_scale_modes
+    saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows
+    ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = (
+        emulate_skinny_fwd, emulate_skinny_bwd, emulate_scale_modes, emulate_dwconv_rows)
     ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = emulate_nchw_to_rows, emulate_rows_to_nchw, emulate_unfold_rows
     saved_m = mo._execute_mmd
     mo._execute_mmd = emulate_mmd
@@ -329,5 +360,5 @@ def emulated_kernels():
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p
         mo._execute_mmd = saved_m
         ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
-        ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes = saved_s
+        ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = saved_s
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

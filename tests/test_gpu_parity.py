@@ -753,3 +753,59 @@ def test_scale_modes_and_fixed_shape_dropout(dtype):
     finally:
         td._empty_draw_impossible = saved
     assert G.rel_err(y_fixed, y_gather.double().cpu()) < (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("B,C,spatial,kernel,stride,padding,dilation", [
+    (4, 288, (14, 14), (3, 3), (1, 1), (1, 1), (1, 1)),
+    (3, 72, (14, 14), (3, 3), (2, 2), (1, 1), (1, 1)),
+    (2, 576, (7, 7), (3, 3), (1, 1), (1, 1), (1, 1)),
+    (2, 40, (9, 11), (3, 2), (1, 2), (2, 0), (2, 1)),
+    (3, 24, (19,), (5,), (2,), (2,), (1,)),
+    (2, 16, (5, 6, 7), (2, 2, 2), (1, 2, 1), (1, 1, 0), (1, 1, 1)),
+])
+def test_dwconv_rows_kernels_vs_torch(B, C, spatial, kernel, stride, padding, dilation):
+    """tlt_dwconv_rows_{fwd,dgrad,wgrad} (channels-last depthwise conv) vs F.conv{1,2,3}d(groups=C) in fp64."""
+    import torch.nn.functional as F
+    from torch_b200 import rows_ops as ro
+    torch.manual_seed(C)
+    nd = len(spatial)
+    fn = {1: F.conv1d, 2: F.conv2d, 3: F.conv3d}[nd]
+    taps = math.prod(kernel)
+    z = torch.randn(B * math.prod(spatial), C, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(taps, C, device=dev()) / math.sqrt(taps)).to(torch.bfloat16).requires_grad_(True)
+    y = ro.dwconv_rows(z, w, B, spatial, kernel, stride, padding, dilation)
+    gy = torch.randn_like(y)
+    gz, gw = torch.autograd.grad(y, [z, w], gy)
+    zo = z.detach().double().cpu().reshape(B, *spatial, C).movedim(-1, 1).requires_grad_(True)
+    wo = w.detach().double().cpu().requires_grad_(True)
+    yo = fn(zo, wo.t().reshape(C, 1, *kernel), None, stride, padding, dilation, C)
+    go = gy.double().cpu().reshape(B, *yo.shape[2:], C).movedim(-1, 1)
+    gzo, gwo = torch.autograd.grad(yo, [zo, wo], go)
+    assert G.rel_err(y, yo.movedim(1, -1).reshape(-1, C)) < 1e-2
+    assert G.rel_err(gz, gzo.movedim(1, -1).reshape(-1, C)) < 1e-2
+    assert G.rel_err(gw, gwo) < 1e-2
+
+
+@pytest.mark.parametrize("cin,cout,hw,stride", [(256, 256, 14, 1), (128, 256, 28, 2), (512, 512, 7, 1), (256, 512, 14, 2)])
+def test_cp_conv_rows_path_vs_oracle(cin, cout, hw, stride):
+    """CP FactorizedConv (bf16, ResNet-18 layer3 / layer4 shapes at a small batch) through the channels-last route vs the
+    fp64 oracle."""
+    import torch_b200 as tlt
+    from oracle import reference_path as rp
+    torch.manual_seed(hw)
+    conv = tlt.FactorizedConv(cin, cout, 3, order=2, stride=stride, padding=1, bias=False, factorization="cp", rank=0.25, device=dev())
+    conv.reset_parameters(std=0.5)
+    conv = conv.to(torch.bfloat16)
+    x = torch.randn(4, cin, hw, hw, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    y = conv(x)
+    gy = torch.randn_like(y)
+    params = dict(conv.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(4)]
+    yo = rp.cp_conv(xo, leaves["weight.weights"], fs, bias=None, stride=[stride] * 2, padding=[1, 1], dilation=[1, 1])
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    assert G.rel_err(y, yo) < 2e-2
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < 3e-2, n

@@ -97,6 +97,9 @@ SYMBOLS = {
     "tlt_rows_to_nchw": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp]),
     "tlt_im2col_rows": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
     "tlt_col2im_rows": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp]),
+    "tlt_dwconv_rows_fwd": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwconv_rows_dgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwconv_rows_wgrad": (C.c_int, [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp]),
     "tlt_skinny_fwd": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "tlt_skinny_bwd": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_scale_modes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), _vp, C.POINTER(C.c_void_p), C.c_float, _vp, _vp]),

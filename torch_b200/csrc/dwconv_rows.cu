@@ -1,0 +1,235 @@
+// Depthwise convolution on channels-last rows: the middle stage of the CP convolution when the feature map is small and
+// odd-sized (14 x 14 = 196 and 7 x 7 = 49 positions are not multiples of 8, so the NCHW tensor-core 1x1 kernel cannot take
+// the layers around it; BASELINE config 3's layer3 / layer4 blocks ran on the generic kernels at 3-5 % of their roofline).
+// On rows every thread owns 8 consecutive channels of one position: each tap is one 16-byte load of the activation and one
+// of the tap weights (taps-major, so neighbouring threads read neighbouring chunks), i.e. the access pattern is coalesced
+// for any spatial size, stride, padding or dilation, 1 to 3 spatial dims.
+//
+//   tlt_dwconv_rows_fwd   : y[(b, o), c] = sum_t z[(b, o*s - p + t*d), c] * w[t, c]
+//   tlt_dwconv_rows_dgrad : dz[(b, i), c] = sum over (o, t) hitting i of g[(b, o), c] * w[t, c]          (gather form)
+//   tlt_dwconv_rows_wgrad : dw[t, c] += sum_{b, o} z[(b, o*s - p + t*d), c] * g[(b, o), c]                  (fp32, caller zeroes)
+//
+// Reference call sites: the depthwise F.conv1d chain of cp_conv (tltorch/functional/convolution.py:268-271, merged into one
+// N-D depthwise conv as cp_conv_mobilenet does at :321-332) and its autograd.
+#include "common.cuh"
+
+namespace tlt {
+
+struct DwRowsGeom {
+  int ndim;
+  long long batch;
+  int cpr;                                   // 16-byte chunks per row (channels / 8)
+  int in_size[3], out_size[3], kernel[3], stride[3], padding[3], dilation[3];
+  int in_sp, out_sp, taps;
+};
+
+__device__ __forceinline__ void dw_tap(const DwRowsGeom& g, int tap, int (&t)[3]) {
+  const int k1 = g.ndim > 1 ? g.kernel[g.ndim - 1] : 1, k2 = g.ndim > 2 ? g.kernel[g.ndim - 2] : 1;
+  if (g.ndim == 1) { t[0] = tap; }
+  else if (g.ndim == 2) { t[0] = tap / k1; t[1] = tap - t[0] * k1; }
+  else { t[2] = tap % k1; const int q = tap / k1; t[1] = q % k2; t[0] = q / k2; }
+}
+
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& a, const uint4& b) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[i]));
+    const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+    acc[2 * i] = fmaf(fa.x, fb.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(fa.y, fb.y, acc[2 * i + 1]);
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
+  uint4 out;
+  __nv_bfloat162 p;
+  p = __floats2bfloat162_rn(acc[0], acc[1]); out.x = *reinterpret_cast<uint32_t*>(&p);
+  p = __floats2bfloat162_rn(acc[2], acc[3]); out.y = *reinterpret_cast<uint32_t*>(&p);
+  p = __floats2bfloat162_rn(acc[4], acc[5]); out.z = *reinterpret_cast<uint32_t*>(&p);
+  p = __floats2bfloat162_rn(acc[6], acc[7]); out.w = *reinterpret_cast<uint32_t*>(&p);
+  return out;
+}
+
+// DGRAD = false: forward (thread per output position);  true: data gradient (thread per input position, gather)
+template <bool DGRAD>
+__global__ void __launch_bounds__(256) dwconv_rows_kernel(const DwRowsGeom g, const uint4* __restrict__ src, const uint4* __restrict__ w,
+                                                          uint4* __restrict__ dst) {
+  const int n_pos = DGRAD ? g.in_sp : g.out_sp, n_src = DGRAD ? g.out_sp : g.in_sp;
+  const long long total = g.batch * n_pos * g.cpr;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % g.cpr);
+    const long long row = e / g.cpr;
+    int pos = (int)(row % n_pos);
+    const long long b = row / n_pos;
+    int idx[3] = {0, 0, 0};
+    for (int d = g.ndim - 1; d >= 0; --d) {
+      const int ext = DGRAD ? g.in_size[d] : g.out_size[d];
+      idx[d] = pos % ext;
+      pos /= ext;
+    }
+    const uint4* sb = src + b * n_src * g.cpr + ch;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < g.taps; ++tap) {
+      int t[3];
+      dw_tap(g, tap, t);
+      int off = 0;
+      bool ok = true;
+      for (int d = 0; d < g.ndim; ++d) {
+        int j;
+        if (!DGRAD) {
+          j = idx[d] * g.stride[d] - g.padding[d] + t[d] * g.dilation[d];
+          ok = ok && j >= 0 && j < g.in_size[d];
+          off = off * g.in_size[d] + j;
+        } else {
+          const int num = idx[d] + g.padding[d] - t[d] * g.dilation[d];
+          j = g.stride[d] == 1 ? num : num / g.stride[d];
+          ok = ok && num >= 0 && j * g.stride[d] == num && j < g.out_size[d];
+          off = off * g.out_size[d] + j;
+        }
+      }
+      if (!ok) continue;
+      fma8(acc, sb[(long long)off * g.cpr], w[tap * g.cpr + ch]);
+    }
+    dst[e] = pack8(acc);
+  }
+}
+
+// block = 256 threads = (cpr_blk chunks) x (256 / cpr_blk position lanes); each block owns a slab of output positions.
+// A thread keeps the 8 channel sums of every tap in registers (TAPS_MAX x 8 fp32) over its positions; position lanes are
+// then summed through shared memory and the block issues one atomicAdd per (tap, channel).
+constexpr int kDwTapsMax = 9;
+__global__ void __launch_bounds__(256) dwconv_rows_wgrad_kernel(const DwRowsGeom g, const uint4* __restrict__ z, const uint4* __restrict__ gy,
+                                                                float* __restrict__ dw, int pos_per_block, int chunks_x) {
+  extern __shared__ float wg_smem[];                               // [lanes][taps][8] per chunk column -> reduced in place
+  const int lanes = 256 / chunks_x;
+  const int cx = threadIdx.x % chunks_x, lane = threadIdx.x / chunks_x;
+  const long long rows_total = g.batch * g.out_sp;
+  const long long row0 = (long long)blockIdx.x * pos_per_block;
+  const long long row1 = row0 + pos_per_block < rows_total ? row0 + pos_per_block : rows_total;
+  for (int c0 = 0; c0 < g.cpr; c0 += chunks_x) {
+    const int ch = c0 + cx;
+    float acc[kDwTapsMax][8];
+#pragma unroll
+    for (int t = 0; t < kDwTapsMax; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+    if (ch < g.cpr && lane < lanes) {
+      for (long long row = row0 + lane; row < row1; row += lanes) {
+        int pos = (int)(row % g.out_sp);
+        const long long b = row / g.out_sp;
+        int base[3] = {0, 0, 0};
+        for (int d = g.ndim - 1; d >= 0; --d) {
+          base[d] = (pos % g.out_size[d]) * g.stride[d] - g.padding[d];
+          pos /= g.out_size[d];
+        }
+        const uint4 gv = gy[row * g.cpr + ch];
+        const uint4* zb = z + b * g.in_sp * g.cpr + ch;
+#pragma unroll
+        for (int tap = 0; tap < kDwTapsMax; ++tap) {
+          if (tap < g.taps) {
+            int t[3];
+            dw_tap(g, tap, t);
+            int off = 0;
+            bool ok = true;
+            for (int d = 0; d < g.ndim; ++d) {
+              const int j = base[d] + t[d] * g.dilation[d];
+              ok = ok && j >= 0 && j < g.in_size[d];
+              off = off * g.in_size[d] + j;
+            }
+            if (ok) fma8(acc[tap], zb[(long long)off * g.cpr], gv);
+          }
+        }
+      }
+    }
+    // reduce the position lanes: wg_smem[lane][tap][cx][8]
+    __syncthreads();
+    if (lane < lanes) {
+#pragma unroll
+      for (int tap = 0; tap < kDwTapsMax; ++tap)
+        if (tap < g.taps) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wg_smem[((lane * g.taps + tap) * chunks_x + cx) * 8 + i] = acc[tap][i];
+        }
+    }
+    __syncthreads();
+    const int n_out = g.taps * chunks_x * 8;
+    for (int o = threadIdx.x; o < n_out; o += 256) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += wg_smem[l * n_out + o];
+      const int tap = o / (chunks_x * 8), rem = o - tap * chunks_x * 8;
+      const int c = (c0 + rem / 8) * 8 + (rem & 7);
+      if (c < g.cpr * 8 && s != 0.f) atomicAdd(dw + (long long)tap * g.cpr * 8 + c, s);
+    }
+  }
+}
+
+static int fill_dw(const tlt_conv_desc* d, DwRowsGeom* g) {
+  TLT_REQUIRE(d && d->dtype == TLT_BF16, "dwconv_rows: bf16 only");
+  TLT_REQUIRE(d->ndim >= 1 && d->ndim <= 3, "dwconv_rows: 1..3 spatial dims");
+  TLT_REQUIRE(d->batch >= 1 && d->channels >= 8 && d->channels % 8 == 0, "dwconv_rows: channels per row must be a multiple of 8");
+  g->ndim = d->ndim; g->batch = d->batch; g->cpr = (int)(d->channels >> 3);
+  long long in_sp = 1, out_sp = 1, taps = 1;
+  for (int i = 0; i < d->ndim; ++i) {
+    TLT_REQUIRE(d->in_size[i] >= 1 && d->out_size[i] >= 1 && d->kernel[i] >= 1 && d->stride[i] >= 1 && d->dilation[i] >= 1 && d->padding[i] >= 0,
+                "dwconv_rows: bad geometry");
+    g->in_size[i] = (int)d->in_size[i]; g->out_size[i] = (int)d->out_size[i];
+    g->kernel[i] = d->kernel[i]; g->stride[i] = d->stride[i]; g->padding[i] = d->padding[i]; g->dilation[i] = d->dilation[i];
+    in_sp *= d->in_size[i]; out_sp *= d->out_size[i]; taps *= d->kernel[i];
+  }
+  TLT_REQUIRE(in_sp < (1LL << 30) && out_sp < (1LL << 30) && taps <= 64, "dwconv_rows: extents out of range");
+  g->in_sp = (int)in_sp; g->out_sp = (int)out_sp; g->taps = (int)taps;
+  return TLT_OK;
+}
+
+}  // namespace tlt
+
+using namespace tlt;
+
+static unsigned dw_grid(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = 148LL * 16;
+  return (unsigned)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+extern "C" int tlt_dwconv_rows_fwd(const tlt_conv_desc* d, const void* z, const void* w, void* y, void* stream) {
+  DwRowsGeom g;
+  int rc = fill_dw(d, &g);
+  if (rc) return rc;
+  TLT_REQUIRE(z && w && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "tlt_dwconv_rows_fwd: 16-byte aligned tensors");
+  dwconv_rows_kernel<false><<<dw_grid(g.batch * g.out_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
+  return check_launch("dwconv_rows_kernel<fwd>");
+}
+
+extern "C" int tlt_dwconv_rows_dgrad(const tlt_conv_desc* d, const void* gy, const void* w, void* dz, void* stream) {
+  DwRowsGeom g;
+  int rc = fill_dw(d, &g);
+  if (rc) return rc;
+  TLT_REQUIRE(gy && w && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)dz % 16) == 0, "tlt_dwconv_rows_dgrad: 16-byte aligned tensors");
+  dwconv_rows_kernel<true><<<dw_grid(g.batch * g.in_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
+  return check_launch("dwconv_rows_kernel<dgrad>");
+}
+
+extern "C" int tlt_dwconv_rows_wgrad(const tlt_conv_desc* d, const void* z, const void* gy, float* dw, void* stream) {
+  DwRowsGeom g;
+  int rc = fill_dw(d, &g);
+  if (rc) return rc;
+  TLT_REQUIRE(z && gy && dw && ((uintptr_t)z % 16) == 0 && ((uintptr_t)gy % 16) == 0, "tlt_dwconv_rows_wgrad: 16-byte aligned tensors");
+  if (g.taps > kDwTapsMax) { set_error("tlt_dwconv_rows_wgrad: more than %d taps", kDwTapsMax); return TLT_ERR_UNSUPPORTED; }
+  const long long rows_total = g.batch * g.out_sp;
+  long long blocks = 148LL * 4;
+  int ppb = (int)((rows_total + blocks - 1) / blocks);
+  if (ppb < 64) ppb = 64;
+  blocks = (rows_total + ppb - 1) / ppb;
+  const int passes = (g.cpr + 31) / 32;                              // chunk columns per pass: balanced, <= 32
+  const int chunks_x = (g.cpr + passes - 1) / passes;
+  const int lanes = 256 / chunks_x;
+  const size_t smem = (size_t)lanes * g.taps * chunks_x * 8 * sizeof(float);
+  static size_t high = 0;
+  if (smem > 48 * 1024 && smem > high) {
+    TLT_CHECK_CUDA(cudaFuncSetAttribute(dwconv_rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    high = smem;
+  }
+  dwconv_rows_wgrad_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)gy, dw, ppb, chunks_x);
+  return check_launch("dwconv_rows_wgrad_kernel");
+}

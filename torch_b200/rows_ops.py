@@ -336,3 +336,92 @@ def scale_modes(x, masks, alpha=1.0):
         raise ValueError("scale_modes: 1..6 modes, float32 / bfloat16")
     modes = [k for k, m in enumerate(masks) if m is not None]
     return _scale_modes_op(x, [masks[k].to(x.dtype) for k in modes], modes, float(alpha))
+
+
+# =====================================================================================================================
+# tltorch::dwconv_rows -- depthwise conv on channels-last rows; CP convolution on rows
+# =====================================================================================================================
+def _execute_dwconv_rows(kind, a, b, out, batch, in_size, out_size, kernel, stride, padding, dilation):
+    """kind 'fwd': out <- conv(a = z, b = w);  'dgrad': out <- conv^T(a = gy, b = w);  'wgrad': out (fp32, +=) <- corr(a = z, b = gy)."""
+    _cuda.require_cuda(a, b, out)
+    ld = a.shape[1]
+    d = _conv_desc(batch, ld, in_size, out_size, kernel, stride, padding, dilation)
+    lib = _cuda.lib()
+    fn = {"fwd": lib.tlt_dwconv_rows_fwd, "dgrad": lib.tlt_dwconv_rows_dgrad, "wgrad": lib.tlt_dwconv_rows_wgrad}[kind]
+    _cuda.check(fn(C.byref(d), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(out), _cuda.stream_ptr(a)), f"tlt_dwconv_rows_{kind}")
+
+
+@torch.library.custom_op("tltorch::dwconv_rows", mutates_args=())
+def _dwrows_op(z: torch.Tensor, w: torch.Tensor, batch: int, in_size: List[int], kernel: List[int], stride: List[int],
+               padding: List[int], dilation: List[int]) -> torch.Tensor:
+    out_size = ops.conv_out_size(in_size, kernel, stride, padding, dilation)
+    y = torch.empty((batch * _prod(out_size), z.shape[1]), dtype=z.dtype, device=z.device)
+    if y.numel():
+        _execute_dwconv_rows("fwd", z.contiguous(), w.contiguous(), y, batch, in_size, out_size, kernel, stride, padding, dilation)
+    return y
+
+
+@_dwrows_op.register_fake
+def _(z, w, batch, in_size, kernel, stride, padding, dilation):
+    out_size = ops.conv_out_size(in_size, kernel, stride, padding, dilation)
+    return z.new_empty((batch * _prod(out_size), z.shape[1]))
+
+
+@torch.library.custom_op("tltorch::dwconv_rows_bwd", mutates_args=())
+def _dwrows_bwd_op(gy: torch.Tensor, z: torch.Tensor, w: torch.Tensor, batch: int, in_size: List[int], kernel: List[int],
+                   stride: List[int], padding: List[int], dilation: List[int], need_dz: bool, need_dw: bool) -> List[torch.Tensor]:
+    out_size = ops.conv_out_size(in_size, kernel, stride, padding, dilation)
+    gy, z, w = gy.contiguous(), z.contiguous(), w.contiguous()
+    dz = torch.empty_like(z) if need_dz else z.new_empty(0)
+    dw = torch.zeros(w.shape, dtype=torch.float32, device=z.device) if need_dw else z.new_empty(0, dtype=torch.float32)
+    if z.numel() and gy.numel():
+        if need_dz:
+            _execute_dwconv_rows("dgrad", gy, w, dz, batch, in_size, out_size, kernel, stride, padding, dilation)
+        if need_dw:
+            _execute_dwconv_rows("wgrad", z, gy, dw, batch, in_size, out_size, kernel, stride, padding, dilation)
+    elif need_dz:
+        dz.zero_()
+    return [dz, dw]
+
+
+@_dwrows_bwd_op.register_fake
+def _(gy, z, w, batch, in_size, kernel, stride, padding, dilation, need_dz, need_dw):
+    return [torch.empty_like(z) if need_dz else z.new_empty(0),
+            z.new_empty(w.shape, dtype=torch.float32) if need_dw else z.new_empty(0, dtype=torch.float32)]
+
+
+def _dwrows_setup(ctx, inputs, output):
+    z, w, ctx.batch, ctx.in_size, ctx.kernel, ctx.stride, ctx.padding, ctx.dilation = inputs
+    ctx.save_for_backward(z, w)
+
+
+def _dwrows_backward(ctx, gy):
+    z, w = ctx.saved_tensors
+    need_dz, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dz, dw = _dwrows_bwd_op(gy, z, w, ctx.batch, ctx.in_size, ctx.kernel, ctx.stride, ctx.padding, ctx.dilation, need_dz, need_dw)
+    return (dz if need_dz else None), (dw.to(w.dtype) if need_dw else None), None, None, None, None, None, None
+
+
+_dwrows_op.register_autograd(_dwrows_backward, setup_context=_dwrows_setup)
+
+DW_ROWS_MAX_TAPS = 9
+
+
+def dwconv_rows(z, w_taps, batch, in_size, kernel, stride, padding, dilation):
+    """z (B * prod(in_size), Cp) bf16, w_taps (prod(kernel), Cp) -> (B * prod(out_size), Cp)."""
+    return _dwrows_op(z, w_taps, batch, list(in_size), list(kernel), list(stride), list(padding), list(dilation))
+
+
+def cp_conv_rows(x, taps, f_in, f_out_scaled, bias, kernel, stride, padding, dilation):
+    """CP convolution on channels-last rows.  x (B, C_in, *S) bf16; taps (R, prod(kernel)) the merged depthwise kernel;
+    f_in (C_in, R); f_out_scaled (C_out, R) with lambda already folded in.
+    x -> rows -> [C_in -> R: GEMM] -> depthwise on rows -> [R -> C_out: GEMM + bias] -> NCHW."""
+    b, spatial = x.shape[0], list(x.shape[2:])
+    r = f_in.shape[1]
+    out_size = ops.conv_out_size(spatial, list(kernel), list(stride), list(padding), list(dilation))
+    xt = nchw_to_rows(x)                                                       # (B S, round8(C_in))
+    z = padded_linear(xt, f_in.t(), None, True)                                # (B S, round8(R)), pad columns zero
+    w_taps = F.pad(taps.t(), (0, _r8(r) - r))                                  # (taps, round8(R)), taps-major
+    z = dwconv_rows(z, w_taps, b, spatial, kernel, stride, padding, dilation)  # (B S', round8(R))
+    yt = padded_linear(z, f_out_scaled, bias, True)                            # (B S', round8(C_out))
+    return rows_to_nchw(yt, b, f_out_scaled.shape[0], out_size)
