@@ -285,6 +285,9 @@ def test_packed_tensor_core_contract(spec, sa, sb, bias_letters):
     (2, 7, 28, 28, (3, 3), (1, 1), (1, 1), (1, 1)),      # fast path, 8-byte staging (bf16)
     (4, 6, 14, 14, (3, 3), (1, 1), (1, 1), (1, 1)),      # fast path, ragged last strip
     (5, 9, 7, 7, (3, 3), (1, 1), (1, 1), (1, 1)),        # fast path, scalar staging
+    (37, 69, 56, 56, (3, 3), (1, 1), (1, 1), (1, 1)),    # TMA-fed path (bf16): many groups per persistent block, tail group
+    (9, 141, 28, 28, (3, 3), (1, 1), (1, 1), (1, 1)),    # TMA-fed path (bf16): 10 planes per group
+    (3, 5, 8, 12, (3, 3), (1, 1), (1, 1), (1, 1)),       # TMA-fed path (bf16): tiny planes
     (2, 4, 10, 13, (3, 3), (1, 1), (1, 1), (1, 1)),
     (3, 5, 56, 56, (3, 3), (2, 2), (1, 1), (1, 1)),      # generic staged path: stride 2
     (2, 3, 17, 9, (3, 1), (1, 1), (1, 0), (1, 1)),       # 1-D taps along H

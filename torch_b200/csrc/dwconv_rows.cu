@@ -164,6 +164,126 @@ __global__ void __launch_bounds__(256) dwconv_rows_wgrad_kernel(const DwRowsGeom
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 2-D specialisations (the CP convolutions of every ResNet block): the position is decoded once per thread, the tap loops
+// are two plain nested loops with the row test hoisted, so a tap costs two 16-byte loads and 8 FMAs plus ~6 integer ops
+// (the generic N-D kernels above spend ~100 instructions per tap on the index arithmetic: 96-103 us per pass over a 29 MB
+// tensor at config 3's layer3 shapes).
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool DGRAD>
+__global__ void __launch_bounds__(256) dwconv_rows2d_kernel(const DwRowsGeom g, const uint4* __restrict__ src, const uint4* __restrict__ w,
+                                                            uint4* __restrict__ dst) {
+  const int H = DGRAD ? g.in_size[0] : g.out_size[0], W = DGRAD ? g.in_size[1] : g.out_size[1];      // extents of dst
+  const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SW = DGRAD ? g.out_size[1] : g.in_size[1];    // extents of src
+  const int KH = g.kernel[0], KW = g.kernel[1], cpr = g.cpr;
+  const int sh = g.stride[0], sw = g.stride[1], ph = g.padding[0], pw = g.padding[1], dh = g.dilation[0], dwl = g.dilation[1];
+  const long long total = g.batch * H * W * cpr;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % cpr);
+    long long row = e / cpr;
+    const int x = (int)(row % W);
+    row /= W;
+    const int y = (int)(row % H);
+    const long long b = row / H;
+    const uint4* sb = src + b * SH * SW * cpr + ch;
+    const uint4* wp = w + ch;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < KH; ++kh) {
+      int sy;
+      if (!DGRAD) {
+        sy = y * sh - ph + kh * dh;
+        if (sy < 0 || sy >= SH) continue;
+      } else {
+        const int num = y + ph - kh * dh;
+        sy = sh == 1 ? num : num / sh;
+        if (num < 0 || sy * sh != num || sy >= SH) continue;
+      }
+      const uint4* srow = sb + (long long)sy * SW * cpr;
+      for (int kw = 0; kw < KW; ++kw) {
+        int sx;
+        if (!DGRAD) {
+          sx = x * sw - pw + kw * dwl;
+          if (sx < 0 || sx >= SW) continue;
+        } else {
+          const int num = x + pw - kw * dwl;
+          sx = sw == 1 ? num : num / sw;
+          if (num < 0 || sx * sw != num || sx >= SW) continue;
+        }
+        fma8(acc, srow[(long long)sx * cpr], wp[(kh * KW + kw) * cpr]);
+      }
+    }
+    dst[e] = pack8(acc);
+  }
+}
+
+// 2-D weight gradient: same block organisation as dwconv_rows_wgrad_kernel, position decoded with two divisions, taps as two
+// nested loops over a register array indexed at compile time (KH, KW <= 3).
+__global__ void __launch_bounds__(256) dwconv_rows2d_wgrad_kernel(const DwRowsGeom g, const uint4* __restrict__ z, const uint4* __restrict__ gy,
+                                                                  float* __restrict__ dw, int pos_per_block, int chunks_x) {
+  extern __shared__ float wg_smem[];
+  const int lanes = 256 / chunks_x;
+  const int cx = threadIdx.x % chunks_x, lane = threadIdx.x / chunks_x;
+  const int OH = g.out_size[0], OW = g.out_size[1], IH = g.in_size[0], IW = g.in_size[1], cpr = g.cpr;
+  const int KH = g.kernel[0], KW = g.kernel[1];
+  const int sh = g.stride[0], sw = g.stride[1], ph = g.padding[0], pw = g.padding[1], dh = g.dilation[0], dwl = g.dilation[1];
+  const long long rows_total = g.batch * g.out_sp;
+  const long long row0 = (long long)blockIdx.x * pos_per_block;
+  const long long row1 = row0 + pos_per_block < rows_total ? row0 + pos_per_block : rows_total;
+  for (int c0 = 0; c0 < cpr; c0 += chunks_x) {
+    const int ch = c0 + cx;
+    float acc[3][3][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[a][c][i] = 0.f;
+    if (ch < cpr && lane < lanes) {
+      for (long long row = row0 + lane; row < row1; row += lanes) {
+        const int ox = (int)(row % OW);
+        const long long r2 = row / OW;
+        const int oy = (int)(r2 % OH);
+        const long long b = r2 / OH;
+        const uint4 gv = gy[row * cpr + ch];
+        const uint4* zb = z + b * IH * IW * cpr + ch;
+        const int y0 = oy * sh - ph, x0 = ox * sw - pw;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int iy = y0 + kh * dh;
+          if (kh < KH && iy >= 0 && iy < IH) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const int ix = x0 + kw * dwl;
+              if (kw < KW && ix >= 0 && ix < IW) fma8(acc[kh][kw], zb[((long long)iy * IW + ix) * cpr], gv);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (lane < lanes) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          if (kh < KH && kw < KW) {
+            const int tap = kh * KW + kw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) wg_smem[((lane * g.taps + tap) * chunks_x + cx) * 8 + i] = acc[kh][kw][i];
+          }
+    }
+    __syncthreads();
+    const int n_out = g.taps * chunks_x * 8;
+    for (int o = threadIdx.x; o < n_out; o += 256) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += wg_smem[l * n_out + o];
+      const int tap = o / (chunks_x * 8), rem = o - tap * chunks_x * 8;
+      const int c = (c0 + rem / 8) * 8 + (rem & 7);
+      if (c < cpr * 8 && s != 0.f) atomicAdd(dw + (long long)tap * cpr * 8 + c, s);
+    }
+  }
+}
+
 static int fill_dw(const tlt_conv_desc* d, DwRowsGeom* g) {
   TLT_REQUIRE(d && d->dtype == TLT_BF16, "dwconv_rows: bf16 only");
   TLT_REQUIRE(d->ndim >= 1 && d->ndim <= 3, "dwconv_rows: 1..3 spatial dims");
@@ -197,6 +317,10 @@ extern "C" int tlt_dwconv_rows_fwd(const tlt_conv_desc* d, const void* z, const 
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(z && w && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "tlt_dwconv_rows_fwd: 16-byte aligned tensors");
+  if (g.ndim == 2) {
+    dwconv_rows2d_kernel<false><<<dw_grid(g.batch * g.out_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
+    return check_launch("dwconv_rows2d_kernel<fwd>");
+  }
   dwconv_rows_kernel<false><<<dw_grid(g.batch * g.out_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
   return check_launch("dwconv_rows_kernel<fwd>");
 }
@@ -206,6 +330,10 @@ extern "C" int tlt_dwconv_rows_dgrad(const tlt_conv_desc* d, const void* gy, con
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(gy && w && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)dz % 16) == 0, "tlt_dwconv_rows_dgrad: 16-byte aligned tensors");
+  if (g.ndim == 2) {
+    dwconv_rows2d_kernel<true><<<dw_grid(g.batch * g.in_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
+    return check_launch("dwconv_rows2d_kernel<dgrad>");
+  }
   dwconv_rows_kernel<true><<<dw_grid(g.batch * g.in_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
   return check_launch("dwconv_rows_kernel<dgrad>");
 }
@@ -229,6 +357,15 @@ extern "C" int tlt_dwconv_rows_wgrad(const tlt_conv_desc* d, const void* z, cons
   if (smem > 48 * 1024 && smem > high) {
     TLT_CHECK_CUDA(cudaFuncSetAttribute(dwconv_rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     high = smem;
+  }
+  if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
+    static size_t high2 = 0;
+    if (smem > 48 * 1024 && smem > high2) {
+      TLT_CHECK_CUDA(cudaFuncSetAttribute(dwconv_rows2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      high2 = smem;
+    }
+    dwconv_rows2d_wgrad_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)gy, dw, ppb, chunks_x);
+    return check_launch("dwconv_rows2d_wgrad_kernel");
   }
   dwconv_rows_wgrad_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)gy, dw, ppb, chunks_x);
   return check_launch("dwconv_rows_wgrad_kernel");

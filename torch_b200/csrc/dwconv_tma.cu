@@ -1,0 +1,265 @@
+// Depthwise 3x3 (stride 1, pad 1) on NCHW bf16 planes, fed by TMA bulk copies -- the middle stage of the CP convolution on
+// the large maps of BASELINE config 3 (56 x 56 and 28 x 28, R = 69 .. 141 channels, batch 256: 111 MB in, 111 MB out).
+//
+// The previous fast path (dwconv.cu: dwconv3x3_fast) staged each group of planes with ld.global + convert-to-fp32 +
+// st.shared, synchronised, and only then computed: ~136 us per pass at 56 x 56 (4x the HBM time), with the load latency
+// exposed once per block.  Here
+//   * a persistent block always has its NEXT group of planes in flight: consecutive (image, channel) planes are one
+//     contiguous span of NCHW memory, so one thread issues ONE cp.async.bulk per group into the other half of a double
+//     buffer and an mbarrier transaction count signals arrival -- no thread touches the data on its way in;
+//   * the planes stay bf16 in shared memory: a thread owns a strip of 4 consecutive outputs and reads, per input row, one
+//     aligned 8-byte word (the 4 centre inputs) and two 2-byte halo elements; rows / columns outside the plane are
+//     predicated to zero instead of being stored as padding;
+//   * weight gradient: the same landing scheme over the planes of ONE channel across images (one bulk copy per plane for
+//     x and for dy), nine tap sums per thread in registers, one atomicAdd per (channel, tap) per block.
+// Requirements (otherwise the callers stay on dwconv.cu): bf16, W % 4 == 0, (H W) % 8 == 0, one plane <= 16 KB.
+// Reference call sites: as dwconv.cu (tltorch/functional/convolution.py:268-271, 321-332 and their autograd).
+#include "tc_common.cuh"
+
+namespace tlt {
+namespace dwt {
+
+struct Params {
+  int H, W, strips;                 // strips per row = W / 4
+  int channels, PB;                 // planes per group
+  long long planes;                 // batch * channels
+  int spp;                          // strips per plane
+  uint32_t m_spp, m_strips;         // magic multipliers: floor(n / d) = umulhi(n, m) for n < 2^31 / ... (d > 1)
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ int fdiv(int n, uint32_t m, int d) { return d > 1 ? (int)__umulhi((uint32_t)n, m) : n; }
+
+// 6 inputs (columns 4 sg - 1 .. 4 sg + 4) of row `r` of a bf16 plane in shared memory, zero outside the plane
+__device__ __forceinline__ void load_row6(const __nv_bfloat16* plane, int r, int sg, const Params& q, float (&in)[6]) {
+  if (r < 0 || r >= q.H) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) in[i] = 0.f;
+    return;
+  }
+  const __nv_bfloat16* rp = plane + r * q.W + 4 * sg;
+  const uint2 mid = *reinterpret_cast<const uint2*>(rp);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mid.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mid.y));
+  in[0] = sg > 0 ? __bfloat162float(rp[-1]) : 0.f;
+  in[1] = a.x; in[2] = a.y; in[3] = b.x; in[4] = b.y;
+  in[5] = sg < q.strips - 1 ? __bfloat162float(rp[4]) : 0.f;
+}
+
+// FLIP = false: y = corr(x, w);  true: dx = corr(dy, reversed w)  (the adjoint at stride 1, pad 1)
+template <bool FLIP>
+__global__ void __launch_bounds__(256) dwconv3x3_tma_kernel(const Params q, const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                                                            long long n_groups) {
+  extern __shared__ __align__(128) unsigned char dwt_smem[];
+  const int psz = q.H * q.W;
+  const uint32_t buf_bytes = (uint32_t)q.PB * psz * 2;
+  __nv_bfloat16* bufs[2] = {reinterpret_cast<__nv_bfloat16*>(dwt_smem), reinterpret_cast<__nv_bfloat16*>(dwt_smem + buf_bytes)};
+  float* ws = reinterpret_cast<float*>(dwt_smem + 2 * buf_bytes);                 // [2][PB][9]
+  const uint32_t bar0 = smem_u32(dwt_smem + 2 * buf_bytes + 2 * q.PB * 9 * 4);    // two mbarriers (8 bytes each)
+  auto issue = [&](long long grp, int slot) {
+    const long long p0 = grp * q.PB;
+    const int npl = (int)min((long long)q.PB, q.planes - p0);
+    const uint32_t bytes = (uint32_t)npl * psz * 2;
+    mbar_expect_tx(bar0 + 8 * slot, bytes);
+    bulk_g2s(smem_u32(bufs[slot]), x + p0 * psz, bytes, bar0 + 8 * slot);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+    if ((long long)blockIdx.x < n_groups) issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+  uint32_t phase[2] = {0, 0};
+  int slot = 0;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x, slot ^= 1) {
+    const long long p0 = grp * q.PB;
+    const int npl = (int)min((long long)q.PB, q.planes - p0);
+    if (threadIdx.x == 0 && grp + gridDim.x < n_groups) issue(grp + gridDim.x, slot ^ 1);     // its readers finished last iteration
+    float* wsl = ws + slot * q.PB * 9;
+    for (int e = threadIdx.x; e < npl * 9; e += blockDim.x) {
+      const int j = e / 9, t = e - j * 9;
+      const int c = (int)((p0 + j) % q.channels);
+      wsl[j * 9 + (FLIP ? 8 - t : t)] = __bfloat162float(w[(long long)c * 9 + t]);
+    }
+    mbar_wait(bar0 + 8 * slot, phase[slot]);
+    phase[slot] ^= 1;
+    __syncthreads();                                                 // weights staged
+    const __nv_bfloat16* buf = bufs[slot];
+    const int total = npl * q.spp;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int j = fdiv(e, q.m_spp, q.spp), r = e - j * q.spp;
+      const int row = fdiv(r, q.m_strips, q.strips), sg = r - row * q.strips;
+      const __nv_bfloat16* plane = buf + j * psz;
+      const float* wp = wsl + j * 9;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t1 = 0; t1 < 3; ++t1) {
+        float in[6];
+        load_row6(plane, row + t1 - 1, sg, q, in);
+#pragma unroll
+        for (int t2 = 0; t2 < 3; ++t2) {
+          const float wk = wp[t1 * 3 + t2];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(in[o + t2], wk, acc[o]);
+        }
+      }
+      __nv_bfloat162 a = __floats2bfloat162_rn(acc[0], acc[1]), b = __floats2bfloat162_rn(acc[2], acc[3]);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(y + (p0 + j) * psz + row * q.W + 4 * sg) = o;
+    }
+    __syncthreads();                                                 // everyone is done with this slot (and its weights)
+  }
+}
+
+// dw[c, t1, t2] += sum_{b, h, w} dy[b,c,h,w] * x[b,c,h + t1 - 1, w + t2 - 1];  grid = (channels, batch chunks)
+__global__ void __launch_bounds__(256) dwconv3x3_wgrad_tma_kernel(const Params q, int batch, int batch_per_block,
+                                                                  const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                  float* __restrict__ dw) {
+  extern __shared__ __align__(128) unsigned char dwt_smem[];
+  __shared__ float red[9 * 8];
+  const int psz = q.H * q.W;
+  const uint32_t half = (uint32_t)q.PB * psz * 2;                   // one operand of one slot
+  // layout: slot 0: xs | gs, slot 1: xs | gs, then two mbarriers
+  auto xs_of = [&](int slot) { return reinterpret_cast<__nv_bfloat16*>(dwt_smem + (size_t)slot * 2 * half); };
+  auto gs_of = [&](int slot) { return reinterpret_cast<__nv_bfloat16*>(dwt_smem + (size_t)slot * 2 * half + half); };
+  const uint32_t bar0 = smem_u32(dwt_smem + 4 * (size_t)half);
+  const int c = blockIdx.x;
+  const int b_begin = blockIdx.y * batch_per_block;
+  const int b_end = min(batch, b_begin + batch_per_block);
+  auto issue = [&](int b0, int slot) {
+    const int npl = min(q.PB, b_end - b0);
+    mbar_expect_tx(bar0 + 8 * slot, (uint32_t)npl * psz * 2 * 2);
+    for (int j = 0; j < npl; ++j) {
+      const long long off = ((long long)(b0 + j) * q.channels + c) * psz;
+      bulk_g2s(smem_u32(xs_of(slot) + j * psz), x + off, (uint32_t)psz * 2, bar0 + 8 * slot);
+      bulk_g2s(smem_u32(gs_of(slot) + j * psz), dy + off, (uint32_t)psz * 2, bar0 + 8 * slot);
+    }
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+    if (b_begin < b_end) issue(b_begin, 0);
+  }
+  __syncthreads();
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  uint32_t phase[2] = {0, 0};
+  int slot = 0;
+  for (int b0 = b_begin; b0 < b_end; b0 += q.PB, slot ^= 1) {
+    const int npl = min(q.PB, b_end - b0);
+    if (threadIdx.x == 0 && b0 + q.PB < b_end) issue(b0 + q.PB, slot ^ 1);
+    mbar_wait(bar0 + 8 * slot, phase[slot]);
+    phase[slot] ^= 1;
+    const __nv_bfloat16* xs = xs_of(slot);
+    const __nv_bfloat16* gs = gs_of(slot);
+    const int total = npl * q.spp;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int j = fdiv(e, q.m_spp, q.spp), r = e - j * q.spp;
+      const int row = fdiv(r, q.m_strips, q.strips), sg = r - row * q.strips;
+      const uint2 g2 = *reinterpret_cast<const uint2*>(gs + j * psz + row * q.W + 4 * sg);
+      const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.x));
+      const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.y));
+      const float g[4] = {ga.x, ga.y, gb.x, gb.y};
+      const __nv_bfloat16* plane = xs + j * psz;
+#pragma unroll
+      for (int t1 = 0; t1 < 3; ++t1) {
+        float in[6];
+        load_row6(plane, row + t1 - 1, sg, q, in);
+#pragma unroll
+        for (int t2 = 0; t2 < 3; ++t2)
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[t1 * 3 + t2] = fmaf(in[o + t2], g[o], acc[t1 * 3 + t2]);
+      }
+    }
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float v = acc[t];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[t * 8 + warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    float v = 0.f;
+    for (int wv = 0; wv < 8; ++wv) v += red[threadIdx.x * 8 + wv];
+    atomicAdd(dw + (long long)c * 9 + threadIdx.x, v);
+  }
+}
+
+static uint32_t magic(int d) { return d > 1 ? (uint32_t)((1ull << 32) / (uint32_t)d) + 1u : 0u; }
+
+}  // namespace dwt
+
+// Entry points used by dwconv.cu's dispatch.  Return TLT_ERR_UNSUPPORTED when the shape does not qualify.
+bool dwconv3x3_tma_ok(int H, int W, const void* a, const void* b) {
+  return W % 4 == 0 && (H * W) % 8 == 0 && H * W * 2 <= 16 * 1024 && (((uintptr_t)a) & 15) == 0 && (((uintptr_t)b) & 15) == 0;
+}
+
+int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const void* x, const void* w, void* y, cudaStream_t st) {
+  dwt::Params q;
+  q.H = H; q.W = W; q.strips = W / 4; q.channels = channels; q.planes = planes;
+  q.spp = H * q.strips;
+  q.m_spp = dwt::magic(q.spp); q.m_strips = dwt::magic(q.strips);
+  const int psz = H * W;
+  // planes per group: ~16 KB per slot so that 3 blocks (2 slots each) fit one SM, at least 1 plane
+  int pb = (16 * 1024) / (psz * 2);
+  if (pb < 1) pb = 1;
+  if ((long long)pb > planes) pb = (int)planes;
+  q.PB = pb;
+  const long long groups = (planes + pb - 1) / pb;
+  const size_t smem = (size_t)2 * pb * psz * 2 + (size_t)2 * pb * 9 * 4 + 16;
+  static size_t high[2] = {0, 0};
+  if (smem > 48 * 1024 && smem > high[flip]) {
+    cudaError_t e = flip ? cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_tma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
+    high[flip] = smem;
+  }
+  const long long cap = 148LL * 4;
+  const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
+  if (flip) dwt::dwconv3x3_tma_kernel<true><<<blocks, 256, smem, st>>>(q, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, groups);
+  else dwt::dwconv3x3_tma_kernel<false><<<blocks, 256, smem, st>>>(q, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, groups);
+  return check_launch("dwconv3x3_tma_kernel");
+}
+
+int dwconv3x3_wgrad_tma(int H, int W, int channels, int batch, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  dwt::Params q;
+  q.H = H; q.W = W; q.strips = W / 4; q.channels = channels; q.planes = (long long)batch * channels;
+  q.spp = H * q.strips;
+  q.m_spp = dwt::magic(q.spp); q.m_strips = dwt::magic(q.strips);
+  const int psz = H * W;
+  long long chunks = (148LL * 6 + channels - 1) / channels;
+  if (chunks > batch) chunks = batch;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  const int bpb = (int)((batch + chunks - 1) / chunks);
+  chunks = (batch + bpb - 1) / bpb;
+  int pb = (8 * 1024) / (psz * 2);                                  // ~8 KB per operand per slot: 32 KB per block
+  if (pb < 1) pb = 1;
+  if (pb > bpb) pb = bpb;
+  q.PB = pb;
+  const size_t smem = (size_t)4 * pb * psz * 2 + 16;
+  static size_t high = 0;
+  if (smem > 48 * 1024 && smem > high) {
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_wgrad_tma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
+    high = smem;
+  }
+  dim3 grid((unsigned)channels, (unsigned)chunks);
+  dwt::dwconv3x3_wgrad_tma_kernel<<<grid, 256, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
+  return check_launch("dwconv3x3_wgrad_tma_kernel");
+}
+
+}  // namespace tlt

@@ -5,6 +5,7 @@ operand so stores are coalesced along the spatial dim), depthwise stages run in 
 dense k x k stages (Tucker core, TT cores, reconstructed kernels) run as unfold + contraction.
 """
 import math
+import os
 
 import torch
 
@@ -97,9 +98,14 @@ def _cp_rows_route(x, cp_tensor, bias, taps, stride):
         return False
     if math.prod(taps.shape[1:]) > rows_ops.DW_ROWS_MAX_TAPS or min(x.shape[1], factors[0].shape[0], factors[0].shape[1]) < 64:
         return False
+    mode = os.environ.get("TLT_CP_ROWS", "auto")          # development switch: all | off | auto
+    if mode in ("all", "off"):
+        return mode == "all"
+    # strided depthwise passes and maps the NCHW tensor-core 1x1 kernel cannot take (spatial extent not a multiple of 8
+    # on either side) go through rows; measured per layer in gpurun_out/s44 (config 3: 64->128 stride 2 3.45 -> 0.98 ms)
     s_in = math.prod(x.shape[2:])
     s_out = math.prod(-(-e // st) for e, st in zip(x.shape[2:], stride))
-    return s_in % 8 != 0 or s_out % 8 != 0
+    return s_in % 8 != 0 or s_out % 8 != 0 or any(st > 1 for st in stride)
 
 
 def _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation):
