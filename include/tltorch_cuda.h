@@ -277,6 +277,19 @@ int tlt_scale_modes(int32_t dtype, int32_t ndim, const int64_t* dims, const void
                     void* y, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Weighted Khatri-Rao product of 1..4 factor matrices:  KR[(i_1..i_n), r] = w_r * prod_k F_k[i_k, r]
+ * F_k (dims[k], R) row-major, weights (R) or NULL, out (prod dims, R); dtype f32 / bf16.
+ *   tlt_khatri_rao_bwd: dF[k] (dims[k], R) fp32 (written, NULL to skip; dF[0] is required when dweights != NULL) and
+ *   dweights (R) fp32 (ACCUMULATED: caller zeroes) from g (prod dims, R).
+ * Replaces: the Khatri-Rao operands of tensor_dot_cp / linear_cp (tltorch/functional/factorized_tensordot.py:70-103) and of
+ * CPTensor.to_tensor (factorized_tensors/factorized_tensors.py:129-130), including the lambda scaling and its gradient.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_khatri_rao_fwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
+                       void* out, void* stream);
+int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
+                       const void* g, float* const* dF, float* dweights, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Small utilities used by the host side.
  * ------------------------------------------------------------------------------------------------------------ */
 /* dst[i] = (dst dtype) src[i], n elements */

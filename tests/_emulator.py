@@ -316,6 +316,37 @@ def emulate_dwconv_rows(kind, a, b, out, batch, in_size, out_size, kernel, strid
     LOG.append(("dwconv_rows_" + kind, tuple(in_size), tuple(kernel), tuple(stride), tuple(padding), tuple(dilation)))
 
 
+def _kr_ref(factors, weights):
+    R = factors[0].shape[1]
+    res = torch.ones((1, R), dtype=torch.float64) if weights is None else weights.double().reshape(1, R)
+    for f in factors:
+        res = (res[:, None, :] * f.double()[None, :, :]).reshape(-1, R)
+    return res
+
+
+def emulate_kr_fwd(factors, weights, out):
+    out.copy_(_kr_ref(factors, weights).to(out.dtype))
+    LOG.append(("khatri_rao_fwd", [tuple(f.shape) for f in factors], weights is not None))
+
+
+def emulate_kr_bwd(factors, weights, g, dfs, dw):
+    R = factors[0].shape[1]
+    dims = [f.shape[0] for f in factors]
+    gt = g.double().reshape(*dims, R)
+    letters = "abcd"[:len(factors)]
+    w = torch.ones(R, dtype=torch.float64) if weights is None else weights.double()
+    for k in range(len(factors)):
+        if dfs[k] is None:
+            continue
+        others = [factors[j].double() for j in range(len(factors)) if j != k]
+        spec = letters + "r," + ",".join(letters[j] + "r" for j in range(len(factors)) if j != k) + "->" + letters[k] + "r"
+        t = torch.einsum(spec, gt, *others) if others else gt
+        dfs[k].copy_((t * w).to(dfs[k].dtype))
+        if k == 0 and dw is not None:
+            dw += (t * factors[0].double()).sum(0).to(dw.dtype)
+    LOG.append(("khatri_rao_bwd", [tuple(f.shape) for f in factors], weights is not None))
+
+
 def emulate_scale_modes(x, masks, alpha, y):
     res = x.double() * alpha
     for k, m in enumerate(masks):
@@ -335,6 +366,9 @@ def emulated_kernels():
     from torch_b200 import modedot_ops as mo
     from torch_b200 import tucker_ops as to
     from torch_b200 import rows_ops as ro
+    from torch_b200 import kr_ops as ko
+    saved_k = ko._execute_kr_fwd, ko._execute_kr_bwd
+    ko._execute_kr_fwd, ko._execute_kr_bwd = emulate_kr_fwd, emulate_kr_bwd
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
     saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows
     ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = (
@@ -359,6 +393,7 @@ def emulated_kernels():
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p
         mo._execute_mmd = saved_m
+        ko._execute_kr_fwd, ko._execute_kr_bwd = saved_k
         ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
         ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = saved_s
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

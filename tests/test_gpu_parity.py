@@ -812,3 +812,30 @@ def test_cp_conv_rows_path_vs_oracle(cin, cout, hw, stride):
     assert G.rel_err(y, yo) < 2e-2
     for n, a, b in zip(["x"] + list(params), grads, go):
         assert G.rel_err(a, b) < 3e-2, n
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dims,R,with_w", [((4, 8, 16), 2341, True), ((4, 8, 16), 2341, False), ((3, 3), 69, True), ((7,), 33, True),
+                                           ((2, 3, 4, 5), 17, True)])
+def test_khatri_rao_kernels_vs_fp64(dims, R, with_w, dtype):
+    """tlt_khatri_rao_fwd / _bwd (weighted Khatri-Rao product; CP linear's operands at config 1's rank) vs fp64 einsum."""
+    from torch_b200 import kr_ops
+    torch.manual_seed(R)
+    fs = [(torch.randn(d, R, device=dev()) * 0.7).to(dtype).requires_grad_(True) for d in dims]
+    w = torch.rand(R, device=dev()).add(0.5).to(dtype).requires_grad_(True) if with_w else None
+    kr = kr_ops.khatri_rao(fs, w)
+    g = torch.randn_like(kr)
+    leaves = fs + ([w] if with_w else [])
+    grads = torch.autograd.grad(kr, leaves, g)
+    fo = [f.detach().double().cpu().requires_grad_(True) for f in fs]
+    wo = w.detach().double().cpu().requires_grad_(True) if with_w else None
+    L = "abcd"[:len(dims)]
+    ref = torch.einsum(",".join(l + "r" for l in L) + "->" + L + "r", *fo)
+    if with_w:
+        ref = ref * wo
+    ref = ref.reshape(-1, R)
+    go = torch.autograd.grad(ref, fo + ([wo] if with_w else []), g.double().cpu())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert G.rel_err(kr, ref) < tol
+    for a, b in zip(grads, go):
+        assert G.rel_err(a, b) < tol

@@ -103,6 +103,9 @@ SYMBOLS = {
     "tlt_skinny_fwd": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "tlt_skinny_bwd": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_scale_modes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), _vp, C.POINTER(C.c_void_p), C.c_float, _vp, _vp]),
+    "tlt_khatri_rao_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, _vp]),
+    "tlt_khatri_rao_bwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp,
+                                     C.POINTER(C.c_void_p), _vp, _vp]),
     "tlt_cast": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, _vp]),
     "tlt_l2_flush": (C.c_int, [_vp, C.c_size_t, _vp]),
 }

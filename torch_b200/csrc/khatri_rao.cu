@@ -1,0 +1,128 @@
+// Weighted Khatri-Rao product of up to 4 factor matrices and its gradients.
+//
+//   KR[(i_1 .. i_n), r] = w_r * prod_k F_k[i_k, r]          F_k (d_k, R) row-major, w (R) optional, KR (prod d_k, R)
+//
+// This is how the CP paths meet their dense operand: tensor_dot_cp / linear_cp contract the activation with
+// KhatriRao(in-mode factors) and expand with lambda * KhatriRao(out-mode factors) (tltorch/functional/
+// factorized_tensordot.py:70-103, the n-ary einsum evaluated in FLOP-sane order), and
+// CPTensor.to_tensor builds the same product (factorized_tensors.py:129-130).  As pairwise contractions the rank index is a
+// BATCH index: every step launched R = 2341 blocks (one 64 x 64 tile each for 4 x 8 useful outputs) and cost 43-57 us, 16
+// such launches per step at BASELINE config 1; the lambda scaling and its gradient added 140 / 387 us more.  Element-wise
+// the whole product is 1.2 M multiplies: one launch forward, one launch per factor backward (thread per (i_k, r), reads
+// coalesced along r, no atomics except the n-term lambda reduction).
+#include "common.cuh"
+
+namespace tlt {
+
+struct KrParams {
+  int n, R;
+  int dims[4];
+  const void* f[4];
+  const void* w;
+  long long rows;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) khatri_rao_fwd_kernel(const KrParams p, T* __restrict__ out) {
+  const long long total = p.rows * p.R;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e % p.R);
+    long long row = e / p.R;
+    float v = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+      if (k < p.n) {
+        const int i = (int)(row % p.dims[k]);
+        row /= p.dims[k];
+        v *= to_f32<T>(static_cast<const T*>(p.f[k])[(long long)i * p.R + r]);
+      }
+    }
+    out[e] = from_f32<T>(v);
+  }
+}
+
+// dF_k[i, r] = w_r * sum_{rows with i_k = i} g[row, r] * prod_{j != k} F_j[i_j, r];   k == 0 also accumulates
+// dw_r += sum_i F_0[i, r] * (the unweighted sum).   grid = (ceil(R / 256), d_k)
+template <typename T>
+__global__ void __launch_bounds__(256) khatri_rao_bwd_kernel(const KrParams p, int k, const T* __restrict__ g, float* __restrict__ dF,
+                                                             float* __restrict__ dw) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ik = blockIdx.y;
+  if (r >= p.R) return;
+  long long others = 1;
+  for (int j = 0; j < p.n; ++j) if (j != k) others *= p.dims[j];
+  float acc = 0.f;
+  for (long long o = 0; o < others; ++o) {
+    // decode the other indices (last factor fastest) and rebuild the row index
+    long long rem = o, row = 0, mul = 1;
+    float v = 1.f;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      if (j < p.n) {
+        int i;
+        if (j == k) i = ik;
+        else {
+          i = (int)(rem % p.dims[j]);
+          rem /= p.dims[j];
+          v *= to_f32<T>(static_cast<const T*>(p.f[j])[(long long)i * p.R + r]);
+        }
+        row += i * mul;
+        mul *= p.dims[j];
+      }
+    }
+    acc = fmaf(to_f32<T>(g[row * p.R + r]), v, acc);
+  }
+  const float wr = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
+  dF[(long long)ik * p.R + r] = wr * acc;
+  if (k == 0 && dw != nullptr) atomicAdd(dw + r, acc * to_f32<T>(static_cast<const T*>(p.f[0])[(long long)ik * p.R + r]));
+}
+
+static int fill_kr(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* w, KrParams* p) {
+  TLT_REQUIRE(dtype == TLT_F32 || dtype == TLT_BF16, "khatri_rao: dtype must be f32 or bf16");
+  TLT_REQUIRE(n >= 1 && n <= 4 && dims && factors && R >= 1 && R < (1LL << 31), "khatri_rao: 1..4 factors");
+  p->n = n; p->R = (int)R; p->w = w; p->rows = 1;
+  for (int k = 0; k < 4; ++k) { p->dims[k] = 1; p->f[k] = nullptr; }
+  for (int k = 0; k < n; ++k) {
+    TLT_REQUIRE(dims[k] >= 1 && dims[k] <= 65535 && factors[k], "khatri_rao: bad factor");
+    p->dims[k] = (int)dims[k]; p->f[k] = factors[k]; p->rows *= dims[k];
+  }
+  return TLT_OK;
+}
+
+}  // namespace tlt
+
+using namespace tlt;
+
+extern "C" int tlt_khatri_rao_fwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors,
+                                  const void* weights, void* out, void* stream) {
+  KrParams p;
+  int rc = fill_kr(dtype, n, dims, R, factors, weights, &p);
+  if (rc) return rc;
+  TLT_REQUIRE(out, "tlt_khatri_rao_fwd: null output");
+  const long long total = p.rows * p.R;
+  const long long blocks = (total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148LL * 8 ? blocks : 148LL * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TLT_BF16) khatri_rao_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (__nv_bfloat16*)out);
+  else khatri_rao_fwd_kernel<float><<<grid, 256, 0, st>>>(p, (float*)out);
+  return check_launch("khatri_rao_fwd_kernel");
+}
+
+extern "C" int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors,
+                                  const void* weights, const void* g, float* const* dF, float* dweights, void* stream) {
+  KrParams p;
+  int rc = fill_kr(dtype, n, dims, R, factors, weights, &p);
+  if (rc) return rc;
+  TLT_REQUIRE(g && dF, "tlt_khatri_rao_bwd: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int k = 0; k < n; ++k) {
+    if (dF[k] == nullptr && !(k == 0 && dweights)) continue;
+    TLT_REQUIRE(dF[k] != nullptr, "tlt_khatri_rao_bwd: the weight gradient needs dF[0]");
+    dim3 grid((unsigned)((p.R + 255) / 256), (unsigned)p.dims[k]);
+    if (dtype == TLT_BF16) khatri_rao_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, k, (const __nv_bfloat16*)g, dF[k], k == 0 ? dweights : nullptr);
+    else khatri_rao_bwd_kernel<float><<<grid, 256, 0, st>>>(p, k, (const float*)g, dF[k], k == 0 ? dweights : nullptr);
+    rc = check_launch("khatri_rao_bwd_kernel");
+    if (rc) return rc;
+  }
+  return TLT_OK;
+}

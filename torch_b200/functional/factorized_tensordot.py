@@ -78,9 +78,8 @@ def tensor_dot_cp(tensor, cp, modes, addend=None):
     free_modes = [i for i in range(len(factors)) if i not in modes_cp]
     if not free_modes:
         return contract(f"{kept}z,z->{kept}", z, cp.weights)
-    kr_out = tenalg.khatri_rao_tensor([factors[m] for m in free_modes])               # (free dims..., R)
+    kr_out = tenalg.khatri_rao_tensor([factors[m] for m in free_modes], cp.weights)   # (free dims..., R), lambda folded in
     free = _L[nt:nt + len(free_modes)]
-    kr_out = contract(f"{free}z,z->{free}z", kr_out, cp.weights)                      # fold lambda into the small side
     if addend is not None:
         return contract(f"{kept}z,{free}z->{kept}{free}", z, kr_out, addend, free)
     return contract(f"{kept}z,{free}z->{kept}{free}", z, kr_out)

@@ -146,8 +146,15 @@ def batched_outer(a, b):
     return contract(f"a{la},a{lb}->a{la}{lb}", a, b)
 
 
-def khatri_rao_tensor(factors):
-    """Column-wise Kronecker of (d_k, R) matrices kept as a (d_1, ..., d_n, R) tensor (row-major = first factor slowest)."""
+def khatri_rao_tensor(factors, weights=None):
+    """Column-wise Kronecker of (d_k, R) matrices kept as a (d_1, ..., d_n, R) tensor (row-major = first factor slowest),
+    optionally scaled by ``weights`` (R).  One element-wise launch (kr_ops) for up to 4 factors."""
+    from . import kr_ops
+    factors = list(factors)
+    if kr_ops.eligible(factors, weights):
+        return kr_ops.khatri_rao(factors, weights).reshape(*[f.shape[0] for f in factors], factors[0].shape[1])
+    if weights is not None:
+        factors = [contract("ar,r->ar", factors[0], weights)] + factors[1:]
     res = factors[0]
     for i, f in enumerate(factors[1:], start=1):
         dims = _L[:i]
@@ -161,13 +168,13 @@ def khatri_rao_tensor(factors):
 def cp_to_tensor(weights, factors):
     """T[i0..] = sum_r w_r prod_k F_k[i_k, r]   (CPTensor.to_tensor, factorized_tensors/factorized_tensors.py:129-130)."""
     factors = list(factors)
-    f0 = factors[0] if weights is None else contract("ar,r->ar", factors[0], weights)
     if len(factors) == 1:
+        f0 = factors[0] if weights is None else contract("ar,r->ar", factors[0], weights)
         ones = torch.ones((), dtype=f0.dtype, device=f0.device).expand(f0.shape[1])
         return contract("ar,r->a", f0, ones)
-    kr = khatri_rao_tensor(factors[1:])
+    kr = khatri_rao_tensor(factors[1:], weights)                 # lambda rides in the element-wise Khatri-Rao launch
     rest = _L[1:len(factors)]
-    return contract(f"az,{rest}z->a{rest}", f0, kr)
+    return contract(f"az,{rest}z->a{rest}", factors[0], kr)
 
 
 def tucker_to_tensor(core, factors):
