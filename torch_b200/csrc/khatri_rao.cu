@@ -41,20 +41,19 @@ __global__ void __launch_bounds__(256) khatri_rao_fwd_kernel(const KrParams p, T
   }
 }
 
-// dF_k[i, r] = w_r * sum_{rows with i_k = i} g[row, r] * prod_{j != k} F_j[i_j, r];   k == 0 also accumulates
-// dw_r += sum_i F_0[i, r] * (the unweighted sum).   grid = (ceil(R / 256), d_k)
+// dF_k[i, r] += w_r * sum_{rows with i_k = i} g[row, r] * prod_{j != k} F_j[i_j, r];   k == 0 also accumulates
+// dw_r += sum_i F_0[i, r] * (the unweighted sum).   grid = (ceil(R / 128), d_k, splits of the other indices); dF zeroed.
 template <typename T>
-__global__ void __launch_bounds__(256) khatri_rao_bwd_kernel(const KrParams p, int k, const T* __restrict__ g, float* __restrict__ dF,
-                                                             float* __restrict__ dw) {
+__global__ void __launch_bounds__(128) khatri_rao_bwd_kernel(const KrParams p, int k, const T* __restrict__ g, float* __restrict__ dF,
+                                                             float* __restrict__ dw, int others, int per_split) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int ik = blockIdx.y;
   if (r >= p.R) return;
-  long long others = 1;
-  for (int j = 0; j < p.n; ++j) if (j != k) others *= p.dims[j];
+  const int o0 = blockIdx.z * per_split, o1 = min(others, o0 + per_split);
   float acc = 0.f;
-  for (long long o = 0; o < others; ++o) {
+  for (int o = o0; o < o1; ++o) {
     // decode the other indices (last factor fastest) and rebuild the row index
-    long long rem = o, row = 0, mul = 1;
+    int rem = o, row = 0, mul = 1;
     float v = 1.f;
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
@@ -62,18 +61,19 @@ __global__ void __launch_bounds__(256) khatri_rao_bwd_kernel(const KrParams p, i
         int i;
         if (j == k) i = ik;
         else {
-          i = (int)(rem % p.dims[j]);
-          rem /= p.dims[j];
+          const int q = rem / p.dims[j];
+          i = rem - q * p.dims[j];
+          rem = q;
           v *= to_f32<T>(static_cast<const T*>(p.f[j])[(long long)i * p.R + r]);
         }
         row += i * mul;
         mul *= p.dims[j];
       }
     }
-    acc = fmaf(to_f32<T>(g[row * p.R + r]), v, acc);
+    acc = fmaf(to_f32<T>(g[(long long)row * p.R + r]), v, acc);
   }
   const float wr = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
-  dF[(long long)ik * p.R + r] = wr * acc;
+  atomicAdd(dF + (long long)ik * p.R + r, wr * acc);
   if (k == 0 && dw != nullptr) atomicAdd(dw + r, acc * to_f32<T>(static_cast<const T*>(p.f[0])[(long long)ik * p.R + r]));
 }
 
@@ -118,9 +118,19 @@ extern "C" int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims,
   for (int k = 0; k < n; ++k) {
     if (dF[k] == nullptr && !(k == 0 && dweights)) continue;
     TLT_REQUIRE(dF[k] != nullptr, "tlt_khatri_rao_bwd: the weight gradient needs dF[0]");
-    dim3 grid((unsigned)((p.R + 255) / 256), (unsigned)p.dims[k]);
-    if (dtype == TLT_BF16) khatri_rao_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, k, (const __nv_bfloat16*)g, dF[k], k == 0 ? dweights : nullptr);
-    else khatri_rao_bwd_kernel<float><<<grid, 256, 0, st>>>(p, k, (const float*)g, dF[k], k == 0 ? dweights : nullptr);
+    const long long others = p.rows / p.dims[k];
+    TLT_REQUIRE(others < (1LL << 31) && p.rows < (1LL << 31), "tlt_khatri_rao_bwd: product of the factor extents out of range");
+    const long long bx = (p.R + 127) / 128;
+    long long splits = (148LL * 16 + bx * p.dims[k] - 1) / (bx * p.dims[k]);          // ~16 blocks of 128 threads per SM
+    if (splits > others) splits = others;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    const int per_split = (int)((others + splits - 1) / splits);
+    splits = (others + per_split - 1) / per_split;
+    TLT_CHECK_CUDA(cudaMemsetAsync(dF[k], 0, (size_t)p.dims[k] * p.R * sizeof(float), st));
+    dim3 grid((unsigned)bx, (unsigned)p.dims[k], (unsigned)splits);
+    if (dtype == TLT_BF16) khatri_rao_bwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(p, k, (const __nv_bfloat16*)g, dF[k], k == 0 ? dweights : nullptr, (int)others, per_split);
+    else khatri_rao_bwd_kernel<float><<<grid, 128, 0, st>>>(p, k, (const float*)g, dF[k], k == 0 ? dweights : nullptr, (int)others, per_split);
     rc = check_launch("khatri_rao_bwd_kernel");
     if (rc) return rc;
   }
