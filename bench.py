@@ -289,8 +289,18 @@ def run_ours(args):
     if peak is None:
         peak, peak_src = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launches": len(prof),
+    # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command (profiles/)
+    traffic, traffic_src = None, None
+    try:
+        cap = json.load(open(os.path.join(REPO, "profiles", "r01_gemm_tc3_traffic.json")))
+        traffic, traffic_src = cap["avg_dram_mbytes_per_launch"] * 1e6, "profiles/r01_gemm_tc3_traffic.json: " + cap["source"]
+    except Exception:
+        pass
+    gemm_bytes = sum(b for *_, b in prof)
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tc3_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gemm_bytes / max(len(prof), 1),
+                "peak_source": peak_src, "launches": len(prof),
                 "avg_launch_ms": gemm_ms / max(len(prof), 1), "kernel_share_of_step": gemm_ms / ms, "step_mode": mode,
                 "algorithmic_flops_per_step": gemm_flops / max(args.steps, 1)}
     per_shape = {}
