@@ -121,7 +121,9 @@ def config3(args):
         if key not in seen:
             torch.manual_seed(1)
             conv = tlt.FactorizedConv(cin, cout, 3, order=2, padding=1, stride=stride, factorization="cp", rank=0.25, bias=False,
-                                      device=dev, dtype=torch.float32).to(torch.bfloat16)
+                                      device=dev, dtype=torch.float32)
+            conv.reset_parameters()                       # like the reference, the constructor leaves the factors uninitialised
+            conv = conv.to(torch.bfloat16)
             x = torch.randn(B, cin, hw, hw, device=dev, dtype=torch.bfloat16).requires_grad_(True)
             ms, mode, n = time_step(fwd_bwd([conv], x), max(args.steps // 4, 5), 3)
             R = int(conv.weight.rank)
@@ -151,7 +153,9 @@ def config4(args):
     torch.manual_seed(2)
     B = 512
     conv = tlt.FactorizedConv(512, 512, 3, order=2, padding=1, factorization="tucker", rank=0.5, bias=True, device=dev,
-                              dtype=torch.float32).to(torch.bfloat16)
+                              dtype=torch.float32)
+    conv.reset_parameters()
+    conv = conv.to(torch.bfloat16)
     x = torch.randn(B, 512, 7, 7, device=dev, dtype=torch.bfloat16).requires_grad_(True)
     ms, mode, n = time_step(fwd_bwd([conv], x), args.steps, args.warmup)
     out.append(report(f"4-conv: tucker conv 512->512 3x3 @7^2 rank={tuple(conv.weight.rank)} B=512 bf16 (no dropout)", ms, mode, n, B, "tensor",

@@ -21,12 +21,16 @@ if what == "trl":
     layer = layer.to(torch.bfloat16)
     x = torch.randn(512, 2048, 7, 7, device=dev, dtype=torch.bfloat16)
 elif what == "tucker_conv":
-    layer = tlt.FactorizedConv(512, 512, 3, order=2, padding=1, factorization="tucker", rank=0.5, bias=True, device=dev).to(torch.bfloat16)
+    layer = tlt.FactorizedConv(512, 512, 3, order=2, padding=1, factorization="tucker", rank=0.5, bias=True, device=dev)
+    layer.reset_parameters()
+    layer = layer.to(torch.bfloat16)
     x = torch.randn(512, 512, 7, 7, device=dev, dtype=torch.bfloat16)
 elif what.startswith("cp_conv"):
     _, cin, cout, hw, stride = what.split(":")
     layer = tlt.FactorizedConv(int(cin), int(cout), 3, order=2, padding=1, stride=int(stride), factorization="cp", rank=0.25, bias=False,
-                               device=dev).to(torch.bfloat16)
+                               device=dev)
+    layer.reset_parameters()
+    layer = layer.to(torch.bfloat16)
     x = torch.randn(256, int(cin), int(hw), int(hw), device=dev, dtype=torch.bfloat16)
 elif what == "tucker_linear":
     layer = tlt.FactorizedLinear((16, 16, 16), (16, 16, 16), bias=True, factorization="tucker", rank=0.75, device=dev).to(torch.bfloat16)
