@@ -170,11 +170,94 @@ __global__ void __launch_bounds__(256) dwconv_rows_wgrad_kernel(const DwRowsGeom
 // (the generic N-D kernels above spend ~100 instructions per tap on the index arithmetic: 96-103 us per pass over a 29 MB
 // tensor at config 3's layer3 shapes).
 // ---------------------------------------------------------------------------------------------------------------------
+// v2: a thread owns 8 channels of a whole output ROW (b, y, :).  The 9 x 8 tap weights are unpacked to fp32 registers once,
+// the three source-row base pointers once per output row, so an output costs 9 16-byte loads + their unpacking + 72 FMAs
+// and a handful of integer ops (v1 decoded the position per output with 64-bit arithmetic: 700 instructions per output,
+// issue-bound at 54-58 us per pass; profiles/r01_dwconv_rows.md).
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
 template <bool DGRAD>
-__global__ void __launch_bounds__(256) dwconv_rows2d_kernel(const DwRowsGeom g, const uint4* __restrict__ src, const uint4* __restrict__ w,
+__global__ void __launch_bounds__(128) dwconv_rows2d_kernel(const DwRowsGeom g, const uint4* __restrict__ src, const uint4* __restrict__ w,
                                                             uint4* __restrict__ dst) {
   const int H = DGRAD ? g.in_size[0] : g.out_size[0], W = DGRAD ? g.in_size[1] : g.out_size[1];      // extents of dst
   const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SW = DGRAD ? g.out_size[1] : g.in_size[1];    // extents of src
+  const int KH = g.kernel[0], KW = g.kernel[1], cpr = g.cpr;
+  const int sh = g.stride[0], sw = g.stride[1], ph = g.padding[0], pw = g.padding[1], dh = g.dilation[0], dwl = g.dilation[1];
+  const long long total = g.batch * H * cpr;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % cpr);
+    const long long row = e / cpr;
+    const int y = (int)(row % H);
+    const long long b = row / H;
+    float wk[3][3][8];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        if (kh < KH && kw < KW) unpack8(w[(kh * KW + kw) * cpr + ch], wk[kh][kw]);
+      }
+    const uint4* srow[3];
+    bool rok[3];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int sy = 0;
+      bool ok = kh < KH;
+      if (!DGRAD) {
+        sy = y * sh - ph + kh * dh;
+        ok = ok && sy >= 0 && sy < SH;
+      } else {
+        const int num = y + ph - kh * dh;
+        sy = sh == 1 ? num : num / sh;
+        ok = ok && num >= 0 && sy * sh == num && sy < SH;
+      }
+      rok[kh] = ok;
+      srow[kh] = src + ((b * SH + (ok ? sy : 0)) * SW) * cpr + ch;
+    }
+    uint4* drow = dst + ((b * H + y) * (long long)W) * cpr + ch;
+    for (int x = 0; x < W; ++x) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int sx = 0;
+        bool ok = kw < KW;
+        if (!DGRAD) {
+          sx = x * sw - pw + kw * dwl;
+          ok = ok && sx >= 0 && sx < SW;
+        } else {
+          const int num = x + pw - kw * dwl;
+          sx = sw == 1 ? num : num / sw;
+          ok = ok && num >= 0 && sx * sw == num && sx < SW;
+        }
+        if (!ok) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          if (rok[kh]) {
+            float v[8];
+            unpack8(srow[kh][sx * cpr], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], wk[kh][kw][i], acc[i]);
+          }
+        }
+      }
+      drow[x * cpr] = pack8(acc);
+    }
+  }
+}
+
+// generic 2-D kernel sizes (> 3 in a dimension): thread per output, taps as runtime loops
+template <bool DGRAD>
+__global__ void __launch_bounds__(256) dwconv_rows2d_big_kernel(const DwRowsGeom g, const uint4* __restrict__ src, const uint4* __restrict__ w,
+                                                                uint4* __restrict__ dst) {
+  const int H = DGRAD ? g.in_size[0] : g.out_size[0], W = DGRAD ? g.in_size[1] : g.out_size[1];
+  const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SW = DGRAD ? g.out_size[1] : g.in_size[1];
   const int KH = g.kernel[0], KW = g.kernel[1], cpr = g.cpr;
   const int sh = g.stride[0], sw = g.stride[1], ph = g.padding[0], pw = g.padding[1], dh = g.dilation[0], dwl = g.dilation[1];
   const long long total = g.batch * H * W * cpr;
@@ -317,9 +400,15 @@ extern "C" int tlt_dwconv_rows_fwd(const tlt_conv_desc* d, const void* z, const 
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(z && w && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "tlt_dwconv_rows_fwd: 16-byte aligned tensors");
-  if (g.ndim == 2) {
-    dwconv_rows2d_kernel<false><<<dw_grid(g.batch * g.out_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
+  if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
+    const long long threads = g.batch * g.out_size[0] * g.cpr;
+    const unsigned blocks = (unsigned)((threads + 127) / 128 < 148LL * 32 ? (threads + 127) / 128 : 148LL * 32);
+    dwconv_rows2d_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
     return check_launch("dwconv_rows2d_kernel<fwd>");
+  }
+  if (g.ndim == 2) {
+    dwconv_rows2d_big_kernel<false><<<dw_grid(g.batch * g.out_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
+    return check_launch("dwconv_rows2d_big_kernel<fwd>");
   }
   dwconv_rows_kernel<false><<<dw_grid(g.batch * g.out_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
   return check_launch("dwconv_rows_kernel<fwd>");
@@ -330,9 +419,15 @@ extern "C" int tlt_dwconv_rows_dgrad(const tlt_conv_desc* d, const void* gy, con
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(gy && w && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)dz % 16) == 0, "tlt_dwconv_rows_dgrad: 16-byte aligned tensors");
-  if (g.ndim == 2) {
-    dwconv_rows2d_kernel<true><<<dw_grid(g.batch * g.in_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
+  if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
+    const long long threads = g.batch * g.in_size[0] * g.cpr;
+    const unsigned blocks = (unsigned)((threads + 127) / 128 < 148LL * 32 ? (threads + 127) / 128 : 148LL * 32);
+    dwconv_rows2d_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
     return check_launch("dwconv_rows2d_kernel<dgrad>");
+  }
+  if (g.ndim == 2) {
+    dwconv_rows2d_big_kernel<true><<<dw_grid(g.batch * g.in_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
+    return check_launch("dwconv_rows2d_big_kernel<dgrad>");
   }
   dwconv_rows_kernel<true><<<dw_grid(g.batch * g.in_sp * g.cpr), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
   return check_launch("dwconv_rows_kernel<dgrad>");

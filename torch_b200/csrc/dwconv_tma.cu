@@ -20,7 +20,7 @@ namespace tlt {
 namespace dwt {
 
 struct Params {
-  int H, W, strips;                 // strips per row = W / 4
+  int H, W, strips;                 // strips per row = W / SW (SW = 8 when W % 8 == 0, else 4)
   int channels, PB;                 // planes per group
   long long planes;                 // batch * channels
   int spp;                          // strips per plane
@@ -33,24 +33,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ int fdiv(int n, uint32_t m, int d) { return d > 1 ? (int)__umulhi((uint32_t)n, m) : n; }
 
-// 6 inputs (columns 4 sg - 1 .. 4 sg + 4) of row `r` of a bf16 plane in shared memory, zero outside the plane
-__device__ __forceinline__ void load_row6(const __nv_bfloat16* plane, int r, int sg, const Params& q, float (&in)[6]) {
+// SW + 2 inputs (columns SW sg - 1 .. SW sg + SW) of row `r` of a bf16 plane in shared memory, zero outside the plane
+template <int SW>
+__device__ __forceinline__ void load_row(const __nv_bfloat16* plane, int r, int sg, const Params& q, float (&in)[SW + 2]) {
   if (r < 0 || r >= q.H) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) in[i] = 0.f;
+    for (int i = 0; i < SW + 2; ++i) in[i] = 0.f;
     return;
   }
-  const __nv_bfloat16* rp = plane + r * q.W + 4 * sg;
-  const uint2 mid = *reinterpret_cast<const uint2*>(rp);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mid.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mid.y));
+  const __nv_bfloat16* rp = plane + r * q.W + SW * sg;
   in[0] = sg > 0 ? __bfloat162float(rp[-1]) : 0.f;
-  in[1] = a.x; in[2] = a.y; in[3] = b.x; in[4] = b.y;
-  in[5] = sg < q.strips - 1 ? __bfloat162float(rp[4]) : 0.f;
+#pragma unroll
+  for (int h = 0; h < SW / 4; ++h) {
+    const uint2 mid = *reinterpret_cast<const uint2*>(rp + 4 * h);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mid.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&mid.y));
+    in[1 + 4 * h] = a.x; in[2 + 4 * h] = a.y; in[3 + 4 * h] = b.x; in[4 + 4 * h] = b.y;
+  }
+  in[SW + 1] = sg < q.strips - 1 ? __bfloat162float(rp[SW]) : 0.f;
 }
 
 // FLIP = false: y = corr(x, w);  true: dx = corr(dy, reversed w)  (the adjoint at stride 1, pad 1)
-template <bool FLIP>
+template <bool FLIP, int SW>
 __global__ void __launch_bounds__(256) dwconv3x3_tma_kernel(const Params q, const __nv_bfloat16* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
                                                             long long n_groups) {
@@ -96,29 +100,37 @@ __global__ void __launch_bounds__(256) dwconv3x3_tma_kernel(const Params q, cons
       const int row = fdiv(r, q.m_strips, q.strips), sg = r - row * q.strips;
       const __nv_bfloat16* plane = buf + j * psz;
       const float* wp = wsl + j * 9;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float wk[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wk[t] = wp[t];
+      float acc[SW];
+#pragma unroll
+      for (int o = 0; o < SW; ++o) acc[o] = 0.f;
 #pragma unroll
       for (int t1 = 0; t1 < 3; ++t1) {
-        float in[6];
-        load_row6(plane, row + t1 - 1, sg, q, in);
+        float in[SW + 2];
+        load_row<SW>(plane, row + t1 - 1, sg, q, in);
 #pragma unroll
-        for (int t2 = 0; t2 < 3; ++t2) {
-          const float wk = wp[t1 * 3 + t2];
+        for (int t2 = 0; t2 < 3; ++t2)
 #pragma unroll
-          for (int o = 0; o < 4; ++o) acc[o] = fmaf(in[o + t2], wk, acc[o]);
-        }
+          for (int o = 0; o < SW; ++o) acc[o] = fmaf(in[o + t2], wk[t1 * 3 + t2], acc[o]);
       }
-      __nv_bfloat162 a = __floats2bfloat162_rn(acc[0], acc[1]), b = __floats2bfloat162_rn(acc[2], acc[3]);
-      uint2 o;
-      o.x = *reinterpret_cast<uint32_t*>(&a);
-      o.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(y + (p0 + j) * psz + row * q.W + 4 * sg) = o;
+      uint32_t packed[SW / 2];
+#pragma unroll
+      for (int o = 0; o < SW / 2; ++o) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(acc[2 * o], acc[2 * o + 1]);
+        packed[o] = *reinterpret_cast<uint32_t*>(&a);
+      }
+      __nv_bfloat16* dptr = y + (p0 + j) * psz + row * q.W + SW * sg;
+      if (SW == 8) *reinterpret_cast<uint4*>(dptr) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      else *reinterpret_cast<uint2*>(dptr) = make_uint2(packed[0], packed[1]);
     }
     __syncthreads();                                                 // everyone is done with this slot (and its weights)
   }
 }
 
 // dw[c, t1, t2] += sum_{b, h, w} dy[b,c,h,w] * x[b,c,h + t1 - 1, w + t2 - 1];  grid = (channels, batch chunks)
+template <int SW>
 __global__ void __launch_bounds__(256) dwconv3x3_wgrad_tma_kernel(const Params q, int batch, int batch_per_block,
                                                                   const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                   float* __restrict__ dw) {
@@ -165,19 +177,23 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_tma_kernel(const Params q
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
       const int j = fdiv(e, q.m_spp, q.spp), r = e - j * q.spp;
       const int row = fdiv(r, q.m_strips, q.strips), sg = r - row * q.strips;
-      const uint2 g2 = *reinterpret_cast<const uint2*>(gs + j * psz + row * q.W + 4 * sg);
-      const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.x));
-      const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.y));
-      const float g[4] = {ga.x, ga.y, gb.x, gb.y};
+      float g[SW];
+#pragma unroll
+      for (int h = 0; h < SW / 4; ++h) {
+        const uint2 g2 = *reinterpret_cast<const uint2*>(gs + j * psz + row * q.W + SW * sg + 4 * h);
+        const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.x));
+        const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g2.y));
+        g[4 * h] = ga.x; g[4 * h + 1] = ga.y; g[4 * h + 2] = gb.x; g[4 * h + 3] = gb.y;
+      }
       const __nv_bfloat16* plane = xs + j * psz;
 #pragma unroll
       for (int t1 = 0; t1 < 3; ++t1) {
-        float in[6];
-        load_row6(plane, row + t1 - 1, sg, q, in);
+        float in[SW + 2];
+        load_row<SW>(plane, row + t1 - 1, sg, q, in);
 #pragma unroll
         for (int t2 = 0; t2 < 3; ++t2)
 #pragma unroll
-          for (int o = 0; o < 4; ++o) acc[t1 * 3 + t2] = fmaf(in[o + t2], g[o], acc[t1 * 3 + t2]);
+          for (int o = 0; o < SW; ++o) acc[t1 * 3 + t2] = fmaf(in[o + t2], g[o], acc[t1 * 3 + t2]);
       }
     }
     __syncthreads();
@@ -209,7 +225,8 @@ bool dwconv3x3_tma_ok(int H, int W, const void* a, const void* b) {
 
 int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const void* x, const void* w, void* y, cudaStream_t st) {
   dwt::Params q;
-  q.H = H; q.W = W; q.strips = W / 4; q.channels = channels; q.planes = planes;
+  const int SWd = W % 8 == 0 ? 8 : 4;
+  q.H = H; q.W = W; q.strips = W / SWd; q.channels = channels; q.planes = planes;
   q.spp = H * q.strips;
   q.m_spp = dwt::magic(q.spp); q.m_strips = dwt::magic(q.strips);
   const int psz = H * W;
@@ -221,22 +238,32 @@ int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const
   const long long groups = (planes + pb - 1) / pb;
   const size_t smem = (size_t)2 * pb * psz * 2 + (size_t)2 * pb * 9 * 4 + 16;
   static size_t high[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > high[flip]) {
-    cudaError_t e = flip ? cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024 && smem > high[0]) {
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_tma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
-    high[flip] = smem;
+    high[0] = smem;
   }
   const long long cap = 148LL * 4;
   const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
-  if (flip) dwt::dwconv3x3_tma_kernel<true><<<blocks, 256, smem, st>>>(q, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, groups);
-  else dwt::dwconv3x3_tma_kernel<false><<<blocks, 256, smem, st>>>(q, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, groups);
+  const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *wp = (const __nv_bfloat16*)w;
+  __nv_bfloat16* yp = (__nv_bfloat16*)y;
+  if (SWd == 8) {
+    if (flip) dwt::dwconv3x3_tma_kernel<true, 8><<<blocks, 256, smem, st>>>(q, xp, wp, yp, groups);
+    else dwt::dwconv3x3_tma_kernel<false, 8><<<blocks, 256, smem, st>>>(q, xp, wp, yp, groups);
+  } else {
+    if (flip) dwt::dwconv3x3_tma_kernel<true, 4><<<blocks, 256, smem, st>>>(q, xp, wp, yp, groups);
+    else dwt::dwconv3x3_tma_kernel<false, 4><<<blocks, 256, smem, st>>>(q, xp, wp, yp, groups);
+  }
   return check_launch("dwconv3x3_tma_kernel");
 }
 
 int dwconv3x3_wgrad_tma(int H, int W, int channels, int batch, const void* x, const void* dy, float* dw, cudaStream_t st) {
   dwt::Params q;
-  q.H = H; q.W = W; q.strips = W / 4; q.channels = channels; q.planes = (long long)batch * channels;
+  const int SWd = W % 8 == 0 ? 8 : 4;
+  q.H = H; q.W = W; q.strips = W / SWd; q.channels = channels; q.planes = (long long)batch * channels;
   q.spp = H * q.strips;
   q.m_spp = dwt::magic(q.spp); q.m_strips = dwt::magic(q.strips);
   const int psz = H * W;
@@ -253,12 +280,14 @@ int dwconv3x3_wgrad_tma(int H, int W, int channels, int batch, const void* x, co
   const size_t smem = (size_t)4 * pb * psz * 2 + 16;
   static size_t high = 0;
   if (smem > 48 * 1024 && smem > high) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_wgrad_tma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
     high = smem;
   }
   dim3 grid((unsigned)channels, (unsigned)chunks);
-  dwt::dwconv3x3_wgrad_tma_kernel<<<grid, 256, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
+  if (SWd == 8) dwt::dwconv3x3_wgrad_tma_kernel<8><<<grid, 256, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
+  else dwt::dwconv3x3_wgrad_tma_kernel<4><<<grid, 256, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
   return check_launch("dwconv3x3_wgrad_tma_kernel");
 }
 

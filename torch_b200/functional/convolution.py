@@ -9,7 +9,7 @@ import os
 
 import torch
 
-from .. import ops, tenalg, pointwise_ops, rows_ops
+from .. import ops, tenalg, pointwise_ops, rows_ops, kr_ops
 from ..ops import contract
 
 
@@ -89,14 +89,14 @@ def general_conv1d(x, kernel, mode, bias=None, stride=1, padding=0, groups=1, di
                     groups=groups)
 
 
-def _cp_rows_route(x, cp_tensor, bias, taps, stride):
+def _cp_rows_route(x, cp_tensor, bias, kernel, stride):
     """Rows route for the CP convolution: bf16, enough channels for the GEMMs, and a map the NCHW tensor-core 1x1 kernel
     cannot take on BOTH sides of the depthwise stage (spatial extents not multiples of 8)."""
     factors = list(cp_tensor.factors)
     order = len(factors) - 2
     if not rows_ops.rows_eligible(x, [cp_tensor.weights, bias] + factors, order):
         return False
-    if math.prod(taps.shape[1:]) > rows_ops.DW_ROWS_MAX_TAPS or min(x.shape[1], factors[0].shape[0], factors[0].shape[1]) < 64:
+    if math.prod(kernel) > rows_ops.DW_ROWS_MAX_TAPS or min(x.shape[1], factors[0].shape[0], factors[0].shape[1]) < 64:
         return False
     mode = os.environ.get("TLT_CP_ROWS", "auto")          # development switch: all | off | auto
     if mode in ("all", "off"):
@@ -112,20 +112,26 @@ def _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation):
     factors = list(cp_tensor.factors)
     order = len(factors) - 2
     stride, padding, dilation = _tuple(stride, order), _tuple(padding, order), _tuple(dilation, order)
-    # depthwise over all spatial modes at once: taps[r, k1..kd] = prod_j F_{2+j}[k_j, r]
-    taps = factors[2].t()
-    for f in factors[3:]:
-        taps = tenalg.batched_outer(taps, f.t())
-    # R -> C_out with lambda folded into the (small) output factor
-    f0 = contract("or,r->or", factors[0], cp_tensor.weights)
-    if _cp_rows_route(x, cp_tensor, bias, taps, stride):
-        # small odd-sized maps (14 x 14, 7 x 7): channels-last rows -- both 1x1 stages are K-major tcgen05 GEMMs and the
+    # depthwise over all spatial modes at once: taps[(k1..kd), r] = lambda_r prod_j F_{2+j}[k_j, r] -- the weighted
+    # Khatri-Rao product of the kernel-mode factors, ONE element-wise launch (kr_ops); lambda rides in the taps, so the
+    # output factor is used as it is (no 'or,r->or' scaling pass and no gradient kernel for it)
+    kernel = [f.shape[0] for f in factors[2:]]
+    if kr_ops.eligible(factors[2:], cp_tensor.weights):
+        taps_t = kr_ops.khatri_rao(factors[2:], cp_tensor.weights)                 # (prod k, R), taps-major
+        f0 = factors[0]
+    else:
+        taps = factors[2].t()
+        for f in factors[3:]:
+            taps = tenalg.batched_outer(taps, f.t())
+        taps_t = taps.reshape(taps.shape[0], -1).t()
+        f0 = contract("or,r->or", factors[0], cp_tensor.weights)                   # lambda folded into the output factor
+    if _cp_rows_route(x, cp_tensor, bias, kernel, stride):
+        # small odd-sized or strided maps: channels-last rows -- both 1x1 stages are K-major tcgen05 GEMMs and the
         # depthwise stage moves 16-byte channel chunks (rows_ops.cp_conv_rows)
-        kernel = list(taps.shape[1:])
-        return rows_ops.cp_conv_rows(x, taps.reshape(taps.shape[0], -1), factors[1], f0, bias, kernel, stride, padding, dilation)
+        return rows_ops.cp_conv_rows(x, taps_t, factors[1], f0, bias, kernel, stride, padding, dilation)
     # C_in -> R : z[b,r,s] = sum_c F1[c,r] x[b,c,s]
     z = _pointwise(x, "co", factors[1])
-    z = ops.dwconv(z, taps, stride, padding, dilation)
+    z = ops.dwconv(z, taps_t.t().reshape(taps_t.shape[1], *kernel), stride, padding, dilation)
     return _pointwise(z, "oc", f0, bias)
 
 

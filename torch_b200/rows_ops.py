@@ -412,16 +412,16 @@ def dwconv_rows(z, w_taps, batch, in_size, kernel, stride, padding, dilation):
     return _dwrows_op(z, w_taps, batch, list(in_size), list(kernel), list(stride), list(padding), list(dilation))
 
 
-def cp_conv_rows(x, taps, f_in, f_out_scaled, bias, kernel, stride, padding, dilation):
-    """CP convolution on channels-last rows.  x (B, C_in, *S) bf16; taps (R, prod(kernel)) the merged depthwise kernel;
-    f_in (C_in, R); f_out_scaled (C_out, R) with lambda already folded in.
+def cp_conv_rows(x, taps_t, f_in, f_out_scaled, bias, kernel, stride, padding, dilation):
+    """CP convolution on channels-last rows.  x (B, C_in, *S) bf16; taps_t (prod(kernel), R) the merged depthwise kernel,
+    taps-major; f_in (C_in, R); f_out_scaled (C_out, R); lambda is folded into the taps or into f_out_scaled by the caller.
     x -> rows -> [C_in -> R: GEMM] -> depthwise on rows -> [R -> C_out: GEMM + bias] -> NCHW."""
     b, spatial = x.shape[0], list(x.shape[2:])
     r = f_in.shape[1]
     out_size = ops.conv_out_size(spatial, list(kernel), list(stride), list(padding), list(dilation))
     xt = nchw_to_rows(x)                                                       # (B S, round8(C_in))
     z = padded_linear(xt, f_in.t(), None, True)                                # (B S, round8(R)), pad columns zero
-    w_taps = F.pad(taps.t(), (0, _r8(r) - r))                                  # (taps, round8(R)), taps-major
+    w_taps = F.pad(taps_t, (0, _r8(r) - r))                                    # (taps, round8(R))
     z = dwconv_rows(z, w_taps, b, spatial, kernel, stride, padding, dilation)  # (B S', round8(R))
     yt = padded_linear(z, f_out_scaled, bias, True)                            # (B S', round8(C_out))
     return rows_to_nchw(yt, b, f_out_scaled.shape[0], out_size)
