@@ -186,17 +186,20 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 
 template <bool DGRAD>
 __global__ void __launch_bounds__(128) dwconv_rows2d_kernel(const DwRowsGeom g, const uint4* __restrict__ src, const uint4* __restrict__ w,
-                                                            uint4* __restrict__ dst) {
+                                                            uint4* __restrict__ dst, int segs, int seg_len) {
   const int H = DGRAD ? g.in_size[0] : g.out_size[0], W = DGRAD ? g.in_size[1] : g.out_size[1];      // extents of dst
   const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SW = DGRAD ? g.out_size[1] : g.in_size[1];    // extents of src
   const int KH = g.kernel[0], KW = g.kernel[1], cpr = g.cpr;
   const int sh = g.stride[0], sw = g.stride[1], ph = g.padding[0], pw = g.padding[1], dh = g.dilation[0], dwl = g.dilation[1];
-  const long long total = g.batch * H * cpr;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+  const long long total = g.batch * H * segs * cpr;                  // a row is cut into `segs` segments when rows alone
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {   // cannot fill the GPU
     const int ch = (int)(e % cpr);
-    const long long row = e / cpr;
+    long long row = e / cpr;
+    const int seg = (int)(row % segs);
+    row /= segs;
     const int y = (int)(row % H);
     const long long b = row / H;
+    const int x_begin = seg * seg_len, x_end = min(W, x_begin + seg_len);
     float wk[3][3][8];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
@@ -222,8 +225,13 @@ __global__ void __launch_bounds__(128) dwconv_rows2d_kernel(const DwRowsGeom g, 
       srow[kh] = src + ((b * SH + (ok ? sy : 0)) * SW) * cpr + ch;
     }
     uint4* drow = dst + ((b * H + y) * (long long)W) * cpr + ch;
-    for (int x = 0; x < W; ++x) {
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int x = x_begin; x < x_end; ++x) {
+      // all nine loads are issued before any arithmetic (clamped addresses, invalid taps zeroed afterwards): with the
+      // loads behind per-tap branches a thread had ONE 16-byte load in flight and the kernel sat on the long scoreboard
+      // at 14 % of the DRAM bandwidth (profiles/r01_dwconv_rows.md)
+      uint4 raw[3][3];
+      bool cok[3];
+      int sxs[3];
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         int sx = 0;
@@ -236,17 +244,25 @@ __global__ void __launch_bounds__(128) dwconv_rows2d_kernel(const DwRowsGeom g, 
           sx = sw == 1 ? num : num / sw;
           ok = ok && num >= 0 && sx * sw == num && sx < SW;
         }
-        if (!ok) continue;
+        cok[kw] = ok;
+        sxs[kw] = ok ? sx : 0;
+      }
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          if (rok[kh]) {
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) raw[kh][kw] = srow[kh][sxs[kw] * cpr];
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          if (kh < 3 && rok[kh] && cok[kw]) {
             float v[8];
-            unpack8(srow[kh][sx * cpr], v);
+            unpack8(raw[kh][kw], v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], wk[kh][kw][i], acc[i]);
           }
         }
-      }
       drow[x * cpr] = pack8(acc);
     }
   }
@@ -330,17 +346,26 @@ __global__ void __launch_bounds__(256) dwconv_rows2d_wgrad_kernel(const DwRowsGe
         const uint4 gv = gy[row * cpr + ch];
         const uint4* zb = z + b * IH * IW * cpr + ch;
         const int y0 = oy * sh - ph, x0 = ox * sw - pw;
+        uint4 raw[3][3];
+        bool okh[3], okw[3];
+        int iys[3], ixs[3];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int iy = y0 + kh * dh;
-          if (kh < KH && iy >= 0 && iy < IH) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-              const int ix = x0 + kw * dwl;
-              if (kw < KW && ix >= 0 && ix < IW) fma8(acc[kh][kw], zb[((long long)iy * IW + ix) * cpr], gv);
-            }
-          }
+        for (int k = 0; k < 3; ++k) {
+          const int iy = y0 + k * dh, ix = x0 + k * dwl;
+          okh[k] = k < KH && iy >= 0 && iy < IH;
+          okw[k] = k < KW && ix >= 0 && ix < IW;
+          iys[k] = okh[k] ? iy : 0;
+          ixs[k] = okw[k] ? ix : 0;
         }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) raw[kh][kw] = zb[((long long)iys[kh] * IW + ixs[kw]) * cpr];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            if (okh[kh] && okw[kw]) fma8(acc[kh][kw], raw[kh][kw], gv);
       }
     }
     __syncthreads();
@@ -389,6 +414,16 @@ static int fill_dw(const tlt_conv_desc* d, DwRowsGeom* g) {
 
 using namespace tlt;
 
+// rows alone give row_threads threads; cut each row of W outputs into segments when there are fewer than ~148 x 768 of them
+static void dw_segments(long long row_threads, int W, int* segs, int* seg_len) {
+  long long want = row_threads >= 148LL * 768 ? 1 : (148LL * 1024 + row_threads - 1) / row_threads;
+  if (want < 1) want = 1;
+  if (want > W) want = W;
+  *seg_len = (int)((W + want - 1) / want);
+  if (*seg_len < 4 && W >= 4) *seg_len = 4;                       // keep a few outputs per thread: the unpacked weights amortise
+  *segs = (W + *seg_len - 1) / *seg_len;
+}
+
 static unsigned dw_grid(long long total) {
   long long blocks = (total + 255) / 256;
   const long long cap = 148LL * 16;
@@ -401,9 +436,11 @@ extern "C" int tlt_dwconv_rows_fwd(const tlt_conv_desc* d, const void* z, const 
   if (rc) return rc;
   TLT_REQUIRE(z && w && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "tlt_dwconv_rows_fwd: 16-byte aligned tensors");
   if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
-    const long long threads = g.batch * g.out_size[0] * g.cpr;
+    int segs, seg_len;
+    dw_segments(g.batch * g.out_size[0] * g.cpr, g.out_size[1], &segs, &seg_len);
+    const long long threads = g.batch * g.out_size[0] * g.cpr * segs;
     const unsigned blocks = (unsigned)((threads + 127) / 128 < 148LL * 32 ? (threads + 127) / 128 : 148LL * 32);
-    dwconv_rows2d_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y);
+    dwconv_rows2d_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)w, (uint4*)y, segs, seg_len);
     return check_launch("dwconv_rows2d_kernel<fwd>");
   }
   if (g.ndim == 2) {
@@ -420,9 +457,11 @@ extern "C" int tlt_dwconv_rows_dgrad(const tlt_conv_desc* d, const void* gy, con
   if (rc) return rc;
   TLT_REQUIRE(gy && w && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)dz % 16) == 0, "tlt_dwconv_rows_dgrad: 16-byte aligned tensors");
   if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
-    const long long threads = g.batch * g.in_size[0] * g.cpr;
+    int segs, seg_len;
+    dw_segments(g.batch * g.in_size[0] * g.cpr, g.in_size[1], &segs, &seg_len);
+    const long long threads = g.batch * g.in_size[0] * g.cpr * segs;
     const unsigned blocks = (unsigned)((threads + 127) / 128 < 148LL * 32 ? (threads + 127) / 128 : 148LL * 32);
-    dwconv_rows2d_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz);
+    dwconv_rows2d_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, (const uint4*)w, (uint4*)dz, segs, seg_len);
     return check_launch("dwconv_rows2d_kernel<dgrad>");
   }
   if (g.ndim == 2) {
