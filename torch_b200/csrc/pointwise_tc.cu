@@ -171,6 +171,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t ebuf = smem_base + L::EPI_OFFSET + (warp - 4) * kPwEpiBuf;
     constexpr int n_chunks = HALF_N / 32;
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t ehalf = 0;                             // bf16 path: the 4 KB staging buffer is two 2 KB halves used alternately
     for (int u = cluster_id; u < num_units; u += num_clusters) {
       int z, tm, tn, kb0, kb1;
       decode(u, z, tm, tn, kb0, kb1);
@@ -195,7 +196,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
         }
         if (!live) continue;
-        if (lane == 0) bulk_wait_read0();                         // previous store of this warp has finished reading ebuf
+        // WGRAD: the previous store of this warp has finished reading ebuf.  Forward: the store issued TWO chunks ago (same
+        // half) has; the latest one may still be in flight, so the transposition of this chunk overlaps its read
+        if (lane == 0) { if (WGRAD) bulk_wait_read0(); else bulk_wait_read1(); }
         __syncwarp();
         if (WGRAD) {
           // fp32 [32 rows][32 cols] block, SWIZZLE_128B, reduce-added into dW
@@ -220,14 +223,15 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(v[i]) + bv[i]);
-            st_shared_b16(ebuf + i * 64 + lane * 2, *(const uint16_t*)&h);
+            st_shared_b16(ebuf + ehalf + i * 64 + lane * 2, *(const uint16_t*)&h);
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&map_c, ebuf, m0, col0, z);
+            tma_store_3d(&map_c, ebuf + ehalf, m0, col0, z);
             bulk_commit();
           }
+          ehalf ^= 2048u;
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -266,6 +270,30 @@ __global__ void pack_kmajor_kernel(const T* __restrict__ src, long long rows, lo
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / ld, c = i - r * ld;
     dst[i] = c < cols ? __float2bfloat16_rn(to_f32<T>(src[r * rs + c * cs])) : __float2bfloat16_rn(0.f);
+  }
+}
+
+// Row-contiguous sources (col_stride == 1, e.g. the 3375 x 3375 Tucker core re-pitched to 3376): one block row per matrix
+// row, a thread assembles 8 consecutive elements and writes one 16-byte chunk -- no 64-bit division per element (the
+// generic kernel above took 35 us for the 23 MB core of BASELINE config 5).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kmajor_rows_kernel(const T* __restrict__ src, long long rows, int cols, long long rs,
+                                                               __nv_bfloat16* __restrict__ dst, int ld) {
+  const int chunks = ld >> 3;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    const T* sp = src + r * rs;
+    uint4* dp = reinterpret_cast<uint4*>(dst + r * (long long)ld);
+    for (int c8 = blockIdx.x * blockDim.x + threadIdx.x; c8 < chunks; c8 += gridDim.x * blockDim.x) {
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c8 * 8 + 2 * i;
+        const float lo = c < cols ? to_f32<T>(sp[c]) : 0.f, hi = c + 1 < cols ? to_f32<T>(sp[c + 1]) : 0.f;
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      dp[c8] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 
@@ -353,6 +381,16 @@ extern "C" int tlt_pack_kmajor(const void* src, int32_t dtype_src, int64_t rows,
   const long long total = rows * dst_ld;
   const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if (col_stride == 1 && dst_ld % 8 == 0 && dst_ld < (1LL << 31) && ((uintptr_t)dst % 16) == 0 && rows * dst_ld >= (1LL << 16) &&
+      (dtype_src == TLT_BF16 || dtype_src == TLT_F32)) {
+    const int chunks = (int)(dst_ld >> 3);
+    dim3 grid((unsigned)((chunks + 255) / 256), (unsigned)(rows < 65535 ? rows : 65535));
+    if (dtype_src == TLT_BF16)
+      pack_kmajor_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, rows, (int)cols, row_stride, (__nv_bfloat16*)dst, (int)dst_ld);
+    else
+      pack_kmajor_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)src, rows, (int)cols, row_stride, (__nv_bfloat16*)dst, (int)dst_ld);
+    return check_launch("pack_kmajor_rows_kernel");
+  }
   if (dtype_src == TLT_BF16)
     pack_kmajor_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)src, rows, cols, row_stride, col_stride, (__nv_bfloat16*)dst, dst_ld);
   else if (dtype_src == TLT_F32)
