@@ -814,6 +814,42 @@ def test_cp_conv_rows_path_vs_oracle(cin, cout, hw, stride):
         assert G.rel_err(a, b) < 3e-2, n
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("ch,hw,batch,bias", [(64, 56, 3, False), (64, 56, 2, True), (128, 28, 5, True), (128, 28, 2, False)])
+def test_cp_conv_fused_path_vs_oracle(ch, hw, batch, bias, variant, monkeypatch):
+    """CP FactorizedConv (bf16, ResNet-18 layer1 / layer2 shapes, small batch) through the one-launch-per-direction fused
+    kernel (tlt_cpconv3x3_fused: 1x1 -> depthwise 3x3 -> 1x1 with the R-channel intermediates in shared memory) vs the fp64
+    oracle of cp_conv (functional/convolution.py:231-283): y, dx and every parameter gradient."""
+    import torch_b200 as tlt
+    from torch_b200 import _cuda
+    from oracle import reference_path as rp
+    monkeypatch.setenv("TLT_CPF_VARIANT", str(variant))
+    monkeypatch.setenv("TLT_CP_FUSED", "on")
+    torch.manual_seed(hw + batch)
+    conv = tlt.FactorizedConv(ch, ch, 3, order=2, stride=1, padding=1, bias=bias, factorization="cp", rank=0.25, device=dev())
+    conv.reset_parameters(std=0.5)
+    if bias:
+        with torch.no_grad():
+            conv.bias.normal_()
+    conv = conv.to(torch.bfloat16)
+    x = torch.randn(batch, ch, hw, hw, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    before = _cuda.launch_count()
+    y = conv(x)
+    fwd_launches = _cuda.launch_count() - before
+    assert fwd_launches <= 3, fwd_launches                 # Khatri-Rao taps + the fused chain (+ nothing else)
+    gy = torch.randn_like(y)
+    params = dict(conv.named_parameters())
+    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(4)]
+    yo = rp.cp_conv(xo, leaves["weight.weights"], fs, bias=leaves.get("bias"), stride=[1, 1], padding=[1, 1], dilation=[1, 1])
+    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+    assert G.rel_err(y, yo) < 2e-2
+    for n, a, b in zip(["x"] + list(params), grads, go):
+        assert G.rel_err(a, b) < 3e-2, n
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("dims,R,with_w", [((4, 8, 16), 2341, True), ((4, 8, 16), 2341, False), ((3, 3), 69, True), ((7,), 33, True),
                                            ((2, 3, 4, 5), 17, True)])

@@ -66,6 +66,12 @@ class Mmd16Desc(C.Structure):
                 ("ld_in", C.c_int64), ("ld_out", C.c_int64)]
 
 
+class CpConvDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("in_channels", C.c_int64), ("out_channels", C.c_int64), ("rank", C.c_int64),
+                ("height", C.c_int64), ("width", C.c_int64), ("flip_taps", C.c_int32), ("dtype_bias", C.c_int32),
+                ("variant", C.c_int32)]
+
+
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -106,6 +112,8 @@ SYMBOLS = {
     "tlt_khatri_rao_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, _vp]),
     "tlt_khatri_rao_bwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp,
                                      C.POINTER(C.c_void_p), _vp, _vp]),
+    "tlt_cpconv3x3_fused_supported": (C.c_int, [C.POINTER(CpConvDesc)]),
+    "tlt_cpconv3x3_fused": (C.c_int, [C.POINTER(CpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_cast": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, _vp]),
     "tlt_l2_flush": (C.c_int, [_vp, C.c_size_t, _vp]),
 }
