@@ -312,6 +312,23 @@ int tlt_cpconv3x3_fused(const tlt_cpconv_desc* desc, const void* x, const void* 
                         const void* bias, void* y, void* z1_out, void* z2_out, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Spatial-modes-first projection of channels-first feature maps (bf16):
+ *   tlt_spatial_project_fwd : t[b, j, c] = sum_s x[b, c, s] k[s, j]            x (B, C, S), k (S, J) -> t (B, J, C)
+ *   tlt_spatial_project_bwd : dx[b, c, s] = sum_j gt[b, j, c] k[s, j];   dk[s, j] += sum_{b,c} x[b, c, s] gt[b, j, c]
+ *                             (dk fp32 (S, J), ACCUMULATED: caller zeroes)
+ * S = prod(spatial extents) <= 64, J = prod(spatial ranks) <= 16, C % 128 == 0; k is the Kronecker product of the spatial
+ * factors.  One pass over the activation where it lies (TMA bulk tiles of 128 channels, HMMA), t comes out channels-last for
+ * the channel-mode GEMM.  Replaces: the spatial modes of tenalg.multi_mode_dot(x, factors[:n], transpose=True) in tucker_trl
+ * (tltorch/functional/tensor_regression.py:40) and of TCL.forward (factorized_layers/tensor_contraction_layers.py:75) on
+ * (B, 2048, 7, 7)-like maps, and their autograd.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_spatial_project_supported(int64_t batch, int64_t channels, int32_t S, int32_t J);
+int tlt_spatial_project_fwd(int64_t batch, int64_t channels, int32_t S, int32_t J, const void* x, const void* k, void* t,
+                            void* stream);
+int tlt_spatial_project_bwd(int64_t batch, int64_t channels, int32_t S, int32_t J, const void* x, const void* k, const void* gt,
+                            void* dx, float* dk, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Small utilities used by the host side.
  * ------------------------------------------------------------------------------------------------------------ */
 /* dst[i] = (dst dtype) src[i], n elements */

@@ -814,6 +814,52 @@ def test_cp_conv_rows_path_vs_oracle(cin, cout, hw, stride):
         assert G.rel_err(a, b) < 3e-2, n
 
 
+@pytest.mark.parametrize("B,C,spatial,ranks", [(3, 2048, (7, 7), (4, 4)), (5, 128, (7, 7), (4, 4)), (2, 256, (4, 4), (2, 2)),
+                                               (2, 384, (8, 8), (4, 4)), (7, 128, (3, 3), (2, 3)), (2, 256, (5,), (3,)),
+                                               (600, 128, (7, 7), (3, 5)), (2, 128, (2, 3, 4), (2, 2, 2))])
+def test_spatial_project_kernels_vs_fp64(B, C, spatial, ranks):
+    """tlt_spatial_project_fwd / _bwd (spatial modes of tucker_trl's input projection, functional/tensor_regression.py:40,
+    on channels-first maps) vs an fp64 einsum: t, dx and dk."""
+    from torch_b200 import spatial_ops
+    torch.manual_seed(C + len(spatial))
+    S, J = math.prod(spatial), math.prod(ranks)
+    x = torch.randn(B, C, S, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    k = (torch.randn(S, J, device=dev()) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    assert spatial_ops.eligible(x, S, J)
+    t = spatial_ops.spatial_project(x, k)
+    assert t.shape == (B, J, C)
+    g = torch.randn_like(t)
+    gx, gk = torch.autograd.grad(t, [x, k], g)
+    xo, ko = x.detach().double().cpu().requires_grad_(True), k.detach().double().cpu().requires_grad_(True)
+    to = torch.einsum("bcs,sj->bjc", xo, ko)
+    gxo, gko = torch.autograd.grad(to, [xo, ko], g.double().cpu())
+    assert G.rel_err(t, to) < 1e-2
+    assert G.rel_err(gx, gxo) < 1e-2
+    assert G.rel_err(gk, gko) < 1e-2
+
+
+@pytest.mark.parametrize("B,C,hw,ranks,out", [(6, 256, 7, (64, 4, 4, 10), 100), (4, 512, 4, (32, 2, 3, 5), 17)])
+def test_trl_spatial_first_plan_vs_rows_plan(B, C, hw, ranks, out, monkeypatch):
+    """Tucker TRL on (B, C, hw, hw) maps: the spatial-modes-first plan (tlt_spatial_project + channel GEMM) and the
+    channels-last-rows plan give the same output and gradients (both stand in for tensor_regression.py:37-49)."""
+    import torch_b200 as tlt
+    torch.manual_seed(C)
+    layer = tlt.TRL((C, hw, hw), (out,), bias=True, rank=ranks, factorization="tucker", device=dev())
+    with torch.no_grad():
+        for p_ in layer.parameters():
+            p_.normal_(0, 0.3)
+    layer = layer.to(torch.bfloat16)
+    x = torch.randn(B, C, hw, hw, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    res = {}
+    for mode in ("on", "off"):
+        monkeypatch.setenv("TLT_SPATIAL_FIRST", mode)
+        y = layer(x)
+        gy = torch.ones_like(y) * 0.5
+        res[mode] = [y] + list(torch.autograd.grad(y, [x] + list(layer.parameters()), gy))
+    for a, b_ in zip(res["on"], res["off"]):
+        assert G.rel_err(a, b_.double().cpu()) < 3e-2
+
+
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("ch,hw,batch,bias", [(64, 56, 3, False), (64, 56, 2, True), (128, 28, 5, True), (128, 28, 2, False)])
 def test_cp_conv_fused_path_vs_oracle(ch, hw, batch, bias, variant, monkeypatch):

@@ -114,6 +114,9 @@ SYMBOLS = {
                                      C.POINTER(C.c_void_p), _vp, _vp]),
     "tlt_cpconv3x3_fused_supported": (C.c_int, [C.POINTER(CpConvDesc)]),
     "tlt_cpconv3x3_fused": (C.c_int, [C.POINTER(CpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_spatial_project_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "tlt_spatial_project_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
+    "tlt_spatial_project_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_cast": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_int64, _vp]),
     "tlt_l2_flush": (C.c_int, [_vp, C.c_size_t, _vp]),
 }

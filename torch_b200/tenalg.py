@@ -89,8 +89,9 @@ def _trailing_modes_first(tensor, pairs, transpose):
     channels: the map is transposed once to channels-last rows (rows_ops), the channel mode runs as ONE K-major tcgen05
     GEMM (batch * spatial, C) x (C, r_0), and the spatial modes then act on the r_0-channel result, which is C / r_0
     times smaller.  Returns None when the shapes do not fit this plan."""
+    import os
     import torch
-    from . import rows_ops
+    from . import rows_ops, spatial_ops
     from .tucker_ops import padded_linear
     nd = tensor.dim()
     if nd < 3 or not tensor.is_contiguous() or tensor.dtype != torch.bfloat16:
@@ -105,6 +106,19 @@ def _trailing_modes_first(tensor, pairs, transpose):
     r0 = m0.shape[0]
     if c < 256 or r0 * 4 > c or b * math.prod(spatial) < 1024 or b > 65535:
         return None
+    S = math.prod(spatial)
+    oriented = [m if transpose else m.t() for m in mats[1:]]                     # (d_i, q_i)
+    J = math.prod(m.shape[1] for m in oriented)
+    if os.environ.get("TLT_SPATIAL_FIRST", "on") != "off" and len(oriented) in (1, 2, 3) and spatial_ops.eligible(tensor, S, J):
+        # spatial modes first: ONE pass over the activation where it lies (no transposition): t[b, (q..), c], then the channel
+        # mode as a K-major tcgen05 GEMM on the S / J times smaller, channels-last t
+        k = oriented[0]
+        for m in oriented[1:]:
+            k = contract("ap,bq->abpq", k, m).reshape(k.shape[0] * m.shape[0], k.shape[1] * m.shape[1])
+        t = spatial_ops.spatial_project(tensor.reshape(b, c, S), k)              # (B, J, C)
+        z = padded_linear(t.reshape(b * J, c), m0, None, True)                   # (B J, round8(r_0)), pad columns zero
+        z = z.reshape(b, *[m.shape[1] for m in oriented], z.shape[1])
+        return z[..., :r0].movedim(-1, 1)
     rows = rows_ops.nchw_to_rows(tensor)                                         # (B S, round8(C))
     z = padded_linear(rows, m0, None, True)                                      # (B S, round8(r_0)), pad columns zero
     z = z.reshape(b, *spatial, z.shape[1])
