@@ -410,6 +410,305 @@ static int fill_dw(const tlt_conv_desc* d, DwRowsGeom* g) {
   return TLT_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory tiled 3x3 kernels (padding 1, dilation 1, stride 1 or 2): the rows-route layers of BASELINE config 3.
+// The register-window kernels above re-fetch every source chunk for each of the taps that touch it through L1 / L2 with ~12
+// resident warps per SM (146 registers) and sit on the long scoreboard: 50 / 54 / 77 us per pass over a 29 MB tensor (ncu:
+// warps active 17 %, issue active 40 %).  Here a block stages the source rows of a strip of destination rows -- CW chunks
+// (CW x 8 channels) of every position, one 16-byte cp.async per chunk, all in flight at once -- and the nine taps read
+// shared memory.  A staged position is CW + 1 chunks wide (odd pitch: conflict-free 16-byte reads along positions and along
+// chunks).
+//   forward / data gradient: thread = (chunk c = tid % CW, position lane tid / CW); 192-byte coalesced runs on both sides
+//   weight gradient: warp = chunk, lane = position; 9 x 8 tap sums per thread in registers across ALL tiles of the block,
+//   one shuffle reduction and one atomicAdd per (tap, channel) per block at the end
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ uint4 lds128_(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// The nine taps themselves run on the tensor cores: a depthwise tap is a product with a DIAGONAL channel matrix, so for a
+// tile of 16 destination positions x 8 channels  D[p][c] = sum_t A_t[p][c'] diag(w_t)[c'][c]  is nine m16n8k8 HMMAs whose A
+// operand is gathered by ldmatrix straight from the staged rows (row addresses are free per lane: the tap shift, the stride
+// and the zero padding -- a shared all-zero row -- cost nothing), and whose B operand is one register per lane from a
+// precomputed table.  7/8 of the multiplies hit zeros, which is irrelevant next to what it replaces: the FFMA version spent
+// ~340 thread instructions per 8-channel output (unpack + FMA + predicates; 19 M warp instructions per pass, issue-bound at
+// 41 us), this one ~3 warp instructions per output.  The weight gradient is the transposed product
+// D[c'][c] = sum_p Z_t[p][c'] G[p][c] (m16n8k16, both operands via ldmatrix.trans), of which only the diagonal is kept.
+__device__ __forceinline__ void ldsm2_(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2t_(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t_(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma1688_(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void mma16816_(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t lds32_(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+constexpr int kDwtThreads = 192;
+
+template <bool DGRAD, int S, int CW>
+__global__ void __launch_bounds__(kDwtThreads) dwrows_tile_kernel(const DwRowsGeom g, const uint4* __restrict__ src,
+                                                                  const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dst, int TR,
+                                                                  int nstrips, long long tiles) {
+  constexpr int NT = kDwtThreads, NW = NT / 32, PITCH = (CW + 1) * 16, HC = CW / 2;
+  extern __shared__ __align__(16) unsigned char dwt_smem[];
+  const uint32_t zero = (uint32_t)__cvta_generic_to_shared(dwt_smem);          // PITCH bytes of zeros
+  const uint32_t diag = zero + PITCH;                                          // [9][CW][32] b32
+  const uint32_t tile = diag + 9 * CW * 128;
+  const int DH = DGRAD ? g.in_size[0] : g.out_size[0], DW = DGRAD ? g.in_size[1] : g.out_size[1];
+  const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SWd = DGRAD ? g.out_size[1] : g.in_size[1];
+  const int cpr = g.cpr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tq = lane & 3;
+  const int cbase = blockIdx.x * CW;
+  for (int e = tid; e < PITCH / 4; e += NT) reinterpret_cast<uint32_t*>(dwt_smem)[e] = 0u;
+  for (int e = tid; e < 9 * CW * 32; e += NT) {
+    const int l = e & 31, cc = (e >> 5) % CW, t = (e >> 5) / CW;
+    const int gg = l >> 2, tt = l & 3;
+    const uint32_t wv = (uint32_t)__bfloat16_as_ushort(w[((size_t)t * cpr + cbase + cc) * 8 + gg]);
+    reinterpret_cast<uint32_t*>(dwt_smem + PITCH)[e] = gg == 2 * tt ? wv : (gg == 2 * tt + 1 ? (wv << 16) : 0u);
+  }
+  for (long long tix = blockIdx.y; tix < tiles; tix += gridDim.y) {
+    const long long b = tix / nstrips;
+    const int y0 = (int)(tix % nstrips) * TR, y1 = min(DH, y0 + TR);
+    int lo, hi;
+    if (!DGRAD) { lo = y0 * S - 1; hi = (y1 - 1) * S + 1; }
+    else { lo = y0 - 1 <= 0 ? 0 : (y0 - 1 + S - 1) / S; hi = y1 / S; }
+    lo = max(lo, 0);
+    hi = min(hi, SH - 1);
+    const int npos = (hi - lo + 1) * SWd;
+    const uint4* sb = src + ((b * SH + lo) * (long long)SWd) * cpr + cbase;
+    for (int idx = tid; idx < npos * CW; idx += NT) {
+      const int cc = idx % CW, pos = idx / CW;
+      cp_async16(tile + pos * PITCH + cc * 16, sb + (long long)pos * cpr + cc);
+    }
+    cp_async_wait();
+    __syncthreads();
+    const int nd = (y1 - y0) * DW;
+    const int units = ((nd + 15) / 16) * 2;
+    __nv_bfloat16* db = dst + ((b * DH + y0) * (long long)DW) * cpr * 8 + (size_t)cbase * 8;
+    for (int u = warp; u < units; u += NW) {
+      const int pt = u >> 1, half = u & 1;
+      // this lane's row of the A operand: destination position pt * 16 + (lane & 15)
+      const int p = pt * 16 + (lane & 15);
+      const int yy = p / DW, x = p - yy * DW, y = y0 + yy;
+      uint32_t addr[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        int sy;
+        bool oky;
+        if (!DGRAD) { sy = y * S - 1 + kh; oky = sy >= 0 && sy < SH; }
+        else { const int ny = y + 1 - kh; sy = ny / S; oky = ny >= 0 && (S == 1 || (ny % S) == 0) && sy < SH; }
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          int sx;
+          bool okx;
+          if (!DGRAD) { sx = x * S - 1 + kw; okx = sx >= 0 && sx < SWd; }
+          else { const int nx = x + 1 - kw; sx = nx / S; okx = nx >= 0 && (S == 1 || (nx % S) == 0) && sx < SWd; }
+          addr[kh * 3 + kw] = (p < nd && oky && okx) ? tile + ((sy - lo) * SWd + sx) * PITCH : zero;
+        }
+      }
+      const int p_lo = pt * 16 + gid, p_hi = p_lo + 8;
+#pragma unroll 2
+      for (int cc = 0; cc < HC; ++cc) {
+        const int c = half * HC + cc;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          uint32_t a0, a1;
+          ldsm2_(a0, a1, addr[t] + c * 16);
+          mma1688_(acc, a0, a1, lds32_(diag + ((t * CW + c) * 32 + lane) * 4));
+        }
+        if (p_lo < nd) *reinterpret_cast<__nv_bfloat162*>(db + (size_t)p_lo * cpr * 8 + c * 8 + 2 * tq) = __floats2bfloat162_rn(acc[0], acc[1]);
+        if (p_hi < nd) *reinterpret_cast<__nv_bfloat162*>(db + (size_t)p_hi * cpr * 8 + c * 8 + 2 * tq) = __floats2bfloat162_rn(acc[2], acc[3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int S, int CW>
+__global__ void __launch_bounds__(16 * CW) dwrows_tile_wgrad_kernel(const DwRowsGeom g, const uint4* __restrict__ z, const uint4* __restrict__ gy,
+                                                                    float* __restrict__ dw, int TR, int nstrips, long long tiles, int zmax) {
+  constexpr int NT = 16 * CW, PITCH = (CW + 1) * 16;                   // one warp per pair of chunks (16 channels)
+  extern __shared__ __align__(16) unsigned char dwt_smem[];
+  const uint32_t zero = (uint32_t)__cvta_generic_to_shared(dwt_smem);
+  const uint32_t ztile = zero + PITCH;
+  const uint32_t gtile = ztile + (uint32_t)zmax * PITCH;
+  const int IH = g.in_size[0], IW = g.in_size[1], OH = g.out_size[0], OW = g.out_size[1];
+  const int cpr = g.cpr, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gid = lane >> 2, tq = lane & 3;
+  const int cbase = blockIdx.x * CW;
+  for (int e = tid; e < PITCH / 4; e += NT) reinterpret_cast<uint32_t*>(dwt_smem)[e] = 0u;
+  float acc[9][2][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[t][h][i] = 0.f;
+  const int ia = (lane & 7) + ((lane >> 4) << 3);                      // A operand: lane -> position of the k16 step
+  const uint32_t ca = (uint32_t)(2 * warp + ((lane >> 3) & 1)) * 16;   //            and chunk of the pair
+  const int ib = lane & 15;                                            // B operand: lanes 0..15 -> positions
+  for (long long tix = blockIdx.y; tix < tiles; tix += gridDim.y) {
+    const long long b = tix / nstrips;
+    const int y0 = (int)(tix % nstrips) * TR, y1 = min(OH, y0 + TR);
+    const int lo = max(y0 * S - 1, 0), hi = min((y1 - 1) * S + 1, IH - 1);
+    const int nz = (hi - lo + 1) * IW, ng = (y1 - y0) * OW;
+    const uint4* zb = z + ((b * IH + lo) * (long long)IW) * cpr + cbase;
+    const uint4* gb = gy + ((b * OH + y0) * (long long)OW) * cpr + cbase;
+    for (int idx = tid; idx < nz * CW; idx += NT) {
+      const int cc = idx % CW, pos = idx / CW;
+      cp_async16(ztile + pos * PITCH + cc * 16, zb + (long long)pos * cpr + cc);
+    }
+    for (int idx = tid; idx < ng * CW; idx += NT) {
+      const int cc = idx % CW, pos = idx / CW;
+      cp_async16(gtile + pos * PITCH + cc * 16, gb + (long long)pos * cpr + cc);
+    }
+    cp_async_wait();
+    __syncthreads();
+    for (int ks = 0; ks < (ng + 15) / 16; ++ks) {
+      const int pb = ks * 16 + ib;
+      const uint32_t gaddr = pb < ng ? gtile + pb * PITCH + 2 * warp * 16 : zero;
+      uint32_t b0[2], b1[2];
+      ldsm2t_(b0[0], b0[1], gaddr);
+      ldsm2t_(b1[0], b1[1], gaddr + 16);
+      const int pa = ks * 16 + ia;
+      const int yy = pa / OW, x = pa - yy * OW, y = y0 + yy;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int sy = y * S - 1 + kh;
+        const bool oky = pa < ng && sy >= 0 && sy < IH;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int sx = x * S - 1 + kw;
+          const uint32_t zaddr = (oky && sx >= 0 && sx < IW) ? ztile + ((sy - lo) * IW + sx) * PITCH + ca : zero;
+          uint32_t a[4];
+          ldsm4t_(a, zaddr);
+          mma16816_(acc[kh * 3 + kw][0], a, b0[0], b0[1]);
+          mma16816_(acc[kh * 3 + kw][1], a, b1[0], b1[1]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // diagonal of D0 (rows 0-7 x chunk 0) and of D1 (rows 8-15 x chunk 1)
+  if (gid == 2 * tq || gid == 2 * tq + 1) {
+    const int odd = gid == 2 * tq + 1;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float* d = dw + (long long)t * cpr * 8 + (cbase + 2 * warp) * 8 + gid;
+      atomicAdd(d, odd ? acc[t][0][1] : acc[t][0][0]);
+      atomicAdd(d + 8, odd ? acc[t][1][3] : acc[t][1][2]);
+    }
+  }
+}
+
+// 0 when the tiled kernels do not take this geometry, else the chunk-group width (12 or 8)
+static int dwt_eligible(const DwRowsGeom& g) {
+  const char* env = getenv("TLT_DWROWS_TILE");
+  if (env && env[0] == 'o' && env[1] == 'f') return 0;
+  if (g.ndim != 2 || g.kernel[0] != 3 || g.kernel[1] != 3 || g.padding[0] != 1 || g.padding[1] != 1 || g.dilation[0] != 1 || g.dilation[1] != 1)
+    return 0;
+  if (g.stride[0] != g.stride[1] || (g.stride[0] != 1 && g.stride[0] != 2)) return 0;
+  if (g.in_size[1] > 64 || g.out_size[1] > 64) return 0;
+  return g.cpr % 12 == 0 ? 12 : (g.cpr % 8 == 0 ? 8 : 0);
+}
+
+template <class Kern>
+static int dwt_smem_attr(Kern kern, size_t smem) {
+  if (smem > 48 * 1024) TLT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return TLT_OK;
+}
+
+// strip height: as many destination rows as fit `budget` bytes of staged source rows, but enough strips to fill the GPU
+template <class RowsFn>
+static int dwt_pick_tr(int DH, long long groups, int pitch, long long budget, RowsFn staged_positions) {
+  int TR = DH;
+  while (TR > 1 && ((long long)staged_positions(TR) * pitch > budget || groups * ((DH + TR - 1) / TR) < 148LL * 3)) --TR;
+  return TR;
+}
+
+template <bool DGRAD, int S, int CW>
+static int dwt_launch(const DwRowsGeom& g, const void* src, const void* w, void* dst, cudaStream_t st) {
+  constexpr int PITCH = (CW + 1) * 16;
+  const int DH = DGRAD ? g.in_size[0] : g.out_size[0];
+  const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SWd = DGRAD ? g.out_size[1] : g.in_size[1];
+  auto rows = [&](int tr) { int n = DGRAD ? tr / S + 2 : (tr - 1) * S + 3; return (long long)(n < SH ? n : SH) * SWd; };
+  const int TR = dwt_pick_tr(DH, g.batch * (g.cpr / CW), PITCH, 64 * 1024, rows);
+  const size_t smem = (size_t)rows(TR) * PITCH + PITCH + 9 * CW * 128;
+  if (smem > 200 * 1024) return 1;                                    // not launched: caller falls back
+  int rc = dwt_smem_attr(dwrows_tile_kernel<DGRAD, S, CW>, smem);
+  if (rc) return rc;
+  const int nstrips = (DH + TR - 1) / TR;
+  const long long tiles = g.batch * nstrips;
+  dim3 grid((unsigned)(g.cpr / CW), (unsigned)(tiles < 32768 ? tiles : 32768));
+  dwrows_tile_kernel<DGRAD, S, CW><<<grid, kDwtThreads, smem, st>>>(g, (const uint4*)src, (const __nv_bfloat16*)w, (__nv_bfloat16*)dst, TR, nstrips, tiles);
+  return check_launch(DGRAD ? "dwrows_tile_kernel<dgrad>" : "dwrows_tile_kernel<fwd>");
+}
+
+template <int S, int CW>
+static int dwt_launch_wgrad(const DwRowsGeom& g, const void* z, const void* gy, float* dw, cudaStream_t st) {
+  constexpr int PITCH = (CW + 1) * 16;
+  const int IH = g.in_size[0], IW = g.in_size[1], OH = g.out_size[0], OW = g.out_size[1];
+  auto zrows = [&](int tr) { int n = (tr - 1) * S + 3; return (long long)(n < IH ? n : IH) * IW; };
+  auto both = [&](int tr) { return zrows(tr) + (long long)tr * OW; };
+  const int TR = dwt_pick_tr(OH, g.batch * (g.cpr / CW), PITCH, 88 * 1024, both);
+  const size_t smem = (size_t)both(TR) * PITCH + PITCH;
+  if (smem > 200 * 1024) return 1;
+  int rc = dwt_smem_attr(dwrows_tile_wgrad_kernel<S, CW>, smem);
+  if (rc) return rc;
+  const int nstrips = (OH + TR - 1) / TR;
+  const long long tiles = g.batch * nstrips;
+  long long by = 148LL * 4 / (g.cpr / CW);
+  if (by < 1) by = 1;
+  if (by > tiles) by = tiles;
+  dim3 grid((unsigned)(g.cpr / CW), (unsigned)by);
+  dwrows_tile_wgrad_kernel<S, CW><<<grid, 16 * CW, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, dw, TR, nstrips, tiles, (int)zrows(TR));
+  return check_launch("dwrows_tile_wgrad_kernel");
+}
+
+// returns TLT_OK / error when handled, 1 when the caller should fall back to the register-window kernels
+template <bool DGRAD>
+static int dwt_dispatch(const DwRowsGeom& g, const void* src, const void* w, void* dst, cudaStream_t st) {
+  const int cw = dwt_eligible(g);
+  if (!cw) return 1;
+  const int s = g.stride[0];
+  if (cw == 12) return s == 1 ? dwt_launch<DGRAD, 1, 12>(g, src, w, dst, st) : dwt_launch<DGRAD, 2, 12>(g, src, w, dst, st);
+  return s == 1 ? dwt_launch<DGRAD, 1, 8>(g, src, w, dst, st) : dwt_launch<DGRAD, 2, 8>(g, src, w, dst, st);
+}
+static int dwt_dispatch_wgrad(const DwRowsGeom& g, const void* z, const void* gy, float* dw, cudaStream_t st) {
+  const int cw = dwt_eligible(g);
+  if (!cw) return 1;
+  const int s = g.stride[0];
+  if (cw == 12) return s == 1 ? dwt_launch_wgrad<1, 12>(g, z, gy, dw, st) : dwt_launch_wgrad<2, 12>(g, z, gy, dw, st);
+  return s == 1 ? dwt_launch_wgrad<1, 8>(g, z, gy, dw, st) : dwt_launch_wgrad<2, 8>(g, z, gy, dw, st);
+}
+
 }  // namespace tlt
 
 using namespace tlt;
@@ -435,6 +734,8 @@ extern "C" int tlt_dwconv_rows_fwd(const tlt_conv_desc* d, const void* z, const 
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(z && w && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)y % 16) == 0, "tlt_dwconv_rows_fwd: 16-byte aligned tensors");
+  rc = dwt_dispatch<false>(g, z, w, y, (cudaStream_t)stream);
+  if (rc != 1) return rc;
   if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
     int segs, seg_len;
     dw_segments(g.batch * g.out_size[0] * g.cpr, g.out_size[1], &segs, &seg_len);
@@ -456,6 +757,8 @@ extern "C" int tlt_dwconv_rows_dgrad(const tlt_conv_desc* d, const void* gy, con
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(gy && w && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)dz % 16) == 0, "tlt_dwconv_rows_dgrad: 16-byte aligned tensors");
+  rc = dwt_dispatch<true>(g, gy, w, dz, (cudaStream_t)stream);
+  if (rc != 1) return rc;
   if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
     int segs, seg_len;
     dw_segments(g.batch * g.in_size[0] * g.cpr, g.in_size[1], &segs, &seg_len);
@@ -477,6 +780,8 @@ extern "C" int tlt_dwconv_rows_wgrad(const tlt_conv_desc* d, const void* z, cons
   int rc = fill_dw(d, &g);
   if (rc) return rc;
   TLT_REQUIRE(z && gy && dw && ((uintptr_t)z % 16) == 0 && ((uintptr_t)gy % 16) == 0, "tlt_dwconv_rows_wgrad: 16-byte aligned tensors");
+  rc = dwt_dispatch_wgrad(g, z, gy, dw, (cudaStream_t)stream);
+  if (rc != 1) return rc;
   if (g.taps > kDwTapsMax) { set_error("tlt_dwconv_rows_wgrad: more than %d taps", kDwTapsMax); return TLT_ERR_UNSUPPORTED; }
   const long long rows_total = g.batch * g.out_sp;
   long long blocks = 148LL * 4;
