@@ -647,9 +647,9 @@ static int dwt_smem_attr(Kern kern, size_t smem) {
 
 // strip height: as many destination rows as fit `budget` bytes of staged source rows, but enough strips to fill the GPU
 template <class RowsFn>
-static int dwt_pick_tr(int DH, long long groups, int pitch, long long budget, RowsFn staged_positions) {
+static int dwt_pick_tr(int DH, long long groups, int pitch, long long budget, long long min_tiles, RowsFn staged_positions) {
   int TR = DH;
-  while (TR > 1 && ((long long)staged_positions(TR) * pitch > budget || groups * ((DH + TR - 1) / TR) < 148LL * 3)) --TR;
+  while (TR > 1 && ((long long)staged_positions(TR) * pitch > budget || groups * ((DH + TR - 1) / TR) < min_tiles)) --TR;
   return TR;
 }
 
@@ -659,14 +659,17 @@ static int dwt_launch(const DwRowsGeom& g, const void* src, const void* w, void*
   const int DH = DGRAD ? g.in_size[0] : g.out_size[0];
   const int SH = DGRAD ? g.out_size[0] : g.in_size[0], SWd = DGRAD ? g.out_size[1] : g.in_size[1];
   auto rows = [&](int tr) { int n = DGRAD ? tr / S + 2 : (tr - 1) * S + 3; return (long long)(n < SH ? n : SH) * SWd; };
-  const int TR = dwt_pick_tr(DH, g.batch * (g.cpr / CW), PITCH, 64 * 1024, rows);
+  const int TR = dwt_pick_tr(DH, g.batch * (g.cpr / CW), PITCH, 28 * 1024, 148LL * 12, rows);
   const size_t smem = (size_t)rows(TR) * PITCH + PITCH + 9 * CW * 128;
   if (smem > 200 * 1024) return 1;                                    // not launched: caller falls back
   int rc = dwt_smem_attr(dwrows_tile_kernel<DGRAD, S, CW>, smem);
   if (rc) return rc;
   const int nstrips = (DH + TR - 1) / TR;
   const long long tiles = g.batch * nstrips;
-  dim3 grid((unsigned)(g.cpr / CW), (unsigned)(tiles < 32768 ? tiles : 32768));
+  // persistent: ~6 blocks per SM in total, each walking several strips (the tap table is built once per block)
+  long long by = (148LL * 6 + g.cpr / CW - 1) / (g.cpr / CW);
+  if (by > tiles) by = tiles;
+  dim3 grid((unsigned)(g.cpr / CW), (unsigned)by);
   dwrows_tile_kernel<DGRAD, S, CW><<<grid, kDwtThreads, smem, st>>>(g, (const uint4*)src, (const __nv_bfloat16*)w, (__nv_bfloat16*)dst, TR, nstrips, tiles);
   return check_launch(DGRAD ? "dwrows_tile_kernel<dgrad>" : "dwrows_tile_kernel<fwd>");
 }
@@ -677,7 +680,7 @@ static int dwt_launch_wgrad(const DwRowsGeom& g, const void* z, const void* gy, 
   const int IH = g.in_size[0], IW = g.in_size[1], OH = g.out_size[0], OW = g.out_size[1];
   auto zrows = [&](int tr) { int n = (tr - 1) * S + 3; return (long long)(n < IH ? n : IH) * IW; };
   auto both = [&](int tr) { return zrows(tr) + (long long)tr * OW; };
-  const int TR = dwt_pick_tr(OH, g.batch * (g.cpr / CW), PITCH, 88 * 1024, both);
+  const int TR = dwt_pick_tr(OH, g.batch * (g.cpr / CW), PITCH, 88 * 1024, 148LL * 3, both);
   const size_t smem = (size_t)both(TR) * PITCH + PITCH;
   if (smem > 200 * 1024) return 1;
   int rc = dwt_smem_attr(dwrows_tile_wgrad_kernel<S, CW>, smem);
