@@ -214,6 +214,126 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_tma_kernel(const Params q
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core version of the forward / data-gradient kernel.  The FFMA kernel above is issue-bound (72 % issue-active, 59 M warp
+// instructions per pass at 56 x 56: 9 FMAs + unpack per output).  A depthwise 3x3 over a plane is
+//      Y = sum_dh  shift_dh(Z) . T_dh          T_dh[w'][w] = tap[dh][w' - w + 1]  (banded Toeplitz, W x W)
+// so per 16-row slab of a plane the vertical taps are three row-shifted ldmatrix reads of the SAME shared-memory plane (a
+// one-row shift keeps the 16-byte alignment because W % 8 == 0; rows outside the plane read a zero row) and the horizontal
+// taps live in the B operand: for the 8-column output tile j only the k16 step that contains it and ONE neighbouring step (for
+// the column just left / right of the tile) are non-zero, i.e. 2 m16n8k16 HMMAs per tile per dh.  B fragments are five register
+// patterns per dh built from the channel's nine taps.  ~0.2 warp instructions per output instead of ~1.1.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm4_(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816_(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t bf16_bits_(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+
+template <bool FLIP, int W>
+__global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                                                            long long n_groups) {
+  constexpr int NKS = (W + 15) / 16, NNT = W / 8, ROWB = W * 2;
+  static_assert(W % 8 == 0 && W <= 64, "row = whole 16-byte chunks, at most four k16 steps");
+  extern __shared__ __align__(128) unsigned char dwt_smem[];
+  const int psz = q.H * W, H = q.H;
+  const uint32_t buf_bytes = (uint32_t)q.PB * psz * 2;
+  const uint32_t slot_stride = (buf_bytes + 32 + 127) / 128 * 128;               // 32 zero bytes behind each landing buffer
+  unsigned char* zrow_g = dwt_smem;                                              // 128 bytes of zeros
+  unsigned char* buf_g = dwt_smem + 128;
+  float* ws = reinterpret_cast<float*>(buf_g + 2 * slot_stride);                 // [2][PB][9]
+  const uint32_t bar0 = smem_u32(reinterpret_cast<unsigned char*>(ws) + 2 * q.PB * 9 * 4);
+  const uint32_t zrow = smem_u32(zrow_g), buf0 = smem_u32(buf_g);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tq = lane & 3;
+  auto issue = [&](long long grp, int slot) {
+    const long long p0 = grp * q.PB;
+    const int npl = (int)min((long long)q.PB, q.planes - p0);
+    const uint32_t bytes = (uint32_t)npl * psz * 2;
+    mbar_expect_tx(bar0 + 8 * slot, bytes);
+    bulk_g2s(buf0 + slot * slot_stride, x + p0 * psz, bytes, bar0 + 8 * slot);
+  };
+  for (int e = threadIdx.x; e < 32; e += blockDim.x) reinterpret_cast<uint32_t*>(zrow_g)[e] = 0u;
+  for (int e = threadIdx.x; e < 16; e += blockDim.x)
+    reinterpret_cast<uint32_t*>(buf_g + (e >> 3) * slot_stride + buf_bytes)[e & 7] = 0u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+    if ((long long)blockIdx.x < n_groups) issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+  const int nmt = (H + 15) / 16;
+  const int i0 = 2 * tq - gid + 1;                                   // tap index of the band entry (k = 2 tq, n = gid); +1 for k + 1
+  const bool f07 = tq == 0 && gid == 7, f30 = tq == 3 && gid == 0;
+  uint32_t phase[2] = {0, 0};
+  int slot = 0;
+  for (long long grp = blockIdx.x; grp < n_groups; grp += gridDim.x, slot ^= 1) {
+    const long long p0 = grp * q.PB;
+    const int npl = (int)min((long long)q.PB, q.planes - p0);
+    if (threadIdx.x == 0 && grp + gridDim.x < n_groups) issue(grp + gridDim.x, slot ^ 1);
+    float* wsl = ws + slot * q.PB * 9;
+    for (int e = threadIdx.x; e < npl * 9; e += blockDim.x) {
+      const int j = e / 9, t = e - j * 9;
+      const int c = (int)((p0 + j) % q.channels);
+      wsl[j * 9 + (FLIP ? 8 - t : t)] = __bfloat162float(w[(long long)c * 9 + t]);
+    }
+    mbar_wait(bar0 + 8 * slot, phase[slot]);
+    phase[slot] ^= 1;
+    __syncthreads();                                                 // weights staged
+    for (int task = warp; task < npl * nmt; task += 8) {
+      const int j = task / nmt, mt = task - j * nmt;
+      const uint32_t plane = buf0 + slot * slot_stride + (uint32_t)j * psz * 2;
+      float acc[NNT][4];
+#pragma unroll
+      for (int n = 0; n < NNT; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+      for (int dh = 0; dh < 3; ++dh) {
+        // B fragments of T_dh: one band fragment (the same for an even tile's first half and an odd tile's second half) and
+        // two single-lane corner entries -- a handful of selects per dh
+        const uint32_t tb0 = bf16_bits_(wsl[j * 9 + dh * 3]), tb1 = bf16_bits_(wsl[j * 9 + dh * 3 + 1]), tb2 = bf16_bits_(wsl[j * 9 + dh * 3 + 2]);
+        const uint32_t lo = i0 == 0 ? tb0 : (i0 == 1 ? tb1 : (i0 == 2 ? tb2 : 0u));
+        const uint32_t hi = i0 == -1 ? tb0 : (i0 == 0 ? tb1 : (i0 == 1 ? tb2 : 0u));
+        const uint32_t band = lo | (hi << 16);
+        const uint32_t c07 = f07 ? tb2 : 0u, c30 = f30 ? (tb0 << 16) : 0u;
+        const uint32_t pe[2] = {band, c07}, plast[2] = {band, 0u}, po[2] = {c30, band}, pl[2] = {0u, c30}, pr[2] = {c07, 0u};
+        const int row = mt * 16 + (lane & 15) + dh - 1;
+        const uint32_t ra = (row >= 0 && row < H ? plane + (uint32_t)row * ROWB : zrow) + (lane >> 4) * 16;
+        uint32_t a[NKS][4];
+#pragma unroll
+        for (int s = 0; s < NKS; ++s) ldsm4_(a[s], ra + s * 32);
+#pragma unroll
+        for (int n = 0; n < NNT; ++n) {
+          const int s = n >> 1;
+          if ((n & 1) == 0) {
+            if (n == NNT - 1) mma16816_(acc[n], a[s], plast[0], plast[1]);
+            else mma16816_(acc[n], a[s], pe[0], pe[1]);
+            if (n > 0) mma16816_(acc[n], a[s - 1], pl[0], pl[1]);
+          } else {
+            mma16816_(acc[n], a[s], po[0], po[1]);
+            if (n < NNT - 1) mma16816_(acc[n], a[s + 1], pr[0], pr[1]);
+          }
+        }
+      }
+      const int r0 = mt * 16 + gid, r1 = r0 + 8;
+      __nv_bfloat16* yp = y + (p0 + j) * psz + 2 * tq;
+#pragma unroll
+      for (int n = 0; n < NNT; ++n) {
+        if (r0 < H) *reinterpret_cast<__nv_bfloat162*>(yp + r0 * W + n * 8) = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
+        if (r1 < H) *reinterpret_cast<__nv_bfloat162*>(yp + r1 * W + n * 8) = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
+      }
+    }
+    __syncthreads();                                                 // everyone is done with this slot (and its weights)
+  }
+}
+
 static uint32_t magic(int d) { return d > 1 ? (uint32_t)((1ull << 32) / (uint32_t)d) + 1u : 0u; }
 
 }  // namespace dwt
@@ -223,7 +343,45 @@ bool dwconv3x3_tma_ok(int H, int W, const void* a, const void* b) {
   return W % 4 == 0 && (H * W) % 8 == 0 && H * W * 2 <= 16 * 1024 && (((uintptr_t)a) & 15) == 0 && (((uintptr_t)b) & 15) == 0;
 }
 
+template <int W>
+static int dwconv3x3_mma_launch(bool flip, int H, int channels, long long planes, const void* x, const void* w, void* y, cudaStream_t st) {
+  dwt::Params q{};
+  q.H = H; q.W = W; q.channels = channels; q.planes = planes;
+  const int psz = H * W;
+  int pb = (32 * 1024) / (psz * 2);                                  // planes per landing buffer
+  if (pb > 4) pb = 4;
+  if (pb < 1) pb = 1;
+  if ((long long)pb > planes) pb = (int)planes;
+  q.PB = pb;
+  const long long groups = (planes + pb - 1) / pb;
+  const size_t slot = ((size_t)pb * psz * 2 + 32 + 127) / 128 * 128;
+  const size_t smem = 128 + 2 * slot + (size_t)2 * pb * 9 * 4 + 16;
+  static size_t high = 0;
+  if (smem > 48 * 1024 && smem > high) {
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_mma_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_mma_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_mma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
+    high = smem;
+  }
+  const long long cap = 148LL * 4;
+  const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
+  const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *wp = (const __nv_bfloat16*)w;
+  if (flip) dwt::dwconv3x3_mma_kernel<true, W><<<blocks, 256, smem, st>>>(q, xp, wp, (__nv_bfloat16*)y, groups);
+  else dwt::dwconv3x3_mma_kernel<false, W><<<blocks, 256, smem, st>>>(q, xp, wp, (__nv_bfloat16*)y, groups);
+  return check_launch("dwconv3x3_mma_kernel");
+}
+
 int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const void* x, const void* w, void* y, cudaStream_t st) {
+  {
+    const char* env = getenv("TLT_DW_MMA");
+    const bool off = env && env[0] == 'o' && env[1] == 'f';
+    if (!off && H <= 64 && H * W * 2 <= 16 * 1024) {
+      if (W == 56) return dwconv3x3_mma_launch<56>(flip, H, channels, planes, x, w, y, st);
+      if (W == 64) return dwconv3x3_mma_launch<64>(flip, H, channels, planes, x, w, y, st);
+      if (W == 32) return dwconv3x3_mma_launch<32>(flip, H, channels, planes, x, w, y, st);
+      if (W == 16) return dwconv3x3_mma_launch<16>(flip, H, channels, planes, x, w, y, st);
+    }
+  }
   dwt::Params q;
   const int SWd = W % 8 == 0 ? 8 : 4;
   q.H = H; q.W = W; q.strips = W / SWd; q.channels = channels; q.planes = planes;
