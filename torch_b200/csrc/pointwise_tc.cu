@@ -248,6 +248,158 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Transposed-role forward / data-gradient kernel: D[out channel][position] = Wt[out channel][k] . X[k][position].
+// The kernel above puts positions on the TMEM lanes, so a thread of the epilogue holds ONE position and 32 channels and has to
+// transpose every 32 x 32 block through shared memory (32 two-byte stores + a TMA store per block: 22.7 M warp instructions,
+// 63 us per launch at 56^2 x 64 -> 69, 2.6 TB/s, epilogue-bound).  Here the WEIGHT tile is the A operand (M = 128 output
+// channels on the lanes) and the activation tile is the MN-major B operand (N = 256 positions, 3-D TMA boxes {64 s, 64 k}
+// straight from NCHW memory): a thread of the epilogue holds one channel and 32 consecutive positions = 64 contiguous bytes
+// of y, which leave as four 16-byte global stores -- no staging, no fences, no TMA store.  One CTA per SM (cta_group::1),
+// persistent over (image, position tile, channel tile) units, 4-stage TMA ring, double-buffered TMEM accumulator (2 x 256 cols).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kTctStages = 4;
+constexpr int kTctX = 4 * BLOCK_K * 128;                 // 256 positions x 64 channels bf16 = 32 KB
+constexpr int kTctW = BLOCK_M * BLOCK_K * 2;             // 128 output channels x 64 k = 16 KB
+constexpr int kTctStage = kTctX + kTctW;
+constexpr int kTctSmem = kTctStages * kTctStage + 256 + 1024;
+
+__global__ void __launch_bounds__(kPwThreads, 1)
+pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const PwParams p,
+                     const void* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
+  constexpr int kStages = kTctStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kStages * kTctStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + kStages * kTctStage + 8 * (2 * kStages + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_units = p.batch * p.tiles_m * p.tiles_n;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  auto decode = [&](int u, int& z, int& ts, int& tn) {
+    tn = u % p.tiles_n;
+    const int r = u / p.tiles_n;
+    ts = r % p.tiles_m; z = r / p.tiles_m;
+  };
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPwEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int z, ts, tn;
+        decode(u, z, ts, tn);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sx = smem_base + stage * kTctStage, sw = sx + kTctX;
+          mbar_expect_tx(full_bar(stage), kTctStage);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)                                              // X: {64 s, 64 k} per 64-position chunk
+            tma_load_3d(sx + c * (BLOCK_K * 128), &map_x, full_bar(stage), ts * 256 + 64 * c, kb * BLOCK_K, z);
+          tma_load_2d(sw, &map_w, full_bar(stage), kb * BLOCK_K, tn * BLOCK_M);    // Wt: {64 k, 128 n}
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, 256, 0, 1);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sx = smem_base + stage * kTctStage, sw = sx + kTctX;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sw + k * (UMMA_K * 2), 16, 1024);             // Wt, K-major
+            const uint64_t db = make_smem_desc(sx + k * (UMMA_K * 128), BLOCK_K * 128, 1024); // X, MN-major, 4 chunks of 64
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == kb_total - 1) umma_commit(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;                  // TMEM lanes [32 quarter, +32) = output channels
+    const int half = (warp - 4) >> 2;              // accumulator columns [128 half, +128) = positions
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      int z, ts, tn;
+      decode(u, z, ts, tn);
+      const int n = tn * BLOCK_M + quarter * 32 + lane;
+      const bool warp_live = tn * BLOCK_M + quarter * 32 < p.N;
+      float bv = 0.f;
+      if (p.has_bias && n < p.N) bv = p.bias_bf16 ? __bfloat162float(((const __nv_bfloat16*)bias)[n]) : ((const float*)bias)[n];
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128);
+      __nv_bfloat16* yrow = y + ((size_t)z * p.N + (n < p.N ? n : 0)) * p.S;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int s0 = ts * 256 + half * 128 + c * 32;
+        const bool live = warp_live && s0 < p.S;                 // warp-uniform
+        uint32_t v[32];
+        if (live) {
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+        }
+        if (c == 3) {                                            // accumulator fully read: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (!live || n >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (s0 + 8 * j < p.S) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + bv, __uint_as_float(v[8 * j + 1]) + bv);
+            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + bv, __uint_as_float(v[8 * j + 3]) + bv);
+            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + bv, __uint_as_float(v[8 * j + 5]) + bv);
+            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + bv, __uint_as_float(v[8 * j + 7]) + bv);
+            *reinterpret_cast<uint4*>(yrow + s0 + 8 * j) = o;
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int BN, int kStages, bool WGRAD>
 static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const PwParams& p, const void* bias,
                      int units, cudaStream_t st) {
@@ -338,6 +490,29 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
   const long long units = (long long)p.batch * p.tiles_m * p.tiles_n;
   TLT_REQUIRE(units < (1LL << 31), "tlt_pointwise_tc: too many tiles");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // opt-in experiment (TLT_PW_T=on): transposed roles -- channels on the TMEM lanes, 256 positions per tile, direct 16-byte
+    // stores of y.  Parity-green but not faster (0.646 vs 0.633 ms per 64 @ 56^2 layer step, 0.445 vs 0.380 ms at 128 @ 28^2
+    // where N = 141 needs two channel tiles): the per-lane 16-byte stores to 32 different rows cost as much as the transposition
+    // they remove, so the pair kernel below stays the default.
+    const char* env = getenv("TLT_PW_T");
+    if (env && env[0] == 'o' && env[1] == 'n') {
+      CUtensorMap mw;
+      if ((rc = make_map(&mw, wt, K, N, d->w_ld, BLOCK_K, BLOCK_M))) return rc;                  // Wt {64 k, 128 n}
+      p.tiles_m = (int)((S + 255) / 256);
+      p.tiles_n = (int)((N + BLOCK_M - 1) / BLOCK_M);
+      const long long un = (long long)p.batch * p.tiles_m * p.tiles_n;
+      TLT_REQUIRE(un < (1LL << 31), "tlt_pointwise_tc: too many tiles");
+      static bool attr_set = false;
+      if (!attr_set) {
+        TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTctSmem));
+        attr_set = true;
+      }
+      const int sms = num_sms();
+      pointwise_tct_kernel<<<(unsigned)(un < sms ? un : sms), kPwThreads, kTctSmem, st>>>(ma, mw, p, bias, (__nv_bfloat16*)y);
+      return check_launch("pointwise_tct_kernel");
+    }
+  }
   if (wide) return pw_launch<256, 6, false>(ma, mb, mc, p, bias, (int)units, st);
   return pw_launch<128, 8, false>(ma, mb, mc, p, bias, (int)units, st);
 }
