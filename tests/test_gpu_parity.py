@@ -289,6 +289,10 @@ def test_packed_tensor_core_contract(spec, sa, sb, bias_letters):
     (9, 141, 28, 28, (3, 3), (1, 1), (1, 1), (1, 1)),    # TMA-fed path (bf16): 10 planes per group
     (3, 5, 8, 12, (3, 3), (1, 1), (1, 1), (1, 1)),       # TMA-fed path (bf16): tiny planes
     (2, 4, 10, 13, (3, 3), (1, 1), (1, 1), (1, 1)),
+    (3, 7, 23, 64, (3, 3), (1, 1), (1, 1), (1, 1)),      # tensor-core path (bf16): W = 64 (last tile odd), ragged 16-row slabs
+    (5, 3, 17, 32, (3, 3), (1, 1), (1, 1), (1, 1)),      # tensor-core path: W = 32
+    (1, 1, 5, 16, (3, 3), (1, 1), (1, 1), (1, 1)),       # tensor-core path: W = 16, a single short plane
+    (2, 9, 64, 56, (3, 3), (1, 1), (1, 1), (1, 1)),      # tensor-core path: W = 56 with H = 64 (four full slabs), tail group
     (3, 5, 56, 56, (3, 3), (2, 2), (1, 1), (1, 1)),      # generic staged path: stride 2
     (2, 3, 17, 9, (3, 1), (1, 1), (1, 0), (1, 1)),       # 1-D taps along H
     (2, 3, 12, 11, (2, 3), (1, 2), (0, 2), (2, 1)),      # dilation, asymmetric everything

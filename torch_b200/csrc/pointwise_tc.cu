@@ -30,6 +30,7 @@ struct PwParams {
   int splits, kb_per_split;      // wgrad
   int has_bias, bias_bf16;
   int c_reduce;
+  int dbg;                       // development only (TLT_PW_DBG): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA store
 };
 
 template <int BN, int kStages>
@@ -195,7 +196,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
         }
-        if (!live) continue;
+        if (!live || (p.dbg & 1)) continue;
         // WGRAD: the previous store of this warp has finished reading ebuf.  Forward: the store issued TWO chunks ago (same
         // half) has; the latest one may still be in flight, so the transposition of this chunk overlaps its read
         if (lane == 0) { if (WGRAD) bulk_wait_read0(); else bulk_wait_read1(); }
@@ -228,7 +229,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&map_c, ebuf + ehalf, m0, col0, z);
+            if (!(p.dbg & 2)) tma_store_3d(&map_c, ebuf + ehalf, m0, col0, z);
             bulk_commit();
           }
           ehalf ^= 2048u;
@@ -487,6 +488,7 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
   p.tiles_m = (int)((S + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
   p.tiles_n = (int)((N + (wide ? 256 : 128) - 1) / (wide ? 256 : 128));
   p.has_bias = bias != nullptr; p.bias_bf16 = d->dtype_bias == TLT_BF16;
+  { const char* e = getenv("TLT_PW_DBG"); p.dbg = e ? atoi(e) : 0; }
   const long long units = (long long)p.batch * p.tiles_m * p.tiles_n;
   TLT_REQUIRE(units < (1LL << 31), "tlt_pointwise_tc: too many tiles");
   cudaStream_t st = (cudaStream_t)stream;
