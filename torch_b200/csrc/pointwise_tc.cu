@@ -30,6 +30,8 @@ struct PwParams {
   int splits, kb_per_split;      // wgrad
   int has_bias, bias_bf16;
   int c_reduce;
+  int w_res, nst;                // forward: weight tile resident in the memory of the last ring stages; ring stages in use
+  int tail16;                    // forward: k16 steps of the LAST k block (4 = a full block)
   int dbg;                       // development only (TLT_PW_DBG): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA store
 };
 
@@ -46,7 +48,8 @@ struct PwSmem {
 template <int BN, int kStages, bool WGRAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_c, const PwParams p, const void* __restrict__ bias) {
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_at, const PwParams p,
+                    const void* __restrict__ bias) {
   using L = PwSmem<BN, kStages>;
   constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr int HALF_N = BN / 2;
@@ -60,6 +63,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kStages + 5);
+  // forward only: the weight tile is the same for every unit when there is one channel tile, so it is loaded ONCE into the
+  // memory of the last ring stages instead of riding in every stage (it was a third of the TMA traffic of a K = 64 layer)
+  const bool w_res = !WGRAD && p.w_res;
+  const int nst = w_res ? p.nst : kStages;
+  const uint32_t wres = smem_base + (uint32_t)nst * L::STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -91,6 +100,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kPwEpiWarps); }
+    mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -106,6 +116,11 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ===================================== TMA producer (both CTAs) =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (w_res) {
+        if (leader) mbar_expect_tx(wfull_bar, 2 * kb_total * L::B_BYTES);
+        for (int kb = 0; kb < kb_total; ++kb)
+          tma_load_2d_2sm(wres + kb * L::B_BYTES, &map_b, wfull_bar, kb * BLOCK_K, (int)cta_rank * HALF_N);
+      }
       for (int u = cluster_id; u < num_units; u += num_clusters) {
         int z, tm, tn, kb0, kb1;
         decode(u, z, tm, tn, kb0, kb1);
@@ -114,19 +129,30 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+          // the last k block of a ragged K (69, 141 channels) only brings the k16 steps that exist: {64 s, 16 k} boxes
+          const int n16 = (!WGRAD && kb == kb_total - 1) ? p.tail16 : BLOCK_K / UMMA_K;
+          if (leader) {
+            if (WGRAD) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+            else mbar_expect_tx(full_bar(stage), 2 * ((BLOCK_M / 64) * n16 * (UMMA_K * 128) + (w_res ? 0 : L::B_BYTES)));
+          }
           if (WGRAD) {
             const int img = kb / p.kpi, s0 = (kb - img * p.kpi) * BLOCK_K;
             tma_load_3d_2sm(sa, &map_a, full_bar(stage), s0, m0, img);            // dY: {64 s, 128 out-channels}
             tma_load_3d_2sm(sb, &map_b, full_bar(stage), s0, n0, img);            // X : {64 s, BN/2 in-channels}
           } else {
             const int k0 = kb * BLOCK_K;
+            if (n16 == BLOCK_K / UMMA_K) {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)                                 // X^T: {64 s, 64 channels} per 64-row chunk
-              tma_load_3d_2sm(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0, z);
-            tma_load_2d_2sm(sb, &map_b, full_bar(stage), k0, n0);                  // Wt: {64 k, BN/2 n}
+              for (int c = 0; c < BLOCK_M / 64; ++c)                               // X^T: {64 s, 64 channels} per 64-row chunk
+                tma_load_3d_2sm(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0, z);
+            } else {
+              for (int c = 0; c < BLOCK_M / 64; ++c)
+                for (int j = 0; j < n16; ++j)
+                  tma_load_3d_2sm(sa + c * (BLOCK_K * 128) + j * (UMMA_K * 128), &map_at, full_bar(stage), m0 + 64 * c, k0 + UMMA_K * j, z);
+            }
+            if (!w_res) tma_load_2d_2sm(sb, &map_b, full_bar(stage), k0, n0);      // Wt: {64 k, BN/2 n}
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -140,6 +166,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t a_kstep = a_mn ? (UMMA_K * 128) : (UMMA_K * 2);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      if (w_res) {
+        mbar_wait(wfull_bar, 0);
+        tc_fence_after();
+      }
       for (int u = cluster_id; u < num_units; u += num_clusters) {
         int z, tm, tn, kb0, kb1;
         decode(u, z, tm, tn, kb0, kb1);
@@ -149,16 +179,20 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t sb = w_res ? wres + kb * L::B_BYTES : sa + L::A_BYTES;
+          const int n16 = (!WGRAD && kb == kb_total - 1) ? p.tail16 : BLOCK_K / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+            if (k < n16) {
+              const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+              const uint64_t db = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+            }
           }
           umma_commit_2sm(empty_bar(stage));
           if (kb == kb1 - 1) umma_commit_2sm(tfull_bar(acc));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -402,8 +436,8 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }
 
 template <int BN, int kStages, bool WGRAD>
-static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const PwParams& p, const void* bias,
-                     int units, cudaStream_t st) {
+static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mat, const PwParams& p,
+                     const void* bias, int units, cudaStream_t st) {
   using L = PwSmem<BN, kStages>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -412,7 +446,7 @@ static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   }
   const int pairs = num_sms() / 2;
   const int clusters = units < pairs ? units : pairs;
-  pointwise_tc_kernel<BN, kStages, WGRAD><<<2 * clusters, kPwThreads, L::TOTAL, st>>>(ma, mb, mc, p, bias);
+  pointwise_tc_kernel<BN, kStages, WGRAD><<<2 * clusters, kPwThreads, L::TOTAL, st>>>(ma, mb, mc, mat, p, bias);
   return check_launch("pointwise_tc_kernel");
 }
 
@@ -515,8 +549,23 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
       return check_launch("pointwise_tct_kernel");
     }
   }
-  if (wide) return pw_launch<256, 6, false>(ma, mb, mc, p, bias, (int)units, st);
-  return pw_launch<128, 8, false>(ma, mb, mc, p, bias, (int)units, st);
+  CUtensorMap mat;
+  if ((rc = make_map3d(&mat, x, S, K, B, S, K * S, 64, UMMA_K, true))) return rc;                // X^T tail chunks {64 s, 16 k}
+  {
+    const int kb_total = (int)((K + BLOCK_K - 1) / BLOCK_K);
+    const int ktail = (int)(K - (int64_t)(kb_total - 1) * BLOCK_K);
+    p.tail16 = (ktail + UMMA_K - 1) / UMMA_K;
+    const char* env = getenv("TLT_PW_RES");
+    const bool res_off = env && env[0] == 'o' && env[1] == 'f';
+    if (res_off) p.tail16 = BLOCK_K / UMMA_K;
+    const int stage_bytes = BLOCK_M * BLOCK_K * 2 + (wide ? 128 : 64) * BLOCK_K * 2, b_bytes = (wide ? 128 : 64) * BLOCK_K * 2;
+    const int res_stages = (kb_total * b_bytes + stage_bytes - 1) / stage_bytes;
+    const int stages = wide ? 6 : 8;
+    p.w_res = (!res_off && p.tiles_n == 1 && stages - res_stages >= 4) ? 1 : 0;
+    p.nst = stages - res_stages;
+  }
+  if (wide) return pw_launch<256, 6, false>(ma, mb, mc, mat, p, bias, (int)units, st);
+  return pw_launch<128, 8, false>(ma, mb, mc, mat, p, bias, (int)units, st);
 }
 
 extern "C" int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* d, const void* dy, const void* x, float* dw, void* stream) {
@@ -548,8 +597,8 @@ extern "C" int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* d, const void* d
   cudaStream_t st = (cudaStream_t)stream;
   if (p.c_reduce) TLT_CHECK_CUDA(cudaMemset2DAsync(dw, (size_t)d->w_ld * 4, 0, (size_t)K * 4, (size_t)N, st));
   const int units = p.tiles_m * p.tiles_n * p.splits;
-  if (wide) return pw_launch<256, 6, true>(ma, mb, mc, p, nullptr, units, st);
-  return pw_launch<128, 8, true>(ma, mb, mc, p, nullptr, units, st);
+  if (wide) return pw_launch<256, 6, true>(ma, mb, mc, mc, p, nullptr, units, st);
+  return pw_launch<128, 8, true>(ma, mb, mc, mc, p, nullptr, units, st);
 }
 
 extern "C" int tlt_pack_kmajor(const void* src, int32_t dtype_src, int64_t rows, int64_t cols, int64_t row_stride,

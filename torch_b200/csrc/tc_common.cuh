@@ -290,9 +290,15 @@ inline int make_map3d(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1,
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = CUDA_SUCCESS;
   for (int attempt = 0; attempt < 2; ++attempt) {
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("TLT_TMA_PROMO")) {                   // development switch: 0 none, 1 64 B, 2 128 B, 3 256 B
+      const int v = atoi(e);
+      promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+            : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_ERROR_INVALID_CONTEXT) break;       // see make_map
     cudaFree(0);
   }
