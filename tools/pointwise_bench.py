@@ -25,7 +25,8 @@ def timed(fn, steps=20, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-for (B, K, N, S) in [(256, 64, 69, 3136), (256, 69, 64, 3136), (256, 128, 141, 784), (256, 141, 128, 784)]:
+for (B, K, N, S) in [(256, 64, 69, 3136), (256, 69, 64, 3136), (256, 128, 141, 784), (256, 141, 128, 784), (32, 64, 69, 3136), (64, 64, 69, 3136),
+                     (512, 64, 69, 3136)]:
     x = torch.randn(B, K, S, device=dev, dtype=torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * 0.1).bfloat16()
     y = torch.empty(B, N, S, device=dev, dtype=torch.bfloat16)
