@@ -96,7 +96,7 @@ def test_config4_trl_full_size():
     assert G.rel_err(gx[rows], want_gx.cpu()) < 2e-2
 
 
-@pytest.mark.parametrize("cin,cout,hw,stride", [(64, 64, 56, 1), (64, 128, 56, 2), (256, 256, 14, 1), (512, 512, 7, 1)])
+@pytest.mark.parametrize("cin,cout,hw,stride", [(64, 64, 56, 1), (128, 128, 28, 1), (64, 128, 56, 2), (256, 256, 14, 1), (512, 512, 7, 1)])
 def test_config3_cp_conv_full_size(cin, cout, hw, stride):
     """CP FactorizedConv layers of ResNet-18 (rank 0.25) at batch 256, bf16: NCHW tensor-core route (56^2), rows route (strided /
     14^2 / 7^2) vs F.conv2d with the reconstructed kernel on a sample of images; dx vs conv_transpose2d."""

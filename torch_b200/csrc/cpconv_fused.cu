@@ -453,6 +453,125 @@ __global__ void __launch_bounds__(K::NT, K::MINB) cpconv3x3_fused_kernel(const P
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Streaming 1x1 channel mix on NCHW activations with the same building blocks:  y[b, n, s] = sum_k wt[n, k] x[b, k, s].
+// A tile = (image, PT consecutive positions): every channel's run is one contiguous span, landed by a 1-D TMA bulk copy into
+// a double buffer (the next tile always in flight); the rank is walked in chunks of 32 output channels with stage1_chunk and
+// each chunk leaves as 16-byte coalesced stores of contiguous runs.  The tcgen05 kernel (pointwise_tc.cu) feeds its MN-major
+// operand with tiled-mode TMA boxes of 128-byte rows and transposes every 32 x 32 block in its epilogue; at config 3's 56^2 /
+// 28^2 shapes it moves 2.6 - 3.3 TB/s (tools/pointwise_bench.py), this kernel is the HBM-bound alternative for small K, N.
+// ---------------------------------------------------------------------------------------------------------------------
+struct PwhParams {
+  const __nv_bfloat16* x;        // (B, C, S)
+  const __nv_bfloat16* wt;       // (N, w_ld) K-major
+  __nv_bfloat16* y;              // (B, N, S)
+  int C, N, S, w_ld, RP;         // RP = N rounded up to 16
+  int tpi;                       // tiles per image
+  long long tiles;
+};
+
+template <int KC, int PT, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1) pointwise_hmma_kernel(const PwhParams p) {
+  constexpr int NT = NWARPS * 32, NG = (PT + 15) / 16, XP = odd16(NG * 32), W1P = odd16(KC * 2);
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, N = p.N, S = p.S, RP = p.RP;
+  unsigned char* xs_g = smem;                                         // [2][KC][XP]
+  unsigned char* zc_g = xs_g + (size_t)2 * KC * XP;                   // [32][XP]
+  unsigned char* w1s_g = zc_g + 32 * XP;                              // [RP + 16][W1P]
+  const uint32_t xs = s_u32(xs_g), zc = s_u32(zc_g), w1s = s_u32(w1s_g), bar0 = s_u32(&bars[0]);
+
+  for (int e = tid; e < 2 * (KC - C) * (XP / 4); e += NT) {           // channel rows C .. KC stay zero (never landed on)
+    const int slot = e / ((KC - C) * (XP / 4)), r = e % ((KC - C) * (XP / 4));
+    reinterpret_cast<uint32_t*>(xs_g + ((size_t)slot * KC + C) * XP)[r] = 0u;
+  }
+  stage_matrix<NT>(w1s_g, W1P, RP + 16, KC, p.wt, N, C, p.w_ld, 1, true, tid);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long tile, int slot) {                        // executed by warp 0
+    const long long b = tile / p.tpi;
+    const int p0 = (int)(tile % p.tpi) * PT;
+    const uint32_t bytes = (uint32_t)min(PT, S - p0) * 2;
+    fence_proxy_async();
+    if (lane == 0) mbar_expect_tx(bar0 + 8 * slot, bytes * C);
+    __syncwarp();
+    const __nv_bfloat16* src = p.x + ((size_t)b * C) * S + p0;
+    for (int c = lane; c < C; c += 32) bulk_g2s(xs + ((uint32_t)slot * KC + c) * XP, src + (size_t)c * S, bytes, bar0 + 8 * slot);
+  };
+  const long long first = blockIdx.x, step = gridDim.x;
+  if (warp == 0 && first < p.tiles) issue(first, 0);
+  int it = 0;
+  for (long long tile = first; tile < p.tiles; tile += step, ++it) {
+    const int slot = it & 1;
+    if (warp == 0 && tile + step < p.tiles) issue(tile + step, slot ^ 1);   // its readers passed the barrier that ended it - 1
+    mbar_wait(bar0 + 8 * slot, (it >> 1) & 1);
+    const long long b = tile / p.tpi;
+    const int p0 = (int)(tile % p.tpi) * PT;
+    const int plen = min(PT, S - p0), cpr = plen / 8;                 // 16-byte chunks per output run
+    const uint32_t xt = xs + (uint32_t)slot * KC * XP;
+    for (int rc = 0; rc < RP; rc += 32) {
+      const bool two = rc + 16 < RP;
+      const int nrows = min(two ? 32 : 16, N - rc);
+      stage1_chunk<KC, NG, NWARPS, XP, W1P>(w1s + rc * W1P, xt, zc, two, warp, lane);
+      __syncthreads();
+      unsigned char* yb = reinterpret_cast<unsigned char*>(p.y + (((size_t)b * N + rc) * S + p0));
+      for (int e = tid; e < nrows * cpr; e += NT) {
+        const int rr = e / cpr, j = e - rr * cpr;
+        *reinterpret_cast<uint4*>(yb + (size_t)rr * S * 2 + j * 16) = lds128(zc + rr * XP + j * 16);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int KC, int PT>
+static int pwh_launch(const PwhParams& p0, cudaStream_t st) {
+  constexpr int NWARPS = 8, NG = (PT + 15) / 16, XP = odd16(NG * 32), W1P = odd16(KC * 2);
+  PwhParams p = p0;
+  p.tpi = (p.S + PT - 1) / PT;
+  const size_t smem = (size_t)2 * KC * XP + 32 * XP + (size_t)(p.RP + 16) * W1P + 64;
+  if (smem > 227 * 1024) return 1;
+  static size_t high = 0;
+  if (smem > high) {
+    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_hmma_kernel<KC, PT, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    high = smem;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    TLT_CHECK_CUDA(cudaGetDevice(&dev));
+    TLT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  long long tiles = p.tiles = (p.tiles /* batch */) * p.tpi;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  pointwise_hmma_kernel<KC, PT, NWARPS><<<grid, NWARPS * 32, smem, st>>>(p);
+  return check_launch("pointwise_hmma_kernel");
+}
+
+}  // namespace cpf
+
+// returns 1 when the shape is not taken (caller falls back to the tcgen05 kernel), else a tlt_status
+int pointwise_hmma(const void* x, const void* wt, void* y, long long batch, long long C, long long N, long long S, long long w_ld,
+                   cudaStream_t st) {
+  if (S % 8 != 0 || C < 16 || C > 144 || N < 1 || N > 160 || batch < 1) return 1;
+  cpf::PwhParams p{};
+  p.x = (const __nv_bfloat16*)x; p.wt = (const __nv_bfloat16*)wt; p.y = (__nv_bfloat16*)y;
+  p.C = (int)C; p.N = (int)N; p.S = (int)S; p.w_ld = (int)w_ld; p.RP = (int)((N + 15) / 16 * 16);
+  p.tiles = batch;
+  const int kc = (int)((C + 15) / 16 * 16);
+  if (kc <= 64) return cpf::pwh_launch<64, 448>(p, st);
+  if (kc <= 80) return cpf::pwh_launch<80, 448>(p, st);
+  if (kc <= 128) return cpf::pwh_launch<128, 224>(p, st);
+  return cpf::pwh_launch<144, 224>(p, st);
+}
+
+namespace cpf {
+
 template <class K>
 static int launch(const Params& p, cudaStream_t st) {
   static size_t cached_smem = 0;
