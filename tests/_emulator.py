@@ -358,6 +358,35 @@ def emulate_scale_modes(x, masks, alpha, y):
     LOG.append(("scale_modes", tuple(x.shape), [m is not None for m in masks], alpha))
 
 
+def emulate_spatial_fwd(x3, k, t):
+    t.copy_(torch.einsum("bcs,sj->bjc", x3.double(), k.double()).to(t.dtype))
+    LOG.append(("spatial_project_fwd", tuple(x3.shape), tuple(k.shape)))
+
+
+def emulate_spatial_bwd(x3, k, gt, dx, dk):
+    dx.copy_(torch.einsum("bjc,sj->bcs", gt.double(), k.double()).to(dx.dtype))
+    dk.add_(torch.einsum("bcs,bjc->sj", x3.double(), gt.double()).to(dk.dtype))
+    LOG.append(("spatial_project_bwd", tuple(x3.shape), tuple(k.shape)))
+
+
+def emulate_cpconv_fused(x, f_in, taps_t, f_out, bias, flip, y, z1, z2, variant):
+    """y = F_out . dw3x3(F_in^T . x) (+ bias) with the intermediates rounded to the activation dtype like the kernel does."""
+    R = f_in.shape[1]
+    a = torch.einsum("cr,bchw->brhw", f_in.double(), x.double()).to(x.dtype)
+    taps = taps_t.double().flip(0) if flip else taps_t.double()
+    w = taps.t().reshape(R, 1, 3, 3)
+    b2 = torch.nn.functional.conv2d(a.double(), w, padding=1, groups=R).to(x.dtype)
+    out = torch.einsum("or,brhw->bohw", f_out.double(), b2.double())
+    if bias is not None:
+        out = out + bias.double().reshape(1, -1, 1, 1)
+    y.copy_(out.to(y.dtype))
+    if z1 is not None:
+        z1.copy_(a)
+    if z2 is not None:
+        z2.copy_(b2)
+    LOG.append(("cpconv3x3_fused", tuple(x.shape), R, bool(flip), z1 is not None))
+
+
 @contextlib.contextmanager
 def emulated_kernels():
     """Swap the launch funnels for the CPU interpreters (tests only)."""
@@ -367,6 +396,12 @@ def emulated_kernels():
     from torch_b200 import tucker_ops as to
     from torch_b200 import rows_ops as ro
     from torch_b200 import kr_ops as ko
+    from torch_b200 import spatial_ops as so
+    from torch_b200 import cpconv_ops as co
+    saved_so = so._execute_spatial_fwd, so._execute_spatial_bwd
+    so._execute_spatial_fwd, so._execute_spatial_bwd = emulate_spatial_fwd, emulate_spatial_bwd
+    saved_co = co._execute_cpconv_fused
+    co._execute_cpconv_fused = emulate_cpconv_fused
     saved_k = ko._execute_kr_fwd, ko._execute_kr_bwd
     ko._execute_kr_fwd, ko._execute_kr_bwd = emulate_kr_fwd, emulate_kr_bwd
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
@@ -389,6 +424,8 @@ def emulated_kernels():
     try:
         yield LOG
     finally:
+        so._execute_spatial_fwd, so._execute_spatial_bwd = saved_so
+        co._execute_cpconv_fused = saved_co
         ops._execute_contract, ops._execute_conv = saved
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p

@@ -266,3 +266,58 @@ def test_fused_multi_mode_dot_host_logic():
                 assert G.rel_err(a, b) < TOL
     finally:
         modedot_ops.MIN_BATCH, modedot_ops.MIN_SAMPLE_ELEMS = old
+
+
+def test_spatial_first_projection_host_logic(monkeypatch):
+    """tenalg.multi_mode_dot on a (B, C, h, w) map with a large channel mode -> spatial modes first (tltorch::spatial_project with
+    the Kronecker product of the spatial factors, then the channel mode as one padded GEMM): plan selection, output layout and the
+    autograd of x and of every factor, with the launch funnels emulated (tucker_trl's input projection, tensor_regression.py:40)."""
+    from torch_b200 import spatial_ops
+    torch.manual_seed(11)
+    monkeypatch.setattr(spatial_ops, "eligible", lambda x, S, J: x.shape[1] % 128 == 0 and S <= 64 and J <= 16)
+    B, C, h, w = 24, 256, 7, 7
+    ranks = (32, 4, 3)
+    x = (torch.randn(B, C, h, w) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    mats = [(torch.randn(d, r) * 0.3).to(torch.bfloat16).requires_grad_(True) for d, r in zip((C, h, w), ranks)]
+    with emulated_kernels() as log:
+        y = tenalg.multi_mode_dot(x, mats, [1, 2, 3], transpose=True)
+        gy = torch.randn_like(y)
+        got = torch.autograd.grad(y, [x] + mats, gy)
+    assert any(e[0] == "spatial_project_fwd" for e in log) and any(e[0] == "spatial_project_bwd" for e in log), log
+    assert tuple(y.shape) == (B, *ranks)
+    xr = x.detach().double().requires_grad_(True)
+    mr = [m.detach().double().requires_grad_(True) for m in mats]
+    ref = torch.einsum("bchw,cp,hq,wr->bpqr", xr, *mr)
+    want = torch.autograd.grad(ref, [xr] + mr, gy.double())
+    assert G.rel_err(y, ref) < 3e-2
+    for a, b in zip(got, want):
+        assert G.rel_err(a, b) < 3e-2
+
+
+def test_cp_conv_fused_op_host_logic():
+    """tltorch::cpconv3x3_fused: the op's autograd (data-gradient chain = the same launch with swapped factors and flipped taps,
+    its two intermediates feeding the three weight-gradient reductions, bias gradient) against fp64 autograd of
+    1x1 -> depthwise 3x3 -> 1x1 (cp_conv, convolution.py:231-283), with the launch funnels emulated."""
+    from torch_b200 import cpconv_ops
+    torch.manual_seed(12)
+    B, C, O, R, H, W = 2, 16, 24, 11, 8, 8
+    x = (torch.randn(B, C, H, W) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    f_in = (torch.randn(C, R) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    f_out = (torch.randn(O, R) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    taps = (torch.randn(9, R) * 0.4).to(torch.bfloat16).requires_grad_(True)
+    bias = torch.randn(O).to(torch.bfloat16).requires_grad_(True)
+    leaves = [x, f_in, taps, f_out, bias]
+    with emulated_kernels() as log:
+        y = cpconv_ops.cp_conv_fused(x, f_in, taps, f_out, bias)
+        gy = torch.randn_like(y)
+        got = torch.autograd.grad(y, leaves, gy)
+    fused = [e for e in log if e[0] == "cpconv3x3_fused"]
+    assert len(fused) == 2 and fused[0][3] is False and fused[1][3] is True and fused[0][4] and fused[1][4], log
+    lr = [t.detach().double().requires_grad_(True) for t in leaves]
+    a = torch.einsum("cr,bchw->brhw", lr[1], lr[0])
+    b2 = torch.nn.functional.conv2d(a, lr[2].t().reshape(R, 1, 3, 3), padding=1, groups=R)
+    ref = torch.einsum("or,brhw->bohw", lr[3], b2) + lr[4].reshape(1, -1, 1, 1)
+    want = torch.autograd.grad(ref, lr, gy.double())
+    assert G.rel_err(y, ref) < 3e-2
+    for t, g, wv in zip(["x", "f_in", "taps", "f_out", "bias"], got, want):
+        assert G.rel_err(g, wv) < 4e-2, t
