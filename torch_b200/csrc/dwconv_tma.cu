@@ -239,15 +239,22 @@ template <bool FLIP, int W>
 __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, const __nv_bfloat16* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y,
                                                             long long n_groups) {
-  constexpr int NKS = (W + 15) / 16, NNT = W / 8, ROWB = W * 2;
-  static_assert(W % 8 == 0 && W <= 64, "row = whole 16-byte chunks, at most four k16 steps");
+  // W % 8 != 0 (28-wide maps): the 56-byte rows of the landed planes break ldmatrix's 16-byte row alignment, so each group is
+  // re-pitched once inside shared memory (8-byte moves) into rows of ROWB bytes -- an odd multiple of 16, zero beyond column W
+  constexpr bool REPITCH = W % 8 != 0;
+  constexpr int NKS = (W + 15) / 16, NNT = (W + 7) / 8;
+  constexpr int ROWB = REPITCH ? ((((W + 7) / 8) * 16 / 16) % 2 == 0 ? ((W + 7) / 8) * 16 + 16 : ((W + 7) / 8) * 16) : W * 2;
+  static_assert(W % 4 == 0 && W <= 64, "rows of whole 8-byte chunks, at most four k16 steps");
+  static_assert(NKS * 32 + 16 <= 128 + 16, "zero row covers every k step");
   extern __shared__ __align__(128) unsigned char dwt_smem[];
   const int psz = q.H * W, H = q.H;
   const uint32_t buf_bytes = (uint32_t)q.PB * psz * 2;
   const uint32_t slot_stride = (buf_bytes + 32 + 127) / 128 * 128;               // 32 zero bytes behind each landing buffer
+  const uint32_t work_bytes = REPITCH ? ((uint32_t)q.PB * H * ROWB + 32 + 127) / 128 * 128 : 0u;
   unsigned char* zrow_g = dwt_smem;                                              // 128 bytes of zeros
   unsigned char* buf_g = dwt_smem + 128;
-  float* ws = reinterpret_cast<float*>(buf_g + 2 * slot_stride);                 // [2][PB][9]
+  unsigned char* work_g = buf_g + 2 * slot_stride;                               // re-pitched planes of the current group
+  float* ws = reinterpret_cast<float*>(work_g + work_bytes);                     // [2][PB][9]
   const uint32_t bar0 = smem_u32(reinterpret_cast<unsigned char*>(ws) + 2 * q.PB * 9 * 4);
   const uint32_t zrow = smem_u32(zrow_g), buf0 = smem_u32(buf_g);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tq = lane & 3;
@@ -261,6 +268,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, cons
   for (int e = threadIdx.x; e < 32; e += blockDim.x) reinterpret_cast<uint32_t*>(zrow_g)[e] = 0u;
   for (int e = threadIdx.x; e < 16; e += blockDim.x)
     reinterpret_cast<uint32_t*>(buf_g + (e >> 3) * slot_stride + buf_bytes)[e & 7] = 0u;
+  if constexpr (REPITCH) {
+    const int words = (int)(work_bytes / 4);
+    for (int e = threadIdx.x; e < words; e += blockDim.x) reinterpret_cast<uint32_t*>(work_g)[e] = 0u;
+  }
   if (threadIdx.x == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -285,10 +296,18 @@ __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, cons
     }
     mbar_wait(bar0 + 8 * slot, phase[slot]);
     phase[slot] ^= 1;
-    __syncthreads();                                                 // weights staged
+    if constexpr (REPITCH) {
+      constexpr int CPR = W / 4;                                      // 8-byte chunks per row
+      const unsigned char* land = buf_g + slot * slot_stride;
+      for (int e = threadIdx.x; e < npl * H * CPR; e += blockDim.x) {
+        const int r = e / CPR, c = e - r * CPR;                       // r = (plane, row)
+        *reinterpret_cast<uint2*>(work_g + (size_t)r * ROWB + c * 8) = *reinterpret_cast<const uint2*>(land + (size_t)r * (W * 2) + c * 8);
+      }
+    }
+    __syncthreads();                                                 // weights staged (and planes re-pitched)
     for (int task = warp; task < npl * nmt; task += 8) {
       const int j = task / nmt, mt = task - j * nmt;
-      const uint32_t plane = buf0 + slot * slot_stride + (uint32_t)j * psz * 2;
+      const uint32_t plane = REPITCH ? smem_u32(work_g) + (uint32_t)j * H * ROWB : buf0 + slot * slot_stride + (uint32_t)j * psz * 2;
       float acc[NNT][4];
 #pragma unroll
       for (int n = 0; n < NNT; ++n)
@@ -313,7 +332,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, cons
         for (int n = 0; n < NNT; ++n) {
           const int s = n >> 1;
           if ((n & 1) == 0) {
-            if (n == NNT - 1) mma16816_(acc[n], a[s], plast[0], plast[1]);
+            if (n == NNT - 1 && !REPITCH) mma16816_(acc[n], a[s], plast[0], plast[1]);
             else mma16816_(acc[n], a[s], pe[0], pe[1]);
             if (n > 0) mma16816_(acc[n], a[s - 1], pl[0], pl[1]);
           } else {
@@ -326,8 +345,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, cons
       __nv_bfloat16* yp = y + (p0 + j) * psz + 2 * tq;
 #pragma unroll
       for (int n = 0; n < NNT; ++n) {
-        if (r0 < H) *reinterpret_cast<__nv_bfloat162*>(yp + r0 * W + n * 8) = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
-        if (r1 < H) *reinterpret_cast<__nv_bfloat162*>(yp + r1 * W + n * 8) = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
+        const bool colok = !REPITCH || n * 8 + 2 * tq < W;
+        if (r0 < H && colok) *reinterpret_cast<__nv_bfloat162*>(yp + r0 * W + n * 8) = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
+        if (r1 < H && colok) *reinterpret_cast<__nv_bfloat162*>(yp + r1 * W + n * 8) = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
       }
     }
     __syncthreads();                                                 // everyone is done with this slot (and its weights)
@@ -348,14 +368,17 @@ static int dwconv3x3_mma_launch(bool flip, int H, int channels, long long planes
   dwt::Params q{};
   q.H = H; q.W = W; q.channels = channels; q.planes = planes;
   const int psz = H * W;
+  constexpr bool REPITCH = W % 8 != 0;
+  constexpr int ROWB = REPITCH ? ((((W + 7) / 8)) % 2 == 0 ? ((W + 7) / 8) * 16 + 16 : ((W + 7) / 8) * 16) : W * 2;
   int pb = (32 * 1024) / (psz * 2);                                  // planes per landing buffer
-  if (pb > 4) pb = 4;
+  if (pb > (REPITCH ? 8 : 4)) pb = REPITCH ? 8 : 4;
   if (pb < 1) pb = 1;
   if ((long long)pb > planes) pb = (int)planes;
   q.PB = pb;
   const long long groups = (planes + pb - 1) / pb;
   const size_t slot = ((size_t)pb * psz * 2 + 32 + 127) / 128 * 128;
-  const size_t smem = 128 + 2 * slot + (size_t)2 * pb * 9 * 4 + 16;
+  const size_t work = REPITCH ? ((size_t)pb * H * ROWB + 32 + 127) / 128 * 128 : 0;
+  const size_t smem = 128 + 2 * slot + work + (size_t)2 * pb * 9 * 4 + 16;
   static size_t high = 0;
   if (smem > 48 * 1024 && smem > high) {
     cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_mma_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -380,6 +403,7 @@ int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const
       if (W == 64) return dwconv3x3_mma_launch<64>(flip, H, channels, planes, x, w, y, st);
       if (W == 32) return dwconv3x3_mma_launch<32>(flip, H, channels, planes, x, w, y, st);
       if (W == 16) return dwconv3x3_mma_launch<16>(flip, H, channels, planes, x, w, y, st);
+      if (W == 28) return dwconv3x3_mma_launch<28>(flip, H, channels, planes, x, w, y, st);
     }
   }
   dwt::Params q;
