@@ -354,6 +354,121 @@ __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, cons
   }
 }
 
+// Weight gradient on the tensor cores: for one channel plane pair (z, g) and one vertical tap dh
+//      D_dh[w'][w] = sum_h z[h + dh - 1][w'] g[h][w]            (m16n8k16, both operands through ldmatrix.trans, k = image row)
+// and dw[dh][dw] is the sum of the diagonal w' - w = dw - 1 of D_dh.  Only the tiles that touch the three diagonals are computed
+// (per 8-column tile of g one 16-row tile of z plus one neighbour for the column just outside), accumulated in registers over all
+// images of the block, and the diagonals are picked out once at the end.  A warp owns one dh; two warps per dh walk alternate planes.
+__device__ __forceinline__ void ldsm4t_(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2t_(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+template <int W>
+__global__ void __launch_bounds__(192) dwconv3x3_wgrad_mma_kernel(const Params q, int batch, int batch_per_block,
+                                                                  const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                  float* __restrict__ dw) {
+  constexpr int NMT = (W + 15) / 16, NNT = W / 8, ROWB = W * 2;
+  static_assert(W % 8 == 0 && W <= 64, "rows of whole 16-byte chunks");
+  extern __shared__ __align__(128) unsigned char dwt_smem[];
+  const int psz = q.H * W, H = q.H;
+  const uint32_t half = ((uint32_t)q.PB * psz * 2 + 32 + 127) / 128 * 128;       // one operand of one slot (+ slack for over-reads)
+  const uint32_t zrow = smem_u32(dwt_smem);                                      // 128 bytes of zeros
+  const uint32_t base = zrow + 128;
+  auto xs_of = [&](int slot) { return base + (uint32_t)slot * 2 * half; };
+  auto gs_of = [&](int slot) { return base + (uint32_t)slot * 2 * half + half; };
+  const uint32_t bar0 = base + 4 * half;
+  const int c = blockIdx.x;
+  const int b_begin = blockIdx.y * batch_per_block;
+  const int b_end = min(batch, b_begin + batch_per_block);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tq = lane & 3;
+  const int dh = warp % 3, pl = warp / 3;                                        // vertical tap of this warp, plane lane (0 / 1)
+  auto issue = [&](int b0, int slot) {
+    const int npl = min(q.PB, b_end - b0);
+    mbar_expect_tx(bar0 + 8 * slot, (uint32_t)npl * psz * 2 * 2);
+    for (int j = 0; j < npl; ++j) {
+      const long long off = ((long long)(b0 + j) * q.channels + c) * psz;
+      bulk_g2s(xs_of(slot) + j * psz * 2, x + off, (uint32_t)psz * 2, bar0 + 8 * slot);
+      bulk_g2s(gs_of(slot) + j * psz * 2, dy + off, (uint32_t)psz * 2, bar0 + 8 * slot);
+    }
+  };
+  for (int e = threadIdx.x; e < 32; e += blockDim.x) reinterpret_cast<uint32_t*>(dwt_smem)[e] = 0u;
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_barrier_init();
+    if (b_begin < b_end) issue(b_begin, 0);
+  }
+  __syncthreads();
+  float accm[NNT][4], accc[NNT][4];                                              // main tiles / neighbour (corner) tiles per n tile
+#pragma unroll
+  for (int n = 0; n < NNT; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { accm[n][i] = 0.f; accc[n][i] = 0.f; }
+  const int ak = (lane & 7) + ((lane >> 4) << 3);                               // A operand: lane -> k row of the step, and
+  const uint32_t am = ((lane >> 3) & 1) * 16;                                    //            which 8-column half of the m16 tile
+  const int nks = (H + 15) / 16;
+  uint32_t phase[2] = {0, 0};
+  int slot = 0;
+  for (int b0 = b_begin; b0 < b_end; b0 += q.PB, slot ^= 1) {
+    const int npl = min(q.PB, b_end - b0);
+    if (threadIdx.x == 0 && b0 + q.PB < b_end) issue(b0 + q.PB, slot ^ 1);
+    mbar_wait(bar0 + 8 * slot, phase[slot]);
+    phase[slot] ^= 1;
+    for (int j = pl; j < npl; j += 2) {
+      const uint32_t zp = xs_of(slot) + (uint32_t)j * psz * 2, gp = gs_of(slot) + (uint32_t)j * psz * 2;
+      for (int ks = 0; ks < nks; ++ks) {
+        const int hb = ks * 16 + (lane & 15);                                    // B operand row (image row of g)
+        const uint32_t gaddr = hb < H ? gp + (uint32_t)hb * ROWB : zrow;
+        const int ha = ks * 16 + ak + dh - 1;                                    // A operand row (image row of z, shifted by the tap)
+        const uint32_t zaddr = (ha >= 0 && ha < H ? zp + (uint32_t)ha * ROWB : zrow) + am;
+        uint32_t a[NMT][4];
+#pragma unroll
+        for (int i = 0; i < NMT; ++i) ldsm4t_(a[i], zaddr + i * 32);
+#pragma unroll
+        for (int n = 0; n < NNT; ++n) {
+          uint32_t b0r, b1r;
+          ldsm2t_(b0r, b1r, gaddr + n * 16);
+          const int i = n >> 1;
+          mma16816_(accm[n], a[i], b0r, b1r);
+          if ((n & 1) == 0) { if (n > 0) mma16816_(accc[n], a[i - 1], b0r, b1r); }
+          else if (i + 1 < NMT) mma16816_(accc[n], a[i + 1], b0r, b1r);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // diagonals w' - w = dw - 1 of the accumulated tiles
+  float sum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int n = 0; n < NNT; ++n) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ml = gid + (e >> 1) * 8, nl = 2 * tq + (e & 1);
+      const int wn = n * 8 + nl;
+      {
+        const int wm = (n >> 1) * 16 + ml, d = wm - wn + 1;
+        if (d >= 0 && d <= 2 && wm < W) sum[d] += accm[n][e];
+      }
+      {
+        const int ic = (n & 1) == 0 ? (n >> 1) - 1 : (n >> 1) + 1;
+        const int wm = ic * 16 + ml, d = wm - wn + 1;
+        if (ic >= 0 && ic < NMT && d >= 0 && d <= 2 && wm < W) sum[d] += accc[n][e];
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float v = sum[d];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) atomicAdd(dw + (long long)c * 9 + dh * 3 + d, v);
+  }
+}
+
 static uint32_t magic(int d) { return d > 1 ? (uint32_t)((1ull << 32) / (uint32_t)d) + 1u : 0u; }
 
 }  // namespace dwt
@@ -442,7 +557,46 @@ int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const
   return check_launch("dwconv3x3_tma_kernel");
 }
 
+template <int W>
+static int dwconv3x3_wgrad_mma_launch(int H, int channels, int batch, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  dwt::Params q{};
+  q.H = H; q.W = W; q.channels = channels; q.planes = (long long)batch * channels;
+  const int psz = H * W;
+  long long chunks = (148LL * 6 + channels - 1) / channels;
+  if (chunks > batch) chunks = batch;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  const int bpb = (int)((batch + chunks - 1) / chunks);
+  chunks = (batch + bpb - 1) / bpb;
+  int pb = (16 * 1024) / (psz * 2);
+  if (pb < 2) pb = 2;
+  if (pb > 8) pb = 8;
+  if (pb > bpb) pb = bpb;
+  q.PB = pb;
+  const size_t half = ((size_t)pb * psz * 2 + 32 + 127) / 128 * 128;
+  const size_t smem = 128 + 4 * half + 16;
+  static size_t high = 0;
+  if (smem > 48 * 1024 && smem > high) {
+    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_wgrad_mma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
+    high = smem;
+  }
+  dim3 grid((unsigned)channels, (unsigned)chunks);
+  dwt::dwconv3x3_wgrad_mma_kernel<W><<<grid, 192, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
+  return check_launch("dwconv3x3_wgrad_mma_kernel");
+}
+
 int dwconv3x3_wgrad_tma(int H, int W, int channels, int batch, const void* x, const void* dy, float* dw, cudaStream_t st) {
+  {
+    const char* env = getenv("TLT_DW_MMA");
+    const bool off = env && env[0] == 'o' && env[1] == 'f';
+    if (!off && H <= 64 && H * W * 2 <= 16 * 1024) {
+      if (W == 56) return dwconv3x3_wgrad_mma_launch<56>(H, channels, batch, x, dy, dw, st);
+      if (W == 64) return dwconv3x3_wgrad_mma_launch<64>(H, channels, batch, x, dy, dw, st);
+      if (W == 32) return dwconv3x3_wgrad_mma_launch<32>(H, channels, batch, x, dy, dw, st);
+      if (W == 16) return dwconv3x3_wgrad_mma_launch<16>(H, channels, batch, x, dy, dw, st);
+    }
+  }
   dwt::Params q;
   const int SWd = W % 8 == 0 ? 8 : 4;
   q.H = H; q.W = W; q.strips = W / SWd; q.channels = channels; q.planes = (long long)batch * channels;
