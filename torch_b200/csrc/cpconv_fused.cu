@@ -111,12 +111,6 @@ struct Params {
   int flip;                      // 1: use taps[8 - t] (data gradient)
   int w3p;                       // row pitch in bytes of operands whose rows run over the rank = odd16(RP * 2)
   long long tiles;
-  // one-pass backward only
-  const __nv_bfloat16* gy;       // (B, O, H, W)
-  __nv_bfloat16* dx;             // (B, C, H, W)
-  float* df_in;                  // (C, R) fp32, accumulated
-  float* df_out;                 // (O, R) fp32, accumulated
-  float* dtaps_t;                // (9, R) fp32, accumulated
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

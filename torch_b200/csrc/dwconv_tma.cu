@@ -233,6 +233,10 @@ __device__ __forceinline__ void mma16816_(float (&c)[4], const uint32_t (&a)[4],
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma1688_(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
 __device__ __forceinline__ uint32_t bf16_bits_(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
 
 template <bool FLIP, int W>
@@ -334,10 +338,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_mma_kernel(const Params q, cons
           if ((n & 1) == 0) {
             if (n == NNT - 1 && !REPITCH) mma16816_(acc[n], a[s], plast[0], plast[1]);
             else mma16816_(acc[n], a[s], pe[0], pe[1]);
-            if (n > 0) mma16816_(acc[n], a[s - 1], pl[0], pl[1]);
+            if (n > 0) mma1688_(acc[n], a[s - 1][2], a[s - 1][3], pl[1]);      // column n0 - 1: second k8 half of the step before
           } else {
             mma16816_(acc[n], a[s], po[0], po[1]);
-            if (n < NNT - 1) mma16816_(acc[n], a[s + 1], pr[0], pr[1]);
+            if (n < NNT - 1) mma1688_(acc[n], a[s + 1][0], a[s + 1][1], pr[0]);  // column n0 + 8: first k8 half of the next step
           }
         }
       }
