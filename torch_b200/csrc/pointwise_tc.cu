@@ -438,6 +438,172 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-CTA weight gradient for small channel counts (N <= 128 per tile, K <= 128):  dW[n][k] += sum_{b,s} dY[b,n,s] X[b,k,s].
+// In the pair kernel above the two CTAs split the M (output-channel) and N (input-channel) extents of the tile; with 69 x 64
+// channels (config 3's 56^2 layers) everything the second CTA loads is out of bounds, so only 74 of the 148 SMs pull data
+// (214 MB at 3.2 TB/s).  Here every CTA is its own cta_group::1 MMA (M = 128 lanes of output channels, N = NB input channels),
+// owns a slice of the (image, 64-position block) reduction range, accumulates it in ONE TMEM buffer and adds its fp32 partial into
+// dW with TMA reduce-add -- all 148 SMs stream.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kW1Stages = 6;
+template <int NB> struct W1Smem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // dY {64 s, 128 n}
+  static constexpr int B_BYTES = NB * BLOCK_K * 2;           // X  {64 s, NB k}
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int EPI_OFFSET = kW1Stages * STAGE;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + kPwEpiWarps * 4096;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kPwThreads, 1)
+pointwise_wgrad1_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ CUtensorMap map_c, const PwParams p) {
+  using L = W1Smem<NB>;
+  constexpr int kStages = kW1Stages;
+  constexpr uint32_t TMEM_COLS = NB < 32 ? 32 : NB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * kStages), tempty_bar = bar_base + 8u * (2 * kStages + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2);
+  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 2));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_units = p.tiles_m * p.splits;
+  const int kb_total = p.batch * p.kpi;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_c); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, kPwEpiWarps);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int tm = u / p.splits, z = u - tm * p.splits;
+        const int kb0 = z * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * L::STAGE, sb = sa + L::A_BYTES;
+          mbar_expect_tx(full_bar(stage), L::STAGE);
+          const int img = kb / p.kpi, s0 = (kb - img * p.kpi) * BLOCK_K;
+          tma_load_3d(sa, &map_a, full_bar(stage), s0, tm * BLOCK_M, img);          // dY: {64 s, 128 out-channels}
+          tma_load_3d(sb, &map_b, full_bar(stage), s0, 0, img);                     // X : {64 s, NB in-channels}
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, NB, 0, 0);
+      int stage = 0; uint32_t phase = 0, acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int tm = u / p.splits, z = u - tm * p.splits;
+        const int kb0 = z * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar, acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::STAGE, sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == kb1 - 1) umma_commit(tfull_bar);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;                  // TMEM lanes [32 quarter, +32) = output channels
+    const int half = (warp - 4) >> 2;              // accumulator columns [NB / 2 * half, +NB / 2) = input channels
+    const uint32_t ebuf = smem_base + L::EPI_OFFSET + (warp - 4) * 4096;
+    constexpr int n_chunks = NB / 2 / 32;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int tm = u / p.splits;
+      const int m0 = tm * BLOCK_M + quarter * 32;
+      mbar_wait(tfull_bar, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (NB / 2));
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        const int col0 = half * (NB / 2) + c * 32;
+        const bool live = m0 < p.N && col0 < p.K;                // warp-uniform
+        uint32_t v[32];
+        if (live) {
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+        }
+        if (c == n_chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar);
+        }
+        if (!live) continue;
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const uint32_t erow = ebuf + lane * 128;
+        const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(erow + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.c_reduce) tma_reduce_add_2d(&map_c, ebuf, col0, m0);
+          else tma_store_2d(&map_c, ebuf, col0, m0);
+          bulk_commit();
+        }
+      }
+      acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int NB>
+static int w1_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const PwParams& p, int units, cudaStream_t st) {
+  using L = W1Smem<NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_wgrad1_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  pointwise_wgrad1_kernel<NB><<<units < sms ? units : sms, kPwThreads, L::TOTAL, st>>>(ma, mb, mc, p);
+  return check_launch("pointwise_wgrad1_kernel");
+}
+
 template <int BN, int kStages, bool WGRAD>
 static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mat, const PwParams& p,
                      const void* bias, int units, cudaStream_t st) {
@@ -589,6 +755,34 @@ extern "C" int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* d, const void* d
   TLT_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dw % 16) == 0, "tlt_pointwise_wgrad_tc: operands must be 16-byte aligned");
   const int64_t S = d->spatial, K = d->in_channels, N = d->out_channels, B = d->batch;
   CUtensorMap ma, mb, mc;
+  {
+    const char* env = getenv("TLT_PW_W1");
+    const bool off = env && env[0] == 'o' && env[1] == 'f';
+    if (!off && K <= 128 && N <= 256) {
+      // small channel counts: one cta_group::1 MMA per SM, the reduction range split over all SMs
+      const int nb = K <= 64 ? 64 : 128;
+      if ((rc = make_map3d(&ma, dy, S, N, B, S, N * S, BLOCK_K, BLOCK_M, true))) return rc;      // dY {64 s, 128 n}
+      if ((rc = make_map3d(&mb, x, S, K, B, S, K * S, BLOCK_K, nb, true))) return rc;            // X  {64 s, NB k}
+      if ((rc = make_map(&mc, dw, K, N, d->w_ld, 32, 32, 1))) return rc;                          // dW fp32 {32 k, 32 n}
+      PwParams p{};
+      p.S = (int)S; p.K = (int)K; p.N = (int)N; p.batch = (int)B;
+      p.tiles_m = (int)((N + BLOCK_M - 1) / BLOCK_M);
+      p.tiles_n = 1;
+      p.kpi = (int)((S + BLOCK_K - 1) / BLOCK_K);
+      const long long kb_total = (long long)p.batch * p.kpi;
+      TLT_REQUIRE(kb_total < (1LL << 31), "tlt_pointwise_wgrad_tc: reduction too long");
+      long long splits = num_sms() / p.tiles_m;
+      if (splits < 1) splits = 1;
+      if (splits > kb_total / 4) splits = kb_total / 4 > 0 ? kb_total / 4 : 1;
+      p.kb_per_split = (int)((kb_total + splits - 1) / splits);
+      p.splits = (int)((kb_total + p.kb_per_split - 1) / p.kb_per_split);
+      p.c_reduce = p.splits > 1;
+      cudaStream_t st1 = (cudaStream_t)stream;
+      if (p.c_reduce) TLT_CHECK_CUDA(cudaMemset2DAsync(dw, (size_t)d->w_ld * 4, 0, (size_t)K * 4, (size_t)N, st1));
+      const int units1 = p.tiles_m * p.splits;
+      return nb == 64 ? w1_launch<64>(ma, mb, mc, p, units1, st1) : w1_launch<128>(ma, mb, mc, p, units1, st1);
+    }
+  }
   const bool wide = K > 128;
   if ((rc = make_map3d(&ma, dy, S, N, B, S, N * S, BLOCK_K, BLOCK_M, true))) return rc;          // dY {64 s, 128 n}
   if ((rc = make_map3d(&mb, x, S, K, B, S, K * S, BLOCK_K, wide ? 128 : 64, true))) return rc;   // X  {64 s, BN/2 k}
