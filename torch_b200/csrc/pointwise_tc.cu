@@ -25,6 +25,10 @@ int pointwise_hmma(const void* x, const void* wt, void* y, long long batch, long
 constexpr int kPwThreads = 384;
 constexpr int kPwEpiWarps = 8;
 constexpr int kPwEpiBuf = 4096;
+// the pair kernel runs 16 epilogue warps (4 per TMEM lane quarter, each a quarter of the tile's columns): its per-unit epilogue --
+// tcgen05.ld, convert, transposing stores -- is instruction-issue bound, and 8 warps left two of them per scheduler
+constexpr int kPw2EpiWarps = 16;
+constexpr int kPw2Threads = 128 + 32 * kPw2EpiWarps;
 
 struct PwParams {
   int S, K, N, batch;            // positions per image, input channels, output channels, images
@@ -44,12 +48,12 @@ struct PwSmem {
   static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = kStages * STAGE_BYTES;
-  static constexpr int BAR_OFFSET = EPI_OFFSET + kPwEpiWarps * kPwEpiBuf;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + kPw2EpiWarps * kPwEpiBuf;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
 template <int BN, int kStages, bool WGRAD>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPwThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPw2Threads, 1)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_at, const PwParams p,
                     const void* __restrict__ bias) {
@@ -102,7 +106,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kPwEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kPw2EpiWarps); }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
@@ -204,21 +208,22 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs, 8 warps) ================================
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
-    const int col_half = (warp - 4) >> 2;          // accumulator columns [HALF_N*col_half, +HALF_N)
+    constexpr int EPI_N = BN / (kPw2EpiWarps / 4);  // accumulator columns per epilogue warp
+    const int col_half = (warp - 4) >> 2;          // accumulator columns [EPI_N*col_half, +EPI_N)
     const uint32_t leader_tempty0 = mapa_u32(tempty_bar(0), 0);
     const uint32_t ebuf = smem_base + L::EPI_OFFSET + (warp - 4) * kPwEpiBuf;
-    constexpr int n_chunks = HALF_N / 32;
+    constexpr int n_chunks = EPI_N / 32;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t ehalf = 0;                             // bf16 path: the 4 KB staging buffer is two 2 KB halves used alternately
     for (int u = cluster_id; u < num_units; u += num_clusters) {
       int z, tm, tn, kb0, kb1;
       decode(u, z, tm, tn, kb0, kb1);
       const int m0 = tm * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M + quarter * 32;     // first accumulator row of this warp
-      const int n0 = tn * BN + col_half * HALF_N;
+      const int n0 = tn * BN + col_half * EPI_N;
       const int m_lim = WGRAD ? p.N : p.S, n_lim = WGRAD ? p.K : p.N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_half * HALF_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_half * EPI_N);
 #pragma unroll 1
       for (int c = 0; c < n_chunks; ++c) {
         const int col0 = n0 + c * 32;
@@ -807,7 +812,7 @@ static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   }
   const int pairs = num_sms() / 2;
   const int clusters = units < pairs ? units : pairs;
-  pointwise_tc_kernel<BN, kStages, WGRAD><<<2 * clusters, kPwThreads, L::TOTAL, st>>>(ma, mb, mc, mat, p, bias);
+  pointwise_tc_kernel<BN, kStages, WGRAD><<<2 * clusters, kPw2Threads, L::TOTAL, st>>>(ma, mb, mc, mat, p, bias);
   return check_launch("pointwise_tc_kernel");
 }
 
@@ -931,7 +936,7 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
     if (res_off) p.tail16 = BLOCK_K / UMMA_K;
     const int stage_bytes = BLOCK_M * BLOCK_K * 2 + (wide ? 128 : 64) * BLOCK_K * 2, b_bytes = (wide ? 128 : 64) * BLOCK_K * 2;
     const int res_stages = (kb_total * b_bytes + stage_bytes - 1) / stage_bytes;
-    const int stages = wide ? 6 : 8;
+    const int stages = wide ? 5 : 6;
     p.w_res = (!res_off && p.tiles_n == 1 && stages - res_stages >= 4) ? 1 : 0;
     p.nst = stages - res_stages;
   }
@@ -949,8 +954,8 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
       return bn == 128 ? f1_launch<128>(ma, mb1, mc, mat, p, bias, u1, st) : f1_launch<256>(ma, mb1, mc, mat, p, bias, u1, st);
     }
   }
-  if (wide) return pw_launch<256, 6, false>(ma, mb, mc, mat, p, bias, (int)units, st);
-  return pw_launch<128, 8, false>(ma, mb, mc, mat, p, bias, (int)units, st);
+  if (wide) return pw_launch<256, 5, false>(ma, mb, mc, mat, p, bias, (int)units, st);
+  return pw_launch<128, 6, false>(ma, mb, mc, mat, p, bias, (int)units, st);
 }
 
 extern "C" int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* d, const void* dy, const void* x, float* dw, void* stream) {
@@ -1010,8 +1015,8 @@ extern "C" int tlt_pointwise_wgrad_tc(const tlt_pointwise_desc* d, const void* d
   cudaStream_t st = (cudaStream_t)stream;
   if (p.c_reduce) TLT_CHECK_CUDA(cudaMemset2DAsync(dw, (size_t)d->w_ld * 4, 0, (size_t)K * 4, (size_t)N, st));
   const int units = p.tiles_m * p.tiles_n * p.splits;
-  if (wide) return pw_launch<256, 6, true>(ma, mb, mc, mc, p, nullptr, units, st);
-  return pw_launch<128, 8, true>(ma, mb, mc, mc, p, nullptr, units, st);
+  if (wide) return pw_launch<256, 5, true>(ma, mb, mc, mc, p, nullptr, units, st);
+  return pw_launch<128, 6, true>(ma, mb, mc, mc, p, nullptr, units, st);
 }
 
 extern "C" int tlt_pack_kmajor(const void* src, int32_t dtype_src, int64_t rows, int64_t cols, int64_t row_stride,
