@@ -307,22 +307,25 @@ constexpr int kTctStages = 4;
 constexpr int kTctX = 4 * BLOCK_K * 128;                 // 256 positions x 64 channels bf16 = 32 KB
 constexpr int kTctW = BLOCK_M * BLOCK_K * 2;             // 128 output channels x 64 k = 16 KB
 constexpr int kTctStage = kTctX + kTctW;
-constexpr int kTctSmem = kTctStages * kTctStage + 256 + 1024;
+constexpr int kTctEpi = kTctStages * kTctStage;                      // 8 epilogue warps x 4 KB staging for the TMA stores
+constexpr int kTctBar = kTctEpi + kPwEpiWarps * kPwEpiBuf;
+constexpr int kTctSmem = kTctBar + 256 + 1024;
 
 __global__ void __launch_bounds__(kPwThreads, 1)
-pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const PwParams p,
-                     const void* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
+pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_xt, const PwParams p,
+                     const void* __restrict__ bias) {
   constexpr int kStages = kTctStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + kStages * kTctStage;
+  const uint32_t bar_base = smem_base + kTctBar;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + kStages * kTctStage + 8 * (2 * kStages + 4));
+  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + kTctBar + 8 * (2 * kStages + 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_units = p.batch * p.tiles_m * p.tiles_n;
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -355,10 +358,18 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sx = smem_base + stage * kTctStage, sw = sx + kTctX;
-          mbar_expect_tx(full_bar(stage), kTctStage);
+          const int n16 = kb == kb_total - 1 ? p.tail16 : BLOCK_K / UMMA_K;        // ragged K: only the k16 steps that exist
+          mbar_expect_tx(full_bar(stage), 4 * n16 * (UMMA_K * 128) + kTctW);
+          if (n16 == BLOCK_K / UMMA_K) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)                                              // X: {64 s, 64 k} per 64-position chunk
-            tma_load_3d(sx + c * (BLOCK_K * 128), &map_x, full_bar(stage), ts * 256 + 64 * c, kb * BLOCK_K, z);
+            for (int c = 0; c < 4; ++c)                                            // X: {64 s, 64 k} per 64-position chunk
+              tma_load_3d(sx + c * (BLOCK_K * 128), &map_x, full_bar(stage), ts * 256 + 64 * c, kb * BLOCK_K, z);
+          } else {
+            for (int c = 0; c < 4; ++c)
+              for (int j = 0; j < n16; ++j)                                        // {64 s, 16 k} boxes
+                tma_load_3d(sx + c * (BLOCK_K * 128) + j * (UMMA_K * 128), &map_xt, full_bar(stage), ts * 256 + 64 * c,
+                            kb * BLOCK_K + UMMA_K * j, z);
+          }
           tma_load_2d(sw, &map_w, full_bar(stage), kb * BLOCK_K, tn * BLOCK_M);    // Wt: {64 k, 128 n}
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -378,11 +389,14 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sx = smem_base + stage * kTctStage, sw = sx + kTctX;
+          const int n16 = kb == kb_total - 1 ? p.tail16 : BLOCK_K / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sw + k * (UMMA_K * 2), 16, 1024);             // Wt, K-major
-            const uint64_t db = make_smem_desc(sx + k * (UMMA_K * 128), BLOCK_K * 128, 1024); // X, MN-major, 4 chunks of 64
-            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k != 0) ? 1u : 0u);
+            if (k < n16) {
+              const uint64_t da = make_smem_desc(sw + k * (UMMA_K * 2), 16, 1024);             // Wt, K-major
+              const uint64_t db = make_smem_desc(sx + k * (UMMA_K * 128), BLOCK_K * 128, 1024); // X, MN-major, 4 chunks of 64
+              umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k != 0) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (kb == kb_total - 1) umma_commit(tfull_bar(acc));
@@ -395,6 +409,7 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   } else if (warp >= 4) {
     const int quarter = warp & 3;                  // TMEM lanes [32 quarter, +32) = output channels
     const int half = (warp - 4) >> 2;              // accumulator columns [128 half, +128) = positions
+    const uint32_t ebuf = smem_base + kTctEpi + (warp - 4) * kPwEpiBuf;
     int acc = 0; uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       int z, ts, tn;
@@ -406,7 +421,7 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + half * 128);
-      __nv_bfloat16* yrow = y + ((size_t)z * p.N + (n < p.N ? n : 0)) * p.S;
+      const int n0 = tn * BLOCK_M + quarter * 32;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int s0 = ts * 256 + half * 128 + c * 32;
@@ -421,21 +436,34 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (!live || n >= p.N) continue;
+        if (!live) continue;
+        // this lane's channel row: 32 positions = 64 bytes = half of a 128-byte row of the [32 channels][64 positions] staging block
+        // (SWIZZLE_128B: 16-byte chunk index ^ (row & 7), conflict-free for the 32 lanes); two chunks leave as ONE TMA store
+        if ((c & 1) == 0) {
+          if (lane == 0) bulk_wait_read0();                      // the previous store has read the block
+          __syncwarp();
+        }
+        const uint32_t erow = ebuf + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (s0 + 8 * j < p.S) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + bv, __uint_as_float(v[8 * j + 1]) + bv);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + bv, __uint_as_float(v[8 * j + 3]) + bv);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + bv, __uint_as_float(v[8 * j + 5]) + bv);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + bv, __uint_as_float(v[8 * j + 7]) + bv);
-            *reinterpret_cast<uint4*>(yrow + s0 + 8 * j) = o;
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(erow + ((((uint32_t)((c & 1) * 4 + j)) ^ (uint32_t)(lane & 7)) << 4),
+                       pack_bf16x2(__uint_as_float(v[8 * j + 0]) + bv, __uint_as_float(v[8 * j + 1]) + bv),
+                       pack_bf16x2(__uint_as_float(v[8 * j + 2]) + bv, __uint_as_float(v[8 * j + 3]) + bv),
+                       pack_bf16x2(__uint_as_float(v[8 * j + 4]) + bv, __uint_as_float(v[8 * j + 5]) + bv),
+                       pack_bf16x2(__uint_as_float(v[8 * j + 6]) + bv, __uint_as_float(v[8 * j + 7]) + bv));
+        if ((c & 1) == 1 || s0 + 32 >= p.S) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_c, ebuf, s0 - (c & 1) * 32, n0, z);  // rows >= N and positions >= S are clipped by the tensor map
+            bulk_commit();
           }
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -902,29 +930,6 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
       if (rc != 1) return rc;
     }
   }
-  {
-    // opt-in experiment (TLT_PW_T=on): transposed roles -- channels on the TMEM lanes, 256 positions per tile, direct 16-byte
-    // stores of y.  Parity-green but not faster (0.646 vs 0.633 ms per 64 @ 56^2 layer step, 0.445 vs 0.380 ms at 128 @ 28^2
-    // where N = 141 needs two channel tiles): the per-lane 16-byte stores to 32 different rows cost as much as the transposition
-    // they remove, so the pair kernel below stays the default.
-    const char* env = getenv("TLT_PW_T");
-    if (env && env[0] == 'o' && env[1] == 'n') {
-      CUtensorMap mw;
-      if ((rc = make_map(&mw, wt, K, N, d->w_ld, BLOCK_K, BLOCK_M))) return rc;                  // Wt {64 k, 128 n}
-      p.tiles_m = (int)((S + 255) / 256);
-      p.tiles_n = (int)((N + BLOCK_M - 1) / BLOCK_M);
-      const long long un = (long long)p.batch * p.tiles_m * p.tiles_n;
-      TLT_REQUIRE(un < (1LL << 31), "tlt_pointwise_tc: too many tiles");
-      static bool attr_set = false;
-      if (!attr_set) {
-        TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTctSmem));
-        attr_set = true;
-      }
-      const int sms = num_sms();
-      pointwise_tct_kernel<<<(unsigned)(un < sms ? un : sms), kPwThreads, kTctSmem, st>>>(ma, mw, p, bias, (__nv_bfloat16*)y);
-      return check_launch("pointwise_tct_kernel");
-    }
-  }
   CUtensorMap mat;
   if ((rc = make_map3d(&mat, x, S, K, B, S, K * S, 64, UMMA_K, true))) return rc;                // X^T tail chunks {64 s, 16 k}
   {
@@ -939,6 +944,33 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
     const int stages = wide ? 5 : 6;
     p.w_res = (!res_off && p.tiles_n == 1 && stages - res_stages >= 4) ? 1 : 0;
     p.nst = stages - res_stages;
+  }
+  {
+    // Transposed roles (pointwise_tct_kernel): output channels on the TMEM lanes, 256 positions per tile, so a thread of the
+    // epilogue owns 32 consecutive positions of ONE channel and y leaves as TMA stores of 128-byte rows ([32 channels][64 positions]
+    // blocks) with 16 convert + 4 store instructions per chunk instead of 64 + a 64-byte-row store.  Measured at 56^2 (tools/
+    // pointwise_bench.py): 64 -> 69 channels 49 us vs 55 us for the pair kernel; with two channel tiles (N > 128) the activation
+    // tile is read twice and the pair kernel wins, on small maps the two are within noise -- hence the shape test.
+    // TLT_PW_T = on | off forces the choice.
+    const char* env = getenv("TLT_PW_T");
+    const bool force_on = env && env[0] == 'o' && env[1] == 'n', force_off = env && env[0] == 'o' && env[1] == 'f';
+    if (force_on || (!force_off && N <= BLOCK_M && S >= 2048)) {
+      CUtensorMap mw, mc64;
+      if ((rc = make_map(&mw, wt, K, N, d->w_ld, BLOCK_K, BLOCK_M))) return rc;                  // Wt {64 k, 128 n}
+      if ((rc = make_map3d(&mc64, y, S, N, B, S, N * S, 64, 32, true))) return rc;              // Y {64 s, 32 n}, 128-byte rows
+      p.tiles_m = (int)((S + 255) / 256);
+      p.tiles_n = (int)((N + BLOCK_M - 1) / BLOCK_M);
+      const long long un = (long long)p.batch * p.tiles_m * p.tiles_n;
+      TLT_REQUIRE(un < (1LL << 31), "tlt_pointwise_tc: too many tiles");
+      static bool attr_set = false;
+      if (!attr_set) {
+        TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTctSmem));
+        attr_set = true;
+      }
+      const int sms = num_sms();
+      pointwise_tct_kernel<<<(unsigned)(un < sms ? un : sms), kPwThreads, kTctSmem, st>>>(ma, mw, mc64, mat, p, bias);
+      return check_launch("pointwise_tct_kernel");
+    }
   }
   {
     const char* env = getenv("TLT_PW_F1");
