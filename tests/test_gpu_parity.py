@@ -225,7 +225,10 @@ def test_blocktt3_fused_linear_vs_oracle(transpose):
 
 
 @pytest.mark.parametrize("B,K,N,S", [(3, 64, 69, 3136), (2, 69, 64, 784), (5, 130, 300, 64), (2, 512, 573, 200), (1, 8, 8, 8),
-                                     (4, 93, 128, 784)])
+                                     (4, 93, 128, 784),
+                                     # transposed-role kernel (N <= 128, S >= 2048): ragged last position tile, N = 128 exactly,
+                                     # tiny N / K with a 16-channel tail block, K = 96 (1.5 k blocks)
+                                     (2, 48, 128, 2056), (1, 17, 5, 4104), (2, 96, 33, 2048)])
 def test_pointwise_tc_kernels_vs_fp64(B, K, N, S):
     """tlt_pointwise_tc (fwd / dgrad) and tlt_pointwise_wgrad_tc straight from NCHW memory, ragged channel counts and
     partial position tiles, against fp64 einsum (the F.conv1d(k=1) stages of functional/convolution.py)."""
