@@ -486,11 +486,17 @@ __global__ void __launch_bounds__(kDwtThreads) dwrows_tile_kernel(const DwRowsGe
   const int gid = lane >> 2, tq = lane & 3;
   const int cbase = blockIdx.x * CW;
   for (int e = tid; e < PITCH / 4; e += NT) reinterpret_cast<uint32_t*>(dwt_smem)[e] = 0u;
-  for (int e = tid; e < 9 * CW * 32; e += NT) {
-    const int l = e & 31, cc = (e >> 5) % CW, t = (e >> 5) / CW;
-    const int gg = l >> 2, tt = l & 3;
-    const uint32_t wv = (uint32_t)__bfloat16_as_ushort(w[((size_t)t * cpr + cbase + cc) * 8 + gg]);
-    reinterpret_cast<uint32_t*>(dwt_smem + PITCH)[e] = gg == 2 * tt ? wv : (gg == 2 * tt + 1 ? (wv << 16) : 0u);
+  // tap table: one 16-byte load of the 8 channel weights per (tap, chunk), expanded to the 32 per-lane B registers
+  for (int e = tid; e < 9 * CW; e += NT) {
+    const int cc = e % CW, t = e / CW;
+    const uint4 q = *reinterpret_cast<const uint4*>(w + ((size_t)t * cpr + cbase + cc) * 8);
+    const uint32_t w8[8] = {q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16};
+    uint32_t* dst = reinterpret_cast<uint32_t*>(dwt_smem + PITCH) + e * 32;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const int gg = l >> 2, tt = l & 3;
+      dst[l] = gg == 2 * tt ? w8[gg] : (gg == 2 * tt + 1 ? (w8[gg] << 16) : 0u);
+    }
   }
   for (long long tix = blockIdx.y; tix < tiles; tix += gridDim.y) {
     const long long b = tix / nstrips;
@@ -707,8 +713,13 @@ static int dwt_launch(const DwRowsGeom& g, const void* src, const void* w, void*
   if (rc) return rc;
   const int nstrips = (DH + TR - 1) / TR;
   const long long tiles = g.batch * nstrips;
-  // persistent: ~6 blocks per SM in total, each walking several strips (the tap table is built once per block)
-  long long by = (148LL * 6 + g.cpr / CW - 1) / (g.cpr / CW);
+  // persistent: exactly one resident wave (occupancy x SMs blocks), each block walking several strips -- the tap table is built
+  // once per block, and a second partial wave would pay it (and the tail) again
+  int occ = 0;
+  TLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwrows_tile_kernel<DGRAD, S, CW>, kDwtThreads, smem));
+  if (occ < 1) occ = 1;
+  long long by = (148LL * occ) / (g.cpr / CW);
+  if (by < 1) by = 1;
   if (by > tiles) by = tiles;
   dim3 grid((unsigned)(g.cpr / CW), (unsigned)by);
   dwrows_tile_kernel<DGRAD, S, CW><<<grid, kDwtThreads, smem, st>>>(g, (const uint4*)src, (const __nv_bfloat16*)w, (__nv_bfloat16*)dst, TR, nstrips, tiles);
