@@ -325,6 +325,10 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kStages + 5);
+  // one channel tile and K <= 64 kStages: every unit uses the same weight blocks, so block kb is loaded ONCE into the weight slot of
+  // ring stage kb (unused otherwise in this mode) instead of riding in every stage
+  const bool w_res = p.w_res != 0;
   volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + kTctBar + 8 * (2 * kStages + 4));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_units = p.batch * p.tiles_m * p.tiles_n;
@@ -338,6 +342,7 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPwEpiWarps); }
+    mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -352,6 +357,11 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (w_res) {
+        mbar_expect_tx(wfull_bar, kb_total * kTctW);
+        for (int kb = 0; kb < kb_total; ++kb)
+          tma_load_2d(smem_base + kb * kTctStage + kTctX, &map_w, wfull_bar, kb * BLOCK_K, 0);
+      }
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         int z, ts, tn;
         decode(u, z, ts, tn);
@@ -359,7 +369,7 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sx = smem_base + stage * kTctStage, sw = sx + kTctX;
           const int n16 = kb == kb_total - 1 ? p.tail16 : BLOCK_K / UMMA_K;        // ragged K: only the k16 steps that exist
-          mbar_expect_tx(full_bar(stage), 4 * n16 * (UMMA_K * 128) + kTctW);
+          mbar_expect_tx(full_bar(stage), 4 * n16 * (UMMA_K * 128) + (w_res ? 0 : kTctW));
           if (n16 == BLOCK_K / UMMA_K) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)                                            // X: {64 s, 64 k} per 64-position chunk
@@ -370,7 +380,7 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 tma_load_3d(sx + c * (BLOCK_K * 128) + j * (UMMA_K * 128), &map_xt, full_bar(stage), ts * 256 + 64 * c,
                             kb * BLOCK_K + UMMA_K * j, z);
           }
-          tma_load_2d(sw, &map_w, full_bar(stage), kb * BLOCK_K, tn * BLOCK_M);    // Wt: {64 k, 128 n}
+          if (!w_res) tma_load_2d(sw, &map_w, full_bar(stage), kb * BLOCK_K, tn * BLOCK_M);    // Wt: {64 k, 128 n}
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -381,6 +391,10 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       const uint32_t idesc = make_idesc(BLOCK_M, 256, 0, 1);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      if (w_res) {
+        mbar_wait(wfull_bar, 0);
+        tc_fence_after();
+      }
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
@@ -388,7 +402,8 @@ pointwise_tct_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sx = smem_base + stage * kTctStage, sw = sx + kTctX;
+          const uint32_t sx = smem_base + stage * kTctStage;
+          const uint32_t sw = w_res ? smem_base + kb * kTctStage + kTctX : sx + kTctX;
           const int n16 = kb == kb_total - 1 ? p.tail16 : BLOCK_K / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -960,6 +975,10 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
       if ((rc = make_map3d(&mc64, y, S, N, B, S, N * S, 64, 32, true))) return rc;              // Y {64 s, 32 n}, 128-byte rows
       p.tiles_m = (int)((S + 255) / 256);
       p.tiles_n = (int)((N + BLOCK_M - 1) / BLOCK_M);
+      {
+        const char* er = getenv("TLT_PW_RES");
+        p.w_res = (!(er && er[0] == 'o' && er[1] == 'f') && p.tiles_n == 1 && (K + BLOCK_K - 1) / BLOCK_K <= kTctStages) ? 1 : 0;
+      }
       const long long un = (long long)p.batch * p.tiles_m * p.tiles_n;
       TLT_REQUIRE(un < (1LL << 31), "tlt_pointwise_tc: too many tiles");
       static bool attr_set = false;
