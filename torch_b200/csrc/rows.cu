@@ -216,6 +216,84 @@ __global__ void __launch_bounds__(256) col2im_rows_kernel(const RowsGeom g, cons
   }
 }
 
+// 2-D specialisations with compile-time taps (the 3 x 3 core of the Tucker / TT convolutions): the position is decoded once, the tap
+// loops are unrolled and ALL tap loads of a thread are issued before the first store / add.  The generic kernels above decode the tap
+// with divisions inside a runtime loop and keep one load in flight per thread: 63 us (im2col) / 83 us (col2im) for a 177 MB cols
+// tensor at BASELINE config 4 -- latency-bound at 2.1 - 3.1 TB/s.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) im2col_rows2d_kernel(const RowsGeom g, const uint4* __restrict__ z, uint4* __restrict__ cols) {
+  const int cpr = (int)(g.ld >> 3);
+  const int OW = g.out_size[1], IH = g.in_size[0], IW = g.in_size[1];
+  const long long total = g.batch * g.out_sp * cpr;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % cpr);
+    const long long row = e / cpr;
+    const int o = (int)(row % g.out_sp);
+    const long long b = row / g.out_sp;
+    const int oy = o / OW, ox = o - oy * OW;
+    const int by = oy * g.stride[0] - g.padding[0], bx = ox * g.stride[1] - g.padding[1];
+    const uint4* zb = z + b * g.in_sp * cpr + ch;
+    uint4* cb = cols + row * (KH * KW) * cpr + ch;
+    uint4 v[KH * KW];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+      const int iy = by + kh * g.dilation[0];
+      const bool oky = iy >= 0 && iy < IH;
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ix = bx + kw * g.dilation[1];
+        const bool ok = oky && ix >= 0 && ix < IW;
+        v[kh * KW + kw] = ok ? zb[(long long)(iy * IW + ix) * cpr] : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t) cb[(long long)t * cpr] = v[t];
+  }
+}
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(256) col2im_rows2d_kernel(const RowsGeom g, const uint4* __restrict__ dcols, uint4* __restrict__ dz) {
+  const long long cpr = g.ld >> 3;
+  const int OH = g.out_size[0], OW = g.out_size[1], IW = g.in_size[1];
+  const long long total = g.batch * g.in_sp * cpr;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long ch = e % cpr;
+    const long long pos = e / cpr;
+    const int ip = (int)(pos % g.in_sp);
+    const long long b = pos / g.in_sp;
+    const int iy = ip / IW, ix = ip - iy * IW;
+    uint4 v[KH * KW];
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+      const int ny = iy + g.padding[0] - kh * g.dilation[0];
+      const int oy = g.stride[0] == 1 ? ny : ny / g.stride[0];
+      const bool oky = ny >= 0 && oy * g.stride[0] == ny && oy < OH;
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const int nx = ix + g.padding[1] - kw * g.dilation[1];
+        const int ox = g.stride[1] == 1 ? nx : nx / g.stride[1];
+        const bool ok = oky && nx >= 0 && ox * g.stride[1] == nx && ox < OW;
+        v[kh * KW + kw] = ok ? dcols[((b * g.out_sp + (long long)(oy * OW + ox)) * (KH * KW) + kh * KW + kw) * cpr + ch] : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t) {
+      acc_bf16x2(v[t].x, acc[0], acc[1]);
+      acc_bf16x2(v[t].y, acc[2], acc[3]);
+      acc_bf16x2(v[t].z, acc[4], acc[5]);
+      acc_bf16x2(v[t].w, acc[6], acc[7]);
+    }
+    uint4 out;
+    __nv_bfloat162 p;
+    p = __floats2bfloat162_rn(acc[0], acc[1]); out.x = *reinterpret_cast<uint32_t*>(&p);
+    p = __floats2bfloat162_rn(acc[2], acc[3]); out.y = *reinterpret_cast<uint32_t*>(&p);
+    p = __floats2bfloat162_rn(acc[4], acc[5]); out.z = *reinterpret_cast<uint32_t*>(&p);
+    p = __floats2bfloat162_rn(acc[6], acc[7]); out.w = *reinterpret_cast<uint32_t*>(&p);
+    dz[e] = out;
+  }
+}
+
 static int fill_rows(const tlt_conv_desc* d, RowsGeom* g) {
   TLT_REQUIRE(d && d->dtype == TLT_BF16, "rows unfold: bf16 only");
   TLT_REQUIRE(d->ndim >= 1 && d->ndim <= 3, "rows unfold: 1..3 spatial dims");
@@ -278,6 +356,10 @@ extern "C" int tlt_im2col_rows(const tlt_conv_desc* d, const void* z, void* cols
   if (rc) return rc;
   TLT_REQUIRE(z && cols && ((uintptr_t)z % 16) == 0 && ((uintptr_t)cols % 16) == 0, "tlt_im2col_rows: tensors must be 16-byte aligned");
   const long long total = g.batch * g.out_sp * (g.ld >> 3);
+  if (g.ndim == 2 && g.kernel[0] == 3 && g.kernel[1] == 3 && g.in_sp < (1 << 24)) {
+    im2col_rows2d_kernel<3, 3><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (uint4*)cols);
+    return check_launch("im2col_rows2d_kernel");
+  }
   im2col_rows_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, (uint4*)cols);
   return check_launch("im2col_rows_kernel");
 }
@@ -288,6 +370,10 @@ extern "C" int tlt_col2im_rows(const tlt_conv_desc* d, const void* dcols, void* 
   if (rc) return rc;
   TLT_REQUIRE(dz && dcols && ((uintptr_t)dz % 16) == 0 && ((uintptr_t)dcols % 16) == 0, "tlt_col2im_rows: tensors must be 16-byte aligned");
   const long long total = g.batch * g.in_sp * (g.ld >> 3);
+  if (g.ndim == 2 && g.kernel[0] == 3 && g.kernel[1] == 3 && g.in_sp < (1 << 24) && g.out_sp < (1 << 24)) {
+    col2im_rows2d_kernel<3, 3><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)dcols, (uint4*)dz);
+    return check_launch("col2im_rows2d_kernel");
+  }
   col2im_rows_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(g, (const uint4*)dcols, (uint4*)dz);
   return check_launch("col2im_rows_kernel");
 }
