@@ -92,7 +92,7 @@ def run_case(name, g, device, dtype, sub=None):
 def all_cases():
     out = []
     for name in G.names():
-        if name in ("reconstruction", "dropout"):
+        if name in ("reconstruction", "dropout") or name.startswith(("nlayers_", "embedding_")):
             continue
         if name == "factorized_linear_dispatch":
             out += [(name, k) for k in G.load(name)]
@@ -108,3 +108,33 @@ def load_case(name, sub):
     if name == "factorized_linear_dispatch":
         return g[sub], None
     return g, sub
+
+
+def module_cases():
+    return [n for n in G.names() if n.startswith(("nlayers_", "embedding_"))]
+
+
+def run_module_case(name, g, device, dtype):
+    """Golden cases recorded from the reference's nn.Modules (n_layers > 1 linears / convs, embeddings): build the product's
+    module with the same constructor arguments, load the reference's state_dict (same key names) and run fwd + bwd.
+    Returns (y, grads{state_dict name}, expected_y, expected_grads)."""
+    ctor = dict(g["ctor"])
+    if name.startswith("nlayers_linear"):
+        layer = tlt.FactorizedLinear(ctor.pop("in_tensorized_features"), ctor.pop("out_tensorized_features"), dtype=torch.float64, **ctor)
+    elif name.startswith("nlayers_conv"):
+        layer = tlt.FactorizedConv(ctor.pop("in_channels"), ctor.pop("out_channels"), ctor.pop("kernel_size"), dtype=torch.float64, **ctor)
+    else:
+        layer = tlt.FactorizedEmbedding(ctor.pop("num_embeddings"), ctor.pop("embedding_dim"), dtype=torch.float64, **ctor)
+    missing = layer.load_state_dict(g["state_dict"], strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    layer = layer.to(device=device, dtype=dtype)
+    x = g["x"].to(device)
+    if x.is_floating_point():
+        x = x.to(dtype).requires_grad_(True)
+    y = layer(x, g["index"]) if g["index"] else layer(x)
+    params = dict(layer.named_parameters())
+    leaves = {"x": x, **params} if x.is_floating_point() else dict(params)
+    names = [n for n in leaves if n in g["grads"]]
+    gy = g["gy"].to(device=device, dtype=dtype)
+    grads = torch.autograd.grad(y, [leaves[n] for n in names], gy, allow_unused=True)
+    return y, dict(zip(names, grads)), g["y"], g["grads"]

@@ -7,8 +7,9 @@ Run in the build container only (the GPU box has no /root/reference):
 tensorly, the reference's un-pinned third-party dependency, is not installable offline, so the reference is
 imported on top of ``oracle/_shim/tensorly`` (an adapter over oracle/tensorly_semantics.py).  Everything that
 lives in the reference itself -- einsum-string construction, conv chains, BlockTT reconstruction, layer
-dispatch, dropout hooks -- is executed as shipped.  Inputs are fp32-representable values evaluated in fp64, so the
-stored outputs are exact to ~1e-15 and can be compared against fp64 (oracle), fp32 and bf16 (CUDA) runs.
+dispatch, dropout hooks -- is executed as shipped.  Inputs (activations, every parameter, upstream gradients) are
+bf16-representable values evaluated in fp64, so the stored outputs are exact to ~1e-15 and the fp64 oracle, the fp32 and
+the bf16 CUDA runs all consume EXACTLY the same numbers: the bf16 parity gate (2e-2) measures the kernels' arithmetic only.
 """
 import os
 import sys
@@ -18,8 +19,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.abspath(os.path.join(HERE, "..", ".."))
 sys.path.insert(0, os.path.join(REPO, "oracle", "_shim"))
-sys.path.insert(0, "/root/reference")
-sys.path.insert(0, REPO)
+sys.path.insert(0, "/root/reference")          # the REAL tltorch must win over the repo's drop-in alias package of the same name
+sys.path.append(REPO)
 
 import warnings  # noqa: E402
 warnings.simplefilter("ignore")
@@ -36,17 +37,17 @@ D = torch.float64
 
 
 def rnd(*shape):
-    """fp32-representable values held in fp64."""
-    return torch.randn(*shape, dtype=torch.float32).to(D)
+    """bf16-representable values held in fp64."""
+    return torch.randn(*shape, dtype=torch.float32).to(torch.bfloat16).to(D)
 
 
 def init(w, std=1.0):
     w.normal_(0, std)
     with torch.no_grad():
         for p in w.parameters():
-            p.copy_(p.to(torch.float32).to(D))
+            p.copy_(p.to(torch.bfloat16).to(D))
         if hasattr(w, "weights") and w.weights is not None:   # make CP lambda non-trivial
-            w.weights.copy_((1 + 0.25 * torch.randn_like(w.weights)).to(torch.float32).to(D))
+            w.weights.copy_((1 + 0.25 * torch.randn_like(w.weights)).to(torch.bfloat16).to(D))
     return w
 
 
@@ -178,7 +179,7 @@ def _():
     layer = tltorch.TCL((4, 5, 6), (2, 3, 5), dtype=D)
     with torch.no_grad():
         for p in layer.parameters():
-            p.copy_(p.to(torch.float32).to(D))
+            p.copy_(p.to(torch.bfloat16).to(D))
     x = rnd(2, 4, 5, 6)
     r = run(lambda t: layer(t), x, layer)
     r.update(x=x, factors=[f.detach().clone() for f in layer.factors])
@@ -222,6 +223,76 @@ def _():
                                                        min_dim=3, seed=1234, rank=w.rank, training=training,
                                                        full=dropped.to_tensor().detach())
     return out
+
+
+# ------------------------------------------------------------------ n_layers > 1 (jointly factorized layers) and embeddings
+def _round_module(m):
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(p.to(torch.bfloat16).to(D))
+    return m
+
+
+def _module_case(layer, x, call):
+    """fwd + bwd of a reference nn.Module; gradients keyed by state_dict name."""
+    x = x.detach().clone()
+    if x.is_floating_point():
+        x.requires_grad_(True)
+    names = [n for n, _ in layer.named_parameters()]
+    leaves = [p for _, p in layer.named_parameters()]
+    y = call(layer, x)
+    gy = rnd(*y.shape)
+    grads = torch.autograd.grad(y, ([x] if x.requires_grad else []) + leaves, gy, allow_unused=True)
+    gnames = (["x"] if x.requires_grad else []) + names
+    return {"x": x.detach(), "y": y.detach(), "gy": gy, "state_dict": {k: v.detach().clone() for k, v in layer.state_dict().items()},
+            "grads": {n: g.detach() for n, g in zip(gnames, grads) if g is not None}}
+
+
+def _nlayers_linear(fact, seed):
+    torch.manual_seed(seed)
+    layer = _round_module(tltorch.FactorizedLinear((4, 3), (3, 2), bias=True, factorization=fact, rank=0.6, n_layers=2, dtype=D))
+    with torch.no_grad():
+        layer.bias.copy_(rnd(*layer.bias.shape))
+    r = _module_case(layer, rnd(5, 12), lambda l, t: l(t, 1))
+    r.update(kind=fact, index=1, ctor=dict(in_tensorized_features=(4, 3), out_tensorized_features=(3, 2), bias=True,
+                                          factorization=fact, rank=0.6, n_layers=2))
+    return r
+
+
+def _nlayers_conv(fact, seed):
+    torch.manual_seed(seed)
+    layer = tltorch.FactorizedConv(4, 5, 3, order=2, padding=1, n_layers=2, factorization=fact, rank=0.5, bias=True, dtype=D)
+    layer.reset_parameters(std=0.5)
+    _round_module(layer)
+    with torch.no_grad():
+        layer.bias.copy_(rnd(*layer.bias.shape))
+    r = _module_case(layer, rnd(2, 4, 6, 5), lambda l, t: l(t, 1))
+    r.update(kind=fact, index=1, ctor=dict(in_channels=4, out_channels=5, kernel_size=3, order=2, padding=1, n_layers=2,
+                                          factorization=fact, rank=0.5, bias=True))
+    return r
+
+
+def _embedding(fact, seed, n_layers=1):
+    torch.manual_seed(seed)
+    ctor = dict(num_embeddings=24, embedding_dim=8, auto_tensorize=False, tensorized_num_embeddings=(2, 3, 4),
+                tensorized_embedding_dim=(2, 2, 2), factorization=fact, rank=3 if fact != "tucker" else 0.8, n_layers=n_layers)
+    layer = tltorch.FactorizedEmbedding(dtype=D, **ctor)
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.copy_((3 * p).to(torch.bfloat16).to(D))
+    idx = torch.tensor([[1, 5, 23], [0, 7, 7]])
+    r = _module_case(layer, idx, (lambda l, t: l(t)) if n_layers == 1 else (lambda l, t: l(t, 1)))
+    r.update(kind=fact, ctor=ctor, index=0 if n_layers == 1 else 1)
+    return r
+
+
+for _f in ("cp", "blocktt"):
+    CASES[f"nlayers_linear_{_f}"] = (lambda f=_f: _nlayers_linear(f, 81))
+for _f in ("cp", "tucker", "tt"):
+    CASES[f"nlayers_conv_{_f}"] = (lambda f=_f: _nlayers_conv(f, 82))
+for _f in ("blocktt", "cp", "tucker"):
+    CASES[f"embedding_{_f}"] = (lambda f=_f: _embedding(f, 83))
+CASES["embedding_blocktt_nlayers"] = lambda: _embedding("blocktt", 84, n_layers=2)
 
 
 def main():

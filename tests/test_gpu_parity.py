@@ -26,26 +26,61 @@ def q(t, dtype):
 
 
 # ------------------------------------------------------------------------------------------------- (a) goldens
+def _tag():
+    import inspect
+    return inspect.stack()[1].function
+
+
+def _report(tag, errs, tol):
+    """Print the measured relative Frobenius errors (pytest -rP / -s shows them; the worst one is in the assertion message)."""
+    worst = max(errs.items(), key=lambda kv: kv[1])
+    print(f"[parity] {tag}: max rel err {worst[1]:.3e} ({worst[0]}) tol {tol:g}; " + ", ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert worst[1] < tol, f"{tag}: {worst[0]} rel err {worst[1]:.3e} >= {tol:g}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("name,sub", _cases.all_cases())
 def test_golden_cases(name, sub, dtype):
+    """Goldens hold bf16-representable inputs (tests/golden/make_golden.py), so fp32 AND bf16 runs consume exactly the numbers the
+    reference consumed: north_star's tolerances apply unchanged to y and to every gradient."""
     import torch_b200 as tlt
     g, sub2 = _cases.load_case(name, sub)
     before = tlt.ops.launch_count()
     y, grads, ey, eg = _cases.run_case(name, g, dev(), dtype, sub2)
     assert tlt.ops.launch_count() > before, "no kernel of libtltorch_cuda.so was launched"
-    tol = TOL[dtype] if dtype == torch.float32 else 3e-2   # goldens were computed from un-rounded fp32 inputs
-    assert G.rel_err(y, ey.reshape(y.shape)) < tol
+    errs = {"y": G.rel_err(y, ey.reshape(y.shape))}
     for n, gr in grads.items():
-        assert G.rel_err(gr, eg[n]) < tol * (1 if dtype == torch.float32 else 1.5), n
+        errs[n] = G.rel_err(gr, eg[n])
+    _report(f"{name}/{sub}/{dtype}", errs, TOL[dtype])
 
 
-def test_golden_reconstruction():
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", _cases.module_cases())
+def test_golden_module_cases(name, dtype):
+    """SURVEY 8(f1) / (f2) on the GPU: n_layers > 1 FactorizedLinear / FactorizedConv (reference: factorized_linear.py:103-113,
+    factorized_convolution.py:198-208, tensorized_matrices.py:136-193,386-489) and FactorizedEmbedding (factorized_embedding.py:96-117)
+    built from the reference's state_dict, against outputs of the real reference."""
+    import torch_b200 as tlt
+    g = G.load(name)
+    before = tlt.ops.launch_count()
+    y, grads, ey, eg = _cases.run_module_case(name, g, dev(), dtype)
+    assert tlt.ops.launch_count() > before, "no kernel of libtltorch_cuda.so was launched"
+    errs = {"y": G.rel_err(y, ey.reshape(y.shape))}
+    assert set(grads) == set(eg)
+    for n, gr in grads.items():
+        errs[n] = G.rel_err(gr, eg[n])
+    _report(f"{name}/{dtype}", errs, TOL[dtype])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_golden_reconstruction(dtype):
     allg = G.load("reconstruction")
+    errs = {}
     for key, g in allg.items():
-        w, _ = _cases.build_weight(g["kind"], g["params"], dev(), torch.float32, g.get("tensorized_shape"))
+        w, _ = _cases.build_weight(g["kind"], g["params"], dev(), dtype, g.get("tensorized_shape"))
         full = w.to_matrix() if key.startswith("matrix_") else w.to_tensor()
-        assert G.rel_err(full, g["full"]) < 1e-5, key
+        errs[key] = G.rel_err(full, g["full"])
+    _report(f"reconstruction/{dtype}", errs, TOL[dtype])
 
 
 # ------------------------------------------------------------------------------------------------- (b) oracle, seeded
@@ -419,7 +454,7 @@ def test_factorized_linear_layer_vs_oracle(fact, dtype):
     tol = TOL[dtype]
     assert G.rel_err(y, yo) < tol
     for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < tol * (1 if dtype == torch.float32 else 1.5), n
+        assert G.rel_err(a, b) < tol, n
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -455,7 +490,7 @@ def test_factorized_conv_layer_vs_oracle(fact, impl, dtype):
     tol = TOL[dtype]
     assert G.rel_err(y, yo) < tol
     for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < tol * (1 if dtype == torch.float32 else 1.5), n
+        assert G.rel_err(a, b) < tol, n
 
 
 def test_trl_and_dropout_vs_oracle():
@@ -595,8 +630,7 @@ def test_tucker3_fused_linear_vs_oracle():
     yo = rp.factorized_linear(xo, "tucker", (leaves["weight.core"], fs), (ts, ts), bias=leaves["bias"], order="sane")
     go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
     assert G.rel_err(y, yo) < 2e-2
-    for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < 3e-2, n
+    _report(_tag(), {"y": G.rel_err(y, yo), **{n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)}}, 2e-2)
 
 
 # ------------------------------------------------------------------------------------------------- rows (channels-last) conv path
@@ -670,8 +704,7 @@ def test_tucker_conv_rows_path_vs_oracle(cin, cout, hw, stride, padding, dilatio
                         dilation=[dilation] * 2)
     go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
     assert G.rel_err(y, yo) < 2e-2
-    for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < 3e-2, n
+    _report(_tag(), {"y": G.rel_err(y, yo), **{n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)}}, 2e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -715,8 +748,7 @@ def test_trl_rows_projection_vs_oracle():
     yo = torch.einsum("bijk,ijkl->bl", xo, W) + leaves["bias"]
     go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
     assert G.rel_err(y, yo) < 2e-2
-    for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < 3e-2, n
+    _report(_tag(), {"y": G.rel_err(y, yo), **{n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)}}, 2e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -817,8 +849,7 @@ def test_cp_conv_rows_path_vs_oracle(cin, cout, hw, stride):
     yo = rp.cp_conv(xo, leaves["weight.weights"], fs, bias=None, stride=[stride] * 2, padding=[1, 1], dilation=[1, 1])
     go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
     assert G.rel_err(y, yo) < 2e-2
-    for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < 3e-2, n
+    _report(_tag(), {"y": G.rel_err(y, yo), **{n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)}}, 2e-2)
 
 
 @pytest.mark.parametrize("B,C,spatial,ranks", [(3, 2048, (7, 7), (4, 4)), (5, 128, (7, 7), (4, 4)), (2, 256, (4, 4), (2, 2)),
@@ -864,7 +895,7 @@ def test_trl_spatial_first_plan_vs_rows_plan(B, C, hw, ranks, out, monkeypatch):
         gy = torch.ones_like(y) * 0.5
         res[mode] = [y] + list(torch.autograd.grad(y, [x] + list(layer.parameters()), gy))
     for a, b_ in zip(res["on"], res["off"]):
-        assert G.rel_err(a, b_.double().cpu()) < 3e-2
+        assert G.rel_err(a, b_.double().cpu()) < 2e-2
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -899,8 +930,7 @@ def test_cp_conv_fused_path_vs_oracle(ch, hw, batch, bias, variant, monkeypatch)
     yo = rp.cp_conv(xo, leaves["weight.weights"], fs, bias=leaves.get("bias"), stride=[1, 1], padding=[1, 1], dilation=[1, 1])
     go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
     assert G.rel_err(y, yo) < 2e-2
-    for n, a, b in zip(["x"] + list(params), grads, go):
-        assert G.rel_err(a, b) < 3e-2, n
+    _report(_tag(), {"y": G.rel_err(y, yo), **{n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)}}, 2e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

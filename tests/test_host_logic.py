@@ -222,9 +222,9 @@ def test_tensor_core_routes_host_logic_bf16():
     kern = torch.einsum("r,or,cr,hr,wr->ochw", lam, f[0], f[1], f[2], f[3])
     yr = torch.nn.functional.conv2d(xr, kern, br, stride=1, padding=1)
     want = torch.autograd.grad(yr, ref_leaves, gy.double())
-    assert G.rel_err(y, yr) < 3e-2
+    assert G.rel_err(y, yr) < 2e-2
     for a, b in zip(got, want):
-        assert G.rel_err(a, b) < 3e-2
+        assert G.rel_err(a, b) < 2e-2
 
 
 def test_fused_multi_mode_dot_host_logic():
@@ -289,9 +289,9 @@ def test_spatial_first_projection_host_logic(monkeypatch):
     mr = [m.detach().double().requires_grad_(True) for m in mats]
     ref = torch.einsum("bchw,cp,hq,wr->bpqr", xr, *mr)
     want = torch.autograd.grad(ref, [xr] + mr, gy.double())
-    assert G.rel_err(y, ref) < 3e-2
+    assert G.rel_err(y, ref) < 2e-2
     for a, b in zip(got, want):
-        assert G.rel_err(a, b) < 3e-2
+        assert G.rel_err(a, b) < 2e-2
 
 
 def test_cp_conv_fused_op_host_logic():
@@ -318,6 +318,34 @@ def test_cp_conv_fused_op_host_logic():
     b2 = torch.nn.functional.conv2d(a, lr[2].t().reshape(R, 1, 3, 3), padding=1, groups=R)
     ref = torch.einsum("or,brhw->bohw", lr[3], b2) + lr[4].reshape(1, -1, 1, 1)
     want = torch.autograd.grad(ref, lr, gy.double())
-    assert G.rel_err(y, ref) < 3e-2
+    assert G.rel_err(y, ref) < 2e-2
     for t, g, wv in zip(["x", "f_in", "taps", "f_out", "bias"], got, want):
-        assert G.rel_err(g, wv) < 4e-2, t
+        assert G.rel_err(g, wv) < 2e-2, t
+
+
+@pytest.mark.parametrize("name", _cases.module_cases())
+def test_module_cases_match_reference_goldens(name):
+    """n_layers > 1 FactorizedLinear / FactorizedConv and FactorizedEmbedding, built from the REAL reference's state_dict
+    (same key names), against its outputs and gradients -- kernels emulated."""
+    g = G.load(name)
+    with emulated_kernels() as log:
+        y, grads, ey, eg = _cases.run_module_case(name, g, "cpu", D)
+    assert log, "no kernel launch was recorded: the path bypassed the custom ops"
+    assert G.rel_err(y, ey.reshape(y.shape)) < TOL
+    assert set(grads) == set(eg)
+    for n, gr in grads.items():
+        assert gr is not None, n
+        assert G.rel_err(gr, eg[n]) < TOL, n
+
+
+def test_tltorch_import_alias_is_the_product():
+    """north_star: the classes "work as drop-ins" -- ``import tltorch`` resolves to this implementation, submodule by submodule."""
+    import tltorch
+    import tltorch.functional.factorized_linear as fl
+    from tltorch.factorized_tensors import CPTensor, BlockTT
+    from tltorch.tensor_hooks import tensor_dropout
+    import torch_b200
+    assert tltorch.FactorizedLinear is torch_b200.FactorizedLinear and tltorch.TRL is torch_b200.TRL
+    assert fl is torch_b200.functional.factorized_linear and CPTensor is torch_b200.CPTensor and BlockTT is torch_b200.BlockTT
+    assert tensor_dropout is torch_b200.tensor_dropout
+    assert tltorch.__file__.startswith(_cases.__file__.rsplit("/tests/", 1)[0])

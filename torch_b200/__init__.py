@@ -15,7 +15,7 @@ from . import functional  # noqa: F401
 from . import factorized_layers  # noqa: F401
 from . import tensor_hooks  # noqa: F401
 
-from .factorized_layers import FactorizedLinear, FactorizedConv, TRL, TCL  # noqa: F401
+from .factorized_layers import FactorizedLinear, FactorizedConv, TRL, TCL, FactorizedEmbedding  # noqa: F401
 from .factorized_tensors import (FactorizedTensor, DenseTensor, CPTensor, TTTensor, TuckerTensor, tensor_init,  # noqa: F401
                                  TensorizedTensor, CPTensorized, BlockTT, TTMatrix, DenseTensorized, TuckerTensorized)
 from .tensor_hooks import tensor_dropout, remove_tensor_dropout  # noqa: F401

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from .. import tenalg
+from .. import tenalg, embedding_ops
 from ..ops import contract
 from ..utils import FactorList
 from .core import TensorizedTensor, flatten_tensorized_shape, _decomposition_unavailable
@@ -95,9 +95,23 @@ class CPTensorized(CPTensor, TensorizedTensor, name="CP"):
     def __getitem__(self, indices):
         """Integer indices on leading plain modes (the n_layers case, reference: tensorized_matrices.py:136-193):
         the selected factor rows are folded into ``weights``."""
+        gather = embedding_ops.parse_row_gather(indices, self.tensorized_shape)
+        if gather is not None:
+            # embedding lookup ``w[(layer,) rows, :]``: the selected rows of the row-mode factors collapse into ONE (P, R)
+            # factor; the result stays factorized (reference: tensorized_matrices.py:171-185) -- to_matrix() gives (P, D)
+            lead, rows = gather
+            factors, weights = list(self.factors), self.weights
+            for pos, index in enumerate(lead):
+                weights = contract("r,r->r", weights, factors[pos][index, :])
+            factors = factors[len(lead):]
+            row_shape = tuple(self.tensorized_shape[len(lead)])
+            rows = embedding_ops._as_index(rows, weights.device)
+            picked = embedding_ops.cp_row_factor(weights, factors[:len(row_shape)], rows, row_shape)
+            return self.__class__(weights, [picked] + factors[len(row_shape):],
+                                  tensorized_shape=(int(rows.numel()), tuple(self.tensorized_shape[len(lead) + 1])))
         lead = _leading_int_index(indices, self.tensorized_shape)
         if lead is None:
-            raise NotImplementedError("CPTensorized indexing supports integer indices on leading plain modes")
+            raise NotImplementedError("CPTensorized indexing supports integer indices on leading plain modes and row gathers")
         factors = list(self.factors)
         weights = self.weights
         for pos, index in enumerate(lead):
@@ -126,9 +140,23 @@ class TuckerTensorized(TensorizedTensor, TuckerTensor, name="Tucker"):
 
     def __getitem__(self, indices):
         """Integer indices on leading plain modes (reference: tensorized_matrices.py:230-311)."""
+        gather = embedding_ops.parse_row_gather(indices, self.tensorized_shape)
+        if gather is not None:
+            # embedding lookup: dense (P, *column modes) tensor (the reference returns a partial-Tucker object whose only use,
+            # FactorizedEmbedding.forward, reshapes it to the dense rows at once -- factorized_embedding.py:111-115)
+            lead, rows = gather
+            factors, core = list(self.factors), self.core
+            for pos, index in enumerate(lead):
+                core = tenalg.mode_dot(core, factors[pos][index, :], 0)
+            factors = factors[len(lead):]
+            row_shape = tuple(self.tensorized_shape[len(lead)])
+            col_shape = tuple(self.tensorized_shape[len(lead) + 1])
+            rows = embedding_ops._as_index(rows, core.device)
+            out = embedding_ops.tucker_rows(core, factors[:len(row_shape)], factors[len(row_shape):], rows, row_shape)
+            return out.reshape(out.shape[0], *col_shape)
         lead = _leading_int_index(indices, self.tensorized_shape)
         if lead is None:
-            raise NotImplementedError("TuckerTensorized indexing supports integer indices on leading plain modes")
+            raise NotImplementedError("TuckerTensorized indexing supports integer indices on leading plain modes and row gathers")
         factors = list(self.factors)
         core = self.core
         for pos, index in enumerate(lead):
@@ -181,9 +209,17 @@ class BlockTT(TensorizedTensor, name="BlockTT"):
     def __getitem__(self, indices):
         """Integer indices on leading plain modes select that slice of every core (reference:
         tensorized_matrices.py:386-489, the ``contraction_op`` free path)."""
+        gather = embedding_ops.parse_row_gather(indices, self.tensorized_shape)
+        if gather is not None:
+            # embedding lookup: dense (P, D) rows, the ``contract_factors`` path of the reference (tensorized_matrices.py:470-486)
+            lead, rows = gather
+            sel = (slice(None),) + tuple(lead)
+            cores = [f[sel] for f in self.factors]
+            rows = embedding_ops._as_index(rows, cores[0].device)
+            return embedding_ops.blocktt_rows(cores, rows, tuple(self.tensorized_shape[len(lead)]))
         lead = _leading_int_index(indices, self.tensorized_shape)
         if lead is None:
-            raise NotImplementedError("BlockTT indexing supports integer indices on leading plain modes")
+            raise NotImplementedError("BlockTT indexing supports integer indices on leading plain modes and row gathers")
         sel = (slice(None),) + tuple(lead)
         factors = [f[sel] for f in self.factors]
         return self.__class__(factors, tuple(self.tensorized_shape[len(lead):]), self.rank)
