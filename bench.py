@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native TensorLy-Torch factorized-layer hot path.
+"""bench.py -- benchmark of the B200-native TensorLy-Torch factorized-layer hot path.
 
-Workload (BASELINE.json configs[1]): FactorizedLinear BlockTT (TT-matrix) layers replacing the BERT-base FFN
-768 -> 3072 -> 768 (tensorized (8,8,12) / (8,12,32), TT rank 16), 64 x 512 = 32768 tokens PER GPU, bf16,
-forward + backward (gradients w.r.t. the input, every TT core and both biases).  A "step" is one fwd+bwd pass of the
-two layers over that batch; with N > 1 GPUs each rank owns its own 32768 tokens (weak scaling) and the core / bias
-gradients are all-reduced (one flat NCCL bucket) inside the step.
+Headline workload (BASELINE.json configs[2], the config the 1/2/4/8-GPU metric is quoted on): the 16 CP-factorized 3x3
+convolutions of ResNet-18 (FactorizedConv, factorization='cp', rank 0.25, bias=False; shapes of SURVEY 8(a) a6) chained in
+network order -- 64@56^2 x4, 64->128 s2, 128@28^2 x3, 128->256 s2, 256@14^2 x3, 256->512 s2, 512@7^2 x3 -- on a batch of 256
+images PER GPU (feature map (256, 64, 56, 56) in, (256, 512, 7, 7) out), bf16, forward + backward (gradient of the input
+and of every factor / lambda).  A "step" is one fwd+bwd pass of the 16 layers, replayed as ONE CUDA graph.  With N > 1 GPUs
+each rank owns its own 256 images (weak scaling) and the factor gradients are all-reduced over NCCL in per-stage buckets
+issued as soon as a stage's backward has finished (they overlap the remaining backward inside the graph).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs all|none|1,2,4,5]
 
-Prints ONE JSON line (contract in the task statement): value = whole-job tokens/s with inputs resident in HBM;
-e2e = same metric with HOST (pinned) inputs, H2D/D2H copies inside the timed region; roofline = tcgen05 GEMM kernel
-against the measured bf16 peak; cpu_baseline = the oracle port of the reference's op sequence on the host cores.
+Prints ONE JSON line: value = whole-job images/s with inputs resident in HBM; e2e = same metric with HOST (pinned) buffers
+in and out through the public API, copies inside the timed region; roofline = algorithmic bytes of SURVEY 8(d) against the
+measured HBM peak; cpu_baseline = oracle port of the reference's op sequence on the host cores.  At N = 1 the line also
+carries `configs`: one entry per other BASELINE.json config (1, 2, 4-conv, 4-conv+dropout, 4-TRL, 5-Tucker, 5-BlockTT) with
+its own ms_per_step / samples_per_s / roofline / cpu_baseline / e2e.
 """
 import argparse
+import gc
 import json
+import math
 import os
 import sys
 import threading
@@ -23,105 +29,116 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-IN_TS, HID_TS = (8, 8, 12), (8, 12, 32)
-IN_F, HID_F = 768, 3072
-TT_RANK = 16
-TOKENS_PER_GPU = 64 * 512
 METRIC = "factorized_layer_fwd_bwd_samples_per_s"
 UNIT = "samples/s"
-WORKLOAD = ("BERT-base FFN 768->3072->768 as two FactorizedLinear(blocktt, tensorized (8,8,12)/(8,12,32), rank 16, "
-            "bias) layers, 64x512 tokens per GPU, bf16, fwd+bwd")
+RESNET18 = [(64, 64, 56, 1)] * 4 + [(64, 128, 56, 2)] + [(128, 128, 28, 1)] * 3 + [(128, 256, 28, 2)] + [(256, 256, 14, 1)] * 3 + \
+           [(256, 512, 14, 2)] + [(512, 512, 7, 1)] * 3
+STAGE_OF = [0] * 5 + [1] * 4 + [2] * 4 + [3] * 3            # gradient-bucket groups (layer index -> group), issued last group first
+IMAGES_PER_GPU = 256
+WORKLOAD = ("ResNet-18's 16 3x3 convs as chained FactorizedConv(cp, rank 0.25, bias=False) layers (64@56^2 x4, 64->128 s2, 128@28^2 x3, "
+            "128->256 s2, 256@14^2 x3, 256->512 s2, 512@7^2 x3), 256 images per GPU, bf16, fwd+bwd")
 
 
-def _config(n_gpus, extra=None):
-    cfg = {"workload": WORKLOAD, "tokens_per_gpu": TOKENS_PER_GPU, "global_tokens": TOKENS_PER_GPU * n_gpus,
-           "parallelism": f"dp{n_gpus}", "l2": "working set per step (~0.9 GB) >> 126 MB L2, no explicit flush",
-           "nonlinearity": "none between the two layers (not part of the factorized-layer path)"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def _peaks():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))), "MEASURED_PEAKS.json"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle restatement of the reference's op sequence (linear_blocktt einsum + bias, autograd backward)
-# ---------------------------------------------------------------------------------------------------------------------
-def _cpu_step_fn(tokens, dtype):
+def cp_rank(cin, cout):
+    return int(round(cout * cin * 9 * 0.25 / (cout + cin + 6)))
+
+
+def config3_algorithmic(batch):
+    """bytes f+b = s (3|x| + 2|y|) + 3 s P per layer; FLOPs f+b = 3 x fwd (1x1 in, two 3-tap depthwise, 1x1 out)."""
+    byts = flops = 0
+    for cin, cout, hw, s in RESNET18:
+        R, ho = cp_rank(cin, cout), hw // s
+        nx, ny = batch * cin * hw * hw, batch * cout * ho * ho
+        byts += 2 * (3 * nx + 2 * ny) + 3 * 2 * R * (cin + cout + 7)
+        flops += 3 * 2 * batch * (hw * hw * cin * R + ho * hw * R * 3 + ho * ho * R * 3 + ho * ho * R * cout)
+    return float(byts), float(flops)
+
+
+# =====================================================================================================================
+# CPU arm: the oracle restatement of the reference's op sequence (test infrastructure; only this leg may call it)
+# =====================================================================================================================
+def _cpu_config3(sample):
     import torch
     from oracle import reference_path as rp
     torch.manual_seed(1234)
-    import math
-
-    def cores(in_ts, out_ts):
-        rank = (1, TT_RANK, TT_RANK, 1)
-        std = (math.sqrt(5) / math.sqrt(math.prod(in_ts)) / math.prod(rank)) ** 0.5
-        return [(torch.randn(rank[k], out_ts[k], in_ts[k], rank[k + 1]) * std).to(dtype).requires_grad_(True) for k in range(3)]
-    up, down = cores(IN_TS, HID_TS), cores(HID_TS, IN_TS)
-    b_up = torch.zeros(HID_F, dtype=dtype, requires_grad=True)
-    b_down = torch.zeros(IN_F, dtype=dtype, requires_grad=True)
-    x = torch.randn(tokens, IN_F).to(dtype).requires_grad_(True)
-    gy = torch.randn(tokens, IN_F).to(dtype)
-    leaves = [x, b_up, b_down] + up + down
+    layers = []
+    for cin, cout, hw, s in RESNET18:
+        R = cp_rank(cin, cout)
+        std = (1.0 / math.sqrt(9 * cin) / math.sqrt(R)) ** 0.25
+        fs = [(torch.randn(d, R) * std).requires_grad_(True) for d in (cout, cin, 3, 3)]
+        layers.append((torch.ones(R, requires_grad=True), fs, s))
+    x = torch.randn(sample, 64, 56, 56, requires_grad=True)
+    gy = torch.randn(sample, 512, 7, 7)
+    leaves = [x] + [t for w, fs, _ in layers for t in [w] + fs]
 
     def step():
-        h = rp.blocktt_linear(x, up, IN_TS) + b_up              # factorized_linear.py:39-60 + linear.py:42-43
-        y = rp.blocktt_linear(h, down, HID_TS) + b_down
-        return torch.autograd.grad(y, leaves, gy)
-    return step
+        h = x
+        for w, fs, s in layers:
+            h = rp.cp_conv(h, w, fs, None, [s, s], [1, 1], [1, 1])       # convolution.py:231-283 as shipped
+        return torch.autograd.grad(h, leaves, gy)
+    return step, sample, f"{sample} images per step through the 16 chained cp_conv layers"
 
 
-def cpu_baseline(sample_tokens=2048, reps=3):
+def _time_cpu(step, reps):
+    step()
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        t.append(time.perf_counter() - t0)
+    return min(t)
+
+
+def cpu_baseline(maker, reps=2, **kw):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    best, best_dt = 0.0, None
-    for dtype in (torch.float32, torch.bfloat16):
-        step = _cpu_step_fn(sample_tokens, dtype)
-        step()
-        t = []
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            step()
-            t.append(time.perf_counter() - t0)
-        thr = sample_tokens / min(t)
-        if thr > best:
-            best, best_dt = thr, str(dtype).replace("torch.", "")
-    return {"value": best, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_tokens} tokens fwd+bwd, oracle port of the reference op sequence (linear_blocktt einsum, "
-                      f"left-to-right), best of {reps} after 1 warm-up, best dtype of fp32/bf16 = {best_dt}, "
-                      f"torch.set_num_threads({cores})"}
+    step, sample, what = maker(**kw)
+    best = _time_cpu(step, reps)
+    return {"value": sample / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{what}, fp32, fwd+bwd, oracle port of the reference op sequence (the reference needs tensorly: not "
+                      f"installable offline), best of {reps} after 1 warm-up, torch.set_num_threads({cores})"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port: tensorly is not installable, so the
-    real package cannot run on the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the headline path (oracle port), all host threads, a bounded
+    sample of the workload per step; rank 0 only."""
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = 2048
-    step = _cpu_step_fn(sample, torch.float32)
-    for _ in range(max(args.warmup, 1)):
+    sample = 8
+    step, _, what = _cpu_config3(sample)
+    for _ in range(max(min(args.warmup, 2), 1)):
         step()
+    steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value = sample * steps / dt
     cb = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-          "sample": f"{sample} tokens per step, fp32, oracle port (reference needs tensorly: not installable offline)"}
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _config(args.gpus, {"sample_tokens": sample}),
+          "sample": f"{what}, fp32, fwd+bwd, {steps} timed steps (reference needs tensorly: not installable offline)"}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": IMAGES_PER_GPU, "sample_images": sample},
             "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-# ---------------------------------------------------------------------------------------------------------------------
+# =====================================================================================================================
 # clocks sampler (NVML, polled during the timed region)
-# ---------------------------------------------------------------------------------------------------------------------
+# =====================================================================================================================
 class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -152,7 +169,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.010)       # NVML queries contend with graph launches on the driver: keep them sparse
+            time.sleep(0.010)
 
     def start(self):
         if self.nv is not None:
@@ -168,22 +185,295 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def _finish(world):
-    """Multi-rank exit: every rank has printed / synchronised; leave without tearing the NCCL communicator down.
-    (destroy_process_group() with captured CUDA graphs that hold NCCL kernels still alive was seen to hang a 2-GPU run for
-    the whole box timeout after the JSON line had been printed.)"""
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs local to GPU `index` (NVML's ideal affinity) BEFORE any pinned host buffer is allocated, so
+    first-touch places the staging buffers on the GPU's own NUMA node and eight ranks do not all stream through node 0."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+# =====================================================================================================================
+# generic timing helpers
+# =====================================================================================================================
+def time_graph(step, steps, warmup, eager=False):
+    """(ms per step, mode, runner, launches per step): warm-up, capture into a CUDA graph, CUDA-event timing of `steps` replays."""
+    import torch
+    from torch_b200 import ops
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count()
+    step()
+    launches = ops.launch_count() - l0
+    run, mode, graphed = step, "eager", None
+    if not eager:
+        try:
+            from torch_b200.graphs import GraphedStep
+            graphed = GraphedStep(step)
+            run, mode = graphed.replay, "cuda_graph"
+        except Exception as exc:
+            print(f"bench.py: CUDA-graph capture failed ({exc!r}); running eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    return run, mode, launches, graphed
+
+
+def profile_entry_points(step, reps=2):
+    """Eager pass with a CUDA-event pair around every launcher call of libtltorch_cuda.so (torch_b200._cuda.PROFILE)."""
+    import torch
+    from torch_b200 import _cuda
+    step()
+    torch.cuda.synchronize()
+    _cuda.PROFILE = []
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    prof, _cuda.PROFILE = _cuda.PROFILE, None
+    table = {}
+    for name, a, b in prof:
+        t = table.setdefault(name, [0.0, 0])
+        t[0] += a.elapsed_time(b)
+        t[1] += 1
+    return {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[1] / reps} for k, v in
+            sorted(table.items(), key=lambda kv: -kv[1][0])}
+
+
+def time_e2e(dev_inputs, run, outputs, steps, world, dist):
+    """Host (pinned) buffers in and out through torch_b200.pipeline.HostPipelinedStep; every copy inside the timed region."""
+    import torch
+    from torch_b200.pipeline import HostPipelinedStep
+    host_in = [torch.randn(t.shape, dtype=torch.float32).to(t.dtype).pin_memory() for t in dev_inputs]
+    outs = outputs()
+    host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+    pipe = HostPipelinedStep(dev_inputs, run, outputs)
+    for _ in range(3):
+        pipe.submit(host_in, host_out)
+    pipe.drain()
     if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.synchronize()
         dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(pipe.h2d)                      # the first timed operation is an H2D copy on this stream
+    for _ in range(steps):
+        pipe.submit(host_in, host_out)
+    pipe.d2h.wait_stream(pipe.compute)
+    pipe.d2h.wait_stream(pipe.h2d)
+    t1.record(pipe.d2h)                      # ... and the last one a D2H copy on this one
+    pipe.drain()
+    ms = t0.elapsed_time(t1) / steps
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    return ms, h2d, d2h
+
+
+def roofline_of(bound, alg_bytes, alg_flops, ms, peaks, peak_src, timed_alone=False):
+    if bound == "hbm":
+        ach, peak, unit = alg_bytes / (ms / 1e3) / 1e9, peaks.get("hbm_gbs", 6650.0), "GB/s"
+        src = f"{peak_src}: hbm_gbs"
+    elif bound == "tensor":
+        key = "bf16_tflops" if timed_alone else "bf16_tflops_sustained"
+        ach, peak, unit = alg_flops / (ms / 1e3) / 1e12, peaks.get(key, 1400.0), "TFLOP/s"
+        src = f"{peak_src}: {key}"
+    else:   # fp32 config: CUDA-core FFMA peak (no measured figure exists: 148 SMs x 128 lanes x 2 x 1.965 GHz)
+        ach, peak, unit = alg_flops / (ms / 1e3) / 1e12, 148 * 128 * 2 * 1.965e9 / 1e12, "TFLOP/s"
+        src = "nominal fp32 FFMA peak 148 x 128 x 2 x 1.965 GHz (1e-5 tolerance rules out TF32; SURVEY 7)"
+    return {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+            "algorithmic_bytes": alg_bytes, "algorithmic_flops": alg_flops, "peak_source": src,
+            "scope": "whole step: algorithmic bytes / FLOPs of SURVEY 8(d) over the CUDA-event time of the graph-replayed step"}
+
+
+# =====================================================================================================================
+# the other BASELINE configs (N = 1 only): name, builder -> (layers, x, samples, bound, bytes, flops, cpu maker)
+# =====================================================================================================================
+def _fwd_bwd_step(layers, x):
+    import torch
+    params = [p for l in layers for p in l.parameters()]
+    holder = {}
+
+    def step():
+        x.grad = None
+        for p in params:
+            p.grad = None
+        y = x
+        for l in layers:
+            y = l(y)
+        if "gy" not in holder:
+            holder["gy"] = torch.randn_like(y)
+        y.backward(holder["gy"])
+
+    def outputs():
+        return [x.grad, torch.cat([p.grad.reshape(-1) for p in params])]
+    return step, outputs, holder, params
+
+
+def other_configs(dev):
+    import torch
+    import torch_b200 as tlt
+    from oracle import reference_path as rp
+
+    def c1():
+        torch.manual_seed(0)
+        ts = (4, 8, 16)
+        layer = tlt.FactorizedLinear(ts, ts, bias=True, factorization="cp", rank=0.5, device=dev, dtype=torch.float32)
+        x = torch.randn(128, 512, device=dev, requires_grad=True)
+
+        def cpu(sample=128):
+            R = 2341
+            w = torch.ones(R, requires_grad=True)
+            fs = [(torch.randn(d, R) * 0.3).requires_grad_(True) for d in ts + ts]
+            b = torch.zeros(512, requires_grad=True)
+            xc, gy = torch.randn(sample, 512, requires_grad=True), torch.randn(sample, 512)
+
+            def step():   # the as-shipped left-to-right einsum is infeasible here (0.4 TB intermediate, SURVEY 0.3): opt_einsum's order
+                y = rp.factorized_linear(xc, "cp", (w, fs), (ts, ts), bias=b, order="sane")
+                return torch.autograd.grad(y, [xc, w, b] + fs, gy)
+            return step, sample, f"{sample} samples, linear_cp in the in-factors-first order"
+        return dict(name="1: FactorizedLinear 512->512 cp rank 0.5 (R=2341), batch 128, fp32", layers=[layer], x=x, samples=128,
+                    bound="ffma", bytes=2.9e6, flops=1.84e9, dtype="f32", cpu=cpu)
+
+    def c2():
+        torch.manual_seed(1234)
+        up = tlt.FactorizedLinear((8, 8, 12), (8, 12, 32), bias=True, factorization="blocktt", rank=16, device=dev).to(torch.bfloat16)
+        down = tlt.FactorizedLinear((8, 12, 32), (8, 8, 12), bias=True, factorization="blocktt", rank=16, device=dev).to(torch.bfloat16)
+        x = torch.randn(64 * 512, 768, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+
+        def cpu(sample=2048):
+            def cores(i, o):
+                return [(torch.randn(r0, o[k], i[k], r1) * 0.2).requires_grad_(True) for k, (r0, r1) in enumerate(((1, 16), (16, 16), (16, 1)))]
+            cu, cd = cores((8, 8, 12), (8, 12, 32)), cores((8, 12, 32), (8, 8, 12))
+            xc, gy = torch.randn(sample, 768, requires_grad=True), torch.randn(sample, 768)
+
+            def step():
+                h = rp.blocktt_linear(xc, cu, (8, 8, 12))
+                return torch.autograd.grad(rp.blocktt_linear(h, cd, (8, 12, 32)), [xc] + cu + cd, gy)
+            return step, sample, f"{sample} tokens, linear_blocktt einsum as shipped (left-to-right), up + down"
+        return dict(name="2: BERT-base FFN 768->3072->768 as two FactorizedLinear(blocktt, rank 16, bias), 64x512 tokens, bf16",
+                    layers=[up, down], x=x, samples=64 * 512, bound="tensor", bytes=553.8e6 + 704.8e6, flops=927.7e9, dtype="bf16", cpu=cpu)
+
+    def c4conv(dropout):
+        torch.manual_seed(2)
+        conv = tlt.FactorizedConv(512, 512, 3, order=2, padding=1, factorization="tucker", rank=0.5, bias=True, device=dev)
+        conv.reset_parameters()
+        conv = conv.to(torch.bfloat16)
+        if dropout:
+            conv.weight = tlt.tensor_dropout(conv.weight, p=0.1)
+            conv.train()
+        x = torch.randn(512, 512, 7, 7, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+
+        def cpu(sample=64):
+            core = (torch.randn(388, 388, 2, 2) * 0.05).requires_grad_(True)
+            fs = [(torch.randn(a, b) * 0.05).requires_grad_(True) for a, b in ((512, 388), (512, 388), (3, 2), (3, 2))]
+            xc, gy = torch.randn(sample, 512, 7, 7, requires_grad=True), torch.randn(sample, 512, 7, 7)
+
+            def step():
+                c, f = core, fs
+                if dropout:
+                    idx = [rp.sample_keep_indices(r, 0.1, 3) for r in core.shape]
+                    c, f = rp.tucker_dropout_apply(core, fs, idx, 0.1, training=True)
+                return torch.autograd.grad(rp.tucker_conv(xc, c, f, None, [1, 1], [1, 1], [1, 1]), [xc, core] + fs, gy)
+            return step, sample, f"{sample} images, tucker_conv chain as shipped" + (" + TuckerDropout" if dropout else "")
+        return dict(name="4-conv: Tucker FactorizedConv 512->512 3x3 @7^2 rank 0.5 -> (388,388,2,2), batch 512, bf16" +
+                         (" + tensor_dropout(p=0.1)" if dropout else ""),
+                    layers=[conv], x=x, samples=512, bound="tensor", bytes=134.4e6, flops=263.8e9, dtype="bf16", cpu=cpu)
+
+    def c4trl():
+        torch.manual_seed(2)
+        trl = tlt.TRL((2048, 7, 7), (1000,), bias=True, factorization="tucker", rank=(64, 4, 4, 10), device=dev)
+        with torch.no_grad():
+            for p in trl.parameters():
+                p.mul_(0.05)
+        trl = trl.to(torch.bfloat16)
+        x = torch.randn(512, 2048, 7, 7, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+
+        def cpu(sample=64):
+            core = (torch.randn(64, 4, 4, 10) * 0.05).requires_grad_(True)
+            fs = [(torch.randn(a, b) * 0.05).requires_grad_(True) for a, b in ((2048, 64), (7, 4), (7, 4), (1000, 10))]
+            xc, gy = torch.randn(sample, 2048, 7, 7, requires_grad=True), torch.randn(sample, 1000)
+
+            def step():   # TRL.forward -> tucker_trl(project_input=False): rebuilds the 100 M-element weight every step, as shipped
+                return torch.autograd.grad(rp.tucker_trl(xc, core, fs), [xc, core] + fs, gy)
+            return step, sample, f"{sample} samples, tucker_trl as shipped (weight rebuilt every step)"
+        return dict(name="4-TRL: TRL (2048,7,7)->1000 tucker rank (64,4,4,10), batch 512, bf16", layers=[trl], x=x, samples=512,
+                    bound="hbm", bytes=311.2e6, flops=23e9, dtype="bf16", cpu=cpu)
+
+    def c5(fact):
+        torch.manual_seed(3)
+        ts = (16, 16, 16)
+        layer = tlt.FactorizedLinear(ts, ts, bias=True, factorization=fact, rank=0.75, device=dev).to(torch.bfloat16)
+        x = torch.randn(8192, 4096, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+
+        def cpu(sample=512):
+            xc, gy = torch.randn(sample, 4096, requires_grad=True), torch.randn(sample, 4096)
+            if fact == "tucker":
+                core = (torch.randn((15,) * 6) * 0.05).requires_grad_(True)
+                fs = [(torch.randn(16, 15) * 0.3).requires_grad_(True) for _ in range(6)]
+
+                def step():
+                    y = rp.factorized_linear(xc, "tucker", (core, fs), (ts, ts), order="sane")
+                    return torch.autograd.grad(y, [xc, core] + fs, gy)
+                return step, sample, f"{sample} tokens, linear_tucker in the in-factors-first order (as shipped: infeasible outer products)"
+            cs = [(torch.randn(a, 16, 16, b) * 0.05).requires_grad_(True) for a, b in ((1, 221), (221, 221), (221, 1))]
+
+            def step():
+                y = rp.factorized_linear(xc, "blocktt", cs, (ts, ts), implementation="reconstructed")
+                return torch.autograd.grad(y, [xc] + cs, gy)
+            return step, sample, f"{sample} tokens, implementation='reconstructed' (the as-shipped TT sweep costs 52.9 TFLOP at rank 221)"
+        flops, byts = (576.6e9, 403.9e6) if fact == "tucker" else (824.6e9, 411.2e6)
+        return dict(name=f"5-{fact}: FactorizedLinear 4096->4096 {fact} rank 0.75 -> {tuple(layer.weight.rank)}, 8192 tokens, bf16",
+                    layers=[layer], x=x, samples=8192, bound="tensor", bytes=byts, flops=flops, dtype="bf16", cpu=cpu)
+
+    return {"1": c1, "2": c2, "4-conv": lambda: c4conv(False), "4-conv+dropout": lambda: c4conv(True), "4-TRL": c4trl,
+            "5-tucker": lambda: c5("tucker"), "5-blocktt": lambda: c5("blocktt")}
+
+
+def run_other_configs(args, dev, peaks, peak_src, which):
+    import torch
+    out = []
+    makers = other_configs(dev)
+    for key, make in makers.items():
+        if which != "all" and key.split("-")[0] not in which and key not in which:
+            continue
+        t_start = time.time()
+        try:
+            c = make()
+            step, outputs, holder, _ = _fwd_bwd_step(c["layers"], c["x"])
+            run, mode, launches, graphed = time_graph(step, args.steps, args.warmup, args.eager)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            entry = {"config": c["name"], "ms_per_step": ms, "samples_per_s": c["samples"] / (ms / 1e3), "dtype": c["dtype"],
+                     "step_mode": mode, "gpu_launches_per_step": launches,
+                     "roofline": roofline_of(c["bound"], c["bytes"], c["flops"], ms, peaks, peak_src),
+                     "l2": "working set per step > 126 MB L2" if c["bytes"] > 2.5e8 else "working set fits L2: warm-L2 number (as in training)"}
+            if not args.skip_extras:
+                e2e_ms, h2d, d2h = time_e2e([c["x"], holder["gy"]], run, outputs, max(5, min(args.steps, 15)), 1, None)
+                entry["e2e"] = {"value": c["samples"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+                entry["cpu_baseline"] = cpu_baseline(c["cpu"])
+            out.append(entry)
+            del c, step, outputs, holder, run, graphed
+        except Exception as exc:        # one config failing must not take the headline line down
+            import traceback
+            traceback.print_exc()
+            out.append({"config": key, "error": repr(exc)})
+        gc.collect()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+        torch.cuda.empty_cache()
+        print(f"  [config {key}: {time.time() - t_start:.1f} s]", file=sys.stderr, flush=True)
+    return out
 
 
-# ---------------------------------------------------------------------------------------------------------------------
+# =====================================================================================================================
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -196,6 +486,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback; use --impl reference for the CPU arm)")
+    affinity = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -203,25 +494,51 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
+    peaks, peak_src = _peaks()
 
+    # ---------------------------------------------------------------- headline: the 16 chained CP convs of ResNet-18
     torch.manual_seed(1234)        # identical parameters on every rank (replicated)
-    up = tlt.FactorizedLinear(IN_TS, HID_TS, bias=True, factorization="blocktt", rank=TT_RANK, device=dev).to(torch.bfloat16)
-    down = tlt.FactorizedLinear(HID_TS, IN_TS, bias=True, factorization="blocktt", rank=TT_RANK, device=dev).to(torch.bfloat16)
-    params = list(up.parameters()) + list(down.parameters())
+    convs = []
+    for cin, cout, hw, s in RESNET18:
+        conv = tlt.FactorizedConv(cin, cout, 3, order=2, padding=1, stride=s, factorization="cp", rank=0.25, bias=False, device=dev)
+        conv.reset_parameters(std=1.0 / math.sqrt(9 * cin))          # variance-preserving, so 16 chained layers stay O(1) in bf16
+        convs.append(conv.to(torch.bfloat16))
+    params = [p for c in convs for p in c.parameters()]
     torch.manual_seed(1234 + rank)  # each rank's own shard of the batch
-    B = TOKENS_PER_GPU
-    x = torch.randn(B, IN_F, device=dev, dtype=torch.bfloat16).requires_grad_(True)
-    gy = torch.randn(B, IN_F, device=dev, dtype=torch.bfloat16)
-    bucket = GradientBucket(params) if world > 1 else None
+    B = args.images
+    x = torch.randn(B, 64, 56, 56, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+    gy = torch.randn(B, 512, 7, 7, device=dev, dtype=torch.bfloat16)
+    buckets = []
+    if world > 1:
+        for g in sorted(set(STAGE_OF)):
+            buckets.append(GradientBucket([p for i, c in enumerate(convs) if STAGE_OF[i] == g for p in c.parameters()]))
 
     def step():
         x.grad = None
         for p in params:
             p.grad = None
-        y = down(up(x))
-        y.backward(gy)
-        if bucket is not None:
-            bucket.allreduce()
+        acts = [x]
+        for c in convs:
+            acts.append(c(acts[-1]))
+        if world == 1:
+            acts[-1].backward(gy)
+            return
+        # backward stage by stage (last stage first); a stage's bucket is all-reduced asynchronously as soon as its gradients
+        # are final, so the exchange overlaps the backward of the earlier stages (one NCCL call per stage, 4 per step)
+        g_out, works = gy, []
+        for grp in sorted(set(STAGE_OF), reverse=True):
+            first = STAGE_OF.index(grp)
+            last = len(STAGE_OF) - 1 - STAGE_OF[::-1].index(grp)
+            inp = acts[first]
+            stage_params = [p for i in range(first, last + 1) for p in convs[i].parameters()]
+            grads = torch.autograd.grad(acts[last + 1], [inp] + stage_params, g_out, retain_graph=False)
+            for p, g in zip(stage_params, grads[1:]):
+                p.grad = g
+            g_out = grads[0]
+            works.append((buckets[grp], buckets[grp].allreduce_async()))
+        x.grad = g_out
+        for b, w in works:
+            b.finish(w)
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,31 +546,11 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
-    # One step = ~26 short kernels; issued eagerly the host (Python dispatch, ~45 us per op) is slower than the GPU, so
-    # the step is captured once into a CUDA graph and replayed (torch_b200.graphs.GraphedStep).  --eager disables it.
-    launches0 = ops.launch_count()
-    step()
-    launches_per_step = ops.launch_count() - launches0
-    run_step, mode = step, "eager"
-    if not args.eager:
-        try:
-            from torch_b200.graphs import GraphedStep
-            run_step, mode = GraphedStep(step).replay, "cuda_graph"
-        except Exception as exc:            # e.g. a collective that cannot be captured on this stack
-            if rank == 0:
-                print(f"bench.py: CUDA-graph capture failed ({exc!r}); running eagerly", file=sys.stderr)
-            torch.cuda.synchronize()
-    for _ in range(3):
-        run_step()
+    run_step, mode, launches_per_step, graphed = time_graph(step, args.steps, args.warmup, args.eager)
     barrier()
 
     # ------------------------------------------------------------------ timed region (device-resident inputs)
-    # clocks are sampled by rank 0 only (its own GPU): eight pollers hammering NVML slowed an 8-GPU step from 0.91 to 1.11 ms
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)       # rank 0 only: eight NVML pollers slowed an 8-GPU step measurably
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if rank == 0:
         sampler.start()
@@ -263,118 +560,110 @@ def run_ours(args):
     e1.record()
     barrier()
     clocks = sampler.stop()
-    launches = launches_per_step * args.steps
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = ms.item()
-    value = world * B * args.steps / (ms / 1e3)
-
-    # per-launch CUDA events cannot be recorded inside a graph replay: the dominant kernel is timed launch by launch in
-    # an eager pass over the same steps (kernel durations do not depend on how the launch was issued)
-    ops.PROFILE = []
-    for _ in range(args.steps):
-        step()
-    barrier()
-    prof, ops.PROFILE = ops.PROFILE, None
-
-    # roofline of the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration, per launch
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b, _, _ in prof)
-    gemm_flops = sum(f for *_, f, _ in prof)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    ms = ms.item() / args.steps
+    value = world * B / (ms / 1e3)
+    alg_bytes, alg_flops = config3_algorithmic(B)
+    roofline = roofline_of("hbm", alg_bytes, alg_flops, ms, peaks, peak_src)
+    try:   # dram bytes of the dominant kernel from the committed `ncu --set full` capture of this command, when one exists
+        cap = json.load(open(os.path.join(REPO, "profiles", "r02_config3_traffic.json")))
+        roofline["traffic"], roofline["traffic_source"] = cap["dram_bytes_per_step"], cap["source"]
     except Exception:
         pass
-    peak = peaks.get("bf16_tflops_sustained")
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-    if peak is None:
-        peak, peak_src = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
-    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this command (profiles/)
-    traffic, traffic_src = None, None
-    try:
-        cap = json.load(open(os.path.join(REPO, "profiles", "r01_gemm_tc3_traffic.json")))
-        traffic, traffic_src = cap["avg_dram_mbytes_per_launch"] * 1e6, "profiles/r01_gemm_tc3_traffic.json: " + cap["source"]
-    except Exception:
-        pass
-    gemm_bytes = sum(b for *_, b in prof)
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tc3_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
-                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": gemm_bytes / max(len(prof), 1),
-                "peak_source": peak_src, "launches": len(prof),
-                "avg_launch_ms": gemm_ms / max(len(prof), 1), "kernel_share_of_step": gemm_ms / ms, "step_mode": mode,
-                "algorithmic_flops_per_step": gemm_flops / max(args.steps, 1)}
-    per_shape = {}
-    for name, a, b, f, _ in prof:
-        t = per_shape.setdefault(name, [0.0, 0, f])
-        t[0] += a.elapsed_time(b)
-        t[1] += 1
-    roofline["per_gemm"] = {k: {"avg_ms": round(v[0] / v[1], 4), "tflops": round(v[2] / (v[0] / v[1] / 1e3) / 1e12, 1)}
-                            for k, v in per_shape.items()}
 
-    if args.skip_extras:
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "roofline": roofline, "clocks": clocks}),
-                  flush=True)
-        _finish(world)
-        return
-
-    # ------------------------------------------------------------------ e2e: host (pinned) inputs, copies inside the timed region
-    x_h = torch.randn(B, IN_F, dtype=torch.bfloat16).pin_memory()
-    gy_h = torch.randn(B, IN_F, dtype=torch.bfloat16).pin_memory()
-    dx_h = torch.empty(B, IN_F, dtype=torch.bfloat16).pin_memory()
-    n_param = sum(p.numel() for p in params)
-    gp_h = torch.empty(n_param, dtype=torch.bfloat16).pin_memory()
-
-    # Host buffers in, host buffers out, through the public API: the three-stream front end (torch_b200.pipeline) overlaps
-    # the H2D copy of step i+1 and the D2H copy of step i-1 with the kernels of step i; every copy is inside the timed region.
-    from torch_b200.pipeline import HostPipelinedStep
-
-    def outputs():
-        return [x.grad, torch.cat([p.grad.reshape(-1) for p in params])]
-    pipe = HostPipelinedStep([x, gy], run_step, outputs)
-    for _ in range(3):
-        pipe.submit([x_h, gy_h], [dx_h, gp_h])
-    pipe.drain()
+    # per-entry-point CUDA-event times of the same step issued eagerly (durations do not depend on how a launch was issued)
+    table = profile_entry_points(step) if world == 1 or rank == 0 else {}
+    if table:
+        total = sum(v["ms_per_step"] for v in table.values())
+        top = next(iter(table.items()))
+        roofline["kernels"] = {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"]}
+                               for k, v in list(table.items())[:8]}
+        roofline["dominant_entry_point"] = top[0]
+        roofline["dominant_share_of_kernel_time"] = top[1]["ms_per_step"] / total if total else None
+        roofline["kernel_time_ms_per_step"] = total
+        roofline["kernel_share_of_step"] = total / ms
     barrier()
-    e2e_steps = max(10, min(args.steps, 30))
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(pipe.h2d)                      # the first timed operation is an H2D copy on this stream
-    for _ in range(e2e_steps):
-        pipe.submit([x_h, gy_h], [dx_h, gp_h])
-    pipe.d2h.wait_stream(pipe.compute)
-    pipe.d2h.wait_stream(pipe.h2d)
-    t1.record(pipe.d2h)                      # ... and the last one a D2H copy on this one
-    pipe.drain()
-    barrier()
-    ms2 = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * B * e2e_steps / (ms2.item() / 1e3), "unit": UNIT, "steps": e2e_steps,
-           "h2d_bytes_per_step": x_h.numel() * 2 + gy_h.numel() * 2, "d2h_bytes_per_step": dx_h.numel() * 2 + gp_h.numel() * 2,
-           "pipeline": "3 streams: H2D(i+1) | kernels(i) | D2H(i-1); pinned host buffers"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": _config(world, {"step_mode": mode}), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline}
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": B, "global_images": B * world, "parallelism": f"dp{world}",
+                       "step_mode": mode, "l2": "working set per step (~2 GB of activations) >> 126 MB L2, no explicit flush",
+                       "between_layers": "none (BN / ReLU / residual adds are not part of the factorized-layer path)",
+                       "exchange": "per-stage flat fp32 buckets (4), NCCL all-reduce(AVG) issued asynchronously inside the graph" if world > 1 else "none",
+                       "cpu_affinity": f"{len(affinity)} CPUs local to the GPU (NVML)" if affinity else "unchanged"},
+            "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "roofline": roofline}
+
+    if not args.skip_extras:
+        def outputs():
+            return [x.grad, torch.cat([p.grad.reshape(-1) for p in params])]
+        e2e_steps = max(5, min(args.steps, 20))
+        e2e_ms, h2d, d2h = time_e2e([x, gy], run_step, outputs, e2e_steps, world, dist if world > 1 else None)
+        t = torch.tensor([e2e_ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.item()
+        line["e2e"] = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "steps": e2e_steps, "ms_per_step": e2e_ms,
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "h2d_gbs_per_gpu": h2d / (e2e_ms / 1e3) / 1e9, "d2h_gbs_per_gpu": d2h / (e2e_ms / 1e3) / 1e9,
+                       "pipeline": "3 streams: H2D(i+1) | kernels(i) | D2H(i-1); pinned host buffers on the GPU's NUMA node; in: input "
+                                   "feature map + upstream gradient; out: input gradient + all factor gradients (the forward output "
+                                   "stays on the device: it is consumed by the backward pass of the same step)"}
+    # release the captured graph (it holds NCCL kernels) BEFORE the other configs and before tearing the communicator down
+    del run_step, graphed
+    gc.collect()
+    torch.cuda.synchronize()
+
+    if rank == 0 and world == 1 and not args.skip_extras:
+        line["cpu_baseline"] = cpu_baseline(_cpu_config3, sample=8)
+        if args.configs != "none":
+            which = "all" if args.configs == "all" else set(args.configs.split(","))
+            del convs, params, x, gy
+            gc.collect()
+            torch.cuda.empty_cache()
+            line["configs"] = [{"config": "3: " + WORKLOAD, "ms_per_step": ms, "samples_per_s": value, "dtype": "bf16", "step_mode": mode,
+                                "gpu_launches_per_step": launches_per_step, "roofline": {k: roofline[k] for k in
+                                ("bound", "achieved", "peak", "unit", "frac", "traffic", "algorithmic_bytes", "algorithmic_flops")},
+                                "e2e": {k: line["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                                "cpu_baseline": line["cpu_baseline"], "headline": True}]
+            line["configs"] += run_other_configs(args, dev, peaks, peak_src, which)
     if rank == 0:
-        if world == 1:
-            line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def _finish(world):
+    """Multi-rank exit.  Round 1 left with os._exit(0) because destroy_process_group() hung: the captured CUDA graph still
+    held NCCL kernels (and the communicator's streams) when the communicator was torn down.  The graph is now destroyed
+    first (run_ours deletes it and synchronises), then the group is destroyed normally; a watchdog turns a teardown that
+    still hangs into a clean exit instead of a box timeout (the JSON line is already out)."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    watchdog = threading.Timer(20.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    dist.destroy_process_group()
+    watchdog.cancel()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU of the headline workload (256 = BASELINE)")
+    ap.add_argument("--configs", default="all", help="N = 1: which other BASELINE configs to time as well: all | none | 1,2,4,5")
     ap.add_argument("--eager", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
-    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: skip the e2e and cpu_baseline legs")
+    ap.add_argument("--skip-extras", action="store_true", help="profiling runs: skip the e2e, cpu_baseline and other-config legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -958,3 +958,58 @@ def test_khatri_rao_kernels_vs_fp64(dims, R, with_w, dtype):
     assert G.rel_err(kr, ref) < tol
     for a, b in zip(grads, go):
         assert G.rel_err(a, b) < tol
+
+
+# ------------------------------------------------------------------------------------------------- CP / TT tensor dropout on the GPU
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("kind,shape,rank,proba", [
+    ("cp", (10, 11, 12), 9, 0.4),                      # gather form (an empty draw is possible: reference's index path)
+    ("cp", (24, 16, 3, 3), 70, 0.12),                  # fixed-shape form (tlt_scale_modes on lambda), conv-kernel shaped
+    ("tt", (10, 11, 12), (1, 6, 3, 1), 0.4),           # gather form
+    ("tt", (9, 40, 40), (1, 36, 37, 1), 0.12),         # fixed-shape form (masks multiplied into the cores)
+    ("tucker", (10, 11, 12), (7, 6, 3), 0.4),
+])
+def test_tensor_dropout_vs_oracle_on_gpu(kind, shape, rank, proba, training, dtype):
+    """CPDropout / TTDropout / TuckerDropout through the real kernels against the oracle's restatement of
+    tltorch/tensor_hooks/_tensor_dropout.py:56-142, the hook's RNG draws replayed on the same device generator: the dropped
+    tensor's reconstruction AND the gradients reaching the un-dropped parameters through it."""
+    import torch_b200 as tlt
+    from torch_b200.tensor_hooks import _tensor_dropout as td
+    from oracle import reference_path as rp
+    torch.manual_seed(3)
+    w = tlt.FactorizedTensor.new(shape, rank=rank, factorization=kind, device=dev())
+    w.normal_(0, 0.5)
+    if kind == "cp":
+        w.weights.data.uniform_(0.5, 1.5)
+    w = w.to(dtype)
+    hook = {"tucker": td.TuckerDropout, "cp": td.CPDropout, "tt": td.TTDropout}[kind](proba, min_dim=3, min_values=1, drop_test=True)
+    ranks = w.rank if kind != "cp" else (w.rank,)
+    torch.manual_seed(1234)
+    if kind == "tt":
+        idx = [rp.sample_keep_indices(r, proba, 3, device=dev()).cpu() for r in ranks[1:]]
+    else:
+        idx = [rp.sample_keep_indices(r, proba, 3, device=dev()).cpu() for r in ranks]
+    torch.manual_seed(1234)
+    before = tlt.ops.launch_count()
+    dropped = hook._apply_tensor_dropout(w, training=training)
+    full = dropped.to_tensor()
+    g = torch.randn_like(full)
+    params = dict(w.named_parameters())
+    grads = torch.autograd.grad(full, list(params.values()), g)
+    assert tlt.ops.launch_count() > before
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
+    fs = [leaves[f"factors.factor_{i}"] for i in range(len(w.factors))]
+    if kind == "cp":
+        w2, f2 = rp.cp_dropout_apply(leaves["weights"], fs, idx[0], proba, training=training)
+        fo = rp.cp_to_tensor(w2, f2)
+    elif kind == "tucker":
+        c2, f2 = rp.tucker_dropout_apply(leaves["core"], fs, idx, proba, training=training)
+        fo = rp.tucker_to_tensor(c2, f2)
+    else:
+        fo = rp.tt_to_tensor(rp.tt_dropout_apply(fs, idx, proba, training=training))
+    go = torch.autograd.grad(fo, list(leaves.values()), g.double().cpu())
+    errs = {"full": G.rel_err(full, fo)}
+    for n, a, b in zip(params, grads, go):
+        errs[n] = G.rel_err(a, b)
+    _report(f"dropout {kind} rank={rank} train={training} {dtype}", errs, TOL[dtype])

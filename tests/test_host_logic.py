@@ -349,3 +349,19 @@ def test_tltorch_import_alias_is_the_product():
     assert fl is torch_b200.functional.factorized_linear and CPTensor is torch_b200.CPTensor and BlockTT is torch_b200.BlockTT
     assert tensor_dropout is torch_b200.tensor_dropout
     assert tltorch.__file__.startswith(_cases.__file__.rsplit("/tests/", 1)[0])
+
+
+def test_conv_transduct_starts_as_framewise_conv():
+    """FactorizedConv.transduct (reference: factorized_convolution.py:346-393): a CP conv transducted 2-D -> 3-D with the
+    centre-delta factor applies the old 2-D conv to every frame."""
+    torch.manual_seed(0)
+    with emulated_kernels():
+        conv = tlt.FactorizedConv(4, 5, 3, order=2, padding=1, bias=True, factorization="cp", rank=0.5, dtype=D)
+        conv.reset_parameters(std=0.5)
+        conv.bias.data.normal_()
+        x = torch.randn(2, 4, 3, 6, 5, dtype=D)
+        y2 = torch.stack([conv(x[:, :, t]) for t in range(3)], dim=2)
+        conv.transduct(3, mode=0, padding=1)
+        assert conv.order == 3 and tuple(conv.weight.shape[2:]) == (3, 3, 3)
+        y3 = conv(x)
+    assert G.rel_err(y3, y2) < TOL

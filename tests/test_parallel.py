@@ -27,7 +27,14 @@ def _worker(rank, world, port, out):
         p.grad = torch.full_like(p, float(full[b:e].sum()) * (i + 1))
     bucket = GradientBucket(params)
     bucket.allreduce(average=False)
-    out[rank] = [p.grad.float().mean().item() for p in params]
+    res = [p.grad.float().mean().item() for p in params]
+    # asynchronous form (what bench.py uses per ResNet stage): two buckets in flight at once, averaged
+    groups = [GradientBucket(params[:2]), GradientBucket(params[2:])]
+    handles = [g.allreduce_async(average=True) for g in groups]
+    for g, h in zip(groups, handles):
+        g.finish(h)
+    res += [p.grad.float().mean().item() for p in params]
+    out[rank] = res
     dist.destroy_process_group()
 
 
@@ -37,7 +44,8 @@ def test_gradient_bucket_allreduce_gloo_world2():
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     total = float(torch.arange(10).sum())
     for rank in (0, 1):
-        assert out[rank] == [total, 2 * total, 3 * total]
+        # after the SUM exchange every rank holds the same gradients, so the AVG exchange that follows leaves them unchanged
+        assert out[rank] == [total, 2 * total, 3 * total] * 2
 
 
 def test_shard_batch_covers_everything_once():

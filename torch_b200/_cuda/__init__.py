@@ -14,6 +14,7 @@ MAX_SUBDIMS = 4
 F32, BF16 = 0, 1
 
 _lib = None
+PROFILE = None     # bench.py / tools: set to a list to collect (entry point, start event, end event) for every launcher call
 
 
 class TltError(RuntimeError):
@@ -136,8 +137,35 @@ def lib():
             fn.argtypes = args
         if handle.tlt_version() != 1:
             raise TltError(f"ABI version mismatch: library reports {handle.tlt_version()}")
-        _lib = handle
+        _lib = _Library(handle)
     return _lib
+
+
+class _Library:
+    """Attribute access to the C entry points.  Launchers (status-returning entry points that take a stream) are wrapped so
+    that, while ``PROFILE`` is a list, each call is bracketed by a CUDA-event pair recorded on torch's current stream -- the
+    stream every launcher is given (``stream_ptr``) -- which is how bench.py times individual kernels inside a step."""
+
+    def __init__(self, handle):
+        self._handle = handle
+
+    def __getattr__(self, name):
+        fn = getattr(self._handle, name)
+        res, args = SYMBOLS.get(name, (None, []))
+        is_launcher = res is C.c_int and name not in ("tlt_version",) and not name.endswith("_supported")
+        if is_launcher:
+            def call(*a, _fn=fn, _name=name):
+                if PROFILE is None:
+                    return _fn(*a)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = _fn(*a)
+                e1.record()
+                PROFILE.append((_name, e0, e1))
+                return rc
+            fn = call
+        setattr(self, name, fn)
+        return fn
 
 
 def check(rc, what):
@@ -163,6 +191,11 @@ def require_cuda(*tensors):
 
 
 def stream_ptr(t):
+    """torch's current stream on ``t``'s device.  Kernels launch on the CURRENT device, so a tensor living on another GPU
+    would be launched on the wrong one: refuse instead (wrap the call in ``torch.cuda.device(t.device)``)."""
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise TltError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                       "launches go to the current device -- use `with torch.cuda.device(tensor.device):`")
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 

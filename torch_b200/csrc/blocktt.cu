@@ -487,16 +487,7 @@ static int fill_btt3(const tlt_blocktt3_desc* d, Btt3Params* p, bool grads, size
 // opt in to > 48 KB of dynamic shared memory, once per (kernel, high-water mark)
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-  static std::mutex mu;
-  static std::unordered_map<const void*, size_t> high;
-  if (bytes <= 48 * 1024) return TLT_OK;
-  std::lock_guard<std::mutex> lock(mu);
-  size_t& h = high[(const void*)kernel];
-  if (bytes > h) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    h = bytes;
-  }
-  return TLT_OK;
+  return ensure_smem((const void*)kernel, bytes);          // per (device, function), see common.cuh
 }
 
 static int pow2_floor(int v) {

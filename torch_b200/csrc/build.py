@@ -27,10 +27,17 @@ def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     objs = []
     procs = []
+    # headers every translation unit depends on: a change there rebuilds everything, a change in one .cu only that object
+    shared = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    shared += [os.path.abspath(os.path.join(HERE, "..", "..", "include", "tltorch_cuda.h")), os.path.abspath(__file__)]
+    newest_shared = max(os.path.getmtime(d) for d in shared)
     for src in SOURCES:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        path = os.path.join(HERE, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(newest_shared, os.path.getmtime(path)):
+            continue
+        cmd = [nvcc, *FLAGS, "-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, pr in procs:

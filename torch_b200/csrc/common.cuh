@@ -52,4 +52,16 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 
 inline size_t dtype_size(int dt) { return dt == TLT_BF16 ? 2 : 4; }
 
+// Opt-in to `smem` bytes of dynamic shared memory for `kernel` on the CURRENT device.  The attribute is per device and per
+// function, so the high-water mark is kept per (device, function) under a mutex (api.cu): safe with several GPUs in one
+// process and with launches from several host threads.  Returns a tlt_status.
+int ensure_smem(const void* kernel, size_t smem);
+// SM count of the current device (cached per device).
+int device_sms();
+#define TLT_ENSURE_SMEM(kernel, smem)                                   \
+  do {                                                                  \
+    int _rc = ::tlt::ensure_smem((const void*)(kernel), (size_t)(smem)); \
+    if (_rc != TLT_OK) return _rc;                                      \
+  } while (0)
+
 }  // namespace tlt

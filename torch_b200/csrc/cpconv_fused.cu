@@ -530,17 +530,8 @@ static int pwh_launch(const PwhParams& p0, cudaStream_t st) {
   p.tpi = (p.S + PT - 1) / PT;
   const size_t smem = (size_t)2 * KC * XP + 32 * XP + (size_t)(p.RP + 16) * W1P + 64;
   if (smem > 227 * 1024) return 1;
-  static size_t high = 0;
-  if (smem > high) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_hmma_kernel<KC, PT, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    high = smem;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    TLT_CHECK_CUDA(cudaGetDevice(&dev));
-    TLT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  TLT_ENSURE_SMEM((pointwise_hmma_kernel<KC, PT, NWARPS>), smem);
+  const int sms = device_sms();
   long long tiles = p.tiles = (p.tiles /* batch */) * p.tpi;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   pointwise_hmma_kernel<KC, PT, NWARPS><<<grid, NWARPS * 32, smem, st>>>(p);
@@ -568,22 +559,15 @@ namespace cpf {
 
 template <class K>
 static int launch(const Params& p, cudaStream_t st) {
-  static size_t cached_smem = 0;
-  static int cached_grid = 0;
   const size_t smem = K::smem_bytes(p.RP, p.w3p);
   if (smem > 227 * 1024) {
     set_error("tlt_cpconv3x3_fused: rank %d needs %zu bytes of shared memory", p.R, smem);
     return TLT_ERR_UNSUPPORTED;
   }
-  if (smem != cached_smem) {
-    int dev = 0, sms = 0, bps = 0;
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(cpconv3x3_fused_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TLT_CHECK_CUDA(cudaGetDevice(&dev));
-    TLT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    TLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cpconv3x3_fused_kernel<K>, K::NT, smem));
-    cached_grid = sms * (bps < 1 ? 1 : bps);
-    cached_smem = smem;
-  }
+  TLT_ENSURE_SMEM(cpconv3x3_fused_kernel<K>, smem);
+  int bps = 0;
+  TLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, cpconv3x3_fused_kernel<K>, K::NT, smem));
+  const int cached_grid = device_sms() * (bps < 1 ? 1 : bps);
   long long grid = cached_grid;
   if (grid > p.tiles) grid = p.tiles;
   cpconv3x3_fused_kernel<K><<<(unsigned)grid, K::NT, smem, st>>>(p);

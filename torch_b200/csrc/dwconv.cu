@@ -622,16 +622,7 @@ static int choose_pb(const DwParams& p, int plane_floats, int items_per_plane) {
 // with identical signatures (fwd / dgrad, FLIP = false / true) share one template instantiation of this helper.
 template <typename K>
 static int dw_set_smem(K kernel, size_t bytes) {
-  static std::mutex mu;
-  static std::unordered_map<const void*, size_t> high;
-  if (bytes <= 48 * 1024) return TLT_OK;
-  std::lock_guard<std::mutex> lock(mu);
-  size_t& h = high[(const void*)kernel];
-  if (bytes > h) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    h = bytes;
-  }
-  return TLT_OK;
+  return ensure_smem((const void*)kernel, bytes);          // per (device, function), see common.cuh
 }
 
 template <typename T>

@@ -688,8 +688,7 @@ static int dwt_eligible(const DwRowsGeom& g) {
 
 template <class Kern>
 static int dwt_smem_attr(Kern kern, size_t smem) {
-  if (smem > 48 * 1024) TLT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return TLT_OK;
+  return ensure_smem((const void*)kern, smem);
 }
 
 // strip height: as many destination rows as fit `budget` bytes of staged source rows, but enough strips to fill the GPU
@@ -847,17 +846,9 @@ extern "C" int tlt_dwconv_rows_wgrad(const tlt_conv_desc* d, const void* z, cons
   const int chunks_x = (g.cpr + passes - 1) / passes;
   const int lanes = 256 / chunks_x;
   const size_t smem = (size_t)lanes * g.taps * chunks_x * 8 * sizeof(float);
-  static size_t high = 0;
-  if (smem > 48 * 1024 && smem > high) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(dwconv_rows_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    high = smem;
-  }
+  TLT_ENSURE_SMEM(dwconv_rows_wgrad_kernel, smem);
   if (g.ndim == 2 && g.kernel[0] <= 3 && g.kernel[1] <= 3) {
-    static size_t high2 = 0;
-    if (smem > 48 * 1024 && smem > high2) {
-      TLT_CHECK_CUDA(cudaFuncSetAttribute(dwconv_rows2d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      high2 = smem;
-    }
+    TLT_ENSURE_SMEM(dwconv_rows2d_wgrad_kernel, smem);
     dwconv_rows2d_wgrad_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(g, (const uint4*)z, (const uint4*)gy, dw, ppb, chunks_x);
     return check_launch("dwconv_rows2d_wgrad_kernel");
   }

@@ -498,13 +498,8 @@ static int dwconv3x3_mma_launch(bool flip, int H, int channels, long long planes
   const size_t slot = ((size_t)pb * psz * 2 + 32 + 127) / 128 * 128;
   const size_t work = REPITCH ? ((size_t)pb * H * ROWB + 32 + 127) / 128 * 128 : 0;
   const size_t smem = 128 + 2 * slot + work + (size_t)2 * pb * 9 * 4 + 16;
-  static size_t high = 0;
-  if (smem > 48 * 1024 && smem > high) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_mma_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_mma_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_mma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
-    high = smem;
-  }
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_mma_kernel<true, W>), smem);
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_mma_kernel<false, W>), smem);
   const long long cap = 148LL * 4;
   const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
   const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *wp = (const __nv_bfloat16*)w;
@@ -538,15 +533,10 @@ int dwconv3x3_tma(bool flip, int H, int W, int channels, long long planes, const
   q.PB = pb;
   const long long groups = (planes + pb - 1) / pb;
   const size_t smem = (size_t)2 * pb * psz * 2 + (size_t)2 * pb * 9 * 4 + 16;
-  static size_t high[2] = {0, 0};
-  if (smem > 48 * 1024 && smem > high[0]) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_tma_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_tma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
-    high[0] = smem;
-  }
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_tma_kernel<true, 8>), smem);
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_tma_kernel<false, 8>), smem);
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_tma_kernel<true, 4>), smem);
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_tma_kernel<false, 4>), smem);
   const long long cap = 148LL * 4;
   const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
   const __nv_bfloat16 *xp = (const __nv_bfloat16*)x, *wp = (const __nv_bfloat16*)w;
@@ -579,12 +569,7 @@ static int dwconv3x3_wgrad_mma_launch(int H, int channels, int batch, const void
   q.PB = pb;
   const size_t half = ((size_t)pb * psz * 2 + 32 + 127) / 128 * 128;
   const size_t smem = 128 + 4 * half + 16;
-  static size_t high = 0;
-  if (smem > 48 * 1024 && smem > high) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_wgrad_mma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
-    high = smem;
-  }
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_wgrad_mma_kernel<W>), smem);
   dim3 grid((unsigned)channels, (unsigned)chunks);
   dwt::dwconv3x3_wgrad_mma_kernel<W><<<grid, 192, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
   return check_launch("dwconv3x3_wgrad_mma_kernel");
@@ -618,13 +603,8 @@ int dwconv3x3_wgrad_tma(int H, int W, int channels, int batch, const void* x, co
   if (pb > bpb) pb = bpb;
   q.PB = pb;
   const size_t smem = (size_t)4 * pb * psz * 2 + 16;
-  static size_t high = 0;
-  if (smem > 48 * 1024 && smem > high) {
-    cudaError_t e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwt::dwconv3x3_wgrad_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dwconv3x3_wgrad_tma_kernel) failed: %s", cudaGetErrorString(e)); return TLT_ERR_CUDA; }
-    high = smem;
-  }
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_wgrad_tma_kernel<8>), smem);
+  TLT_ENSURE_SMEM((dwt::dwconv3x3_wgrad_tma_kernel<4>), smem);
   dim3 grid((unsigned)channels, (unsigned)chunks);
   if (SWd == 8) dwt::dwconv3x3_wgrad_tma_kernel<8><<<grid, 256, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);
   else dwt::dwconv3x3_wgrad_tma_kernel<4><<<grid, 256, smem, st>>>(q, batch, bpb, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dw);

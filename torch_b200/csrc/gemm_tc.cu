@@ -464,11 +464,7 @@ static int launch_gemm2(const tlt_gemm_desc* d, const void* A, const void* B, co
   p.alpha = d->alpha;
   p.tiles_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   p.tiles_n = (p.N + BN - 1) / BN;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  TLT_ENSURE_SMEM((gemm_bf16_tc2_kernel<BN, kStages>), L::TOTAL);
   int tiles = p.tiles_m * p.tiles_n;
   int pairs = num_sms() / 2;
   int clusters = tiles < pairs ? tiles : pairs;
@@ -505,11 +501,7 @@ static int launch_gemm3(const tlt_gemm_desc* d, int splits, const void* A, const
   p.c_reduce = (p.accumulate || p.splits > 1) ? 1 : 0;
   if (p.splits > 1 && !p.accumulate)                                   // split-K partials are reduce-added into zeros
     TLT_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc3_kernel<BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  TLT_ENSURE_SMEM((gemm_bf16_tc3_kernel<BN, kStages>), L::TOTAL);
   int units = p.tiles_m * p.tiles_n * p.splits;
   int pairs = num_sms() / 2;
   int clusters = units < pairs ? units : pairs;

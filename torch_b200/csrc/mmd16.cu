@@ -533,16 +533,7 @@ static int fill(const tlt_mmd16_desc* d, Params* p) {
   return TLT_OK;
 }
 
-static int num_sms16() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms16() { return device_sms(); }
 
 }  // namespace m16
 }  // namespace tlt
@@ -559,10 +550,7 @@ extern "C" int tlt_mmd16_fwd(const tlt_mmd16_desc* d, const void* x, const void*
   if (rc) return rc;
   TLT_REQUIRE(x && y, "tlt_mmd16_fwd: null tensor");
   TLT_REQUIRE(ALIGNED16(x) && ALIGNED16(y) && ALIGNED16(addend), "tlt_mmd16_fwd: tensors must be 16-byte aligned");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mmd16_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem); });
-  TLT_CHECK_CUDA(attr_err);
+  TLT_ENSURE_SMEM(mmd16_fwd_kernel, kFwdSmem);
   long long blocks = d->batch;
   const long long cap = (long long)num_sms16() * kFwdCtasPerSm;
   if (blocks > cap) blocks = cap;
@@ -580,10 +568,7 @@ extern "C" int tlt_mmd16_bwd(const tlt_mmd16_desc* d, const void* u, const void*
   TLT_REQUIRE(g && (du || dM), "tlt_mmd16_bwd: null tensor");
   TLT_REQUIRE(!dM || u, "tlt_mmd16_bwd: the matrix gradients need the forward input");
   TLT_REQUIRE(ALIGNED16(u) && ALIGNED16(g) && ALIGNED16(du), "tlt_mmd16_bwd: tensors must be 16-byte aligned");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mmd16_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem); });
-  TLT_CHECK_CUDA(attr_err);
+  TLT_ENSURE_SMEM(mmd16_bwd_kernel, kBwdSmem);
   long long blocks = d->batch;
   const long long cap = (long long)num_sms16() * kBwdCtasPerSm;
   if (blocks > cap) blocks = cap;

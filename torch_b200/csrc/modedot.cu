@@ -222,17 +222,9 @@ extern "C" int tlt_multi_mode_dot(const tlt_mmd_desc* d, const void* x, const vo
   const size_t smem = (size_t)total * 4;
   cudaStream_t st = (cudaStream_t)stream;
   long long blocks = d->batch < 148LL * 8 ? d->batch : 148LL * 8;
-  static std::mutex mu;
-  static size_t high[2] = {0, 0};
   const int ti = d->dtype == TLT_BF16;
-  if (smem > 48 * 1024) {
-    std::lock_guard<std::mutex> lock(mu);
-    if (smem > high[ti]) {
-      if (ti) TLT_CHECK_CUDA(cudaFuncSetAttribute(multi_mode_dot_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else TLT_CHECK_CUDA(cudaFuncSetAttribute(multi_mode_dot_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      high[ti] = smem;
-    }
-  }
+  if (ti) TLT_ENSURE_SMEM(multi_mode_dot_kernel<__nv_bfloat16>, smem);
+  else TLT_ENSURE_SMEM(multi_mode_dot_kernel<float>, smem);
   if (ti)
     multi_mode_dot_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>(p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)m0,
         (const __nv_bfloat16*)m1, (const __nv_bfloat16*)m2, d->transpose[0], d->transpose[1], d->transpose[2], (const __nv_bfloat16*)addend, (__nv_bfloat16*)y);

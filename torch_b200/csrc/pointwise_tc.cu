@@ -644,11 +644,7 @@ pointwise_wgrad1_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 template <int NB>
 static int w1_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const PwParams& p, int units, cudaStream_t st) {
   using L = W1Smem<NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_wgrad1_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  TLT_ENSURE_SMEM((pointwise_wgrad1_kernel<NB>), L::TOTAL);
   const int sms = num_sms();
   pointwise_wgrad1_kernel<NB><<<units < sms ? units : sms, kPwThreads, L::TOTAL, st>>>(ma, mb, mc, p);
   return check_launch("pointwise_wgrad1_kernel");
@@ -834,11 +830,7 @@ template <int BN>
 static int f1_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mat, const PwParams& p,
                      const void* bias, long long units, cudaStream_t st) {
   using L = F1Smem<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_fwd1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  TLT_ENSURE_SMEM((pointwise_fwd1_kernel<BN>), L::TOTAL);
   const int sms = num_sms();
   pointwise_fwd1_kernel<BN><<<(unsigned)(units < sms ? units : sms), kPwThreads, L::TOTAL, st>>>(ma, mb, mc, mat, p, bias);
   return check_launch("pointwise_fwd1_kernel");
@@ -848,11 +840,7 @@ template <int BN, int kStages, bool WGRAD>
 static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mat, const PwParams& p,
                      const void* bias, int units, cudaStream_t st) {
   using L = PwSmem<BN, kStages>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tc_kernel<BN, kStages, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  TLT_ENSURE_SMEM((pointwise_tc_kernel<BN, kStages, WGRAD>), L::TOTAL);
   const int pairs = num_sms() / 2;
   const int clusters = units < pairs ? units : pairs;
   pointwise_tc_kernel<BN, kStages, WGRAD><<<2 * clusters, kPw2Threads, L::TOTAL, st>>>(ma, mb, mc, mat, p, bias);
@@ -981,11 +969,7 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
       }
       const long long un = (long long)p.batch * p.tiles_m * p.tiles_n;
       TLT_REQUIRE(un < (1LL << 31), "tlt_pointwise_tc: too many tiles");
-      static bool attr_set = false;
-      if (!attr_set) {
-        TLT_CHECK_CUDA(cudaFuncSetAttribute(pointwise_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTctSmem));
-        attr_set = true;
-      }
+      TLT_ENSURE_SMEM(pointwise_tct_kernel, kTctSmem);
       const int sms = num_sms();
       pointwise_tct_kernel<<<(unsigned)(un < sms ? un : sms), kPwThreads, kTctSmem, st>>>(ma, mw, mc64, mat, p, bias);
       return check_launch("pointwise_tct_kernel");

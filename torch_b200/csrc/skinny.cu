@@ -142,11 +142,7 @@ template <typename T>
 static int launch_skinny_fwd(const void* a, const void* k, void* y, long long rows, int I, int J, int k_trans, cudaStream_t st) {
   const int IP = (I + 3) & ~3;
   const size_t smem = (size_t)J * IP * 4 + ((((size_t)kSkRows * I + 7) & ~(size_t)7) + (size_t)kSkRows * J + 8) * sizeof(T);
-  static size_t high = 0;
-  if (smem > 48 * 1024 && smem > high) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(skinny_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    high = smem;
-  }
+  TLT_ENSURE_SMEM((skinny_fwd_kernel<T>), smem);
   long long tiles = (rows + kSkRows - 1) / kSkRows;
   const long long cap = 148LL * 6;
   skinny_fwd_kernel<T><<<(unsigned)(tiles < cap ? tiles : cap), kSkRows, smem, st>>>((const T*)a, (const T*)k, (T*)y, rows, I, J, k_trans);
@@ -156,11 +152,7 @@ static int launch_skinny_fwd(const void* a, const void* k, void* y, long long ro
 template <typename T>
 static int launch_skinny_dk(const void* a, const void* g, float* dk, long long rows, int I, int J, cudaStream_t st) {
   const size_t smem = (((size_t)J * I * 4 + 15) & ~(size_t)15) + ((((size_t)kSkRows * I + 7) & ~(size_t)7) + (size_t)kSkRows * J + 8) * sizeof(T);
-  static size_t high = 0;
-  if (smem > 48 * 1024 && smem > high) {
-    TLT_CHECK_CUDA(cudaFuncSetAttribute(skinny_dk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    high = smem;
-  }
+  TLT_ENSURE_SMEM((skinny_dk_kernel<T>), smem);
   long long tiles = (rows + kSkRows - 1) / kSkRows;
   const long long cap = 148LL * 2;
   skinny_dk_kernel<T><<<(unsigned)(tiles < cap ? tiles : cap), 256, smem, st>>>((const T*)a, (const T*)g, dk, rows, I, J);

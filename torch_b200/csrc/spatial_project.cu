@@ -311,7 +311,7 @@ static int check_shape(int64_t batch, int64_t channels, int32_t S, int32_t J) {
 template <class Kern>
 static int grid_for(Kern kern, size_t smem, long long tiles, int* grid) {
   int dev = 0, sms = 0, bps = 0;
-  TLT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TLT_ENSURE_SMEM(kern, smem);
   TLT_CHECK_CUDA(cudaGetDevice(&dev));
   TLT_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   TLT_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kThreads, smem));

@@ -310,16 +310,7 @@ inline int make_map3d(CUtensorMap* map, const void* ptr, int64_t d0, int64_t d1,
   return TLT_OK;
 }
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+inline int num_sms() { return device_sms(); }
 
 
 }  // namespace tlt

@@ -193,6 +193,26 @@ class FactorizedConv(nn.Module):
             instance.reset_parameters()
         return instance
 
+    @classmethod
+    def from_conv_list(cls, conv_list, rank="same", implementation="reconstructed", factorization="cp",
+                       decompose_weights=True, decomposition_kwargs=dict(), **kwargs):
+        """Jointly factorized version of a list of nn.ConvNd layers of identical kernel shape (reference: :318-344)."""
+        conv_layer = conv_list[0]
+        out_channels, in_channels, *kernel_size = conv_layer.weight.shape
+        instance = cls(in_channels, out_channels, kernel_size, implementation=implementation, rank=rank, factorization=factorization,
+                       padding=conv_layer.padding, stride=conv_layer.stride[0], bias=True, dilation=conv_layer.dilation,
+                       n_layers=len(conv_list), fixed_rank_modes=None, device=conv_layer.weight.device,
+                       dtype=conv_layer.weight.dtype, **kwargs)
+        if decompose_weights:
+            with torch.no_grad():
+                weight_tensor = torch.stack([kernel_to_tensor(factorization, layer.weight.data) for layer in conv_list])
+                instance.weight.init_from_tensor(weight_tensor, **decomposition_kwargs)
+        else:
+            instance.reset_parameters()
+        for i, layer in enumerate(conv_list):
+            instance.set(i, stride=layer.stride, padding=layer.padding, dilation=layer.dilation, bias=layer.bias)
+        return instance
+
     def transduct(self, kernel_size, mode=0, padding=0, stride=1, dilation=1, fine_tune_transduction_only=True):
         """Add a new spatial dimension to the convolution (e.g. 2-D -> 3-D) by transducting the factorization."""
         if fine_tune_transduction_only:
@@ -205,8 +225,20 @@ class FactorizedConv(nn.Module):
         self.dilation = np.insert(self.dilation, mode, dilation, axis=-1)
         self.kernel_size = self.kernel_size[:mode] + (kernel_size,) + self.kernel_size[mode:]
         self.kernel_shape = self.kernel_shape[:mode + 2] + (kernel_size,) + self.kernel_shape[mode + 2:]
-        transduction_mode = mode + 1 if self.factorization.lower() == "tt" else mode + 2
-        self.weight = self.weight.transduct(kernel_size, transduction_mode)
+        # like the reference (:380-391): dispatch on the weight's TYPE (``self.factorization`` may be a tensor object when the
+        # layer was built from one); a CP weight gets the centre-delta factor, so the transducted conv starts as the
+        # frame-wise application of the old one (identity along the new dimension) instead of a sum over the window
+        from ..factorized_tensors import CPTensor, TTTensor
+        if isinstance(self.weight, CPTensor):
+            ref = self.weight.factors[0]
+            new_factor = torch.zeros(kernel_size, self.weight.rank, dtype=ref.dtype, device=ref.device)
+            new_factor[kernel_size // 2, :] = 1
+            transduction_mode = mode + 2
+        elif isinstance(self.weight, TTTensor):
+            new_factor, transduction_mode = None, mode + 1
+        else:
+            new_factor, transduction_mode = None, mode + 2
+        self.weight = self.weight.transduct(kernel_size, transduction_mode, new_factor)
         self.shape = self.weight.shape
         self.forward_fun = _get_factorized_conv(self.weight, self.implementation)
         return self

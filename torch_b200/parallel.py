@@ -78,6 +78,29 @@ class GradientBucket:
             self.unpack(1.0 / world if average else 1.0)
 
 
+    # ---- asynchronous form: issue the exchange as soon as this bucket's gradients are final, finish it later ---------------------
+    def allreduce_async(self, group: Optional[dist.ProcessGroup] = None, average: bool = True):
+        """Pack and start the all-reduce; returns a handle for ``finish``.  The collective runs on the backend's own stream
+        (NCCL) after everything queued so far on the current stream, so kernels launched between this call and ``finish`` --
+        the backward pass of the layers whose gradients are not in this bucket -- overlap the exchange.  Capturable in a CUDA
+        graph (the fork / join become graph dependencies)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        self.pack()
+        world = dist.get_world_size(group)
+        if average and dist.get_backend(group) == "nccl":
+            return (dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=True), 1.0)
+        return (dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True), 1.0 / world if average else 1.0)
+
+    def finish(self, handle):
+        """Wait (on the current stream) for the exchange started by ``allreduce_async`` and write the reduced gradients back."""
+        if handle is None:
+            return
+        work, scale = handle
+        work.wait()
+        self.unpack(scale)
+
+
 def shard_batch(total: int, rank: int, world_size: int):
     """[begin, end) of this rank's slice of a batch of ``total`` independent samples (ragged tail goes to low ranks)."""
     base, rem = divmod(total, world_size)
