@@ -365,3 +365,30 @@ def test_conv_transduct_starts_as_framewise_conv():
         assert conv.order == 3 and tuple(conv.weight.shape[2:]) == (3, 3, 3)
         y3 = conv(x)
     assert G.rel_err(y3, y2) < TOL
+
+
+def test_channels_last_input_takes_the_rows_route_without_transposes():
+    """A torch.channels_last activation is the (B H W, C) rows matrix already: the CP / Tucker conv rows routes view it (no
+    nchw_to_rows / rows_to_nchw launch), return a channels_last output, and agree with the NCHW-contiguous result."""
+    torch.manual_seed(3)
+    for fact, rank in (("cp", 0.25), ("tucker", 0.8)):
+        conv = tlt.FactorizedConv(64, 72, 3, order=2, padding=1, stride=2, bias=True, factorization=fact, rank=rank)
+        conv.reset_parameters(std=0.3)
+        conv.bias.data.normal_()
+        conv = conv.to(torch.bfloat16)
+        x = torch.randn(2, 64, 9, 10).to(torch.bfloat16)
+        xcl = x.contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        xn = x.clone().requires_grad_(True)
+        with emulated_kernels() as log_n:
+            yn = conv(xn)
+            gn = torch.autograd.grad(yn, [xn] + list(conv.parameters()), torch.ones_like(yn))
+            log_n = list(log_n)
+        with emulated_kernels() as log_c:
+            yc = conv(xcl)
+            gc_ = torch.autograd.grad(yc, [xcl] + list(conv.parameters()), torch.ones_like(yc))
+        assert any(e[0] in ("nchw_to_rows", "rows_to_nchw") for e in log_n)
+        assert not any(e[0] in ("nchw_to_rows", "rows_to_nchw") for e in log_c), [e[0] for e in log_c]
+        assert yc.is_contiguous(memory_format=torch.channels_last) and yc.shape == yn.shape
+        assert G.rel_err(yc, yn.double()) < 1e-2
+        for a, b in zip(gc_, gn):
+            assert G.rel_err(a, b.double()) < 2e-2

@@ -101,6 +101,8 @@ def _cp_rows_route(x, cp_tensor, bias, kernel, stride):
     mode = os.environ.get("TLT_CP_ROWS", "auto")          # development switch: all | off | auto
     if mode in ("all", "off"):
         return mode == "all"
+    if rows_ops.is_channels_last(x):
+        return True        # the activation already IS the rows matrix: no transposition on either side of the chain
     # strided depthwise passes and maps the NCHW tensor-core 1x1 kernel cannot take (spatial extent not a multiple of 8
     # on either side) go through rows; measured per layer in gpurun_out/s44 (config 3: 64->128 stride 2 3.45 -> 0.98 ms)
     s_in = math.prod(x.shape[2:])

@@ -111,12 +111,29 @@ _to_rows_op.register_autograd(_to_rows_backward, setup_context=_to_rows_setup)
 _to_nchw_op.register_autograd(_to_nchw_backward, setup_context=_to_nchw_setup)
 
 
+def is_channels_last(x):
+    """True when (B, C, *S) ``x`` is stored channels-last (torch.channels_last / channels_last_3d strides) with a channel count
+    whose rows are 16-byte aligned: its memory IS the (B * prod(S), C) rows matrix -- no transposition pass is needed."""
+    if x.dim() < 3 or x.shape[1] % 8 != 0 or x.shape[1] == 1:
+        return False
+    perm = [0] + list(range(2, x.dim())) + [1]
+    return x.permute(perm).is_contiguous() and not x.is_contiguous()
+
+
 def nchw_to_rows(x):
-    """(B, C, *S) bf16 -> (B * prod(S), round8(C)); pad channels are zero."""
+    """(B, C, *S) bf16 -> (B * prod(S), round8(C)); pad channels are zero.  A channels-last tensor is viewed, not copied."""
+    if is_channels_last(x):
+        perm = [0] + list(range(2, x.dim())) + [1]
+        return x.permute(perm).reshape(-1, x.shape[1])
     return _to_rows_op(x)
 
 
-def rows_to_nchw(rows, batch, channels, spatial):
+def rows_to_nchw(rows, batch, channels, spatial, channels_last=False):
+    """rows (B * prod(S), round8(C)) -> (B, C, *S).  channels_last=True (and C % 8 == 0) returns the rows themselves viewed as a
+    channels-last (B, C, *S) tensor: the output memory format follows the input's, as for torch's own convolutions."""
+    if channels_last and channels % 8 == 0 and rows.shape[1] == channels and rows.is_contiguous():
+        nd = len(spatial)
+        return rows.view(batch, *spatial, channels).permute(0, nd + 1, *range(1, nd + 1))
     return _to_nchw_op(rows, batch, channels, list(spatial))
 
 
@@ -204,7 +221,7 @@ def tucker_conv_rows(x, w, f_in, f_out, bias, stride, padding, dilation):
     wc = F.pad(w.reshape(r0, r1, taps).permute(0, 2, 1), (0, _r8(r1) - r1))    # (r0, taps, round8(r1)): K index = (tap, channel)
     h = padded_linear(cols, wc.reshape(r0, taps * _r8(r1)), None, True)        # (B S', round8(r0))
     yt = padded_linear(h, f_out, bias, True)                                   # (B S', round8(C_out))
-    return rows_to_nchw(yt, b, f_out.shape[0], out_size)
+    return rows_to_nchw(yt, b, f_out.shape[0], out_size, channels_last=is_channels_last(x))
 
 
 # =====================================================================================================================
@@ -424,4 +441,4 @@ def cp_conv_rows(x, taps_t, f_in, f_out_scaled, bias, kernel, stride, padding, d
     w_taps = F.pad(taps_t, (0, _r8(r) - r))                                    # (taps, round8(R))
     z = dwconv_rows(z, w_taps, b, spatial, kernel, stride, padding, dilation)  # (B S', round8(R))
     yt = padded_linear(z, f_out_scaled, bias, True)                            # (B S', round8(C_out))
-    return rows_to_nchw(yt, b, f_out_scaled.shape[0], out_size)
+    return rows_to_nchw(yt, b, f_out_scaled.shape[0], out_size, channels_last=is_channels_last(x))
