@@ -312,6 +312,36 @@ int tlt_cpconv3x3_fused(const tlt_cpconv_desc* desc, const void* x, const void* 
                         const void* bias, void* y, void* z1_out, void* z2_out, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Op-level fused CP convolution on channels-last rows (bf16): x (B, H, W, C_in) -> y (B, H/s, W/s, C_out),
+ *     y = F_out . dw3x3( F_in^T . x )  with separable taps kh (3, R), kw (3, R) and CP weights lambda (R), padding 1.
+ * ONE launch per direction; the R-channel intermediates stay in TMEM / shared memory (csrc/cpconv_rows.cu).
+ *   tlt_cpconv_rows_workspace_size      bytes of the packed-operand workspace `ws`
+ *   tlt_cpconv_rows_grad_workspace_size bytes of the fp32 gradient accumulators `acc`
+ *   tlt_cpconv_rows_pack      ws <- (F_in (C_in, R), F_out (C_out, R), kh, kw, lambda), all bf16: tile-padded operand matrices
+ *   tlt_cpconv_rows_fwd       y <- x, ws (+ fp32 bias (C_out) or NULL)
+ *   tlt_cpconv_rows_bwd       dx <- x, dy, ws; acc <- fp32 sums for every parameter gradient (zeroed by the call)   [stride 1]
+ *   tlt_cpconv_rows_finalize  bf16 gradients of F_out, F_in, kh, kw, lambda <- acc
+ * Supported: W = 56, H even; (C_in, C_out, stride) = (64, 64, 1) forward + backward, (64, 128, 2) forward; R <= 128.
+ * Replaces: cp_conv / cp_conv_mobilenet (tltorch/functional/convolution.py:231-345: 1x1 conv -> one depthwise 1-D conv per
+ * kernel mode -> 1x1 conv, each a full HBM round trip of the R-channel tensor) and their autograd, for BASELINE config 3's
+ * HBM-bound 56^2 layers.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t batch, in_channels, out_channels, rank, height, width;
+  int32_t stride;
+} tlt_cpconv_rows_desc;
+int tlt_cpconv_rows_supported(const tlt_cpconv_rows_desc* desc);
+size_t tlt_cpconv_rows_workspace_size(const tlt_cpconv_rows_desc* desc);
+size_t tlt_cpconv_rows_grad_workspace_size(const tlt_cpconv_rows_desc* desc);
+int tlt_cpconv_rows_pack(const tlt_cpconv_rows_desc* desc, const void* f_in, const void* f_out, const void* kh, const void* kw,
+                         const void* lambda, void* ws, void* stream);
+int tlt_cpconv_rows_fwd(const tlt_cpconv_rows_desc* desc, const void* x, const void* ws, const float* bias, void* y, void* stream);
+int tlt_cpconv_rows_bwd(const tlt_cpconv_rows_desc* desc, const void* x, const void* dy, const void* ws, void* dx, float* acc,
+                        void* stream);
+int tlt_cpconv_rows_finalize(const tlt_cpconv_rows_desc* desc, const float* acc, const void* kh, const void* kw, const void* lambda,
+                             void* g_fout, void* g_fin, void* g_kh, void* g_kw, void* g_lambda, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Spatial-modes-first projection of channels-first feature maps (bf16):
  *   tlt_spatial_project_fwd : t[b, j, c] = sum_s x[b, c, s] k[s, j]            x (B, C, S), k (S, J) -> t (B, J, C)
  *   tlt_spatial_project_bwd : dx[b, c, s] = sum_j gt[b, j, c] k[s, j];   dk[s, j] += sum_{b,c} x[b, c, s] gt[b, j, c]

@@ -73,6 +73,11 @@ class CpConvDesc(C.Structure):
                 ("variant", C.c_int32)]
 
 
+class CpConvRowsDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("in_channels", C.c_int64), ("out_channels", C.c_int64), ("rank", C.c_int64),
+                ("height", C.c_int64), ("width", C.c_int64), ("stride", C.c_int32)]
+
+
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -115,6 +120,13 @@ SYMBOLS = {
                                      C.POINTER(C.c_void_p), _vp, _vp]),
     "tlt_cpconv3x3_fused_supported": (C.c_int, [C.POINTER(CpConvDesc)]),
     "tlt_cpconv3x3_fused": (C.c_int, [C.POINTER(CpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cpconv_rows_supported": (C.c_int, [C.POINTER(CpConvRowsDesc)]),
+    "tlt_cpconv_rows_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
+    "tlt_cpconv_rows_grad_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
+    "tlt_cpconv_rows_pack": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cpconv_rows_fwd": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cpconv_rows_bwd": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cpconv_rows_finalize": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_spatial_project_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "tlt_spatial_project_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "tlt_spatial_project_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),

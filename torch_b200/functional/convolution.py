@@ -9,7 +9,7 @@ import os
 
 import torch
 
-from .. import ops, tenalg, pointwise_ops, rows_ops, kr_ops, cpconv_ops
+from .. import ops, tenalg, pointwise_ops, rows_ops, kr_ops, cpconv_ops, cprows_ops
 from ..ops import contract
 
 
@@ -118,6 +118,10 @@ def _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation):
     # Khatri-Rao product of the kernel-mode factors, ONE element-wise launch (kr_ops); lambda rides in the taps, so the
     # output factor is used as it is (no 'or,r->or' scaling pass and no gradient kernel for it)
     kernel = [f.shape[0] for f in factors[2:]]
+    if cprows_ops.eligible(x, cp_tensor.weights, factors, bias, kernel, stride, padding, dilation):
+        # HBM-bound 3x3 layers on channels-last maps (config 3's 56^2 layers): the whole chain -- and, going back, every gradient --
+        # in one launch per direction, the R-channel intermediates in TMEM / shared memory (cprows_ops, csrc/cpconv_rows.cu)
+        return cprows_ops.cp_conv_rows_fused(x, cp_tensor.weights, factors, bias, stride[0])
     if kr_ops.eligible(factors[2:], cp_tensor.weights):
         taps_t = kr_ops.khatri_rao(factors[2:], cp_tensor.weights)                 # (prod k, R), taps-major
         f0 = factors[0]
