@@ -23,10 +23,11 @@
 namespace tlt {
 namespace cpr {
 
-constexpr int kThreads = 512;          // warps: 0 TMA | 1 MMA | 2 TMEM alloc | 3 spare | 4-11 depthwise (2 groups x 4) | 12-15 epilogue
+constexpr int kThreads = 512;          // warps: 0 TMA | 1 stage-1 MMA | 2 TMEM alloc | 3 stage-3 MMA | 4-11 depthwise (2 groups x 4) | 12-15 epilogue
 constexpr int NP = 112;                // positions per chunk = per stage-3 tile
 constexpr int NS = 3;                  // TMEM ring slots
-constexpr int XS = 3;                  // input-chunk smem stages
+constexpr int XS_MAX = 8;               // input-chunk smem stages: per configuration (Cfg::XS), as deep as shared memory allows
+constexpr int OS_MAX = 4;
 constexpr int kChunkBytes = NP * 128;  // one chunk, one 64-channel block
 constexpr int kZBytes = 2 * 128 * 128; // z2 tile: 2 blocks of 64 positions x 128 rank rows x 128 B
 constexpr int kDwWarps = 8;
@@ -56,6 +57,10 @@ template <int MODE, int STRIDE, int C_IN, int C_OUT> struct Cfg {
   // x (C_OUT channels).  In BWD_WEIGHT "in" is x (C_IN), the other tensor is dy (C_OUT channels).
   static constexpr int KB_OTHER = C_OTHER / 64;
   static constexpr int ND = (MODE == MODE_FWD && NS * NP + 2 * C_OUT <= 512) ? 2 : 1;
+  // TMA ring depths: HBM latency x the SM's share of the bandwidth is ~60 KB in flight; three 14 KB stages held the forward
+  // kernel at 2.1 TB/s (the depthwise warps waited on stage 1), so every configuration takes what its shared memory allows
+  static constexpr int XS = MODE == MODE_FWD ? (C_OUT == 64 ? 6 : 4) : 4;
+  static constexpr int OS = 3;
   // TMEM columns
   static constexpr int COL_D = NS * NP;                            // stage-3 accumulator(s)
   static constexpr int COL_C = NS * NP;                            // BWD_WEIGHT: dz2 centre
@@ -71,14 +76,14 @@ template <int MODE, int STRIDE, int C_IN, int C_OUT> struct Cfg {
   static constexpr int Y_STAGE = KB_OUT * kChunkBytes;
   static constexpr int OFF_O = OFF_Y + (HAS_OUT ? 2 * Y_STAGE : 0);
   static constexpr int O_STAGE = KB_OTHER * kChunkBytes;
-  static constexpr int OFF_BAR = OFF_O + (HAS_OTHER ? 2 * O_STAGE : 0);
+  static constexpr int OFF_BAR = OFF_O + (HAS_OTHER ? OS * O_STAGE : 0);
   static constexpr int SMEM = OFF_BAR + 512 + 1024;
 };
 
 // ---- barrier slots ---------------------------------------------------------------------------------------------------------
-enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS, B_SFULL = B_XEMPTY + XS, B_SEMPTY = B_SFULL + NS, B_ZFULL = B_SEMPTY + NS,
-       B_ZEMPTY = B_ZFULL + 2, B_DFULL = B_ZEMPTY + 2, B_DEMPTY = B_DFULL + 2, B_OFULL = B_DEMPTY + 2, B_OEMPTY = B_OFULL + 2,
-       B_WFULL = B_OEMPTY + 2, B_CFULL, B_CEMPTY, B_FFULL, B_COUNT };
+enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_MAX, B_SFULL = B_XEMPTY + XS_MAX, B_SEMPTY = B_SFULL + NS, B_ZFULL = B_SEMPTY + NS,
+       B_ZEMPTY = B_ZFULL + 2, B_DFULL = B_ZEMPTY + 2, B_DEMPTY = B_DFULL + 2, B_OFULL = B_DEMPTY + 2, B_OEMPTY = B_OFULL + OS_MAX,
+       B_WFULL = B_OEMPTY + OS_MAX, B_CFULL, B_CEMPTY, B_FFULL, B_COUNT };
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -127,6 +132,25 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 #define F(u) __uint_as_float(u)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// shared-memory matrix descriptors as (lo, hi) words: hi is the same for every operand here (SBO = 1024, version 1, SWIZZLE_128B),
+// lo = start address | leading byte offset, both in 16-byte units -- an operand's k-step / stage offset is one 32-bit add
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+      : "memory");
+}
 
 // z2 tile address of (position m, rank row r): [m / 64][r][128 B], 16-byte chunk index XOR (r & 7)  (SWIZZLE_128B)
 __device__ __forceinline__ uint32_t z_addr(uint32_t zbuf, int m, int r) {
@@ -264,7 +288,8 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
                    const __grid_constant__ CUtensorMap map_other, const __grid_constant__ CUtensorMap map_a,
                    const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b, const Params p) {
   using C = Cfg<MODE, STRIDE, C_IN, C_OUT>;
-  constexpr int G = C::G;
+  constexpr int G = C::G, XS = C::XS, OS = C::OS;
+  static_assert(XS <= XS_MAX && OS <= OS_MAX, "ring depth");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -289,8 +314,8 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(B_ZFULL + s), kDwWarps); mbar_init(bar(B_ZEMPTY + s), 1);
       mbar_init(bar(B_DFULL + s), 1); mbar_init(bar(B_DEMPTY + s), 4);
-      mbar_init(bar(B_OFULL + s), 1); mbar_init(bar(B_OEMPTY + s), 1);
     }
+    for (int s = 0; s < OS; ++s) { mbar_init(bar(B_OFULL + s), 1); mbar_init(bar(B_OEMPTY + s), 1); }
     mbar_init(bar(B_WFULL), 1); mbar_init(bar(B_CFULL), 1); mbar_init(bar(B_CEMPTY), kDwWarps); mbar_init(bar(B_FFULL), 1);
     fence_barrier_init();
   }
@@ -318,121 +343,138 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
 
   if (warp == 0) {
     // ===================================================================================== TMA producer
-    if (lane == 0 && has_work) {
-      uint32_t wbytes = C::KB_IN * 16384 + (C::HAS_OUT ? 2 * C_OUT * 128 : 0) + (MODE == MODE_BWD_WEIGHT ? C::KB_OUT * 16384 : 0);
-      mbar_expect_tx(bar(B_WFULL), wbytes);
-      for (int kb = 0; kb < C::KB_IN; ++kb) tma_load_2d(smem_base + C::OFF_A + kb * 16384, &map_a, bar(B_WFULL), kb * 64, 0);
-      if (MODE == MODE_BWD_WEIGHT)
-        for (int kb = 0; kb < C::KB_OUT; ++kb) tma_load_2d(smem_base + C::OFF_A2 + kb * 16384, &map_a2, bar(B_WFULL), kb * 64, 0);
-      if (C::HAS_OUT)
-        for (int rb = 0; rb < 2; ++rb) tma_load_2d(smem_base + C::OFF_B + rb * (C_OUT * 128), &map_b, bar(B_WFULL), rb * 64, 0);
+    if (has_work) {
+      if (elect_one()) {
+        const uint32_t wbytes = C::KB_IN * 16384 + (C::HAS_OUT ? 2 * C_OUT * 128 : 0) + (MODE == MODE_BWD_WEIGHT ? C::KB_OUT * 16384 : 0);
+        mbar_expect_tx(bar(B_WFULL), wbytes);
+        for (int kb = 0; kb < C::KB_IN; ++kb) tma_load_2d(smem_base + C::OFF_A + kb * 16384, &map_a, bar(B_WFULL), kb * 64, 0);
+        if (MODE == MODE_BWD_WEIGHT)
+          for (int kb = 0; kb < C::KB_OUT; ++kb) tma_load_2d(smem_base + C::OFF_A2 + kb * 16384, &map_a2, bar(B_WFULL), kb * 64, 0);
+        if (C::HAS_OUT)
+          for (int rb = 0; rb < 2; ++rb) tma_load_2d(smem_base + C::OFF_B + rb * (C_OUT * 128), &map_b, bar(B_WFULL), rb * 64, 0);
+      }
+      __syncwarp();
       uint32_t xq = 0, oq = 0;
       auto load_chunk = [&](int n, int c) {
         const uint32_t st = xq % XS;
         mbar_wait(bar(B_XEMPTY + st), ((xq / XS) & 1) ^ 1);
-        mbar_expect_tx(bar(B_XFULL + st), C::X_STAGE);
-        for (int kb = 0; kb < C::KB_IN; ++kb)
-          tma_load_4d(smem_base + C::OFF_X + st * C::X_STAGE + kb * kChunkBytes, &map_in, bar(B_XFULL + st), kb * 64, 0, 2 * c - 1, n);
+        if (elect_one()) {
+          mbar_expect_tx(bar(B_XFULL + st), C::X_STAGE);
+#pragma unroll
+          for (int kb = 0; kb < C::KB_IN; ++kb)
+            tma_load_4d(smem_base + C::OFF_X + st * C::X_STAGE + kb * kChunkBytes, &map_in, bar(B_XFULL + st), kb * 64, 0, 2 * c - 1, n);
+        }
+        __syncwarp();
         ++xq;
       };
       walk([&](int n, int u, int uu, int gi, bool fresh, bool last) {
         if (fresh) load_chunk(n, u);
         load_chunk(n, u + 1);
         if (C::HAS_OTHER) {
-          const uint32_t st = oq & 1;
-          mbar_wait(bar(B_OEMPTY + st), ((oq >> 1) & 1) ^ 1);
-          mbar_expect_tx(bar(B_OFULL + st), C::O_STAGE);
-          for (int kb = 0; kb < C::KB_OTHER; ++kb)
-            tma_load_4d(smem_base + C::OFF_O + st * C::O_STAGE + kb * kChunkBytes, &map_other, bar(B_OFULL + st), kb * 64, 0, 2 * u, n);
+          const uint32_t st = oq % OS;
+          mbar_wait(bar(B_OEMPTY + st), ((oq / OS) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar(B_OFULL + st), C::O_STAGE);
+#pragma unroll
+            for (int kb = 0; kb < C::KB_OTHER; ++kb)
+              tma_load_4d(smem_base + C::OFF_O + st * C::O_STAGE + kb * kChunkBytes, &map_other, bar(B_OFULL + st), kb * 64, 0, 2 * u, n);
+          }
+          __syncwarp();
           ++oq;
         }
       });
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================================================================================== MMA issuer
-    if (lane == 0 && has_work) {
+    // ===================================================================================== stage-1 issuer (z1 ring, dz2 centre)
+    // Two issuing warps (this one and warp 3): a single thread walking every wait and every descriptor of a unit took ~3.5 k
+    // cycles per unit and was the critical path of the first version; stage 1 now runs ahead as far as the TMEM ring allows.
+    if (has_work) {
       constexpr uint32_t idesc1 = make_idesc(128, NP, 0, 0);            // D1[r][pos] : A K-major, chunk K-major
-      constexpr uint32_t idesc2 = make_idesc(128, C_OUT, 1, 0);         // D2[pos][o] : z2 MN-major, B K-major
-      constexpr uint32_t idesc3 = make_idesc(128, C::HAS_OTHER ? C::C_OTHER : 64, 0, 1);   // dF[r][c] : z K-major (rows = rank), chunk MN-major
-      const int ksteps = p.KR / 16;
       mbar_wait(bar(B_WFULL), 0);
-      tc_fence_after();
-      uint32_t xq = 0, q = 0, zq = 0, oq = 0;
-      bool pending = false, first_w = true;
+      const uint32_t a_lo = desc_lo(smem_base + C::OFF_A, 16), a2_lo = desc_lo(smem_base + C::OFF_A2, 16);
+      const uint32_t x_lo = desc_lo(smem_base + C::OFF_X, 16), o_lo = desc_lo(smem_base + C::OFF_O, 16);
+      uint32_t xq = 0, q = 0, oq = 0;
       auto mma1 = [&]() {
         const uint32_t st = xq % XS, slot = q % NS;
         mbar_wait(bar(B_XFULL + st), (xq / XS) & 1);
         mbar_wait(bar(B_SEMPTY + slot), ((q / NS) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sx = smem_base + C::OFF_X + st * C::X_STAGE;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < C::KB_IN * 4; ++kk) {
-          const uint64_t da = make_smem_desc(smem_base + C::OFF_A + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(sx + (kk >> 2) * kChunkBytes + (kk & 3) * 32, 16, 1024);
-          umma_bf16(tmem_base + slot * NP, da, db, idesc1, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < C::KB_IN * 4; ++kk)
+            umma_lo(tmem_base + slot * NP, a_lo + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                    x_lo + ((st * C::X_STAGE + (kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4), idesc1, kk > 0 ? 1u : 0u);
+          umma_commit(bar(B_XEMPTY + st));
+          umma_commit(bar(B_SFULL + slot));
         }
-        umma_commit(bar(B_XEMPTY + st));
-        umma_commit(bar(B_SFULL + slot));
+        __syncwarp();
         ++xq; ++q;
-      };
-      auto finish_group = [&]() {          // stage 3 and / or the weight-gradient product of group zq
-        const uint32_t zb = zq & 1;
-        const uint32_t zbuf = smem_base + C::OFF_Z + zb * kZBytes;
-        mbar_wait(bar(B_ZFULL + zb), (zq >> 1) & 1);
-        if (C::HAS_OUT) {
-          const uint32_t dbuf = zq % C::ND;
-          mbar_wait(bar(B_DEMPTY + dbuf), ((zq / C::ND) & 1) ^ 1);
-          tc_fence_after();
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t da = make_smem_desc(zbuf + kk * 2048, 16384, 1024);
-            const uint64_t db = make_smem_desc(smem_base + C::OFF_B + (kk >> 2) * (C_OUT * 128) + (kk & 3) * 32, 16, 1024);
-            umma_bf16(tmem_base + C::COL_D + dbuf * C_OUT, da, db, idesc2, kk > 0 ? 1u : 0u);
-          }
-          umma_commit(bar(B_DFULL + dbuf));
-        }
-        if (C::HAS_OTHER) {
-          const uint32_t ost = zq & 1;       // stride 1: group == unit, the other-tensor stage of this unit
-          if (MODE == MODE_BWD_DATA) mbar_wait(bar(B_OFULL + ost), (zq >> 1) & 1);   // (BWD_WEIGHT waited in mma_centre)
-          tc_fence_after();
-          const uint32_t so = smem_base + C::OFF_O + ost * C::O_STAGE;
-#pragma unroll
-          for (int s = 0; s < NP / 16; ++s) {
-            const uint64_t da = make_smem_desc(zbuf + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(so + s * 2048, kChunkBytes, 1024);
-            umma_bf16(tmem_base + C::COL_F, da, db, idesc3, (first_w && s == 0) ? 0u : 1u);
-          }
-          first_w = false;
-          umma_commit(bar(B_OEMPTY + ost));
-        }
-        umma_commit(bar(B_ZEMPTY + zb));
-        ++zq;
       };
       walk([&](int n, int u, int uu, int gi, bool fresh, bool last) {
         if (fresh) mma1();
         mma1();
         if (MODE == MODE_BWD_WEIGHT) {       // dz2 of the unit's own rows: D[r][pos] = F_out^T . dy chunk
-          const uint32_t ost = oq & 1;
-          mbar_wait(bar(B_OFULL + ost), (oq >> 1) & 1);
+          const uint32_t ost = oq % OS;
+          mbar_wait(bar(B_OFULL + ost), (oq / OS) & 1);
           mbar_wait(bar(B_CEMPTY), (oq & 1) ^ 1);
           tc_fence_after();
-          const uint32_t so = smem_base + C::OFF_O + ost * C::O_STAGE;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < C::KB_OUT * 4; ++kk) {
-            const uint64_t da = make_smem_desc(smem_base + C::OFF_A2 + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(so + (kk >> 2) * kChunkBytes + (kk & 3) * 32, 16, 1024);
-            umma_bf16(tmem_base + C::COL_C, da, db, idesc1, kk > 0 ? 1u : 0u);
+            for (int kk = 0; kk < C::KB_OUT * 4; ++kk)
+              umma_lo(tmem_base + C::COL_C, a2_lo + (((kk >> 2) * 16384 + (kk & 3) * 32) >> 4),
+                      o_lo + ((ost * C::O_STAGE + (kk >> 2) * kChunkBytes + (kk & 3) * 32) >> 4), idesc1, kk > 0 ? 1u : 0u);
+            umma_commit(bar(B_CFULL));
           }
-          umma_commit(bar(B_CFULL));
+          __syncwarp();
           ++oq;
         }
-        if (uu == 0 && pending) { finish_group(); pending = false; }
-        if (uu == G - 1) pending = true;
       });
-      if (pending) finish_group();
-      umma_commit(bar(B_FFULL));
     }
-    __syncwarp();
+  } else if (warp == 3) {
+    // ===================================================================================== stage-3 / weight-gradient issuer
+    if (has_work) {
+      constexpr uint32_t idesc2 = make_idesc(128, C_OUT, 1, 0);         // D2[pos][o] : z2 MN-major, B K-major
+      constexpr uint32_t idesc3 = make_idesc(128, C::HAS_OTHER ? C::C_OTHER : 64, 0, 1);   // dF[r][c] : z K-major (rows = rank), chunk MN-major
+      const int ksteps = p.KR / 16;
+      mbar_wait(bar(B_WFULL), 0);
+      const uint32_t zm_lo = desc_lo(smem_base + C::OFF_Z, 16384), zk_lo = desc_lo(smem_base + C::OFF_Z, 16);
+      const uint32_t b_lo = desc_lo(smem_base + C::OFF_B, 16), o_lo = desc_lo(smem_base + C::OFF_O, kChunkBytes);
+      bool first_w = true;
+      for (uint32_t zq = 0; zq < (uint32_t)(g_end - g_begin); ++zq) {      // stage 3 and / or the weight-gradient product of group zq
+        const uint32_t zb = zq & 1;
+        mbar_wait(bar(B_ZFULL + zb), (zq >> 1) & 1);
+        if (C::HAS_OUT) {
+          const uint32_t dbuf = zq % C::ND;
+          mbar_wait(bar(B_DEMPTY + dbuf), ((zq / C::ND) & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_lo(tmem_base + C::COL_D + dbuf * C_OUT, zm_lo + ((zb * kZBytes + kk * 2048) >> 4),
+                      b_lo + (((kk >> 2) * (C_OUT * 128) + (kk & 3) * 32) >> 4), idesc2, kk > 0 ? 1u : 0u);
+            umma_commit(bar(B_DFULL + dbuf));
+          }
+          __syncwarp();
+        }
+        if (C::HAS_OTHER) {
+          const uint32_t ost = zq % OS;      // stride 1: group == unit, the other-tensor stage of this unit
+          mbar_wait(bar(B_OFULL + ost), (zq / OS) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < NP / 16; ++s)
+              umma_lo(tmem_base + C::COL_F, zk_lo + ((zb * kZBytes + (s >> 2) * 16384 + (s & 3) * 32) >> 4),
+                      o_lo + ((ost * C::O_STAGE + s * 2048) >> 4), idesc3, (first_w && s == 0) ? 0u : 1u);
+            umma_commit(bar(B_OEMPTY + ost));
+          }
+          __syncwarp();
+          first_w = false;
+        }
+        if (elect_one()) umma_commit(bar(B_ZEMPTY + zb));
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(bar(B_FFULL));
+      __syncwarp();
+    }
   } else if (warp >= 4 && warp < 4 + kDwWarps) {
     // ===================================================================================== depthwise stage
     const int wg = (warp - 4) >> 2, quarter = warp & 3;
@@ -490,6 +532,7 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     const int m = quarter * 32 + lane;                      // position of the tile = TMEM lane
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     if (C::HAS_OUT) {
+      const bool has_bias = p.bias != nullptr;
       uint32_t gq = 0;
       for (int g = g_begin; g < g_end; ++g, ++gq) {
         const int n = g / p.gpi, gi = g - n * p.gpi;
@@ -515,7 +558,11 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
             for (int j = 0; j < 4; ++j) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = F(v[8 * j + e]) + (p.bias ? __ldg(p.bias + cb * 32 + 8 * j + e) : 0.f);
+              for (int e = 0; e < 8; ++e) f[e] = F(v[8 * j + e]);
+              if (has_bias) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += __ldg(p.bias + cb * 32 + 8 * j + e);
+              }
               st_shared_v4(row + ((((uint32_t)((cb & 1) * 4 + j)) ^ (uint32_t)(m & 7)) << 4), pack_bf16x2(f[0], f[1]),
                            pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
             }
