@@ -170,66 +170,82 @@ __device__ __forceinline__ void z_store8(uint32_t zbuf, int m, int r, const floa
   }
 }
 
+// ---- packed fp32 pairs -------------------------------------------------------------------------------------------------------
+// A three-register FFMA issues every other cycle per SM sub-partition on this part; fma.rn.f32x2 does two FMAs in the same slot.
+// Adjacent TMEM columns land in adjacent registers (tcgen05.ld .x8), so a pair of columns IS an aligned 64-bit register pair.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 pku(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // --------------------------------------------------------------------------------------------------------------------------------
 // Depthwise stage of one output row, stride 1.  t0/t1/t2: TMEM addresses (lane bits included) of column 0 of input rows h-1, h,
 // h+1; the thread's channel is its lane.  z2[w] = sum_j kw[j] v[w + j - 1],  v[w] = sum_i kh[i] z1[h + i - 1][w].
 // Column pieces of 8: the loads of piece p+1 are in flight while piece p is finished; outputs lag one column behind the loads,
-// so a 16-byte group of 8 outputs completes when the first column of the next piece arrives.
-// WGRAD (BWD_WEIGHT): tc = dz2 of row h (same columns); dT[i][j] += dz2[w] * z1[h + i - 1][w + j - 1].
+// so a 16-byte group of 8 outputs completes when the first column of the next piece arrives.  Column pairs are packed (f2):
+// H pass = 3 packed ops per pair; W pass = 2 packed ops (outer taps, both operands even-aligned pairs) + 2 scalar FMAs (centre tap).
+// WGRAD (BWD_WEIGHT): tc = dz2 of row h (same columns); dT[3 i + j] += dz2[w] * z1[h + i - 1][w + j - 1].  The z1 operand is
+// always an even-aligned pair; dz2 comes even-aligned (j = 1) and odd-aligned (a second tcgen05.ld one column further; j = 0, 2).
+// kk: taps duplicated into pairs (kh0 kh1 kh2 kw0 kw1 kw2); k: the scalar taps.
 // --------------------------------------------------------------------------------------------------------------------------------
 template <bool WGRAD>
-__device__ __forceinline__ void dw_row_s1(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t tc, const float (&k)[6], uint32_t zbuf,
-                                          int m_base, int r, float (&dT)[9]) {
-  uint32_t a[8], b[8], c[8], d[8];
+__device__ __forceinline__ void dw_row_s1(uint32_t t0, uint32_t t1, uint32_t t2, uint32_t tc, const f2 (&kk)[6], const float (&k)[6],
+                                          uint32_t zbuf, int m_base, int r, f2 (&dT)[9]) {
+  uint32_t a[8], b[8], c[8], d[8], e[8];
   float pend[7];
-  float v6 = 0.f, v7 = 0.f;                       // v[8p-2], v[8p-1]
-  float a6 = 0.f, a7 = 0.f, b6 = 0.f, b7 = 0.f, c6 = 0.f, c7 = 0.f, d7 = 0.f;   // WGRAD carries: z1[.][8p-2], z1[.][8p-1], dz2[8p-1]
+  f2 vp = 0ull;                                    // (v[8p-2], v[8p-1])
+  f2 dprev = 0ull;                                 // WGRAD: (dz2[8p-1], dz2[8p])
   tmem_ld8(t0, a); tmem_ld8(t1, b); tmem_ld8(t2, c);
-  if (WGRAD) tmem_ld8(tc, d);
+  if (WGRAD) { tmem_ld8(tc, d); tmem_ld8(tc + 1, e); }
 #pragma unroll
   for (int p = 0; p < 7; ++p) {
     tmem_wait8(a); tmem_wait8(b); tmem_wait8(c);
-    if (WGRAD) tmem_wait8(d);
-    float v[8], za[8], zb[8], zc[8], dd[8];
+    if (WGRAD) { tmem_wait8(d); tmem_wait8(e); }
+    f2 za[4], zb[4], zc[4], v[4], de[4], dod[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      za[i] = F(a[i]); zb[i] = F(b[i]); zc[i] = F(c[i]);
-      v[i] = fmaf(k[2], zc[i], fmaf(k[1], zb[i], k[0] * za[i]));
-      if (WGRAD) dd[i] = F(d[i]);
+    for (int i = 0; i < 4; ++i) {
+      za[i] = pku(a[2 * i], a[2 * i + 1]); zb[i] = pku(b[2 * i], b[2 * i + 1]); zc[i] = pku(c[2 * i], c[2 * i + 1]);
+      v[i] = fma2(kk[2], zc[i], fma2(kk[1], zb[i], mul2(kk[0], za[i])));
+      if (WGRAD) {
+        de[i] = pku(d[2 * i], d[2 * i + 1]);
+        dod[i] = pku(e[2 * i], (p == 6 && i == 3) ? 0u : e[2 * i + 1]);      // column 56 does not exist
+      }
     }
+    if (WGRAD && p == 0) dprev = pku(0u, d[0]);
     if (p + 1 < 7) {
       tmem_ld8(t0 + 8 * (p + 1), a); tmem_ld8(t1 + 8 * (p + 1), b); tmem_ld8(t2 + 8 * (p + 1), c);
-      if (WGRAD) tmem_ld8(tc + 8 * (p + 1), d);
+      if (WGRAD) { tmem_ld8(tc + 8 * (p + 1), d); tmem_ld8(tc + 8 * (p + 1) + 1, e); }
     }
     if (WGRAD) {
-      // centre column 8p-1 (its right neighbour is column 8p = index 0 of this piece), then centres 8p .. 8p+6
-      dT[0] = fmaf(d7, a6, dT[0]); dT[1] = fmaf(d7, a7, dT[1]); dT[2] = fmaf(d7, za[0], dT[2]);
-      dT[3] = fmaf(d7, b6, dT[3]); dT[4] = fmaf(d7, b7, dT[4]); dT[5] = fmaf(d7, zb[0], dT[5]);
-      dT[6] = fmaf(d7, c6, dT[6]); dT[7] = fmaf(d7, c7, dT[7]); dT[8] = fmaf(d7, zc[0], dT[8]);
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const float l0 = i == 0 ? a7 : za[i - 1], l1 = i == 0 ? b7 : zb[i - 1], l2 = i == 0 ? c7 : zc[i - 1];
-        dT[0] = fmaf(dd[i], l0, dT[0]); dT[1] = fmaf(dd[i], za[i], dT[1]); dT[2] = fmaf(dd[i], za[i + 1], dT[2]);
-        dT[3] = fmaf(dd[i], l1, dT[3]); dT[4] = fmaf(dd[i], zb[i], dT[4]); dT[5] = fmaf(dd[i], zb[i + 1], dT[5]);
-        dT[6] = fmaf(dd[i], l2, dT[6]); dT[7] = fmaf(dd[i], zc[i], dT[7]); dT[8] = fmaf(dd[i], zc[i + 1], dT[8]);
+      for (int i = 0; i < 4; ++i) {
+        const f2 dl = i == 0 ? dprev : dod[i - 1];     // centres one column left of the z pair  (tap j = 2)
+        dT[0] = fma2(dod[i], za[i], dT[0]); dT[1] = fma2(de[i], za[i], dT[1]); dT[2] = fma2(dl, za[i], dT[2]);
+        dT[3] = fma2(dod[i], zb[i], dT[3]); dT[4] = fma2(de[i], zb[i], dT[4]); dT[5] = fma2(dl, zb[i], dT[5]);
+        dT[6] = fma2(dod[i], zc[i], dT[6]); dT[7] = fma2(de[i], zc[i], dT[7]); dT[8] = fma2(dl, zc[i], dT[8]);
       }
-      a6 = za[6]; a7 = za[7]; b6 = zb[6]; b7 = zb[7]; c6 = zc[6]; c7 = zc[7]; d7 = dd[7];
+      dprev = dod[3];
     }
-    const float o_prev = fmaf(k[5], v[0], fmaf(k[4], v7, k[3] * v6));        // column 8p-1
+    // outputs 8p-1 .. 8p+6 as pairs (o[8p+2i-1], o[8p+2i]) = kw0 (v[2i-2], v[2i-1]) + kw2 (v[2i], v[2i+1]) + kw1 (v[2i-1], v[2i])
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const f2 vl = i == 0 ? vp : v[i - 1];
+      const f2 t = fma2(kk[5], v[i], mul2(kk[3], vl));
+      o[2 * i] = fmaf(k[4], hi_of(vl), lo_of(t));
+      o[2 * i + 1] = fmaf(k[4], lo_of(v[i]), hi_of(t));
+    }
     if (p > 0)
       st_shared_v4(z_addr(zbuf, m_base + 8 * (p - 1), r), pack_bf16x2(pend[0], pend[1]), pack_bf16x2(pend[2], pend[3]),
-                   pack_bf16x2(pend[4], pend[5]), pack_bf16x2(pend[6], o_prev));
-    pend[0] = fmaf(k[5], v[1], fmaf(k[4], v[0], k[3] * v7));
+                   pack_bf16x2(pend[4], pend[5]), pack_bf16x2(pend[6], o[0]));
 #pragma unroll
-    for (int i = 1; i < 7; ++i) pend[i] = fmaf(k[5], v[i + 1], fmaf(k[4], v[i], k[3] * v[i - 1]));
-    v6 = v[6]; v7 = v[7];
+    for (int i = 0; i < 7; ++i) pend[i] = o[i + 1];
+    vp = v[3];
   }
-  if (WGRAD) {   // centre column 55: right neighbours are the zero padding
-    dT[0] = fmaf(d7, a6, dT[0]); dT[1] = fmaf(d7, a7, dT[1]);
-    dT[3] = fmaf(d7, b6, dT[3]); dT[4] = fmaf(d7, b7, dT[4]);
-    dT[6] = fmaf(d7, c6, dT[6]); dT[7] = fmaf(d7, c7, dT[7]);
-  }
-  const float o_last = fmaf(k[4], v7, k[3] * v6);                             // column 55
+  const float o_last = fmaf(k[4], hi_of(vp), k[3] * lo_of(vp));               // column 55
   st_shared_v4(z_addr(zbuf, m_base + 48, r), pack_bf16x2(pend[0], pend[1]), pack_bf16x2(pend[2], pend[3]),
                pack_bf16x2(pend[4], pend[5]), pack_bf16x2(pend[6], o_last));
 }
@@ -238,8 +254,8 @@ __device__ __forceinline__ void dw_row_s1(uint32_t t0, uint32_t t1, uint32_t t2,
 // Depthwise stage of one output row, stride 2 (28 outputs from 56 inputs): out[wo] = sum_j kw[j] v[2 wo + j - 1].  Output pieces
 // of 8 = input pieces of 16; pieces [p_begin, p_end) of 4 (the last one holds 4 outputs from 8 input columns).
 // --------------------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dw_row_s2(uint32_t t0, uint32_t t1, uint32_t t2, const float (&k)[6], uint32_t zbuf, int m_base,
-                                          int r, int p_begin, int p_end) {
+__device__ __forceinline__ void dw_row_s2(uint32_t t0, uint32_t t1, uint32_t t2, const f2 (&kk)[6], const float (&k)[6], uint32_t zbuf,
+                                          int m_base, int r, int p_begin, int p_end) {
   float vl = 0.f;                                   // v[16p - 1]
   if (p_begin > 0) {
     uint32_t a[1], b[1], c[1];
@@ -253,24 +269,26 @@ __device__ __forceinline__ void dw_row_s2(uint32_t t0, uint32_t t1, uint32_t t2,
       uint32_t a[16], b[16], c[16];
       tmem_ld16(t0 + 16 * p, a); tmem_ld16(t1 + 16 * p, b); tmem_ld16(t2 + 16 * p, c);
       tmem_wait16(a); tmem_wait16(b); tmem_wait16(c);
-      float v[16];
+      f2 v[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaf(k[2], F(c[i]), fmaf(k[1], F(b[i]), k[0] * F(a[i])));
+      for (int i = 0; i < 8; ++i)
+        v[i] = fma2(kk[2], pku(c[2 * i], c[2 * i + 1]), fma2(kk[1], pku(b[2 * i], b[2 * i + 1]), mul2(kk[0], pku(a[2 * i], a[2 * i + 1]))));
       float o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(k[5], v[2 * i + 1], fmaf(k[4], v[2 * i], k[3] * (i == 0 ? vl : v[2 * i - 1])));
-      vl = v[15];
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(k[5], hi_of(v[i]), fmaf(k[4], lo_of(v[i]), k[3] * (i == 0 ? vl : hi_of(v[i - 1]))));
+      vl = hi_of(v[7]);
       z_store8(zbuf, m_base + 8 * p, r, o);
     } else {
       uint32_t a[8], b[8], c[8];
       tmem_ld8(t0 + 48, a); tmem_ld8(t1 + 48, b); tmem_ld8(t2 + 48, c);
       tmem_wait8(a); tmem_wait8(b); tmem_wait8(c);
-      float v[8];
+      f2 v[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = fmaf(k[2], F(c[i]), fmaf(k[1], F(b[i]), k[0] * F(a[i])));
+      for (int i = 0; i < 4; ++i)
+        v[i] = fma2(kk[2], pku(c[2 * i], c[2 * i + 1]), fma2(kk[1], pku(b[2 * i], b[2 * i + 1]), mul2(kk[0], pku(a[2 * i], a[2 * i + 1]))));
       float o[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = fmaf(k[5], v[2 * i + 1], fmaf(k[4], v[2 * i], k[3] * (i == 0 ? vl : v[2 * i - 1])));
+      for (int i = 0; i < 4; ++i) o[i] = fmaf(k[5], hi_of(v[i]), fmaf(k[4], lo_of(v[i]), k[3] * (i == 0 ? vl : hi_of(v[i - 1]))));
       st_shared_v2(z_addr4(zbuf, m_base + 24, r), pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
     }
   }
@@ -282,7 +300,7 @@ __device__ __forceinline__ void dw_row_s2(uint32_t t0, uint32_t t1, uint32_t t2,
 //   stride 2: unit j = output row j; it reads chunk j (rows 2j-1, 2j) and the first row of chunk j+1; group = 4 units.
 // A CTA owns a contiguous range of the batch's groups; the first unit of a range / of an image starts a fresh chunk pair.
 // --------------------------------------------------------------------------------------------------------------------------------
-template <int MODE, int STRIDE, int C_IN, int C_OUT>
+template <int MODE, int STRIDE, int C_IN, int C_OUT, bool BIAS>
 __global__ void __launch_bounds__(kThreads, 1)
 cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out,
                    const __grid_constant__ CUtensorMap map_other, const __grid_constant__ CUtensorMap map_a,
@@ -482,11 +500,12 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     const bool active = quarter * 32 < p.KR;
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     float k[6];
+    f2 kk[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) k[i] = __ldg(p.taps + i * 128 + r);
-    float dT[9];
+    for (int i = 0; i < 6; ++i) { k[i] = __ldg(p.taps + i * 128 + r); kk[i] = pk(k[i], k[i]); }
+    f2 dT[9];                                       // (sum over even columns, sum over odd columns)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) dT[i] = 0.f;
+    for (int i = 0; i < 9; ++i) dT[i] = 0ull;
     uint32_t q = 0, zq = 0, uq = 0, qb_prev = 0;
     walk([&](int n, int u, int uu, int gi, bool fresh, bool last) {
       uint32_t qa, qb;
@@ -504,10 +523,10 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
           // rows 2u-1, 2u | 2u+1, 2u+2 ; this warp group's output row is 2u + wg
           const uint32_t t0 = wg == 0 ? ta : ta + 56, t1 = wg == 0 ? ta + 56 : tb, t2 = wg == 0 ? tb : tb + 56;
           const uint32_t tc = tmem_base + lane_bits + C::COL_C + wg * 56;
-          dw_row_s1<MODE == MODE_BWD_WEIGHT>(t0, t1, t2, tc, k, zbuf, wg * 56, r, dT);
+          dw_row_s1<MODE == MODE_BWD_WEIGHT>(t0, t1, t2, tc, kk, k, zbuf, wg * 56, r, dT);
         } else {
           // rows 2u-1, 2u (chunk a) and 2u+1 (first row of chunk b); warp group 0 takes outputs 0..15, group 1 outputs 16..27
-          dw_row_s2(ta, ta + 56, tb, k, zbuf, uu * 28, r, wg * 2, wg * 2 + 2);
+          dw_row_s2(ta, ta + 56, tb, kk, k, zbuf, uu * 28, r, wg * 2, wg * 2 + 2);
         }
       }
       tc_fence_before();
@@ -524,7 +543,7 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     });
     if (MODE == MODE_BWD_WEIGHT && active && r < p.R) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) red_add_f32(p.dT + i * 128 + r, dT[i]);
+      for (int i = 0; i < 9; ++i) red_add_f32(p.dT + i * 128 + r, lo_of(dT[i]) + hi_of(dT[i]));
     }
   } else if (warp >= 12) {
     // ===================================================================================== epilogue
@@ -532,7 +551,6 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     const int m = quarter * 32 + lane;                      // position of the tile = TMEM lane
     const uint32_t lane_bits = (uint32_t)(quarter * 32) << 16;
     if (C::HAS_OUT) {
-      const bool has_bias = p.bias != nullptr;
       uint32_t gq = 0;
       for (int g = g_begin; g < g_end; ++g, ++gq) {
         const int n = g / p.gpi, gi = g - n * p.gpi;
@@ -559,7 +577,7 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = F(v[8 * j + e]);
-              if (has_bias) {
+              if (BIAS) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] += __ldg(p.bias + cb * 32 + 8 * j + e);
               }
@@ -741,11 +759,17 @@ static int launch(const tlt_cpconv_rows_desc* d, const void* in, void* out, cons
   p.gpi = Ho * Wo / NP;
   p.groups_total = B * p.gpi;
   p.taps = taps; p.bias = bias; p.dF = dF; p.dT = dT;
-  auto kern = cpconv_rows_kernel<MODE, STRIDE, C_IN, C_OUT>;
-  TLT_ENSURE_SMEM(kern, C::SMEM);
   int grid = num_sms();
   if (grid > p.groups_total) grid = p.groups_total;
-  kern<<<grid, kThreads, C::SMEM, st>>>(m_in, m_out, m_other, m_a, m_a2, m_b, p);
+  if (MODE == MODE_FWD && bias != nullptr) {
+    auto kern = cpconv_rows_kernel<MODE, STRIDE, C_IN, C_OUT, MODE == MODE_FWD>;
+    TLT_ENSURE_SMEM(kern, C::SMEM);
+    kern<<<grid, kThreads, C::SMEM, st>>>(m_in, m_out, m_other, m_a, m_a2, m_b, p);
+  } else {
+    auto kern = cpconv_rows_kernel<MODE, STRIDE, C_IN, C_OUT, false>;
+    TLT_ENSURE_SMEM(kern, C::SMEM);
+    kern<<<grid, kThreads, C::SMEM, st>>>(m_in, m_out, m_other, m_a, m_a2, m_b, p);
+  }
   return check_launch("cpconv_rows_kernel");
 }
 
