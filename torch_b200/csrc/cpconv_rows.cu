@@ -18,20 +18,16 @@
 // The weight-gradient accumulators live in TMEM for the whole kernel ([rank lane][channel column]) and are flushed once per CTA
 // with fp32 reductions; the nine tap gradients are per-thread registers (thread = rank channel).
 // Stride 2 (FWD only): a unit is one output row (28 positions), four units fill one stage-3 tile.
-#include "tc_common.cuh"
+#include "cprows_common.cuh"
 
 namespace tlt {
 namespace cpr {
 
 constexpr int kThreads = 512;          // warps: 0 TMA | 1 stage-1 MMA | 2 TMEM alloc | 3 stage-3 MMA | 4-11 depthwise (2 groups x 4) | 12-15 epilogue
-constexpr int NP = 112;                // positions per chunk = per stage-3 tile
 constexpr int NS = 3;                  // TMEM ring slots
 constexpr int XS_MAX = 8;               // input-chunk smem stages: per configuration (Cfg::XS), as deep as shared memory allows
 constexpr int OS_MAX = 4;
-constexpr int kChunkBytes = NP * 128;  // one chunk, one 64-channel block
 constexpr int kZBytes = 2 * 128 * 128; // z2 tile: 2 blocks of 64 positions x 128 rank rows x 128 B
-constexpr int kDwWarps = 8;
-constexpr int kEpiThreads = 128;
 
 enum { MODE_FWD = 0, MODE_BWD_DATA = 1, MODE_BWD_WEIGHT = 2 };
 
@@ -84,102 +80,6 @@ template <int MODE, int STRIDE, int C_IN, int C_OUT> struct Cfg {
 enum { B_XFULL = 0, B_XEMPTY = B_XFULL + XS_MAX, B_SFULL = B_XEMPTY + XS_MAX, B_SEMPTY = B_SFULL + NS, B_ZFULL = B_SEMPTY + NS,
        B_ZEMPTY = B_ZFULL + 2, B_DFULL = B_ZEMPTY + 2, B_DEMPTY = B_DFULL + 2, B_OFULL = B_DEMPTY + 2, B_OEMPTY = B_OFULL + OS_MAX,
        B_WFULL = B_OEMPTY + OS_MAX, B_CFULL, B_CEMPTY, B_FFULL, B_COUNT };
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr) : "memory");
-}
-// tcgen05.wait::ld that also "touches" the loaded registers, so no consumer of them can be scheduled above the wait
-__device__ __forceinline__ void tmem_wait8(uint32_t* v) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
-}
-__device__ __forceinline__ void tmem_wait16(uint32_t* v) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
-}
-__device__ __forceinline__ void tmem_wait1(uint32_t* v) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v[0]) :: "memory");
-}
-__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void red_add_f32(float* p, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-#define F(u) __uint_as_float(u)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-// shared-memory matrix descriptors as (lo, hi) words: hi is the same for every operand here (SBO = 1024, version 1, SWIZZLE_128B),
-// lo = start address | leading byte offset, both in 16-byte units -- an operand's k-step / stage offset is one 32-bit add
-constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16); }
-__device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
-      : "memory");
-}
-
-// z2 tile address of (position m, rank row r): [m / 64][r][128 B], 16-byte chunk index XOR (r & 7)  (SWIZZLE_128B)
-__device__ __forceinline__ uint32_t z_addr(uint32_t zbuf, int m, int r) {
-  return zbuf + (uint32_t)((m >> 6) * 16384 + r * 128) + ((uint32_t)((((m & 63) >> 3) ^ (r & 7))) << 4);
-}
-
-// 8-byte slot of positions m .. m+3 (m a multiple of 4) of rank row r
-__device__ __forceinline__ uint32_t z_addr4(uint32_t zbuf, int m, int r) { return z_addr(zbuf, m, r) | (uint32_t)((m & 4) << 1); }
-// eight consecutive outputs starting at position m (a multiple of 4): one 16-byte store when aligned, two 8-byte stores otherwise
-__device__ __forceinline__ void z_store8(uint32_t zbuf, int m, int r, const float (&o)[8]) {
-  const uint32_t w0 = pack_bf16x2(o[0], o[1]), w1 = pack_bf16x2(o[2], o[3]), w2 = pack_bf16x2(o[4], o[5]), w3 = pack_bf16x2(o[6], o[7]);
-  if ((m & 7) == 0) {
-    st_shared_v4(z_addr(zbuf, m, r), w0, w1, w2, w3);
-  } else {
-    st_shared_v2(z_addr4(zbuf, m, r), w0, w1);
-    st_shared_v2(z_addr4(zbuf, m + 4, r), w2, w3);
-  }
-}
-
-// ---- packed fp32 pairs -------------------------------------------------------------------------------------------------------
-// A three-register FFMA issues every other cycle per SM sub-partition on this part; fma.rn.f32x2 does two FMAs in the same slot.
-// Adjacent TMEM columns land in adjacent registers (tcgen05.ld .x8), so a pair of columns IS an aligned 64-bit register pair.
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f2 pku(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // --------------------------------------------------------------------------------------------------------------------------------
 // Depthwise stage of one output row, stride 1.  t0/t1/t2: TMEM addresses (lane bits included) of column 0 of input rows h-1, h,
@@ -626,14 +526,27 @@ cpconv_rows_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
 // --------------------------------------------------------------------------------------------------------------------------------
 // Operand packing: one launch builds every matrix the three kernels read, zero-padded to the tcgen05 tile shapes.
 //   ws (bf16): A_in [128][C_in] = F_in^T | B_in [C_in][128] = F_in | A_out [128][C_out] = F_out^T | B_out [C_out][128] = F_out
-//   then fp32 taps_fwd [6][128] (kh0 kh1 kh2, lambda kw0, lambda kw1, lambda kw2) and taps_bwd [6][128] (both reversed).
+//   then fp32 taps_fwd [6][128] (kh0 kh1 kh2, lambda kw0, lambda kw1, lambda kw2) and taps_bwd [6][128] (both reversed),
+//   then (bf16) the tap-folded stage-1 operands of the second-generation kernels (cpconv_rows2.cu):
+//   A3_fwd [3][128][C_in] = kh[i, r] F_in[c, r]   and   A3_bwd [3][128][C_out] = lambda_r kw[2 - i, r] F_out[o, r].
 // --------------------------------------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const __nv_bfloat16* __restrict__ f_in, const __nv_bfloat16* __restrict__ f_out,
                             const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kw,
                             const __nv_bfloat16* __restrict__ lam, int c_in, int c_out, int R, __nv_bfloat16* __restrict__ ws,
-                            float* __restrict__ taps) {
+                            float* __restrict__ taps, __nv_bfloat16* __restrict__ a3) {
   const int n_in = 128 * c_in, n_out = 128 * c_out;
   const int total = 2 * n_in + 2 * n_out + 2 * 6 * 128;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * (n_in + n_out); i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < 3 * n_in) {
+      const int t = i / n_in, j = i - t * n_in, r = j / c_in, c = j - r * c_in;
+      if (r < R) v = __bfloat162float(kh[t * R + r]) * __bfloat162float(f_in[c * R + r]);
+    } else {
+      const int i2 = i - 3 * n_in, t = i2 / n_out, j = i2 - t * n_out, r = j / c_out, c = j - r * c_out;
+      if (r < R) v = __bfloat162float(lam[r]) * __bfloat162float(kw[(2 - t) * R + r]) * __bfloat162float(f_out[c * R + r]);
+    }
+    a3[i] = __float2bfloat16_rn(v);
+  }
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int j = i;
@@ -658,7 +571,7 @@ __global__ void pack_kernel(const __nv_bfloat16* __restrict__ f_in, const __nv_b
 // Gradient finalisation: fp32 accumulators -> the five parameter gradients (bf16).
 //   acc: dF_in [C_in][128] | dF_out [C_out][128] | dT [9][128]   (dT[3 i + j][r] = sum dz2 * z1(+tap i, j))
 __global__ void finalize_kernel(const float* __restrict__ acc, const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kw,
-                                const __nv_bfloat16* __restrict__ lam, int c_in, int c_out, int R, __nv_bfloat16* __restrict__ g_fout,
+                                const __nv_bfloat16* __restrict__ lam, int c_in, int c_out, int R, int folded, __nv_bfloat16* __restrict__ g_fout,
                                 __nv_bfloat16* __restrict__ g_fin, __nv_bfloat16* __restrict__ g_kh, __nv_bfloat16* __restrict__ g_kw,
                                 __nv_bfloat16* __restrict__ g_lam) {
   const int n_in = c_in * R, n_out = c_out * R;
@@ -678,8 +591,9 @@ __global__ void finalize_kernel(const float* __restrict__ acc, const __nv_bfloat
     float gl = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const float gh = l * (w[0] * t[3 * a] + w[1] * t[3 * a + 1] + w[2] * t[3 * a + 2]);      // d kh[a]
-      const float gwl = h[0] * t[a] + h[1] * t[3 + a] + h[2] * t[6 + a];                        // d (lambda kw[a])
+      // folded kernels: t[0..2] = d (lambda kw[a]) from BWD_WEIGHT, t[3..5] = d kh[2 - a] from the column-order BWD_DATA
+      const float gh = folded ? t[3 + (2 - a)] : l * (w[0] * t[3 * a] + w[1] * t[3 * a + 1] + w[2] * t[3 * a + 2]);      // d kh[a]
+      const float gwl = folded ? t[a] : h[0] * t[a] + h[1] * t[3 + a] + h[2] * t[6 + a];                                  // d (lambda kw[a])
       g_kh[a * R + r] = __float2bfloat16_rn(gh);
       g_kw[a * R + r] = __float2bfloat16_rn(l * gwl);
       gl += w[a] * gwl;
@@ -714,7 +628,7 @@ static int make_map4d(CUtensorMap* map, const void* ptr, int64_t c, int64_t w, i
 }
 
 struct Ws {        // byte offsets into the packed-operand workspace
-  size_t a_in, b_in, a_out, b_out, taps_fwd, taps_bwd, total;
+  size_t a_in, b_in, a_out, b_out, taps_fwd, taps_bwd, a3_fwd, a3_bwd, total;
 };
 static Ws ws_layout(int c_in, int c_out) {
   Ws w;
@@ -724,7 +638,9 @@ static Ws ws_layout(int c_in, int c_out) {
   w.b_out = w.a_out + (size_t)128 * c_out * 2;
   w.taps_fwd = w.b_out + (size_t)128 * c_out * 2;
   w.taps_bwd = w.taps_fwd + 6 * 128 * 4;
-  w.total = w.taps_bwd + 6 * 128 * 4;
+  w.a3_fwd = w.taps_bwd + 6 * 128 * 4;
+  w.a3_bwd = w.a3_fwd + (size_t)3 * 128 * c_in * 2;
+  w.total = w.a3_bwd + (size_t)3 * 128 * c_out * 2;
   return w;
 }
 
@@ -776,8 +692,23 @@ static int launch(const tlt_cpconv_rows_desc* d, const void* in, void* out, cons
 }  // namespace cpr
 }  // namespace tlt
 
+namespace tlt {
+namespace cpr2 {
+int fwd_64(int batch, int rank, const void* x, void* y, const void* a3, const void* b, const float* taps, const float* bias, cudaStream_t st);
+int bwd_data_64(int batch, int rank, const void* dy, void* dx, const void* x, const void* a3, const void* a2, const void* b,
+                const float* taps, float* dF, float* dG, cudaStream_t st);
+int bwd_weight_64(int batch, int rank, const void* x, const void* dy, const void* a3, const void* a2, const float* taps, float* dF,
+                  float* dG, cudaStream_t st);
+}  // namespace cpr2
+}  // namespace tlt
+
 using namespace tlt;
 using namespace tlt::cpr;
+
+// the second-generation kernels (first separable pass folded into the stage-1 MMA): square 56 x 56 maps, 64 -> 64, rank <= 80
+static bool folded_ok(const tlt_cpconv_rows_desc* d) {
+  return d->stride == 1 && d->height == 56 && d->width == 56 && d->in_channels == 64 && d->out_channels == 64 && d->rank <= 80;
+}
 
 extern "C" int tlt_cpconv_rows_supported(const tlt_cpconv_rows_desc* d) { return d && shape_ok(d) ? 1 : 0; }
 
@@ -795,7 +726,7 @@ extern "C" int tlt_cpconv_rows_pack(const tlt_cpconv_rows_desc* d, const void* f
   pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)f_in, (const __nv_bfloat16*)f_out, (const __nv_bfloat16*)kh,
                                                     (const __nv_bfloat16*)kw, (const __nv_bfloat16*)lam, (int)d->in_channels,
                                                     (int)d->out_channels, (int)d->rank, (__nv_bfloat16*)ws,
-                                                    (float*)((uint8_t*)ws + w.taps_fwd));
+                                                    (float*)((uint8_t*)ws + w.taps_fwd), (__nv_bfloat16*)((uint8_t*)ws + w.a3_fwd));
   return check_launch("cpconv_rows pack_kernel");
 }
 
@@ -804,6 +735,8 @@ extern "C" int tlt_cpconv_rows_fwd(const tlt_cpconv_rows_desc* d, const void* x,
   const Ws w = ws_layout((int)d->in_channels, (int)d->out_channels);
   const uint8_t* base = (const uint8_t*)ws;
   cudaStream_t st = (cudaStream_t)stream;
+  if (folded_ok(d))
+    return cpr2::fwd_64((int)d->batch, (int)d->rank, x, y, base + w.a3_fwd, base + w.b_out, (const float*)(base + w.taps_fwd) + 3 * 128, bias, st);
   if (d->stride == 1)
     return launch<MODE_FWD, 1, 64, 64>(d, x, y, nullptr, base + w.a_in, nullptr, base + w.b_out, (const float*)(base + w.taps_fwd), bias,
                                        nullptr, nullptr, st);
@@ -821,6 +754,15 @@ extern "C" int tlt_cpconv_rows_bwd(const tlt_cpconv_rows_desc* d, const void* x,
   float* dF_in = acc;
   float* dF_out = acc + (size_t)d->in_channels * 128;
   float* dT = dF_out + (size_t)d->out_channels * 128;
+  if (folded_ok(d)) {
+    // column-order data gradient: "in" = dy, fold lambda kw (flipped) into F_out^T, pass = kh (flipped); centre z1 = F_in^T x  -> dx, dF_in, d kh
+    int rc = cpr2::bwd_data_64((int)d->batch, (int)d->rank, dy, dx, x, base + w.a3_bwd, base + w.a_in, base + w.b_in,
+                               (const float*)(base + w.taps_bwd), dF_in, dT + 3 * 128, st);
+    if (rc != TLT_OK) return rc;
+    // row-order weight gradient: "in" = x, fold kh into F_in^T, pass = lambda kw; centre dz2 = F_out^T dy  -> dF_out, d (lambda kw)
+    return cpr2::bwd_weight_64((int)d->batch, (int)d->rank, x, dy, base + w.a3_fwd, base + w.a_out,
+                               (const float*)(base + w.taps_fwd) + 3 * 128, dF_out, dT, st);
+  }
   // data gradient (+ dF_in): "in" = dy, A = F_out^T, B = F_in, other = x
   int rc = launch<MODE_BWD_DATA, 1, 64, 64>(d, dy, dx, x, base + w.a_out, nullptr, base + w.b_in, (const float*)(base + w.taps_bwd),
                                             nullptr, dF_in, nullptr, st);
@@ -834,7 +776,8 @@ extern "C" int tlt_cpconv_rows_finalize(const tlt_cpconv_rows_desc* d, const flo
                                         void* g_fout, void* g_fin, void* g_kh, void* g_kw, void* g_lam, void* stream) {
   TLT_REQUIRE(d && shape_ok(d), "tlt_cpconv_rows_finalize: unsupported shape");
   finalize_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(acc, (const __nv_bfloat16*)kh, (const __nv_bfloat16*)kw, (const __nv_bfloat16*)lam,
-                                                        (int)d->in_channels, (int)d->out_channels, (int)d->rank, (__nv_bfloat16*)g_fout,
+                                                        (int)d->in_channels, (int)d->out_channels, (int)d->rank, folded_ok(d) ? 1 : 0,
+                                                        (__nv_bfloat16*)g_fout,
                                                         (__nv_bfloat16*)g_fin, (__nv_bfloat16*)g_kh, (__nv_bfloat16*)g_kw,
                                                         (__nv_bfloat16*)g_lam);
   return check_launch("cpconv_rows finalize_kernel");
