@@ -290,28 +290,6 @@ int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R,
                        const void* g, float* const* dF, float* dweights, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
- * Fused CP convolution, 3x3 / stride 1 / padding 1, NCHW bf16:   y = F_out . dw3x3(F_in^T . x) (+ bias)  in ONE launch, the
- * R-channel intermediates staying in shared memory (HMMA 1x1 stages, fp32 depthwise stage, rank walked in chunks of 16).
- *   x (B, C, H, W);  f_in (C, R), f_out (O, R) row-major bf16 as the reference stores the CP factors;  taps_t (9, R) bf16 =
- *   lambda_r F_kh[i, r] F_kw[j, r] (taps-major, t = 3 i + j);  bias (O) bf16 / fp32 (desc->dtype_bias) or NULL;  y (B, O, H, W).
- *   flip_taps = 1 uses taps_t[8 - t]: with (f_in, f_out) swapped the same call is the data gradient.
- *   z1_out / z2_out (B, R, H, W) bf16 or NULL: the intermediates before / after the depthwise stage (for the unfused
- *   weight-gradient kernels).  variant: 0 default tiling, 1 alternative strip height (development switch).
- * Supported (C, O, W): (64, 64, 56), (128, 128, 28) with H % 4 == 0 -- tlt_cpconv3x3_fused_supported tells.
- * Replaces: cp_conv / cp_conv_mobilenet (tltorch/functional/convolution.py:231-345) and their autograd for BASELINE config 3's
- * HBM-bound layers.
- * ------------------------------------------------------------------------------------------------------------ */
-typedef struct {
-  int64_t batch, in_channels, out_channels, rank, height, width;
-  int32_t flip_taps;
-  int32_t dtype_bias;
-  int32_t variant;
-} tlt_cpconv_desc;
-int tlt_cpconv3x3_fused_supported(const tlt_cpconv_desc* desc);
-int tlt_cpconv3x3_fused(const tlt_cpconv_desc* desc, const void* x, const void* f_in, const void* taps_t, const void* f_out,
-                        const void* bias, void* y, void* z1_out, void* z2_out, void* stream);
-
-/* --------------------------------------------------------------------------------------------------------------
  * Op-level fused CP convolution on channels-last rows (bf16): x (B, H, W, C_in) -> y (B, H/s, W/s, C_out),
  *     y = F_out . dw3x3( F_in^T . x )  with separable taps kh (3, R), kw (3, R) and CP weights lambda (R), padding 1.
  * ONE launch per direction; the R-channel intermediates stay in TMEM / shared memory (csrc/cpconv_rows.cu).

@@ -369,22 +369,59 @@ def emulate_spatial_bwd(x3, k, gt, dx, dk):
     LOG.append(("spatial_project_bwd", tuple(x3.shape), tuple(k.shape)))
 
 
-def emulate_cpconv_fused(x, f_in, taps_t, f_out, bias, flip, y, z1, z2, variant):
-    """y = F_out . dw3x3(F_in^T . x) (+ bias) with the intermediates rounded to the activation dtype like the kernel does."""
-    R = f_in.shape[1]
-    a = torch.einsum("cr,bchw->brhw", f_in.double(), x.double()).to(x.dtype)
-    taps = taps_t.double().flip(0) if flip else taps_t.double()
-    w = taps.t().reshape(R, 1, 3, 3)
-    b2 = torch.nn.functional.conv2d(a.double(), w, padding=1, groups=R).to(x.dtype)
-    out = torch.einsum("or,brhw->bohw", f_out.double(), b2.double())
+_CPROWS_WS, _CPROWS_ACC = {}, {}     # workspace / accumulator address -> what the kernels would have put there
+
+
+def _cprows_chain(x, lam, f_out, f_in, kh, kw, stride):
+    """(B, H, W, C) rows -> (B, H/s, W/s, O): 1x1 -> depthwise (3, 1) -> depthwise (1, 3) -> 1x1, in the given precision."""
+    r = lam.shape[0]
+    z = torch.einsum("bhwc,cr->brhw", x, f_in)
+    z = F.conv2d(z, kh.t().reshape(r, 1, 3, 1), stride=(stride, 1), padding=(1, 0), groups=r)
+    z = F.conv2d(z, (kw * lam).t().reshape(r, 1, 1, 3), stride=(1, stride), padding=(0, 1), groups=r)
+    return torch.einsum("brhw,or->bhwo", z, f_out)
+
+
+def emulate_cprows_pack(d, f_in, f_out, kh, kw, lam, ws):
+    _CPROWS_WS[ws.data_ptr()] = tuple(t.detach().clone() for t in (lam, f_out, f_in, kh, kw))
+    LOG.append(("cpconv_rows_pack", int(d.in_channels), int(d.out_channels), int(d.rank)))
+
+
+def emulate_cprows_fwd(d, x, ws, bias, y):
+    lam, f_out, f_in, kh, kw = (t.double() for t in _CPROWS_WS[ws.data_ptr()])
+    out = _cprows_chain(x.double(), lam, f_out, f_in, kh, kw, int(d.stride))
     if bias is not None:
-        out = out + bias.double().reshape(1, -1, 1, 1)
+        out = out + bias.double()
     y.copy_(out.to(y.dtype))
-    if z1 is not None:
-        z1.copy_(a)
-    if z2 is not None:
-        z2.copy_(b2)
-    LOG.append(("cpconv3x3_fused", tuple(x.shape), R, bool(flip), z1 is not None))
+    LOG.append(("cpconv_rows_fwd", tuple(x.shape), int(d.rank), int(d.stride), bias is not None))
+
+
+def emulate_cprows_bwd(d, x, gy, ws, dx, acc):
+    """Closed-form backward of _cprows_chain (custom-op bodies run below autograd, so no torch.autograd.grad here)."""
+    from torch.nn.grad import conv2d_input, conv2d_weight
+    lam, f_out, f_in, kh, kw = (t.double() for t in _CPROWS_WS[ws.data_ptr()])
+    st, r = int(d.stride), lam.shape[0]
+    x64, g64 = x.double(), gy.double()
+    wh, ww = kh.t().reshape(r, 1, 3, 1).contiguous(), (kw * lam).t().reshape(r, 1, 1, 3).contiguous()
+    z1 = torch.einsum("bhwc,cr->brhw", x64, f_in)
+    u = F.conv2d(z1, wh, stride=(st, 1), padding=(1, 0), groups=r)
+    z2 = F.conv2d(u, ww, stride=(1, st), padding=(0, 1), groups=r)
+    dz2 = torch.einsum("bhwo,or->brhw", g64, f_out).contiguous()
+    g_fout = torch.einsum("bhwo,brhw->or", g64, z2)
+    du = conv2d_input(u.shape, ww, dz2, stride=(1, st), padding=(0, 1), groups=r)
+    g_kwl = conv2d_weight(u, ww.shape, dz2, stride=(1, st), padding=(0, 1), groups=r).reshape(r, 3).t()
+    dz1 = conv2d_input(z1.shape, wh, du, stride=(st, 1), padding=(1, 0), groups=r)
+    g_kh = conv2d_weight(z1, wh.shape, du, stride=(st, 1), padding=(1, 0), groups=r).reshape(r, 3).t()
+    dx.copy_(torch.einsum("brhw,cr->bhwc", dz1, f_in).to(dx.dtype))
+    g_fin = torch.einsum("bhwc,brhw->cr", x64, dz1)
+    _CPROWS_ACC[acc.data_ptr()] = ((kw * g_kwl).sum(0), g_fout, g_fin, g_kh, g_kwl * lam)
+    LOG.append(("cpconv_rows_bwd", tuple(x.shape), int(d.rank)))
+
+
+def emulate_cprows_finalize(d, acc, kh, kw, lam, g_fout, g_fin, g_kh, g_kw, g_lam):
+    gl, gfo, gfi, gkh, gkw = _CPROWS_ACC.pop(acc.data_ptr())
+    for dst, src in ((g_lam, gl), (g_fout, gfo), (g_fin, gfi), (g_kh, gkh), (g_kw, gkw)):
+        dst.copy_(src.to(dst.dtype))
+    LOG.append(("cpconv_rows_finalize", int(d.rank)))
 
 
 @contextlib.contextmanager
@@ -397,11 +434,13 @@ def emulated_kernels():
     from torch_b200 import rows_ops as ro
     from torch_b200 import kr_ops as ko
     from torch_b200 import spatial_ops as so
-    from torch_b200 import cpconv_ops as co
+    from torch_b200 import cprows_ops as co
     saved_so = so._execute_spatial_fwd, so._execute_spatial_bwd
     so._execute_spatial_fwd, so._execute_spatial_bwd = emulate_spatial_fwd, emulate_spatial_bwd
-    saved_co = co._execute_cpconv_fused
-    co._execute_cpconv_fused = emulate_cpconv_fused
+    saved_co = co._execute_pack, co._execute_fwd, co._execute_bwd, co._execute_finalize, co._ws_bytes, co._acc_bytes
+    co._execute_pack, co._execute_fwd, co._execute_bwd, co._execute_finalize = (
+        emulate_cprows_pack, emulate_cprows_fwd, emulate_cprows_bwd, emulate_cprows_finalize)
+    co._ws_bytes = co._acc_bytes = lambda d: 64
     saved_k = ko._execute_kr_fwd, ko._execute_kr_bwd
     ko._execute_kr_fwd, ko._execute_kr_bwd = emulate_kr_fwd, emulate_kr_bwd
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
@@ -425,7 +464,7 @@ def emulated_kernels():
         yield LOG
     finally:
         so._execute_spatial_fwd, so._execute_spatial_bwd = saved_so
-        co._execute_cpconv_fused = saved_co
+        co._execute_pack, co._execute_fwd, co._execute_bwd, co._execute_finalize, co._ws_bytes, co._acc_bytes = saved_co
         ops._execute_contract, ops._execute_conv = saved
         bo._execute_btt3_reconstruct, bo._execute_btt3_core_grads, bo._execute_gemm = saved_b
         po._execute_pointwise, po._execute_pointwise_wgrad = saved_p

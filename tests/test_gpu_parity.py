@@ -898,39 +898,49 @@ def test_trl_spatial_first_plan_vs_rows_plan(B, C, hw, ranks, out, monkeypatch):
         assert G.rel_err(a, b_.double().cpu()) < 2e-2
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("ch,hw,batch,bias", [(64, 56, 3, False), (64, 56, 2, True), (128, 28, 5, True), (128, 28, 2, False)])
-def test_cp_conv_fused_path_vs_oracle(ch, hw, batch, bias, variant, monkeypatch):
-    """CP FactorizedConv (bf16, ResNet-18 layer1 / layer2 shapes, small batch) through the one-launch-per-direction fused
-    kernel (tlt_cpconv3x3_fused: 1x1 -> depthwise 3x3 -> 1x1 with the R-channel intermediates in shared memory) vs the fp64
-    oracle of cp_conv (functional/convolution.py:231-283): y, dx and every parameter gradient."""
+@pytest.mark.parametrize("cin,cout,stride,height,rank,batch,bias,train", [
+    (64, 64, 1, 56, 0.25, 3, False, True),      # config 3 layer1: rank 69, second-generation kernels (pass folded into the MMA)
+    (64, 64, 1, 56, 0.25, 7, True, True),       # ranges that cross image boundaries, bias
+    (64, 64, 1, 56, 0.4, 2, False, True),       # rank 110 > 80: first-generation kernels (TMEM-resident z1 with halo)
+    (64, 64, 1, 24, 0.25, 5, True, True),       # H != 56: first-generation kernels
+    (64, 128, 2, 56, 0.25, 5, False, False),    # config 3 layer2[0] (stride 2, rank 93): fused forward
+    (64, 128, 2, 56, 0.25, 3, True, False),
+])
+def test_cp_conv_rows_fused_vs_oracle(cin, cout, stride, height, rank, batch, bias, train):
+    """CP FactorizedConv (bf16, channels-last 56-wide maps) through the op-level fused kernels (tlt_cpconv_rows_fwd / _bwd:
+    1x1 -> depthwise 3x3 -> 1x1 in one launch per direction, rank intermediates in TMEM / shared memory, every gradient
+    accumulated on chip) vs the fp64 oracle of cp_conv (functional/convolution.py:231-283): y, dx and every parameter gradient."""
     import torch_b200 as tlt
     from torch_b200 import _cuda
     from oracle import reference_path as rp
-    monkeypatch.setenv("TLT_CPF_VARIANT", str(variant))
-    monkeypatch.setenv("TLT_CP_FUSED", "on")
-    torch.manual_seed(hw + batch)
-    conv = tlt.FactorizedConv(ch, ch, 3, order=2, stride=1, padding=1, bias=bias, factorization="cp", rank=0.25, device=dev())
+    torch.manual_seed(height + batch)
+    conv = tlt.FactorizedConv(cin, cout, 3, order=2, stride=stride, padding=1, bias=bias, factorization="cp", rank=rank, device=dev())
     conv.reset_parameters(std=0.5)
     if bias:
         with torch.no_grad():
             conv.bias.normal_()
     conv = conv.to(torch.bfloat16)
-    x = torch.randn(batch, ch, hw, hw, device=dev(), dtype=torch.bfloat16, requires_grad=True)
-    before = _cuda.launch_count()
-    y = conv(x)
-    fwd_launches = _cuda.launch_count() - before
-    assert fwd_launches <= 3, fwd_launches                 # Khatri-Rao taps + the fused chain (+ nothing else)
-    gy = torch.randn_like(y)
+    x = torch.randn(batch, cin, height, 56, device=dev(), dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(train)
     params = dict(conv.named_parameters())
-    grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
     leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in params.items()}
     xo = x.detach().double().cpu().requires_grad_(True)
     fs = [leaves[f"weight.factors.factor_{i}"] for i in range(4)]
-    yo = rp.cp_conv(xo, leaves["weight.weights"], fs, bias=leaves.get("bias"), stride=[1, 1], padding=[1, 1], dilation=[1, 1])
-    go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
-    assert G.rel_err(y, yo) < 2e-2
-    _report(_tag(), {"y": G.rel_err(y, yo), **{n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)}}, 2e-2)
+    yo = rp.cp_conv(xo, leaves["weight.weights"], fs, bias=leaves.get("bias"), stride=[stride] * 2, padding=[1, 1], dilation=[1, 1])
+    before = _cuda.launch_count()
+    with torch.set_grad_enabled(train):
+        y = conv(x)
+    assert _cuda.launch_count() - before == 2, "operand packing + the fused chain, nothing else"
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    errs = {"y": G.rel_err(y, yo)}
+    if train:
+        gy = torch.randn_like(y)
+        before = _cuda.launch_count()
+        grads = torch.autograd.grad(y, [x] + list(params.values()), gy)
+        assert _cuda.launch_count() - before <= 3 + (1 if bias else 0)      # data + weight gradient kernels, finalisation
+        go = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double().cpu())
+        errs.update({n: G.rel_err(a, b) for n, a, b in zip(["x"] + list(params), grads, go)})
+    _report(_tag(), errs, 2e-2)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

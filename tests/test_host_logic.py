@@ -294,33 +294,38 @@ def test_spatial_first_projection_host_logic(monkeypatch):
         assert G.rel_err(a, b) < 2e-2
 
 
-def test_cp_conv_fused_op_host_logic():
-    """tltorch::cpconv3x3_fused: the op's autograd (data-gradient chain = the same launch with swapped factors and flipped taps,
-    its two intermediates feeding the three weight-gradient reductions, bias gradient) against fp64 autograd of
-    1x1 -> depthwise 3x3 -> 1x1 (cp_conv, convolution.py:231-283), with the launch funnels emulated."""
-    from torch_b200 import cpconv_ops
+def test_cp_conv_rows_fused_op_host_logic():
+    """tltorch::cpconv_rows_fwd / _bwd (the op-level fused CP convolution on channels-last rows): routing from FactorizedConv
+    (channels-last 56 x 56 map, 64 -> 64, CP rank 0.25 -> the fused op, two launches forward, two backward, no Khatri-Rao and no
+    transposition launch), autograd plumbing and the bias gradient, against fp64 autograd of 1x1 -> depthwise -> 1x1 (cp_conv,
+    convolution.py:231-283), with the launch funnels emulated."""
     torch.manual_seed(12)
-    B, C, O, R, H, W = 2, 16, 24, 11, 8, 8
-    x = (torch.randn(B, C, H, W) * 0.5).to(torch.bfloat16).requires_grad_(True)
-    f_in = (torch.randn(C, R) * 0.3).to(torch.bfloat16).requires_grad_(True)
-    f_out = (torch.randn(O, R) * 0.3).to(torch.bfloat16).requires_grad_(True)
-    taps = (torch.randn(9, R) * 0.4).to(torch.bfloat16).requires_grad_(True)
-    bias = torch.randn(O).to(torch.bfloat16).requires_grad_(True)
-    leaves = [x, f_in, taps, f_out, bias]
+    conv = tlt.FactorizedConv(64, 64, 3, order=2, padding=1, bias=True, factorization="cp", rank=0.25)
+    conv.reset_parameters(std=0.4)
+    conv.bias.data.normal_()
+    conv = conv.to(torch.bfloat16)
+    x = (torch.randn(2, 64, 56, 56) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    params = list(conv.parameters())
     with emulated_kernels() as log:
-        y = cpconv_ops.cp_conv_fused(x, f_in, taps, f_out, bias)
+        y = conv(x)
         gy = torch.randn_like(y)
-        got = torch.autograd.grad(y, leaves, gy)
-    fused = [e for e in log if e[0] == "cpconv3x3_fused"]
-    assert len(fused) == 2 and fused[0][3] is False and fused[1][3] is True and fused[0][4] and fused[1][4], log
-    lr = [t.detach().double().requires_grad_(True) for t in leaves]
-    a = torch.einsum("cr,bchw->brhw", lr[1], lr[0])
-    b2 = torch.nn.functional.conv2d(a, lr[2].t().reshape(R, 1, 3, 3), padding=1, groups=R)
-    ref = torch.einsum("or,brhw->bohw", lr[3], b2) + lr[4].reshape(1, -1, 1, 1)
-    want = torch.autograd.grad(ref, lr, gy.double())
+        got = torch.autograd.grad(y, [x] + params, gy)
+        names = [e[0] for e in log]
+    assert names == ["cpconv_rows_pack", "cpconv_rows_fwd", "cpconv_rows_bwd", "cpconv_rows_finalize"], names
+    assert y.shape == (2, 64, 56, 56) and y.is_contiguous(memory_format=torch.channels_last)
+    xr = x.detach().double().requires_grad_(True)
+    pr = {n: p.detach().double().requires_grad_(True) for n, p in conv.named_parameters()}
+    fs = [pr[f"weight.factors.factor_{i}"] for i in range(4)]
+    w = torch.einsum("r,or,cr,hr,wr->ochw", pr["weight.weights"], *fs)
+    ref = torch.nn.functional.conv2d(xr, w, pr["bias"], padding=1)
+    want = torch.autograd.grad(ref, [xr] + [pr[n] for n, _ in conv.named_parameters()], gy.double())
     assert G.rel_err(y, ref) < 2e-2
-    for t, g, wv in zip(["x", "f_in", "taps", "f_out", "bias"], got, want):
-        assert G.rel_err(g, wv) < 2e-2, t
+    for (n, _), g, wv in zip([("x", None)] + list(conv.named_parameters()), got, want):
+        assert G.rel_err(g, wv) < 2e-2, n
+    # an NCHW-contiguous input, another map size or stride-2 training keep the unfused routes
+    with emulated_kernels() as log:
+        conv(x.detach().contiguous())
+        assert "cpconv_rows_fwd" not in [e[0] for e in log]
 
 
 @pytest.mark.parametrize("name", _cases.module_cases())

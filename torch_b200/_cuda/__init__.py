@@ -67,12 +67,6 @@ class Mmd16Desc(C.Structure):
                 ("ld_in", C.c_int64), ("ld_out", C.c_int64)]
 
 
-class CpConvDesc(C.Structure):
-    _fields_ = [("batch", C.c_int64), ("in_channels", C.c_int64), ("out_channels", C.c_int64), ("rank", C.c_int64),
-                ("height", C.c_int64), ("width", C.c_int64), ("flip_taps", C.c_int32), ("dtype_bias", C.c_int32),
-                ("variant", C.c_int32)]
-
-
 class CpConvRowsDesc(C.Structure):
     _fields_ = [("batch", C.c_int64), ("in_channels", C.c_int64), ("out_channels", C.c_int64), ("rank", C.c_int64),
                 ("height", C.c_int64), ("width", C.c_int64), ("stride", C.c_int32)]
@@ -118,8 +112,6 @@ SYMBOLS = {
     "tlt_khatri_rao_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, _vp]),
     "tlt_khatri_rao_bwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp,
                                      C.POINTER(C.c_void_p), _vp, _vp]),
-    "tlt_cpconv3x3_fused_supported": (C.c_int, [C.POINTER(CpConvDesc)]),
-    "tlt_cpconv3x3_fused": (C.c_int, [C.POINTER(CpConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_cpconv_rows_supported": (C.c_int, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_grad_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),

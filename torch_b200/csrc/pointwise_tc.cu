@@ -19,9 +19,6 @@
 
 namespace tlt {
 
-int pointwise_hmma(const void* x, const void* wt, void* y, long long batch, long long C, long long N, long long S, long long w_ld,
-                   cudaStream_t st);               // cpconv_fused.cu
-
 constexpr int kPwThreads = 384;
 constexpr int kPwEpiWarps = 8;
 constexpr int kPwEpiBuf = 4096;
@@ -923,16 +920,6 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
   const long long units = (long long)p.batch * p.tiles_m * p.tiles_n;
   TLT_REQUIRE(units < (1LL << 31), "tlt_pointwise_tc: too many tiles");
   cudaStream_t st = (cudaStream_t)stream;
-  if (bias == nullptr) {
-    // opt-in experiment (TLT_PW_HMMA=on): streaming HMMA kernel fed by 1-D bulk copies of channel runs (cpconv_fused.cu).
-    // Parity-green, but one 8-warp CTA per SM walking load -> MMA -> store phases is latency-bound: 100 us vs 68 us at
-    // 56^2 x 64 -> 69, 95 us vs 41 us at 28^2 x 128 -> 141 (tools/pointwise_bench.py)
-    const char* env = getenv("TLT_PW_HMMA");
-    if (env && env[0] == 'o' && env[1] == 'n') {
-      rc = pointwise_hmma(x, wt, y, B, K, N, S, d->w_ld, st);
-      if (rc != 1) return rc;
-    }
-  }
   CUtensorMap mat;
   if ((rc = make_map3d(&mat, x, S, K, B, S, K * S, 64, UMMA_K, true))) return rc;                // X^T tail chunks {64 s, 16 k}
   {

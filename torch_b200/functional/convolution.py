@@ -9,7 +9,7 @@ import os
 
 import torch
 
-from .. import ops, tenalg, pointwise_ops, rows_ops, kr_ops, cpconv_ops, cprows_ops
+from .. import ops, tenalg, pointwise_ops, rows_ops, kr_ops, cprows_ops
 from ..ops import contract
 
 
@@ -131,10 +131,6 @@ def _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation):
             taps = tenalg.batched_outer(taps, f.t())
         taps_t = taps.reshape(taps.shape[0], -1).t()
         f0 = contract("or,r->or", factors[0], cp_tensor.weights)                   # lambda folded into the output factor
-    if cpconv_ops.eligible(x, factors[1], taps_t, f0, bias, kernel, stride, padding, dilation):
-        # HBM-bound 3x3 layers (config 3's 56^2 / 28^2 maps): the whole chain in one launch per direction, R-channel
-        # intermediates in shared memory (cpconv_ops.cp_conv_fused)
-        return cpconv_ops.cp_conv_fused(x, factors[1], taps_t, f0, bias)
     if _cp_rows_route(x, cp_tensor, bias, kernel, stride):
         # small odd-sized or strided maps: channels-last rows -- both 1x1 stages are K-major tcgen05 GEMMs and the
         # depthwise stage moves 16-byte channel chunks (rows_ops.cp_conv_rows)
