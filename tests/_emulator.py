@@ -316,6 +316,60 @@ def emulate_dwconv_rows(kind, a, b, out, batch, in_size, out_size, kernel, strid
     LOG.append(("dwconv_rows_" + kind, tuple(in_size), tuple(kernel), tuple(stride), tuple(padding), tuple(dilation)))
 
 
+def emulate_dwsep_taps(kh, kw, lam, ld, flip, taps):
+    r = kh.shape[1]
+    t = torch.cat([kh.double(), kw.double() * lam.double()], 0)                       # (6, R)
+    if flip:
+        t = torch.cat([t[:3].flip(0), t[3:].flip(0)], 0)
+    taps.zero_()
+    taps[:, :r] = t.to(taps.dtype)
+    LOG.append(("dwsep_taps", r, ld, bool(flip)))
+
+
+def emulate_dwsep(kind, a, b, out, batch, height, width, stride):
+    ld = a.shape[1]
+    ho, wo = height // stride, width // stride
+
+    def img(rows, h, w):
+        return rows.double().reshape(batch, h, w, ld).movedim(-1, 1).contiguous()
+
+    def rows_of(t):
+        return t.movedim(1, -1).reshape(-1, ld)
+
+    def weight(taps):
+        t = taps.double()
+        return torch.einsum("ir,jr->rij", t[:3], t[3:]).reshape(ld, 1, 3, 3)
+
+    conv = lambda t, w: F.conv2d(t, w, None, stride, 1, 1, ld)      # noqa: E731
+    if kind == "fwd":
+        out.copy_(rows_of(conv(img(a, height, width), weight(b))).to(out.dtype))
+    elif kind == "dgrad":
+        taps = torch.cat([b[:3].flip(0), b[3:].flip(0)], 0) if stride == 1 else b     # stride 1 hands the reversed taps
+        w = weight(taps)
+        with torch.enable_grad():
+            zz = torch.zeros((batch, ld, height, width), dtype=torch.float64)
+            res = torch.func.vjp(lambda t: conv(t, w), zz)[1](img(a, ho, wo))[0]
+        out.copy_(rows_of(res).to(out.dtype))
+    else:
+        zz = img(a, height, width)
+        with torch.enable_grad():
+            w0 = torch.zeros((ld, 1, 3, 3), dtype=torch.float64)
+            res = torch.func.vjp(lambda w: conv(zz, w), w0)[1](img(b, ho, wo))[0]
+        out.copy_(res.reshape(ld, 9).t().to(out.dtype))
+    LOG.append(("dwsep_rows_" + kind, (height, width), stride))
+
+
+def emulate_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam):
+    r = kh.shape[1]
+    t = acc.double()[:, :r].reshape(3, 3, r)                                          # [i][j][r]
+    h, w, l = kh.double(), kw.double(), lam.double()
+    g_kh.copy_((l * torch.einsum("jr,ijr->ir", w, t)).to(g_kh.dtype))
+    gwl = torch.einsum("ir,ijr->jr", h, t)
+    g_kw.copy_((l * gwl).to(g_kw.dtype))
+    g_lam.copy_((w * gwl).sum(0).to(g_lam.dtype))
+    LOG.append(("dwsep_finalize", r))
+
+
 def _kr_ref(factors, weights):
     R = factors[0].shape[1]
     res = torch.ones((1, R), dtype=torch.float64) if weights is None else weights.double().reshape(1, R)
@@ -445,6 +499,8 @@ def emulated_kernels():
     ko._execute_kr_fwd, ko._execute_kr_bwd = emulate_kr_fwd, emulate_kr_bwd
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
     saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows
+    saved_ds = ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize
+    ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize = emulate_dwsep_taps, emulate_dwsep, emulate_dwsep_finalize
     ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = (
         emulate_skinny_fwd, emulate_skinny_bwd, emulate_scale_modes, emulate_dwconv_rows)
     ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = emulate_nchw_to_rows, emulate_rows_to_nchw, emulate_unfold_rows
@@ -472,4 +528,5 @@ def emulated_kernels():
         ko._execute_kr_fwd, ko._execute_kr_bwd = saved_k
         ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
         ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = saved_s
+        ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize = saved_ds
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

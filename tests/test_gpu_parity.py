@@ -898,6 +898,37 @@ def test_trl_spatial_first_plan_vs_rows_plan(B, C, hw, ranks, out, monkeypatch):
         assert G.rel_err(a, b_.double().cpu()) < 2e-2
 
 
+@pytest.mark.parametrize("stride,h,w,r,batch", [(1, 28, 28, 141, 3), (1, 7, 7, 573, 5), (1, 14, 14, 285, 2), (2, 28, 28, 189, 3),
+                                                (2, 14, 14, 381, 2), (2, 56, 56, 93, 2), (1, 5, 9, 13, 3), (1, 3, 2, 8, 1)])
+def test_dwsep_rows_kernels_vs_fp64(stride, h, w, r, batch):
+    """tlt_dwsep_rows_fwd / _dgrad / _wgrad / _finalize (separable 3x3 depthwise sweep on channels-last rows, config 3's rank
+    widths and map sizes, odd maps, a ragged channel chunk) vs fp64 autograd of the two depthwise 1-D convolutions of cp_conv
+    (functional/convolution.py:251-269)."""
+    from torch_b200 import rows_ops
+    torch.manual_seed(h * w + r)
+    ld = (r + 7) // 8 * 8
+    z = torch.zeros(batch * h * w, ld, device=dev(), dtype=torch.bfloat16)
+    z[:, :r] = torch.randn(batch * h * w, r, device=dev()).to(torch.bfloat16)
+    z.requires_grad_(True)
+    kh = (torch.randn(3, r, device=dev()) * 0.6).to(torch.bfloat16).requires_grad_(True)
+    kw = (torch.randn(3, r, device=dev()) * 0.6).to(torch.bfloat16).requires_grad_(True)
+    lam = (1 + 0.2 * torch.randn(r, device=dev())).to(torch.bfloat16).requires_grad_(True)
+    y = rows_ops._dwsep_op(z, kh, kw, lam, batch, h, w, stride)
+    gy = torch.zeros_like(y)
+    gy[:, :r] = torch.randn(y.shape[0], r, device=dev()).to(torch.bfloat16)
+    grads = torch.autograd.grad(y, [z, kh, kw, lam], gy)
+    zo, kho, kwo, lo = (t.detach().double().cpu().requires_grad_(True) for t in (z, kh, kw, lam))
+    img = zo[:, :r].reshape(batch, h, w, r).permute(0, 3, 1, 2)
+    u = torch.nn.functional.conv2d(img, kho.t().reshape(r, 1, 3, 1), stride=(stride, 1), padding=(1, 0), groups=r)
+    v = torch.nn.functional.conv2d(u, (kwo * lo).t().reshape(r, 1, 1, 3), stride=(1, stride), padding=(0, 1), groups=r)
+    yo = v.permute(0, 2, 3, 1).reshape(-1, r)
+    go = torch.autograd.grad(yo, [zo, kho, kwo, lo], gy[:, :r].double().cpu())
+    assert float(y[:, r:].abs().max()) == 0.0 if ld > r else True
+    errs = {"y": G.rel_err(y[:, :r], yo), "dz": G.rel_err(grads[0][:, :r], go[0][:, :r]), "dkh": G.rel_err(grads[1], go[1]),
+            "dkw": G.rel_err(grads[2], go[2]), "dlam": G.rel_err(grads[3], go[3])}
+    _report(_tag(), errs, 1e-2)
+
+
 @pytest.mark.parametrize("cin,cout,stride,height,rank,batch,bias,train", [
     (64, 64, 1, 56, 0.25, 3, False, True),      # config 3 layer1: rank 69, second-generation kernels (pass folded into the MMA)
     (64, 64, 1, 56, 0.25, 7, True, True),       # ranges that cross image boundaries, bias

@@ -328,6 +328,34 @@ def test_cp_conv_rows_fused_op_host_logic():
         assert "cpconv_rows_fwd" not in [e[0] for e in log]
 
 
+@pytest.mark.parametrize("stride,hw", [(1, (7, 7)), (2, (14, 14)), (1, (6, 10))])
+def test_cp_conv_rows_separable_route_host_logic(stride, hw):
+    """Channels-last CP convolution outside the fused shapes: GEMM -> tltorch::dwsep_rows (both depthwise passes in one sweep,
+    the CP taps unmerged: no Khatri-Rao launch forward or backward) -> GEMM, against fp64 autograd of the dense convolution with
+    the reconstructed kernel (cp_conv, convolution.py:231-283); launch funnels emulated."""
+    torch.manual_seed(5 + stride)
+    conv = tlt.FactorizedConv(64, 72, 3, order=2, padding=1, stride=stride, bias=True, factorization="cp", rank=0.3)
+    conv.reset_parameters(std=0.4)
+    conv.bias.data.normal_()
+    conv = conv.to(torch.bfloat16)
+    x = (torch.randn(2, 64, *hw) * 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    with emulated_kernels() as log:
+        y = conv(x)
+        gy = torch.randn_like(y)
+        got = torch.autograd.grad(y, [x] + list(conv.parameters()), gy)
+        names = [e[0] for e in log]
+    assert "dwsep_rows_fwd" in names and "dwsep_rows_dgrad" in names and "dwsep_rows_wgrad" in names and "dwsep_finalize" in names
+    assert not any(n.startswith("khatri_rao") or n.startswith("dwconv_rows") for n in names), names
+    xr = x.detach().double().requires_grad_(True)
+    pr = {n: p.detach().double().requires_grad_(True) for n, p in conv.named_parameters()}
+    w = torch.einsum("r,or,cr,hr,wr->ochw", pr["weight.weights"], *[pr[f"weight.factors.factor_{i}"] for i in range(4)])
+    ref = torch.nn.functional.conv2d(xr, w, pr["bias"], stride=stride, padding=1)
+    want = torch.autograd.grad(ref, [xr] + [pr[n] for n, _ in conv.named_parameters()], gy.double())
+    assert G.rel_err(y, ref) < 2e-2
+    for (n, _), g, wv in zip([("x", None)] + list(conv.named_parameters()), got, want):
+        assert G.rel_err(g, wv) < 2e-2, n
+
+
 @pytest.mark.parametrize("name", _cases.module_cases())
 def test_module_cases_match_reference_goldens(name):
     """n_layers > 1 FactorizedLinear / FactorizedConv and FactorizedEmbedding, built from the REAL reference's state_dict

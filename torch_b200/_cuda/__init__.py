@@ -67,6 +67,10 @@ class Mmd16Desc(C.Structure):
                 ("ld_in", C.c_int64), ("ld_out", C.c_int64)]
 
 
+class DwSepDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("height", C.c_int64), ("width", C.c_int64), ("ld", C.c_int64), ("stride", C.c_int32)]
+
+
 class CpConvRowsDesc(C.Structure):
     _fields_ = [("batch", C.c_int64), ("in_channels", C.c_int64), ("out_channels", C.c_int64), ("rank", C.c_int64),
                 ("height", C.c_int64), ("width", C.c_int64), ("stride", C.c_int32)]
@@ -112,6 +116,11 @@ SYMBOLS = {
     "tlt_khatri_rao_fwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, _vp]),
     "tlt_khatri_rao_bwd": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp,
                                      C.POINTER(C.c_void_p), _vp, _vp]),
+    "tlt_dwsep_rows_taps": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int32, _vp, _vp]),
+    "tlt_dwsep_rows_fwd": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwsep_rows_dgrad": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwsep_rows_wgrad": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
+    "tlt_dwsep_rows_finalize": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "tlt_cpconv_rows_supported": (C.c_int, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_grad_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),

@@ -1,0 +1,358 @@
+// Separable 3x3 depthwise convolution on channels-last rows (bf16, padding 1, stride 1 or 2) -- the middle stage of the CP
+// convolution chain when it is not fused into the 1x1 stages (cp_conv, tltorch/functional/convolution.py:251-269: one
+// depthwise 1-D convolution per kernel mode, each its own pass over the R-channel tensor; here both passes in one sweep).
+//
+//   z2[n, ho, wo, r] = sum_{i,j} kh[i, r] kw'[j, r] z1[n, s ho + i - 1, s wo + j - 1, r]          kw' = lambda kw
+//
+// Rows are (B H W, ld) with ld = round8(R); a thread owns one 16-byte chunk (8 channels) of one output row of one image and
+// WALKS along W: the H pass of a column is computed once when the column arrives, the W pass runs on the three most recent
+// columns in registers -- 3 loads, 24 packed FMAs and one store per 8-channel output, all channel PAIRS as fma.rn.f32x2
+// (a bf16x2 word unpacks into exactly such a pair).  The generic tap-loop kernels this replaces (dwconv_rows.cu) were
+// instruction-issue bound at 93-116 us per pass on config 3's 28^2 layers (HBM floor 18 us).
+//   forward / data gradient (stride 1: the same sweep with both tap vectors reversed; stride 2: the transposed sweep)
+//   weight gradient: dT[3 i + j][r] = sum dz2[n, ho, wo, r] z1[n, s ho + i - 1, s wo + j - 1, r] in registers (a 3 x 3 window of
+//   unpacked columns rotating through an unrolled loop), shared-memory then global fp32 reductions; tlt_dwsep_rows_finalize
+//   turns dT into the gradients of kh, kw and lambda.
+#include "common.cuh"
+
+namespace tlt {
+namespace dws {
+
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 pku(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+struct Geom {
+  int batch, H, W, Ho, Wo, cpr;      // cpr = ld / 8 chunks per row
+  long long items;                   // threads' work items: (image, row, chunk)
+};
+
+// 8 bf16 channels -> 4 fp32 pairs (channels 2i, 2i+1)
+__device__ __forceinline__ void unpack(const uint4& v, f2 (&o)[4]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = pku(w[i] << 16, w[i] & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack(const f2 (&o)[4]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo_of(o[i]), hi_of(o[i]));
+    w[i] = *(uint32_t*)&h;
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ldg16(const uint4* p, bool ok) { return ok ? __ldg(p) : make_uint4(0u, 0u, 0u, 0u); }
+
+// taps [6][ld] fp32 (kh0 kh1 kh2 kw0 kw1 kw2) -> this chunk's 8 channels as pairs
+__device__ __forceinline__ void load_taps(const float* __restrict__ taps, int ld, int c, f2 (&k)[6][4]) {
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    const float4 a = __ldg((const float4*)(taps + (size_t)t * ld + c * 8));
+    const float4 b = __ldg((const float4*)(taps + (size_t)t * ld + c * 8) + 1);
+    k[t][0] = pk(a.x, a.y); k[t][1] = pk(a.z, a.w); k[t][2] = pk(b.x, b.y); k[t][3] = pk(b.z, b.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward sweep (and the stride-1 data gradient, called with reversed taps): item = (n, ho, chunk), walk over the input columns.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(128) dwsep_fwd_kernel(const Geom g, const uint4* __restrict__ src, const float* __restrict__ taps,
+                                                        uint4* __restrict__ dst) {
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < g.items; item += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(item % g.cpr);
+    const long long t = item / g.cpr;
+    const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
+    f2 k[6][4];
+    load_taps(taps, g.cpr * 8, c, k);
+    const int h1 = ho * STRIDE;
+    const bool ok0 = h1 >= 1, ok2 = h1 + 1 < g.H;
+    const uint4* r1 = src + ((long long)(n * g.H + h1) * g.W) * g.cpr + c;
+    const uint4* r0 = r1 - (long long)g.W * g.cpr;
+    const uint4* r2 = r1 + (long long)g.W * g.cpr;
+    uint4* out = dst + ((long long)(n * g.Ho + ho) * g.Wo) * g.cpr + c;
+    f2 va[4], vb[4];                                   // H-pass results of columns w-2, w-1
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { va[i] = 0ull; vb[i] = 0ull; }
+    uint4 q0 = ldg16(r0, ok0), q1 = __ldg(r1), q2 = ldg16(r2, ok2);
+    for (int w = 0; w < g.W; ++w) {
+      f2 a[4], b[4], d[4], v[4];
+      unpack(q0, a); unpack(q1, b); unpack(q2, d);
+      if (w + 1 < g.W) {                               // next column in flight while this one is finished
+        const long long off = (long long)(w + 1) * g.cpr;
+        q0 = ldg16(r0 + off, ok0); q1 = __ldg(r1 + off); q2 = ldg16(r2 + off, ok2);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fma2(k[2][i], d[i], fma2(k[1][i], b[i], mul2(k[0][i], a[i])));
+      // output column w-1 (stride 1) or (w-1)/2 (stride 2, w odd) : kw0 v[w-2] + kw1 v[w-1] + kw2 v[w]
+      if (w >= 1 && (STRIDE == 1 || (w & 1))) {
+        f2 o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = fma2(k[5][i], v[i], fma2(k[4][i], vb[i], mul2(k[3][i], va[i])));
+        out[(long long)((w - 1) / STRIDE) * g.cpr] = pack(o);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { va[i] = vb[i]; vb[i] = v[i]; }
+    }
+    if (STRIDE == 1) {                                 // last column: right neighbour is the zero padding
+      f2 o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = fma2(k[4][i], vb[i], mul2(k[3][i], va[i]));
+      out[(long long)(g.W - 1) * g.cpr] = pack(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stride-2 data gradient: item = (n, hi, chunk) at INPUT resolution, walk over the output-resolution columns b.
+//   g[b]        = kh1 dz2[a][b]                         (hi = 2a)      |  kh2 dz2[a][b] + kh0 dz2[a+1][b]   (hi = 2a + 1)
+//   dz1[hi][2b] = kw1 g[b],   dz1[hi][2b-1] = kw2 g[b-1] + kw0 g[b]
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) dwsep_dgrad2_kernel(const Geom g, const uint4* __restrict__ gy, const float* __restrict__ taps,
+                                                           uint4* __restrict__ dz) {
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < g.items; item += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(item % g.cpr);
+    const long long t = item / g.cpr;
+    const int hi = (int)(t % g.H), n = (int)(t / g.H);
+    f2 k[6][4];
+    load_taps(taps, g.cpr * 8, c, k);
+    const int a = hi >> 1;
+    const bool odd = hi & 1, ok1 = odd && a + 1 < g.Ho;
+    const uint4* ra = gy + ((long long)(n * g.Ho + a) * g.Wo) * g.cpr + c;
+    const uint4* rb = ra + (long long)g.Wo * g.cpr;
+    uint4* out = dz + ((long long)(n * g.H + hi) * g.W) * g.cpr + c;
+    f2 gp[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gp[i] = 0ull;
+    uint4 qa = __ldg(ra), qb = ldg16(rb, ok1);
+    for (int b = 0; b < g.Wo; ++b) {
+      f2 ya[4], yb[4], gb[4], o[4];
+      unpack(qa, ya); unpack(qb, yb);
+      if (b + 1 < g.Wo) { qa = __ldg(ra + (long long)(b + 1) * g.cpr); qb = ldg16(rb + (long long)(b + 1) * g.cpr, ok1); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gb[i] = odd ? fma2(k[0][i], yb[i], mul2(k[2][i], ya[i])) : mul2(k[1][i], ya[i]);
+      if (b >= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = fma2(k[3][i], gb[i], mul2(k[5][i], gp[i]));
+        out[(long long)(2 * b - 1) * g.cpr] = pack(o);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = mul2(k[4][i], gb[i]);
+      out[(long long)(2 * b) * g.cpr] = pack(o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gp[i] = gb[i];
+    }
+    f2 o[4];                                           // column W-1 = 2 (Wo-1) + 1: g[Wo] is the zero padding
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = mul2(k[5][i], gp[i]);
+    out[(long long)(g.W - 1) * g.cpr] = pack(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient: item = (n, ho, chunk), walk over the output columns with a 3 x 3 window of unpacked z1 columns.
+// acc [9][ld] fp32 += per-block partial sums (shared-memory reduction over the block's rows first).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int STRIDE>
+__global__ void __launch_bounds__(128) dwsep_wgrad_kernel(const Geom g, const uint4* __restrict__ z, const uint4* __restrict__ gy,
+                                                          float* __restrict__ acc) {
+  extern __shared__ float sacc[];                      // [9][ld]
+  const int ld = g.cpr * 8;
+  for (int i = threadIdx.x; i < 9 * ld; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < g.items; item += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(item % g.cpr);
+    const long long t = item / g.cpr;
+    const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
+    const int h1 = ho * STRIDE;
+    const bool ok0 = h1 >= 1, ok2 = h1 + 1 < g.H;
+    const uint4* r1 = z + ((long long)(n * g.H + h1) * g.W) * g.cpr + c;
+    const uint4* r0 = r1 - (long long)g.W * g.cpr;
+    const uint4* r2 = r1 + (long long)g.W * g.cpr;
+    const uint4* rg = gy + ((long long)(n * g.Ho + ho) * g.Wo) * g.cpr + c;
+    f2 dT[9][4];
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dT[a][i] = 0ull;
+    f2 win[3][3][4];                                   // [column slot][row][pair]; slot of input column x is (x + 1) % 3
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) win[s][r][i] = 0ull;
+    auto load_col = [&](int x, f2 (&col)[3][4]) {      // column x of the three input rows (zero outside the map)
+      const bool okx = x >= 0 && x < g.W;
+      const long long off = (long long)x * g.cpr;
+      unpack(ldg16(r0 + off, okx && ok0), col[0]);
+      unpack(ldg16(r1 + off, okx), col[1]);
+      unpack(ldg16(r2 + off, okx && ok2), col[2]);
+    };
+    // centre wo reads input columns s wo - 1, s wo, s wo + 1; three centres per trip so the slots rotate at compile time
+    if (STRIDE == 1) load_col(0, win[1]);
+    for (int w0 = 0; w0 < g.Wo; w0 += 3) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int wo = w0 + u;
+        if (wo < g.Wo) {
+          f2 d[4];
+          unpack(__ldg(rg + (long long)wo * g.cpr), d);
+          if (STRIDE == 1) {
+            // slots: column wo-1 -> u % 3, wo -> (u+1) % 3, wo+1 -> (u+2) % 3 (w0 is a multiple of 3)
+            load_col(wo + 1, win[(u + 2) % 3]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dT[3 * r + j][i] = fma2(d[i], win[(u + j) % 3][r][i], dT[3 * r + j][i]);
+          } else {
+            // columns 2wo-1 (kept from the previous centre in slot 0), 2wo -> slot 1, 2wo+1 -> slot 2
+            if (wo == 0) load_col(-1, win[0]);
+            load_col(2 * wo, win[1]);
+            load_col(2 * wo + 1, win[2]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dT[3 * r + j][i] = fma2(d[i], win[j][r][i], dT[3 * r + j][i]);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) win[0][r][i] = win[2][r][i];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(sacc + a * ld + c * 8 + 2 * i, lo_of(dT[a][i]));
+        atomicAdd(sacc + a * ld + c * 8 + 2 * i + 1, hi_of(dT[a][i]));
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * ld; i += blockDim.x) atomicAdd(acc + i, sacc[i]);
+}
+
+// taps [6][ld] fp32 = kh0 kh1 kh2, lambda kw0, lambda kw1, lambda kw2 (flip: both triples reversed), pad channels zero
+__global__ void dwsep_taps_kernel(const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kw,
+                                  const __nv_bfloat16* __restrict__ lam, int R, int ld, int flip, float* __restrict__ taps) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 6 * ld; i += gridDim.x * blockDim.x) {
+    const int t = i / ld, r = i - t * ld;
+    float v = 0.f;
+    if (r < R) {
+      const int tt = flip ? (t < 3 ? 2 - t : 8 - t) : t;
+      v = tt < 3 ? __bfloat162float(kh[tt * R + r]) : __bfloat162float(kw[(tt - 3) * R + r]) * __bfloat162float(lam[r]);
+    }
+    taps[i] = v;
+  }
+}
+
+// dT [9][ld] -> bf16 gradients of kh (3, R), kw (3, R), lambda (R)
+__global__ void dwsep_finalize_kernel(const float* __restrict__ dT, const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kw,
+                                      const __nv_bfloat16* __restrict__ lam, int R, int ld, __nv_bfloat16* __restrict__ g_kh,
+                                      __nv_bfloat16* __restrict__ g_kw, __nv_bfloat16* __restrict__ g_lam) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    float h[3], w[3], t[9];
+    const float l = __bfloat162float(lam[r]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { h[a] = __bfloat162float(kh[a * R + r]); w[a] = __bfloat162float(kw[a * R + r]); }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) t[a] = dT[a * ld + r];
+    float gl = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float gh = l * (w[0] * t[3 * a] + w[1] * t[3 * a + 1] + w[2] * t[3 * a + 2]);
+      const float gwl = h[0] * t[a] + h[1] * t[3 + a] + h[2] * t[6 + a];
+      g_kh[a * R + r] = __float2bfloat16_rn(gh);
+      g_kw[a * R + r] = __float2bfloat16_rn(l * gwl);
+      gl += w[a] * gwl;
+    }
+    g_lam[r] = __float2bfloat16_rn(gl);
+  }
+}
+
+static int fill(const tlt_dwsep_desc* d, Geom* g, bool input_rows) {
+  TLT_REQUIRE(d && d->batch >= 1 && d->height >= 1 && d->width >= 2 && d->ld >= 8 && d->ld % 8 == 0 && (d->stride == 1 || d->stride == 2),
+              "tlt_dwsep_rows: bad descriptor");
+  TLT_REQUIRE(d->stride == 1 || (d->height % 2 == 0 && d->width % 2 == 0), "tlt_dwsep_rows: stride 2 needs even map extents");
+  g->batch = (int)d->batch; g->H = (int)d->height; g->W = (int)d->width;
+  g->Ho = g->H / d->stride; g->Wo = g->W / d->stride; g->cpr = (int)(d->ld / 8);
+  g->items = (long long)g->batch * (input_rows ? g->H : g->Ho) * g->cpr;
+  TLT_REQUIRE((long long)g->batch * g->H * g->W * g->cpr < (1LL << 40), "tlt_dwsep_rows: tensor too large");
+  return TLT_OK;
+}
+static unsigned grid_for(long long items) {
+  const long long blocks = (items + 127) / 128, cap = (long long)device_sms() * 16;
+  return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace dws
+}  // namespace tlt
+
+using namespace tlt;
+using namespace tlt::dws;
+
+extern "C" int tlt_dwsep_rows_taps(const void* kh, const void* kw, const void* lam, int64_t rank, int64_t ld, int32_t flip, float* taps,
+                                   void* stream) {
+  TLT_REQUIRE(kh && kw && lam && taps && rank >= 1 && ld >= rank && ld % 8 == 0, "tlt_dwsep_rows_taps: bad arguments");
+  dwsep_taps_kernel<<<(unsigned)((6 * ld + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)kh, (const __nv_bfloat16*)kw,
+                                                                                       (const __nv_bfloat16*)lam, (int)rank, (int)ld, flip, taps);
+  return check_launch("dwsep_taps_kernel");
+}
+
+extern "C" int tlt_dwsep_rows_fwd(const tlt_dwsep_desc* d, const void* z, const float* taps, void* y, void* stream) {
+  Geom g;
+  int rc = fill(d, &g, false);
+  if (rc) return rc;
+  TLT_REQUIRE(z && taps && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)taps % 16) == 0, "tlt_dwsep_rows_fwd: 16-byte aligned tensors");
+  if (d->stride == 1) dwsep_fwd_kernel<1><<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, taps, (uint4*)y);
+  else dwsep_fwd_kernel<2><<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, taps, (uint4*)y);
+  return check_launch("dwsep_fwd_kernel");
+}
+
+// taps_flipped: tlt_dwsep_rows_taps(..., flip = 1) for stride 1; the UNFLIPPED taps for stride 2 (the transposed sweep indexes them itself)
+extern "C" int tlt_dwsep_rows_dgrad(const tlt_dwsep_desc* d, const void* gy, const float* taps, void* dz, void* stream) {
+  Geom g;
+  int rc = fill(d, &g, true);
+  if (rc) return rc;
+  TLT_REQUIRE(gy && taps && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)dz % 16) == 0 && ((uintptr_t)taps % 16) == 0, "tlt_dwsep_rows_dgrad: 16-byte aligned tensors");
+  if (d->stride == 1) dwsep_fwd_kernel<1><<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, taps, (uint4*)dz);
+  else dwsep_dgrad2_kernel<<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, taps, (uint4*)dz);
+  return check_launch("dwsep dgrad kernel");
+}
+
+extern "C" int tlt_dwsep_rows_wgrad(const tlt_dwsep_desc* d, const void* z, const void* gy, float* acc, void* stream) {
+  Geom g;
+  int rc = fill(d, &g, false);
+  if (rc) return rc;
+  TLT_REQUIRE(z && gy && acc && ((uintptr_t)z % 16) == 0 && ((uintptr_t)gy % 16) == 0, "tlt_dwsep_rows_wgrad: 16-byte aligned tensors");
+  const size_t smem = (size_t)9 * d->ld * sizeof(float);
+  TLT_REQUIRE(smem <= 48 * 1024, "tlt_dwsep_rows_wgrad: ld too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  TLT_CHECK_CUDA(cudaMemsetAsync(acc, 0, smem, st));
+  const long long blocks = (g.items + 127) / 128, cap = (long long)device_sms() * 4;
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  if (d->stride == 1) dwsep_wgrad_kernel<1><<<grid, 128, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
+  else dwsep_wgrad_kernel<2><<<grid, 128, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
+  return check_launch("dwsep_wgrad_kernel");
+}
+
+extern "C" int tlt_dwsep_rows_finalize(const float* acc, const void* kh, const void* kw, const void* lam, int64_t rank, int64_t ld, void* g_kh,
+                                       void* g_kw, void* g_lam, void* stream) {
+  TLT_REQUIRE(acc && kh && kw && lam && g_kh && g_kw && g_lam && rank >= 1 && ld >= rank, "tlt_dwsep_rows_finalize: bad arguments");
+  dwsep_finalize_kernel<<<(unsigned)((rank + 127) / 128), 128, 0, (cudaStream_t)stream>>>(acc, (const __nv_bfloat16*)kh, (const __nv_bfloat16*)kw,
+                                                                                         (const __nv_bfloat16*)lam, (int)rank, (int)ld,
+                                                                                         (__nv_bfloat16*)g_kh, (__nv_bfloat16*)g_kw,
+                                                                                         (__nv_bfloat16*)g_lam);
+  return check_launch("dwsep_finalize_kernel");
+}

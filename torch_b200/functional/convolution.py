@@ -122,6 +122,10 @@ def _cp_conv_impl(x, cp_tensor, bias, stride, padding, dilation):
         # HBM-bound 3x3 layers on channels-last maps (config 3's 56^2 layers): the whole chain -- and, going back, every gradient --
         # in one launch per direction, the R-channel intermediates in TMEM / shared memory (cprows_ops, csrc/cpconv_rows.cu)
         return cprows_ops.cp_conv_rows_fused(x, cp_tensor.weights, factors, bias, stride[0])
+    if order == 2 and rows_ops.dwsep_eligible(factors, kernel, stride, padding, dilation, list(x.shape[2:])) and \
+            _cp_rows_route(x, cp_tensor, bias, kernel, stride):
+        # channels-last rows with the separable depthwise sweep: the taps go in unmerged (rows_ops.cp_conv_rows_sep)
+        return rows_ops.cp_conv_rows_sep(x, cp_tensor.weights, factors, bias, stride[0])
     if kr_ops.eligible(factors[2:], cp_tensor.weights):
         taps_t = kr_ops.khatri_rao(factors[2:], cp_tensor.weights)                 # (prod k, R), taps-major
         f0 = factors[0]

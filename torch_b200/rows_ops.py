@@ -424,6 +424,108 @@ _dwrows_op.register_autograd(_dwrows_backward, setup_context=_dwrows_setup)
 DW_ROWS_MAX_TAPS = 9
 
 
+# =====================================================================================================================
+# separable 3x3 depthwise on rows (tlt_dwsep_rows_*): both passes in one sweep, the CP taps go in unmerged
+# =====================================================================================================================
+def _dwsep_desc(batch, height, width, ld, stride):
+    d = _cuda.DwSepDesc()
+    d.batch, d.height, d.width, d.ld, d.stride = batch, height, width, ld, stride
+    return d
+
+
+def _execute_dwsep_taps(kh, kw, lam, ld, flip, taps):
+    _cuda.require_cuda(kh, kw, lam, taps)
+    _cuda.check(_cuda.lib().tlt_dwsep_rows_taps(_cuda.ptr(kh), _cuda.ptr(kw), _cuda.ptr(lam), kh.shape[1], ld, 1 if flip else 0,
+                                                _cuda.ptr(taps), _cuda.stream_ptr(taps)), "tlt_dwsep_rows_taps")
+
+
+def _execute_dwsep(kind, a, b, out, batch, height, width, stride):
+    """kind 'fwd': out = sweep(a; taps b); 'dgrad': out = sweep^T(a; taps b); 'wgrad': out (9, ld) fp32 = sum a(+tap) * b."""
+    _cuda.require_cuda(a, b, out)
+    d = _dwsep_desc(batch, height, width, a.shape[1], stride)
+    fn = {"fwd": "tlt_dwsep_rows_fwd", "dgrad": "tlt_dwsep_rows_dgrad", "wgrad": "tlt_dwsep_rows_wgrad"}[kind]
+    _cuda.check(getattr(_cuda.lib(), fn)(C.byref(d), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(out), _cuda.stream_ptr(a)), fn)
+
+
+def _execute_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam):
+    _cuda.require_cuda(acc, kh, kw, lam, g_kh, g_kw, g_lam)
+    _cuda.check(_cuda.lib().tlt_dwsep_rows_finalize(_cuda.ptr(acc), _cuda.ptr(kh), _cuda.ptr(kw), _cuda.ptr(lam), kh.shape[1],
+                                                    acc.shape[1], _cuda.ptr(g_kh), _cuda.ptr(g_kw), _cuda.ptr(g_lam),
+                                                    _cuda.stream_ptr(acc)), "tlt_dwsep_rows_finalize")
+
+
+@torch.library.custom_op("tltorch::dwsep_rows", mutates_args=())
+def _dwsep_op(z: torch.Tensor, kh: torch.Tensor, kw: torch.Tensor, lam: torch.Tensor, batch: int, height: int, width: int,
+              stride: int) -> torch.Tensor:
+    z, kh, kw, lam = z.contiguous(), kh.contiguous(), kw.contiguous(), lam.contiguous()
+    taps = torch.empty((6, z.shape[1]), dtype=torch.float32, device=z.device)
+    _execute_dwsep_taps(kh, kw, lam, z.shape[1], False, taps)
+    y = torch.empty((batch * (height // stride) * (width // stride), z.shape[1]), dtype=z.dtype, device=z.device)
+    _execute_dwsep("fwd", z, taps, y, batch, height, width, stride)
+    return y
+
+
+@_dwsep_op.register_fake
+def _(z, kh, kw, lam, batch, height, width, stride):
+    return z.new_empty((batch * (height // stride) * (width // stride), z.shape[1]))
+
+
+@torch.library.custom_op("tltorch::dwsep_rows_bwd", mutates_args=())
+def _dwsep_bwd_op(gy: torch.Tensor, z: torch.Tensor, kh: torch.Tensor, kw: torch.Tensor, lam: torch.Tensor, batch: int, height: int,
+                  width: int, stride: int) -> List[torch.Tensor]:
+    gy, z, kh, kw, lam = gy.contiguous(), z.contiguous(), kh.contiguous(), kw.contiguous(), lam.contiguous()
+    ld = z.shape[1]
+    taps = torch.empty((6, ld), dtype=torch.float32, device=z.device)
+    _execute_dwsep_taps(kh, kw, lam, ld, stride == 1, taps)      # stride 1: the same sweep with reversed taps
+    dz = torch.empty_like(z)
+    _execute_dwsep("dgrad", gy, taps, dz, batch, height, width, stride)
+    acc = torch.empty((9, ld), dtype=torch.float32, device=z.device)
+    _execute_dwsep("wgrad", z, gy, acc, batch, height, width, stride)
+    g_kh, g_kw, g_lam = torch.empty_like(kh), torch.empty_like(kw), torch.empty_like(lam)
+    _execute_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam)
+    return [dz, g_kh, g_kw, g_lam]
+
+
+@_dwsep_bwd_op.register_fake
+def _(gy, z, kh, kw, lam, batch, height, width, stride):
+    return [torch.empty_like(z), torch.empty_like(kh), torch.empty_like(kw), torch.empty_like(lam)]
+
+
+def _dwsep_setup(ctx, inputs, output):
+    z, kh, kw, lam, ctx.batch, ctx.height, ctx.width, ctx.stride = inputs
+    ctx.save_for_backward(z, kh, kw, lam)
+
+
+def _dwsep_backward(ctx, gy):
+    z, kh, kw, lam = ctx.saved_tensors
+    dz, g_kh, g_kw, g_lam = _dwsep_bwd_op(gy, z, kh, kw, lam, ctx.batch, ctx.height, ctx.width, ctx.stride)
+    return dz, g_kh, g_kw, g_lam, None, None, None, None
+
+
+_dwsep_op.register_autograd(_dwsep_backward, setup_context=_dwsep_setup)
+
+
+def dwsep_eligible(factors, kernel, stride, padding, dilation, spatial):
+    """2-D 3x3, padding 1, dilation 1, equal strides 1 or 2 (even maps), rank small enough for the kernel's shared accumulators."""
+    if len(factors) != 4 or list(kernel) != [3, 3] or list(padding) != [1, 1] or list(dilation) != [1, 1]:
+        return False
+    if stride[0] != stride[1] or stride[0] not in (1, 2) or spatial[1] < 2 or _r8(factors[2].shape[1]) * 36 > 48 * 1024:
+        return False
+    return stride[0] == 1 or (spatial[0] % 2 == 0 and spatial[1] % 2 == 0)
+
+
+def cp_conv_rows_sep(x, weights, factors, bias, stride):
+    """CP convolution on channels-last rows with the separable depthwise sweep: x (B, C_in, H, W) bf16; factors = [F_out (C_out, R),
+    F_in (C_in, R), kh (3, R), kw (3, R)], weights = lambda (R).  x -> rows -> [C_in -> R: GEMM] -> separable depthwise (lambda in
+    the W taps) -> [R -> C_out: GEMM + bias] -> NCHW; no Khatri-Rao product of the taps and no gradient kernel for it."""
+    b, h, w = x.shape[0], x.shape[2], x.shape[3]
+    xt = nchw_to_rows(x)                                                       # (B S, round8(C_in))
+    z = padded_linear(xt, factors[1].t(), None, True)                          # (B S, round8(R)), pad columns zero
+    z = _dwsep_op(z, factors[2], factors[3], weights, b, h, w, stride)         # (B S', round8(R))
+    yt = padded_linear(z, factors[0], bias, True)                              # (B S', round8(C_out))
+    return rows_to_nchw(yt, b, factors[0].shape[0], [h // stride, w // stride], channels_last=is_channels_last(x))
+
+
 def dwconv_rows(z, w_taps, batch, in_size, kernel, stride, padding, dilation):
     """z (B * prod(in_size), Cp) bf16, w_taps (prod(kernel), Cp) -> (B * prod(out_size), Cp)."""
     return _dwrows_op(z, w_taps, batch, list(in_size), list(kernel), list(stride), list(padding), list(dilation))
