@@ -296,8 +296,9 @@ int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R,
  *   tlt_dwsep_rows_taps      taps [6][ld] fp32 <- kh (3, R), kw (3, R), lambda (R) bf16 (flip = 1: both triples reversed)
  *   tlt_dwsep_rows_fwd       z2 <- z1, taps
  *   tlt_dwsep_rows_dgrad     dz1 <- dz2, taps (stride 1: the FLIPPED taps; stride 2: the unflipped ones)
- *   tlt_dwsep_rows_wgrad     acc [9][ld] fp32 <- z1, dz2 (zeroed by the call): acc[3 i + j][r] = sum dz2 * z1(+i-1, +j-1)
- *   tlt_dwsep_rows_finalize  bf16 gradients of kh, kw, lambda <- acc
+ *   tlt_dwsep_rows_wgrad     acc [parts][9][ld] fp32 <- z1, dz2: per-block partial sums of dz2 * z1(+i-1, +j-1) at [3 i + j][r];
+ *                            parts = tlt_dwsep_rows_wgrad_parts() (the call writes every element)
+ *   tlt_dwsep_rows_finalize  bf16 gradients of kh, kw, lambda <- the partial sums
  * Replaces: the per-mode depthwise convolutions of cp_conv (tltorch/functional/convolution.py:251-269) and their autograd, and
  * the Khatri-Rao product of the kernel-mode factors that the merged-tap kernels needed.
  * ------------------------------------------------------------------------------------------------------------ */
@@ -308,9 +309,10 @@ typedef struct {
 int tlt_dwsep_rows_taps(const void* kh, const void* kw, const void* lambda, int64_t rank, int64_t ld, int32_t flip, float* taps, void* stream);
 int tlt_dwsep_rows_fwd(const tlt_dwsep_desc* desc, const void* z, const float* taps, void* y, void* stream);
 int tlt_dwsep_rows_dgrad(const tlt_dwsep_desc* desc, const void* gy, const float* taps, void* dz, void* stream);
+int tlt_dwsep_rows_wgrad_parts(void);
 int tlt_dwsep_rows_wgrad(const tlt_dwsep_desc* desc, const void* z, const void* gy, float* acc, void* stream);
-int tlt_dwsep_rows_finalize(const float* acc, const void* kh, const void* kw, const void* lambda, int64_t rank, int64_t ld, void* g_kh,
-                            void* g_kw, void* g_lambda, void* stream);
+int tlt_dwsep_rows_finalize(const float* acc, int32_t parts, const void* kh, const void* kw, const void* lambda, int64_t rank, int64_t ld,
+                            void* g_kh, void* g_kw, void* g_lambda, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * Op-level fused CP convolution on channels-last rows (bf16): x (B, H, W, C_in) -> y (B, H/s, W/s, C_out),

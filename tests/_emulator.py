@@ -355,13 +355,14 @@ def emulate_dwsep(kind, a, b, out, batch, height, width, stride):
         with torch.enable_grad():
             w0 = torch.zeros((ld, 1, 3, 3), dtype=torch.float64)
             res = torch.func.vjp(lambda w: conv(zz, w), w0)[1](img(b, ho, wo))[0]
-        out.copy_(res.reshape(ld, 9).t().to(out.dtype))
+        out.zero_()
+        out[0].copy_(res.reshape(ld, 9).t().to(out.dtype))
     LOG.append(("dwsep_rows_" + kind, (height, width), stride))
 
 
 def emulate_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam):
     r = kh.shape[1]
-    t = acc.double()[:, :r].reshape(3, 3, r)                                          # [i][j][r]
+    t = acc.double().sum(0)[:, :r].reshape(3, 3, r)                                   # [i][j][r]
     h, w, l = kh.double(), kw.double(), lam.double()
     g_kh.copy_((l * torch.einsum("jr,ijr->ir", w, t)).to(g_kh.dtype))
     gwl = torch.einsum("ir,ijr->jr", h, t)
@@ -499,8 +500,9 @@ def emulated_kernels():
     ko._execute_kr_fwd, ko._execute_kr_bwd = emulate_kr_fwd, emulate_kr_bwd
     saved_r = ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows
     saved_s = ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows
-    saved_ds = ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize
+    saved_ds = ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize, ro._dwsep_parts
     ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize = emulate_dwsep_taps, emulate_dwsep, emulate_dwsep_finalize
+    ro._dwsep_parts = lambda: 2
     ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = (
         emulate_skinny_fwd, emulate_skinny_bwd, emulate_scale_modes, emulate_dwconv_rows)
     ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = emulate_nchw_to_rows, emulate_rows_to_nchw, emulate_unfold_rows
@@ -528,5 +530,5 @@ def emulated_kernels():
         ko._execute_kr_fwd, ko._execute_kr_bwd = saved_k
         ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
         ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = saved_s
-        ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize = saved_ds
+        ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize, ro._dwsep_parts = saved_ds
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

@@ -120,7 +120,8 @@ SYMBOLS = {
     "tlt_dwsep_rows_fwd": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
     "tlt_dwsep_rows_dgrad": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
     "tlt_dwsep_rows_wgrad": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
-    "tlt_dwsep_rows_finalize": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
+    "tlt_dwsep_rows_wgrad_parts": (C.c_int, []),
+    "tlt_dwsep_rows_finalize": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
     "tlt_cpconv_rows_supported": (C.c_int, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_grad_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
@@ -165,7 +166,7 @@ class _Library:
     def __getattr__(self, name):
         fn = getattr(self._handle, name)
         res, args = SYMBOLS.get(name, (None, []))
-        is_launcher = res is C.c_int and name not in ("tlt_version",) and not name.endswith("_supported")
+        is_launcher = res is C.c_int and name not in ("tlt_version", "tlt_dwsep_rows_wgrad_parts") and not name.endswith("_supported")
         if is_launcher:
             def call(*a, _fn=fn, _name=name):
                 if PROFILE is None:

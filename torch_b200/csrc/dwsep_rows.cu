@@ -79,25 +79,43 @@ __global__ void __launch_bounds__(128) dwsep_fwd_kernel(const Geom g, const uint
     f2 va[4], vb[4];                                   // H-pass results of columns w-2, w-1
 #pragma unroll
     for (int i = 0; i < 4; ++i) { va[i] = 0ull; vb[i] = 0ull; }
-    uint4 q0 = ldg16(r0, ok0), q1 = __ldg(r1), q2 = ldg16(r2, ok2);
-    for (int w = 0; w < g.W; ++w) {
-      f2 a[4], b[4], d[4], v[4];
-      unpack(q0, a); unpack(q1, b); unpack(q2, d);
-      if (w + 1 < g.W) {                               // next column in flight while this one is finished
-        const long long off = (long long)(w + 1) * g.cpr;
-        q0 = ldg16(r0 + off, ok0); q1 = __ldg(r1 + off); q2 = ldg16(r2 + off, ok2);
+    // two columns per trip; the next two are in flight while these are finished (the sweep is latency-bound otherwise)
+    uint4 q[2][3];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool okw = u < g.W;
+      q[u][0] = ldg16(r0 + (long long)u * g.cpr, ok0 && okw); q[u][1] = ldg16(r1 + (long long)u * g.cpr, okw);
+      q[u][2] = ldg16(r2 + (long long)u * g.cpr, ok2 && okw);
+    }
+    for (int w0 = 0; w0 < g.W; w0 += 2) {
+      f2 a[2][4], b[2][4], d[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { unpack(q[u][0], a[u]); unpack(q[u][1], b[u]); unpack(q[u][2], d[u]); }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int x = w0 + 2 + u;
+        const bool okw = x < g.W;
+        const long long off = (long long)x * g.cpr;
+        q[u][0] = ldg16(r0 + off, ok0 && okw); q[u][1] = ldg16(r1 + off, okw); q[u][2] = ldg16(r2 + off, ok2 && okw);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = fma2(k[2][i], d[i], fma2(k[1][i], b[i], mul2(k[0][i], a[i])));
-      // output column w-1 (stride 1) or (w-1)/2 (stride 2, w odd) : kw0 v[w-2] + kw1 v[w-1] + kw2 v[w]
-      if (w >= 1 && (STRIDE == 1 || (w & 1))) {
-        f2 o[4];
+      for (int u = 0; u < 2; ++u) {
+        const int w = w0 + u;
+        if (w < g.W) {
+          f2 v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = fma2(k[5][i], v[i], fma2(k[4][i], vb[i], mul2(k[3][i], va[i])));
-        out[(long long)((w - 1) / STRIDE) * g.cpr] = pack(o);
+          for (int i = 0; i < 4; ++i) v[i] = fma2(k[2][i], d[u][i], fma2(k[1][i], b[u][i], mul2(k[0][i], a[u][i])));
+          // output column w-1 (stride 1) or (w-1)/2 (stride 2, w odd) : kw0 v[w-2] + kw1 v[w-1] + kw2 v[w]
+          if (w >= 1 && (STRIDE == 1 || u == 1)) {
+            f2 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = fma2(k[5][i], v[i], fma2(k[4][i], vb[i], mul2(k[3][i], va[i])));
+            out[(long long)((w - 1) / STRIDE) * g.cpr] = pack(o);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { va[i] = vb[i]; vb[i] = v[i]; }
+        }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { va[i] = vb[i]; vb[i] = v[i]; }
     }
     if (STRIDE == 1) {                                 // last column: right neighbour is the zero padding
       f2 o[4];
@@ -159,74 +177,89 @@ __global__ void __launch_bounds__(128) dwsep_dgrad2_kernel(const Geom g, const u
 // acc [9][ld] fp32 += per-block partial sums (shared-memory reduction over the block's rows first).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int STRIDE>
-__global__ void __launch_bounds__(128) dwsep_wgrad_kernel(const Geom g, const uint4* __restrict__ z, const uint4* __restrict__ gy,
-                                                          float* __restrict__ acc) {
+__global__ void __launch_bounds__(256) dwsep_wgrad_kernel(const Geom g, const uint4* __restrict__ z, const uint4* __restrict__ gy,
+                                                          float* __restrict__ part) {
   extern __shared__ float sacc[];                      // [9][ld]
   const int ld = g.cpr * 8;
   for (int i = threadIdx.x; i < 9 * ld; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
-  for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < g.items; item += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(item % g.cpr);
-    const long long t = item / g.cpr;
-    const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
-    const int h1 = ho * STRIDE;
-    const bool ok0 = h1 >= 1, ok2 = h1 + 1 < g.H;
-    const uint4* r1 = z + ((long long)(n * g.H + h1) * g.W) * g.cpr + c;
-    const uint4* r0 = r1 - (long long)g.W * g.cpr;
-    const uint4* r2 = r1 + (long long)g.W * g.cpr;
-    const uint4* rg = gy + ((long long)(n * g.Ho + ho) * g.Wo) * g.cpr + c;
-    f2 dT[9][4];
+  // a thread keeps ONE channel chunk for the whole kernel and walks many (image, row) items: its 72 sums stay in registers and
+  // are reduced once -- shared memory across the block's row lanes, then one plain store per block into part[block][9][ld]
+  const int lanes = blockDim.x / g.cpr;
+  const int c = threadIdx.x % g.cpr, lane = threadIdx.x / g.cpr;
+  const long long rows_total = (long long)g.batch * g.Ho;
+  f2 dT[9][4];
 #pragma unroll
-    for (int a = 0; a < 9; ++a)
+  for (int a = 0; a < 9; ++a)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dT[a][i] = 0ull;
-    f2 win[3][3][4];                                   // [column slot][row][pair]; slot of input column x is (x + 1) % 3
+    for (int i = 0; i < 4; ++i) dT[a][i] = 0ull;
+  if (lane < lanes) {
+    for (long long t = (long long)blockIdx.x * lanes + lane; t < rows_total; t += (long long)gridDim.x * lanes) {
+      const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
+      const int h1 = ho * STRIDE;
+      const bool ok0 = h1 >= 1, ok2 = h1 + 1 < g.H;
+      const uint4* r1 = z + ((long long)(n * g.H + h1) * g.W) * g.cpr + c;
+      const uint4* r0 = r1 - (long long)g.W * g.cpr;
+      const uint4* r2 = r1 + (long long)g.W * g.cpr;
+      const uint4* rg = gy + ((long long)(n * g.Ho + ho) * g.Wo) * g.cpr + c;
+      f2 win[3][3][4];                                 // [column slot][row][pair]
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+      for (int s = 0; s < 3; ++s)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) win[s][r][i] = 0ull;
-    auto load_col = [&](int x, f2 (&col)[3][4]) {      // column x of the three input rows (zero outside the map)
-      const bool okx = x >= 0 && x < g.W;
-      const long long off = (long long)x * g.cpr;
-      unpack(ldg16(r0 + off, okx && ok0), col[0]);
-      unpack(ldg16(r1 + off, okx), col[1]);
-      unpack(ldg16(r2 + off, okx && ok2), col[2]);
-    };
-    // centre wo reads input columns s wo - 1, s wo, s wo + 1; three centres per trip so the slots rotate at compile time
-    if (STRIDE == 1) load_col(0, win[1]);
-    for (int w0 = 0; w0 < g.Wo; w0 += 3) {
+          for (int i = 0; i < 4; ++i) win[s][r][i] = 0ull;
+      // raw loads of the NEXT centre's new columns are in flight while the current centre is accumulated
+      constexpr int NC = STRIDE == 1 ? 1 : 2;          // new input columns per centre
+      uint4 qz[NC][3], qg;
+      auto issue = [&](int wo) {                       // centre wo needs columns wo+1 (stride 1) / 2wo, 2wo+1 (stride 2)
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int wo = w0 + u;
-        if (wo < g.Wo) {
-          f2 d[4];
-          unpack(__ldg(rg + (long long)wo * g.cpr), d);
-          if (STRIDE == 1) {
-            // slots: column wo-1 -> u % 3, wo -> (u+1) % 3, wo+1 -> (u+2) % 3 (w0 is a multiple of 3)
-            load_col(wo + 1, win[(u + 2) % 3]);
+        for (int u = 0; u < NC; ++u) {
+          const int x = STRIDE == 1 ? wo + 1 : 2 * wo + u;
+          const bool okx = wo < g.Wo && x < g.W;
+          const long long off = (long long)x * g.cpr;
+          qz[u][0] = ldg16(r0 + off, okx && ok0); qz[u][1] = ldg16(r1 + off, okx); qz[u][2] = ldg16(r2 + off, okx && ok2);
+        }
+        qg = ldg16(rg + (long long)wo * g.cpr, wo < g.Wo);
+      };
+      if (STRIDE == 1) {                               // column 0 -> slot 1 (column -1 = slot 0 stays zero)
+        unpack(ldg16(r0, ok0), win[1][0]); unpack(__ldg(r1), win[1][1]); unpack(ldg16(r2, ok2), win[1][2]);
+      }
+      issue(0);
+      for (int w0 = 0; w0 < g.Wo; w0 += 3) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
+        for (int u = 0; u < 3; ++u) {
+          const int wo = w0 + u;
+          if (wo < g.Wo) {
+            f2 d[4];
+            unpack(qg, d);
+            if (STRIDE == 1) {
+              // slots: column wo-1 -> u % 3, wo -> (u+1) % 3, wo+1 -> (u+2) % 3 (w0 is a multiple of 3)
+#pragma unroll
+              for (int r = 0; r < 3; ++r) unpack(qz[0][r], win[(u + 2) % 3][r]);
+              issue(wo + 1);
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) dT[3 * r + j][i] = fma2(d[i], win[(u + j) % 3][r][i], dT[3 * r + j][i]);
+            } else {
+              // columns 2wo-1 (kept from the previous centre in slot 0; zero for wo = 0), 2wo -> slot 1, 2wo+1 -> slot 2
+#pragma unroll
+              for (int r = 0; r < 3; ++r) { unpack(qz[0][r], win[1][r]); unpack(qz[1][r], win[2][r]); }
+              issue(wo + 1);
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) dT[3 * r + j][i] = fma2(d[i], win[j][r][i], dT[3 * r + j][i]);
 #pragma unroll
               for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dT[3 * r + j][i] = fma2(d[i], win[(u + j) % 3][r][i], dT[3 * r + j][i]);
-          } else {
-            // columns 2wo-1 (kept from the previous centre in slot 0), 2wo -> slot 1, 2wo+1 -> slot 2
-            if (wo == 0) load_col(-1, win[0]);
-            load_col(2 * wo, win[1]);
-            load_col(2 * wo + 1, win[2]);
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-#pragma unroll
-              for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dT[3 * r + j][i] = fma2(d[i], win[j][r][i], dT[3 * r + j][i]);
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) win[0][r][i] = win[2][r][i];
+                for (int i = 0; i < 4; ++i) win[0][r][i] = win[2][r][i];
+            }
           }
         }
       }
@@ -240,7 +273,8 @@ __global__ void __launch_bounds__(128) dwsep_wgrad_kernel(const Geom g, const ui
       }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 9 * ld; i += blockDim.x) atomicAdd(acc + i, sacc[i]);
+  float* out = part + (size_t)blockIdx.x * 9 * ld;
+  for (int i = threadIdx.x; i < 9 * ld; i += blockDim.x) out[i] = sacc[i];
 }
 
 // taps [6][ld] fp32 = kh0 kh1 kh2, lambda kw0, lambda kw1, lambda kw2 (flip: both triples reversed), pad channels zero
@@ -258,8 +292,9 @@ __global__ void dwsep_taps_kernel(const __nv_bfloat16* __restrict__ kh, const __
 }
 
 // dT [9][ld] -> bf16 gradients of kh (3, R), kw (3, R), lambda (R)
-__global__ void dwsep_finalize_kernel(const float* __restrict__ dT, const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kw,
-                                      const __nv_bfloat16* __restrict__ lam, int R, int ld, __nv_bfloat16* __restrict__ g_kh,
+__global__ void dwsep_finalize_kernel(const float* __restrict__ dT, int parts, const __nv_bfloat16* __restrict__ kh,
+                                      const __nv_bfloat16* __restrict__ kw, const __nv_bfloat16* __restrict__ lam, int R, int ld,
+                                      __nv_bfloat16* __restrict__ g_kh,
                                       __nv_bfloat16* __restrict__ g_kw, __nv_bfloat16* __restrict__ g_lam) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
     float h[3], w[3], t[9];
@@ -267,7 +302,10 @@ __global__ void dwsep_finalize_kernel(const float* __restrict__ dT, const __nv_b
 #pragma unroll
     for (int a = 0; a < 3; ++a) { h[a] = __bfloat162float(kh[a * R + r]); w[a] = __bfloat162float(kw[a * R + r]); }
 #pragma unroll
-    for (int a = 0; a < 9; ++a) t[a] = dT[a * ld + r];
+    for (int a = 0; a < 9; ++a) t[a] = 0.f;
+    for (int p = 0; p < parts; ++p)
+#pragma unroll
+      for (int a = 0; a < 9; ++a) t[a] += dT[((size_t)p * 9 + a) * ld + r];
     float gl = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -331,28 +369,29 @@ extern "C" int tlt_dwsep_rows_dgrad(const tlt_dwsep_desc* d, const void* gy, con
   return check_launch("dwsep dgrad kernel");
 }
 
+extern "C" int tlt_dwsep_rows_wgrad_parts(void) { return device_sms(); }   // one 256-thread block per SM (the kernel is register-heavy)
+
+// acc: fp32 [tlt_dwsep_rows_wgrad_parts()][9][ld], fully written by the call (no zeroing needed)
 extern "C" int tlt_dwsep_rows_wgrad(const tlt_dwsep_desc* d, const void* z, const void* gy, float* acc, void* stream) {
   Geom g;
   int rc = fill(d, &g, false);
   if (rc) return rc;
   TLT_REQUIRE(z && gy && acc && ((uintptr_t)z % 16) == 0 && ((uintptr_t)gy % 16) == 0, "tlt_dwsep_rows_wgrad: 16-byte aligned tensors");
   const size_t smem = (size_t)9 * d->ld * sizeof(float);
-  TLT_REQUIRE(smem <= 48 * 1024, "tlt_dwsep_rows_wgrad: ld too large");
+  TLT_REQUIRE(smem <= 48 * 1024 && g.cpr <= 256, "tlt_dwsep_rows_wgrad: ld too large");
   cudaStream_t st = (cudaStream_t)stream;
-  TLT_CHECK_CUDA(cudaMemsetAsync(acc, 0, smem, st));
-  const long long blocks = (g.items + 127) / 128, cap = (long long)device_sms() * 4;
-  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
-  if (d->stride == 1) dwsep_wgrad_kernel<1><<<grid, 128, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
-  else dwsep_wgrad_kernel<2><<<grid, 128, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
+  const unsigned grid = (unsigned)tlt_dwsep_rows_wgrad_parts();
+  if (d->stride == 1) dwsep_wgrad_kernel<1><<<grid, 256, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
+  else dwsep_wgrad_kernel<2><<<grid, 256, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
   return check_launch("dwsep_wgrad_kernel");
 }
 
-extern "C" int tlt_dwsep_rows_finalize(const float* acc, const void* kh, const void* kw, const void* lam, int64_t rank, int64_t ld, void* g_kh,
-                                       void* g_kw, void* g_lam, void* stream) {
-  TLT_REQUIRE(acc && kh && kw && lam && g_kh && g_kw && g_lam && rank >= 1 && ld >= rank, "tlt_dwsep_rows_finalize: bad arguments");
-  dwsep_finalize_kernel<<<(unsigned)((rank + 127) / 128), 128, 0, (cudaStream_t)stream>>>(acc, (const __nv_bfloat16*)kh, (const __nv_bfloat16*)kw,
-                                                                                         (const __nv_bfloat16*)lam, (int)rank, (int)ld,
-                                                                                         (__nv_bfloat16*)g_kh, (__nv_bfloat16*)g_kw,
-                                                                                         (__nv_bfloat16*)g_lam);
+extern "C" int tlt_dwsep_rows_finalize(const float* acc, int32_t parts, const void* kh, const void* kw, const void* lam, int64_t rank,
+                                       int64_t ld, void* g_kh, void* g_kw, void* g_lam, void* stream) {
+  TLT_REQUIRE(acc && parts >= 1 && kh && kw && lam && g_kh && g_kw && g_lam && rank >= 1 && ld >= rank, "tlt_dwsep_rows_finalize: bad arguments");
+  dwsep_finalize_kernel<<<(unsigned)((rank + 63) / 64), 64, 0, (cudaStream_t)stream>>>(acc, parts, (const __nv_bfloat16*)kh,
+                                                                                       (const __nv_bfloat16*)kw, (const __nv_bfloat16*)lam,
+                                                                                       (int)rank, (int)ld, (__nv_bfloat16*)g_kh,
+                                                                                       (__nv_bfloat16*)g_kw, (__nv_bfloat16*)g_lam);
   return check_launch("dwsep_finalize_kernel");
 }

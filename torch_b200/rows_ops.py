@@ -447,10 +447,15 @@ def _execute_dwsep(kind, a, b, out, batch, height, width, stride):
     _cuda.check(getattr(_cuda.lib(), fn)(C.byref(d), _cuda.ptr(a), _cuda.ptr(b), _cuda.ptr(out), _cuda.stream_ptr(a)), fn)
 
 
+def _dwsep_parts():
+    """Number of per-block partial-sum slabs the weight-gradient kernel writes (tlt_dwsep_rows_wgrad_parts)."""
+    return int(_cuda.lib().tlt_dwsep_rows_wgrad_parts())
+
+
 def _execute_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam):
     _cuda.require_cuda(acc, kh, kw, lam, g_kh, g_kw, g_lam)
-    _cuda.check(_cuda.lib().tlt_dwsep_rows_finalize(_cuda.ptr(acc), _cuda.ptr(kh), _cuda.ptr(kw), _cuda.ptr(lam), kh.shape[1],
-                                                    acc.shape[1], _cuda.ptr(g_kh), _cuda.ptr(g_kw), _cuda.ptr(g_lam),
+    _cuda.check(_cuda.lib().tlt_dwsep_rows_finalize(_cuda.ptr(acc), acc.shape[0], _cuda.ptr(kh), _cuda.ptr(kw), _cuda.ptr(lam),
+                                                    kh.shape[1], acc.shape[2], _cuda.ptr(g_kh), _cuda.ptr(g_kw), _cuda.ptr(g_lam),
                                                     _cuda.stream_ptr(acc)), "tlt_dwsep_rows_finalize")
 
 
@@ -479,7 +484,7 @@ def _dwsep_bwd_op(gy: torch.Tensor, z: torch.Tensor, kh: torch.Tensor, kw: torch
     _execute_dwsep_taps(kh, kw, lam, ld, stride == 1, taps)      # stride 1: the same sweep with reversed taps
     dz = torch.empty_like(z)
     _execute_dwsep("dgrad", gy, taps, dz, batch, height, width, stride)
-    acc = torch.empty((9, ld), dtype=torch.float32, device=z.device)
+    acc = torch.empty((_dwsep_parts(), 9, ld), dtype=torch.float32, device=z.device)
     _execute_dwsep("wgrad", z, gy, acc, batch, height, width, stride)
     g_kh, g_kw, g_lam = torch.empty_like(kh), torch.empty_like(kw), torch.empty_like(lam)
     _execute_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam)
