@@ -291,21 +291,38 @@ __global__ void dwsep_taps_kernel(const __nv_bfloat16* __restrict__ kh, const __
   }
 }
 
-// dT [9][ld] -> bf16 gradients of kh (3, R), kw (3, R), lambda (R)
-__global__ void dwsep_finalize_kernel(const float* __restrict__ dT, int parts, const __nv_bfloat16* __restrict__ kh,
-                                      const __nv_bfloat16* __restrict__ kw, const __nv_bfloat16* __restrict__ lam, int R, int ld,
-                                      __nv_bfloat16* __restrict__ g_kh,
-                                      __nv_bfloat16* __restrict__ g_kw, __nv_bfloat16* __restrict__ g_lam) {
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
-    float h[3], w[3], t[9];
+// partial sums [parts][9][ld] -> bf16 gradients of kh (3, R), kw (3, R), lambda (R).  Block = 8 channels x 32 part lanes: the slabs
+// are summed 32 at a time (a serial walk over all of them by one thread per channel cost 64 us), shared-memory tree, 8 writers.
+__global__ void __launch_bounds__(256) dwsep_finalize_kernel(const float* __restrict__ dT, int parts, const __nv_bfloat16* __restrict__ kh,
+                                                             const __nv_bfloat16* __restrict__ kw, const __nv_bfloat16* __restrict__ lam, int R,
+                                                             int ld, __nv_bfloat16* __restrict__ g_kh, __nv_bfloat16* __restrict__ g_kw,
+                                                             __nv_bfloat16* __restrict__ g_lam) {
+  __shared__ float red[9][32][8];
+  const int ch = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int r = blockIdx.x * 8 + ch;
+  float t[9];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) t[a] = 0.f;
+  if (r < R)
+    for (int p = pl; p < parts; p += 32)
+#pragma unroll
+      for (int a = 0; a < 9; ++a) t[a] += dT[((size_t)p * 9 + a) * ld + r];
+#pragma unroll
+  for (int a = 0; a < 9; ++a) red[a][pl][ch] = t[a];
+  __syncthreads();
+  for (int s = 16; s >= 1; s >>= 1) {
+    if (pl < s)
+#pragma unroll
+      for (int a = 0; a < 9; ++a) red[a][pl][ch] += red[a][pl + s][ch];
+    __syncthreads();
+  }
+  if (pl == 0 && r < R) {
+    float h[3], w[3];
     const float l = __bfloat162float(lam[r]);
 #pragma unroll
     for (int a = 0; a < 3; ++a) { h[a] = __bfloat162float(kh[a * R + r]); w[a] = __bfloat162float(kw[a * R + r]); }
 #pragma unroll
-    for (int a = 0; a < 9; ++a) t[a] = 0.f;
-    for (int p = 0; p < parts; ++p)
-#pragma unroll
-      for (int a = 0; a < 9; ++a) t[a] += dT[((size_t)p * 9 + a) * ld + r];
+    for (int a = 0; a < 9; ++a) t[a] = red[a][0][ch];
     float gl = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -389,7 +406,7 @@ extern "C" int tlt_dwsep_rows_wgrad(const tlt_dwsep_desc* d, const void* z, cons
 extern "C" int tlt_dwsep_rows_finalize(const float* acc, int32_t parts, const void* kh, const void* kw, const void* lam, int64_t rank,
                                        int64_t ld, void* g_kh, void* g_kw, void* g_lam, void* stream) {
   TLT_REQUIRE(acc && parts >= 1 && kh && kw && lam && g_kh && g_kw && g_lam && rank >= 1 && ld >= rank, "tlt_dwsep_rows_finalize: bad arguments");
-  dwsep_finalize_kernel<<<(unsigned)((rank + 63) / 64), 64, 0, (cudaStream_t)stream>>>(acc, parts, (const __nv_bfloat16*)kh,
+  dwsep_finalize_kernel<<<(unsigned)((rank + 7) / 8), 256, 0, (cudaStream_t)stream>>>(acc, parts, (const __nv_bfloat16*)kh,
                                                                                        (const __nv_bfloat16*)kw, (const __nv_bfloat16*)lam,
                                                                                        (int)rank, (int)ld, (__nv_bfloat16*)g_kh,
                                                                                        (__nv_bfloat16*)g_kw, (__nv_bfloat16*)g_lam);
