@@ -315,6 +315,21 @@ int tlt_dwsep_rows_finalize(const float* acc, int32_t parts, const void* kh, con
                             void* g_kh, void* g_kw, void* g_lambda, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
+ * Operand preparation / gradient finalisation of the unfused CP-convolution chain on rows (csrc/cpchain.cu):
+ *   tlt_cpchain_prep  wp_in [round8(R)][round8(C_in)] = F_in^T, wp_out [round8(C_out)][round8(R)] = F_out (bf16, zero pads),
+ *                     taps_f / taps_d [6][round8(R)] fp32 for tlt_dwsep_rows_fwd / _dgrad  -- one launch
+ *   tlt_cpchain_post  bf16 gradients of F_out (C_out, R), F_in (C_in, R), kh, kw, lambda from the fp32 results of the two
+ *                     weight-gradient GEMMs (dw_out [C_out][round8(R)], dw_in [R][round8(C_in)]) and the sweep's slabs -- one launch
+ * Replaces the per-op weight re-pitching, pad zero-fills, fp32 -> bf16 casts and slicing copies around the chain's GEMMs.
+ * ------------------------------------------------------------------------------------------------------------ */
+int tlt_cpchain_prep(int64_t c_in, int64_t c_out, int64_t rank, int32_t flip_dgrad_taps, const void* f_in, const void* f_out,
+                     const void* kh, const void* kw, const void* lambda, void* wp_in, void* wp_out, float* taps_f, float* taps_d,
+                     void* stream);
+int tlt_cpchain_post(int64_t c_in, int64_t c_out, int64_t rank, const float* dw_out, const float* dw_in, const float* acc,
+                     int32_t parts, const void* kh, const void* kw, const void* lambda, void* g_fout, void* g_fin, void* g_kh,
+                     void* g_kw, void* g_lambda, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
  * Op-level fused CP convolution on channels-last rows (bf16): x (B, H, W, C_in) -> y (B, H/s, W/s, C_out),
  *     y = F_out . dw3x3( F_in^T . x )  with separable taps kh (3, R), kw (3, R) and CP weights lambda (R), padding 1.
  * ONE launch per direction; the R-channel intermediates stay in TMEM / shared memory (csrc/cpconv_rows.cu).

@@ -371,6 +371,24 @@ def emulate_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam):
     LOG.append(("dwsep_finalize", r))
 
 
+def emulate_chain_prep(c_in, c_out, rank, flip_d, f_in, f_out, kh, kw, lam, wp_in, wp_out, taps_f, taps_d):
+    wp_in.zero_(); wp_out.zero_()
+    wp_in[:rank, :c_in] = f_in.t()
+    wp_out[:c_out, :rank] = f_out
+    emulate_dwsep_taps(kh, kw, lam, taps_f.shape[1], False, taps_f)
+    emulate_dwsep_taps(kh, kw, lam, taps_d.shape[1], flip_d, taps_d)
+    del LOG[-2:]
+    LOG.append(("cpchain_prep", c_in, c_out, rank))
+
+
+def emulate_chain_post(c_in, c_out, rank, dw_out, dw_in, acc, kh, kw, lam, g_fout, g_fin, g_kh, g_kw, g_lam):
+    g_fout.copy_(dw_out[:, :rank].to(g_fout.dtype))
+    g_fin.copy_(dw_in[:, :c_in].t().to(g_fin.dtype))
+    emulate_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam)
+    del LOG[-1:]
+    LOG.append(("cpchain_post", c_in, c_out, rank))
+
+
 def _kr_ref(factors, weights):
     R = factors[0].shape[1]
     res = torch.ones((1, R), dtype=torch.float64) if weights is None else weights.double().reshape(1, R)
@@ -503,6 +521,8 @@ def emulated_kernels():
     saved_ds = ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize, ro._dwsep_parts
     ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize = emulate_dwsep_taps, emulate_dwsep, emulate_dwsep_finalize
     ro._dwsep_parts = lambda: 2
+    saved_ch = ro._execute_chain_prep, ro._execute_chain_post
+    ro._execute_chain_prep, ro._execute_chain_post = emulate_chain_prep, emulate_chain_post
     ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = (
         emulate_skinny_fwd, emulate_skinny_bwd, emulate_scale_modes, emulate_dwconv_rows)
     ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = emulate_nchw_to_rows, emulate_rows_to_nchw, emulate_unfold_rows
@@ -531,4 +551,5 @@ def emulated_kernels():
         ro._execute_nchw_to_rows, ro._execute_rows_to_nchw, ro._execute_unfold_rows = saved_r
         ro._execute_skinny_fwd, ro._execute_skinny_bwd, ro._execute_scale_modes, ro._execute_dwconv_rows = saved_s
         ro._execute_dwsep_taps, ro._execute_dwsep, ro._execute_dwsep_finalize, ro._dwsep_parts = saved_ds
+        ro._execute_chain_prep, ro._execute_chain_post = saved_ch
         to._execute_mmd16_fwd, to._execute_mmd16_bwd, to._execute_pack_kmajor = saved_t

@@ -122,6 +122,8 @@ SYMBOLS = {
     "tlt_dwsep_rows_wgrad": (C.c_int, [C.POINTER(DwSepDesc), _vp, _vp, _vp, _vp]),
     "tlt_dwsep_rows_wgrad_parts": (C.c_int, []),
     "tlt_dwsep_rows_finalize": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp]),
+    "tlt_cpchain_prep": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cpchain_post": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_cpconv_rows_supported": (C.c_int, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),
     "tlt_cpconv_rows_grad_workspace_size": (C.c_size_t, [C.POINTER(CpConvRowsDesc)]),

@@ -211,21 +211,31 @@ __global__ void __launch_bounds__(256) dwsep_wgrad_kernel(const Geom g, const ui
           for (int i = 0; i < 4; ++i) win[s][r][i] = 0ull;
       // raw loads of the NEXT centre's new columns are in flight while the current centre is accumulated
       constexpr int NC = STRIDE == 1 ? 1 : 2;          // new input columns per centre
-      uint4 qz[NC][3], qg;
-      auto issue = [&](int wo) {                       // centre wo needs columns wo+1 (stride 1) / 2wo, 2wo+1 (stride 2)
+      // two centres ahead: qz / qg hold the centre being consumed next, nz / ng the one after it
+      uint4 qz[NC][3], qg, nz[NC][3], ng;
+      auto fetch = [&](int wo, uint4 (&tz)[NC][3], uint4& tg) {   // centre wo needs columns wo+1 (stride 1) / 2wo, 2wo+1 (stride 2)
 #pragma unroll
         for (int u = 0; u < NC; ++u) {
           const int x = STRIDE == 1 ? wo + 1 : 2 * wo + u;
           const bool okx = wo < g.Wo && x < g.W;
           const long long off = (long long)x * g.cpr;
-          qz[u][0] = ldg16(r0 + off, okx && ok0); qz[u][1] = ldg16(r1 + off, okx); qz[u][2] = ldg16(r2 + off, okx && ok2);
+          tz[u][0] = ldg16(r0 + off, okx && ok0); tz[u][1] = ldg16(r1 + off, okx); tz[u][2] = ldg16(r2 + off, okx && ok2);
         }
-        qg = ldg16(rg + (long long)wo * g.cpr, wo < g.Wo);
+        tg = ldg16(rg + (long long)wo * g.cpr, wo < g.Wo);
+      };
+      auto issue = [&](int wo) {                       // called once the current centre's raw registers are unpacked
+#pragma unroll
+        for (int u = 0; u < NC; ++u)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) qz[u][r] = nz[u][r];
+        qg = ng;
+        fetch(wo + 1, nz, ng);
       };
       if (STRIDE == 1) {                               // column 0 -> slot 1 (column -1 = slot 0 stays zero)
         unpack(ldg16(r0, ok0), win[1][0]); unpack(__ldg(r1), win[1][1]); unpack(ldg16(r2, ok2), win[1][2]);
       }
-      issue(0);
+      fetch(0, qz, qg);
+      fetch(1, nz, ng);
       for (int w0 = 0; w0 < g.Wo; w0 += 3) {
 #pragma unroll
         for (int u = 0; u < 3; ++u) {

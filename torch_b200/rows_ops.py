@@ -9,7 +9,7 @@ Reference: tucker_conv (tltorch/functional/convolution.py:140-173); the same bui
 reconstructed kernels (:16-53).  CPU tensors raise NotImplementedError (no fallback); tests/_emulator.py swaps the funnels.
 """
 import ctypes as C
-from typing import List
+from typing import List, Optional
 
 import torch
 import torch.nn.functional as F
@@ -519,15 +519,122 @@ def dwsep_eligible(factors, kernel, stride, padding, dilation, spatial):
     return stride[0] == 1 or (spatial[0] % 2 == 0 and spatial[1] % 2 == 0)
 
 
+def _execute_chain_prep(c_in, c_out, rank, flip_d, f_in, f_out, kh, kw, lam, wp_in, wp_out, taps_f, taps_d):
+    _cuda.require_cuda(f_in, f_out, kh, kw, lam, wp_in, wp_out, taps_f, taps_d)
+    _cuda.check(_cuda.lib().tlt_cpchain_prep(c_in, c_out, rank, 1 if flip_d else 0, _cuda.ptr(f_in), _cuda.ptr(f_out), _cuda.ptr(kh),
+                                             _cuda.ptr(kw), _cuda.ptr(lam), _cuda.ptr(wp_in), _cuda.ptr(wp_out), _cuda.ptr(taps_f),
+                                             _cuda.ptr(taps_d), _cuda.stream_ptr(wp_in)), "tlt_cpchain_prep")
+
+
+def _execute_chain_post(c_in, c_out, rank, dw_out, dw_in, acc, kh, kw, lam, g_fout, g_fin, g_kh, g_kw, g_lam):
+    _cuda.require_cuda(dw_out, dw_in, acc, kh, kw, lam, g_fout, g_fin, g_kh, g_kw, g_lam)
+    _cuda.check(_cuda.lib().tlt_cpchain_post(c_in, c_out, rank, _cuda.ptr(dw_out), _cuda.ptr(dw_in), _cuda.ptr(acc), acc.shape[0],
+                                             _cuda.ptr(kh), _cuda.ptr(kw), _cuda.ptr(lam), _cuda.ptr(g_fout), _cuda.ptr(g_fin),
+                                             _cuda.ptr(g_kh), _cuda.ptr(g_kw), _cuda.ptr(g_lam), _cuda.stream_ptr(acc)), "tlt_cpchain_post")
+
+
+@torch.library.custom_op("tltorch::cpconv_chain_fwd", mutates_args=())
+def _chain_fwd_op(xr: torch.Tensor, lam: torch.Tensor, f_out: torch.Tensor, f_in: torch.Tensor, kh: torch.Tensor, kw: torch.Tensor,
+                  bias: Optional[torch.Tensor], batch: int, height: int, width: int, stride: int) -> List[torch.Tensor]:
+    """xr (B H W, round8(C_in)) -> [y (B H' W', round8(C_out)), z1, z2, wp_in, wp_out, taps_d]: the unfused chain as ONE op --
+    prep launch, GEMM, separable sweep, GEMM (4 launches); everything the backward op needs comes back as outputs."""
+    from .blocktt_ops import _execute_gemm
+    xr = xr.contiguous()
+    (c_in, r), c_out = f_in.shape, f_out.shape[0]
+    cin_p, cout_p, ld = _r8(c_in), _r8(c_out), _r8(r)
+    dev, bf = xr.device, torch.bfloat16
+    wp_in, wp_out = torch.empty((ld, cin_p), dtype=bf, device=dev), torch.empty((cout_p, ld), dtype=bf, device=dev)
+    taps_f, taps_d = torch.empty((6, ld), dtype=torch.float32, device=dev), torch.empty((6, ld), dtype=torch.float32, device=dev)
+    _execute_chain_prep(c_in, c_out, r, stride == 1, f_in.contiguous(), f_out.contiguous(), kh.contiguous(), kw.contiguous(),
+                        lam.contiguous(), wp_in, wp_out, taps_f, taps_d)
+    p_in, p_out = xr.shape[0], batch * (height // stride) * (width // stride)
+    z1 = torch.empty((p_in, ld), dtype=bf, device=dev)
+    _execute_gemm(xr, wp_in, None, z1, M=p_in, N=ld, K=cin_p, lda=xr.stride(0), ldb=cin_p, a_major=0, b_major=0)
+    z2 = torch.empty((p_out, ld), dtype=bf, device=dev)
+    _execute_dwsep("fwd", z1, taps_f, z2, batch, height, width, stride)
+    y = torch.empty((p_out, cout_p), dtype=bf, device=dev)
+    if bias is not None and cout_p != c_out:
+        bias = torch.cat([bias, bias.new_zeros(cout_p - c_out)])
+    _execute_gemm(z2, wp_out, bias, y, M=p_out, N=cout_p, K=ld, lda=ld, ldb=ld, a_major=0, b_major=0)
+    return [y, z1, z2, wp_in, wp_out, taps_d]
+
+
+@_chain_fwd_op.register_fake
+def _(xr, lam, f_out, f_in, kh, kw, bias, batch, height, width, stride):
+    (c_in, r), c_out = f_in.shape, f_out.shape[0]
+    cin_p, cout_p, ld = _r8(c_in), _r8(c_out), _r8(r)
+    p_out = batch * (height // stride) * (width // stride)
+    return [xr.new_empty((p_out, cout_p)), xr.new_empty((xr.shape[0], ld)), xr.new_empty((p_out, ld)), xr.new_empty((ld, cin_p)),
+            xr.new_empty((cout_p, ld)), xr.new_empty((6, ld), dtype=torch.float32)]
+
+
+@torch.library.custom_op("tltorch::cpconv_chain_bwd", mutates_args=())
+def _chain_bwd_op(gy: torch.Tensor, xr: torch.Tensor, z1: torch.Tensor, z2: torch.Tensor, wp_in: torch.Tensor, wp_out: torch.Tensor,
+                  taps_d: torch.Tensor, lam: torch.Tensor, kh: torch.Tensor, kw: torch.Tensor, c_in: int, c_out: int, batch: int,
+                  height: int, width: int, stride: int) -> List[torch.Tensor]:
+    """-> [dx, g_lambda, g_f_out, g_f_in, g_kh, g_kw]: 2 data-gradient GEMMs + transposed sweep, sweep + 2 GEMMs for the weight
+    gradients, one finalisation launch (7 launches)."""
+    from .blocktt_ops import _execute_gemm
+    gy, xr = gy.contiguous(), xr.contiguous()
+    r = lam.shape[0]
+    cin_p, cout_p, ld = wp_in.shape[1], wp_out.shape[0], wp_in.shape[0]
+    dev, bf, f32 = xr.device, torch.bfloat16, torch.float32
+    p_in, p_out = xr.shape[0], gy.shape[0]
+    dz2 = torch.empty((p_out, ld), dtype=bf, device=dev)                 # dz2[b, r] = sum_o gy[b, o] F_out[o, r]
+    _execute_gemm(gy, wp_out, None, dz2, M=p_out, N=ld, K=cout_p, lda=gy.stride(0), ldb=ld, a_major=0, b_major=1)
+    dz1 = torch.empty((p_in, ld), dtype=bf, device=dev)
+    _execute_dwsep("dgrad", dz2, taps_d, dz1, batch, height, width, stride)
+    dx = torch.empty((p_in, cin_p), dtype=bf, device=dev)                # dx[b, c] = sum_r dz1[b, r] F_in[c, r]
+    _execute_gemm(dz1, wp_in, None, dx, M=p_in, N=cin_p, K=ld, lda=ld, ldb=cin_p, a_major=0, b_major=1)
+    acc = torch.empty((_dwsep_parts(), 9, ld), dtype=f32, device=dev)
+    _execute_dwsep("wgrad", z1, dz2, acc, batch, height, width, stride)
+    dw_out = torch.empty((c_out, ld), dtype=f32, device=dev)             # dW_out[o, r] = sum_b gy[b, o] z2[b, r]   (split-K, fp32)
+    _execute_gemm(gy, z2, None, dw_out, M=c_out, N=ld, K=p_out, lda=gy.stride(0), ldb=ld, a_major=1, b_major=1)
+    dw_in = torch.empty((r, cin_p), dtype=f32, device=dev)               # dW_in[r, c] = sum_b dz1[b, r] x[b, c]
+    _execute_gemm(dz1, xr, None, dw_in, M=r, N=cin_p, K=p_in, lda=ld, ldb=xr.stride(0), a_major=1, b_major=1)
+    g_lam, g_kh, g_kw = torch.empty_like(lam), torch.empty_like(kh), torch.empty_like(kw)
+    g_fout, g_fin = torch.empty((c_out, r), dtype=lam.dtype, device=dev), torch.empty((c_in, r), dtype=lam.dtype, device=dev)
+    _execute_chain_post(c_in, c_out, r, dw_out, dw_in, acc, kh.contiguous(), kw.contiguous(), lam.contiguous(), g_fout, g_fin, g_kh,
+                        g_kw, g_lam)
+    return [dx, g_lam, g_fout, g_fin, g_kh, g_kw]
+
+
+@_chain_bwd_op.register_fake
+def _(gy, xr, z1, z2, wp_in, wp_out, taps_d, lam, kh, kw, c_in, c_out, batch, height, width, stride):
+    r = lam.shape[0]
+    return [torch.empty_like(xr), torch.empty_like(lam), lam.new_empty((c_out, r)), lam.new_empty((c_in, r)), torch.empty_like(kh),
+            torch.empty_like(kw)]
+
+
+def _chain_setup(ctx, inputs, output):
+    xr, lam, f_out, f_in, kh, kw, bias, ctx.batch, ctx.height, ctx.width, ctx.stride = inputs
+    ctx.c_in, ctx.c_out = f_in.shape[0], f_out.shape[0]
+    ctx.bias_dtype = None if bias is None else bias.dtype
+    ctx.save_for_backward(xr, output[1], output[2], output[3], output[4], output[5], lam, kh, kw)
+
+
+def _chain_backward(ctx, grads):
+    gy = grads[0].contiguous()
+    xr, z1, z2, wp_in, wp_out, taps_d, lam, kh, kw = ctx.saved_tensors
+    dx, g_lam, g_fout, g_fin, g_kh, g_kw = _chain_bwd_op(gy, xr, z1, z2, wp_in, wp_out, taps_d, lam, kh, kw, ctx.c_in, ctx.c_out,
+                                                         ctx.batch, ctx.height, ctx.width, ctx.stride)
+    g_bias = None
+    if ctx.bias_dtype is not None and ctx.needs_input_grad[6]:
+        g_bias = ops.reduce_to(gy, "bo", "o")[:ctx.c_out].to(ctx.bias_dtype)
+    return dx, g_lam, g_fout, g_fin, g_kh, g_kw, g_bias, None, None, None, None
+
+
+_chain_fwd_op.register_autograd(_chain_backward, setup_context=_chain_setup)
+
+
 def cp_conv_rows_sep(x, weights, factors, bias, stride):
     """CP convolution on channels-last rows with the separable depthwise sweep: x (B, C_in, H, W) bf16; factors = [F_out (C_out, R),
     F_in (C_in, R), kh (3, R), kw (3, R)], weights = lambda (R).  x -> rows -> [C_in -> R: GEMM] -> separable depthwise (lambda in
-    the W taps) -> [R -> C_out: GEMM + bias] -> NCHW; no Khatri-Rao product of the taps and no gradient kernel for it."""
+    the W taps) -> [R -> C_out: GEMM + bias] -> NCHW, as one op: 4 launches forward, 7 backward, no Khatri-Rao product of the taps,
+    no re-pitching / casting / slicing kernels around the GEMMs (csrc/cpchain.cu)."""
     b, h, w = x.shape[0], x.shape[2], x.shape[3]
     xt = nchw_to_rows(x)                                                       # (B S, round8(C_in))
-    z = padded_linear(xt, factors[1].t(), None, True)                          # (B S, round8(R)), pad columns zero
-    z = _dwsep_op(z, factors[2], factors[3], weights, b, h, w, stride)         # (B S', round8(R))
-    yt = padded_linear(z, factors[0], bias, True)                              # (B S', round8(C_out))
+    yt = _chain_fwd_op(xt, weights, factors[0], factors[1], factors[2], factors[3], bias, b, h, w, stride)[0]
     return rows_to_nchw(yt, b, factors[0].shape[0], [h // stride, w // stride], channels_last=is_channels_last(x))
 
 
@@ -537,8 +644,9 @@ def dwconv_rows(z, w_taps, batch, in_size, kernel, stride, padding, dilation):
 
 
 def cp_conv_rows(x, taps_t, f_in, f_out_scaled, bias, kernel, stride, padding, dilation):
-    """CP convolution on channels-last rows.  x (B, C_in, *S) bf16; taps_t (prod(kernel), R) the merged depthwise kernel,
-    taps-major; f_in (C_in, R); f_out_scaled (C_out, R); lambda is folded into the taps or into f_out_scaled by the caller.
+    """CP convolution on channels-last rows, generic kernel shapes (1-D / 3-D, dilation, other paddings).  x (B, C_in, *S) bf16;
+    taps_t (prod(kernel), R) the merged depthwise kernel, taps-major; f_in (C_in, R); f_out_scaled (C_out, R); lambda is folded
+    into the taps or into f_out_scaled by the caller.
     x -> rows -> [C_in -> R: GEMM] -> depthwise on rows -> [R -> C_out: GEMM + bias] -> NCHW."""
     b, spatial = x.shape[0], list(x.shape[2:])
     r = f_in.shape[1]
