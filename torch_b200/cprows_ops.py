@@ -144,9 +144,12 @@ def _setup(ctx, inputs, output):
     ctx.bias_dtype = None if bias is None else bias.dtype
     ctx.stride, ctx.out_channels = stride, f_out.shape[0]
     ctx.save_for_backward(x, output[1], lam, kh, kw)
+    ctx.set_materialize_grads(False)       # the workspace output never gets a gradient: no zero tensor for it
 
 
 def _backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 8
     gy = grads[0]
     x, ws, lam, kh, kw = ctx.saved_tensors
     if ctx.stride != 1:

@@ -611,9 +611,12 @@ def _chain_setup(ctx, inputs, output):
     ctx.c_in, ctx.c_out = f_in.shape[0], f_out.shape[0]
     ctx.bias_dtype = None if bias is None else bias.dtype
     ctx.save_for_backward(xr, output[1], output[2], output[3], output[4], output[5], lam, kh, kw)
+    ctx.set_materialize_grads(False)       # the auxiliary outputs never get gradients: no zero tensors for them
 
 
 def _chain_backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 11
     gy = grads[0].contiguous()
     xr, z1, z2, wp_in, wp_out, taps_d, lam, kh, kw = ctx.saved_tensors
     dx, g_lam, g_fout, g_fin, g_kh, g_kw = _chain_bwd_op(gy, xr, z1, z2, wp_in, wp_out, taps_d, lam, kh, kw, ctx.c_in, ctx.c_out,
