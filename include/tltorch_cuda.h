@@ -319,7 +319,7 @@ int tlt_dwsep_rows_finalize(const float* acc, int32_t parts, const void* kh, con
  *   tlt_cpchain_prep  wp_in [round8(R)][round8(C_in)] = F_in^T, wp_out [round8(C_out)][round8(R)] = F_out (bf16, zero pads),
  *                     taps_f / taps_d [6][round8(R)] fp32 for tlt_dwsep_rows_fwd / _dgrad  -- one launch
  *   tlt_cpchain_post  bf16 gradients of F_out (C_out, R), F_in (C_in, R), kh, kw, lambda from the fp32 results of the two
- *                     weight-gradient GEMMs (dw_out [C_out][round8(R)], dw_in [R][round8(C_in)]) and the sweep's slabs -- one launch
+ *                     weight-gradient GEMMs (dw_out [C_out][round8(R)], dw_in [C_in][round8(R)]) and the sweep's slabs -- one launch
  * Replaces the per-op weight re-pitching, pad zero-fills, fp32 -> bf16 casts and slicing copies around the chain's GEMMs.
  * ------------------------------------------------------------------------------------------------------------ */
 int tlt_cpchain_prep(int64_t c_in, int64_t c_out, int64_t rank, int32_t flip_dgrad_taps, const void* f_in, const void* f_out,

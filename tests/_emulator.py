@@ -383,7 +383,7 @@ def emulate_chain_prep(c_in, c_out, rank, flip_d, f_in, f_out, kh, kw, lam, wp_i
 
 def emulate_chain_post(c_in, c_out, rank, dw_out, dw_in, acc, kh, kw, lam, g_fout, g_fin, g_kh, g_kw, g_lam):
     g_fout.copy_(dw_out[:, :rank].to(g_fout.dtype))
-    g_fin.copy_(dw_in[:, :c_in].t().to(g_fin.dtype))
+    g_fin.copy_(dw_in[:, :rank].to(g_fin.dtype))
     emulate_dwsep_finalize(acc, kh, kw, lam, g_kh, g_kw, g_lam)
     del LOG[-1:]
     LOG.append(("cpchain_post", c_in, c_out, rank))

@@ -34,7 +34,7 @@ __global__ void prep_kernel(const __nv_bfloat16* __restrict__ f_in, const __nv_b
 }
 
 // blocks [0, tap_blocks): 8 rank channels x 32 slab lanes -> gradients of kh, kw, lambda from the sweep's partial sums
-// blocks [tap_blocks, ..): element-wise  g_fout (C_out, R) <- dW_out [C_out][ld] fp32,  g_fin (C_in, R) <- dW_in [R][cin_p] fp32 transposed
+// blocks [tap_blocks, ..): element-wise  g_fout (C_out, R) <- dW_out [C_out][ld] fp32,  g_fin (C_in, R) <- dW_in [C_in][ld] fp32
 __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ dw_out, const float* __restrict__ dw_in, const float* __restrict__ dT,
                                                    int parts, const __nv_bfloat16* __restrict__ kh, const __nv_bfloat16* __restrict__ kw,
                                                    const __nv_bfloat16* __restrict__ lam, int c_in, int c_out, int R, int cin_p, int ld,
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ dw_
     const int n_out = c_out * R, n_in = c_in * R;
     for (int i = (blockIdx.x - tap_blocks) * blockDim.x + threadIdx.x; i < n_out + n_in; i += (gridDim.x - tap_blocks) * blockDim.x) {
       if (i < n_out) { const int c = i / R, r = i - c * R; g_fout[i] = __float2bfloat16_rn(dw_out[(size_t)c * ld + r]); }
-      else { const int j = i - n_out, c = j / R, r = j - c * R; g_fin[j] = __float2bfloat16_rn(dw_in[(size_t)r * cin_p + c]); }
+      else { const int j = i - n_out, c = j / R, r = j - c * R; g_fin[j] = __float2bfloat16_rn(dw_in[(size_t)c * ld + r]); }
     }
     return;
   }

@@ -590,8 +590,8 @@ def _chain_bwd_op(gy: torch.Tensor, xr: torch.Tensor, z1: torch.Tensor, z2: torc
     _execute_dwsep("wgrad", z1, dz2, acc, batch, height, width, stride)
     dw_out = torch.empty((c_out, ld), dtype=f32, device=dev)             # dW_out[o, r] = sum_b gy[b, o] z2[b, r]   (split-K, fp32)
     _execute_gemm(gy, z2, None, dw_out, M=c_out, N=ld, K=p_out, lda=gy.stride(0), ldb=ld, a_major=1, b_major=1)
-    dw_in = torch.empty((r, cin_p), dtype=f32, device=dev)               # dW_in[r, c] = sum_b dz1[b, r] x[b, c]
-    _execute_gemm(dz1, xr, None, dw_in, M=r, N=cin_p, K=p_in, lda=ld, ldb=xr.stride(0), a_major=1, b_major=1)
+    dw_in = torch.empty((c_in, ld), dtype=f32, device=dev)               # dW_in[c, r] = sum_b x[b, c] dz1[b, r]   (F_in's own layout)
+    _execute_gemm(xr, dz1, None, dw_in, M=c_in, N=ld, K=p_in, lda=xr.stride(0), ldb=ld, a_major=1, b_major=1)
     g_lam, g_kh, g_kw = torch.empty_like(lam), torch.empty_like(kh), torch.empty_like(kw)
     g_fout, g_fin = torch.empty((c_out, r), dtype=lam.dtype, device=dev), torch.empty((c_in, r), dtype=lam.dtype, device=dev)
     _execute_chain_post(c_in, c_out, r, dw_out, dw_in, acc, kh.contiguous(), kw.contiguous(), lam.contiguous(), g_fout, g_fin, g_kh,
