@@ -494,7 +494,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a mismatched collective fails, not hangs
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
     peaks, peak_src = _peaks()
@@ -579,7 +580,9 @@ def run_ours(args):
         pass
 
     # per-entry-point CUDA-event times of the same step issued eagerly (durations do not depend on how a launch was issued)
-    table = profile_entry_points(step) if world == 1 or rank == 0 else {}
+    # every rank runs the profiled step (it contains the gradient exchange: a rank that skipped it would leave the others' all-reduce
+    # unmatched -- a 2-GPU run hung exactly there); rank 0's table is the one reported
+    table = profile_entry_points(step)
     if table:
         total = sum(v["ms_per_step"] for v in table.values())
         top = next(iter(table.items()))
