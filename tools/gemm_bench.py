@@ -80,5 +80,17 @@ def run(M, N, K, a_mn, b_mn, out_dtype, split, iters=20):
 if __name__ == "__main__":
     print("TLT_GEMM_IMPL =", os.environ.get("TLT_GEMM_IMPL", "(default 3)"), flush=True)
     shapes = SHAPES[:3] if "--quick" in sys.argv else SHAPES
+    if "--chain" in sys.argv:      # the six GEMMs of every unfused CP-conv rows chain layer of config 3 (256 images)
+        shapes = []
+        r8 = lambda v: (v + 7) // 8 * 8
+        for cin, cout, hw, s, r in [(64, 128, 56, 2, 93), (128, 128, 28, 1, 141), (128, 256, 28, 2, 189), (256, 256, 14, 1, 285),
+                                    (256, 512, 14, 2, 381), (512, 512, 7, 1, 573)]:
+            pin, pout, ld = 256 * hw * hw, 256 * (hw // s) ** 2, r8(r)
+            bf, f32 = torch.bfloat16, torch.float32
+            print(f"--- {cin}->{cout} @{hw}^2 s{s} R={r}")
+            for sh in [(pin, ld, cin, 0, 0, bf, 0), (pout, cout, ld, 0, 0, bf, 0), (pout, ld, cout, 0, 1, bf, 0), (pin, cin, ld, 0, 1, bf, 0),
+                       (cout, ld, pout, 1, 1, f32, 0), (cin, ld, pin, 1, 1, f32, 0)]:
+                run(*sh, iters=10)
+        sys.exit(0)
     for s in shapes:
         run(*s)

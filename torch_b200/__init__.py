@@ -18,5 +18,8 @@ from . import tensor_hooks  # noqa: F401
 from .factorized_layers import FactorizedLinear, FactorizedConv, TRL, TCL, FactorizedEmbedding  # noqa: F401
 from .factorized_tensors import (FactorizedTensor, DenseTensor, CPTensor, TTTensor, TuckerTensor, tensor_init,  # noqa: F401
                                  TensorizedTensor, CPTensorized, BlockTT, TTMatrix, DenseTensorized, TuckerTensorized)
-from .tensor_hooks import tensor_dropout, remove_tensor_dropout  # noqa: F401
-from .utils import FactorList, ParameterList, get_tensorized_shape  # noqa: F401
+from .tensor_hooks import tensor_dropout, remove_tensor_dropout, tensor_lasso, remove_tensor_lasso  # noqa: F401
+from .factorized_tensors import (ComplexCPTensor, ComplexTuckerTensor, ComplexTTTensor, ComplexDenseTensor,  # noqa: F401
+                                 ComplexCPTensorized, ComplexBlockTT, ComplexDenseTensorized, ComplexTuckerTensorized)
+from . import decomposition  # noqa: F401
+from .utils import FactorList, ParameterList, ComplexFactorList, get_tensorized_shape  # noqa: F401

@@ -55,7 +55,8 @@ class TRL(nn.Module):
                 self.bias.uniform_(-1, 1)
 
     def init_from_linear(self, linear, unsqueezed_modes=None, **kwargs):
-        """Initialise from a fully connected layer (needs a tensor decomposition: init-time, outside the hot path)."""
+        """Initialise from a fully connected layer: its weight, viewed as the regression tensor, is decomposed into this layer's
+        factorization (reference: tensor_regression_layers.py:96-133)."""
         if unsqueezed_modes is not None:
             if self.factorization != "Tucker":
                 raise ValueError(f'unsqueezed_modes is only supported for factorization="tucker" but factorization '

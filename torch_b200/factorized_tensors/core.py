@@ -174,9 +174,3 @@ def _is_tensorized(cls):
         return issubclass(cls, TensorizedTensor)
     except NameError:          # while TensorizedTensor itself is being defined
         return False
-
-
-def _decomposition_unavailable(what):
-    raise NotImplementedError(
-        f"{what}: initialisation by decomposing a dense tensor (tensorly parafac / tucker / tensor_train) is init-time "
-        "host code outside the factorized-layer hot path (SURVEY.md section 2, rows 6/7/10/11; 8(f) item 3)")

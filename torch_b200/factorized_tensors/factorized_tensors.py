@@ -15,7 +15,8 @@ from torch import nn
 from .. import tenalg
 from ..ops import contract
 from ..utils import FactorList
-from .core import FactorizedTensor, _decomposition_unavailable
+from .core import FactorizedTensor
+from .. import decomposition
 
 
 def _register(module, name, value):
@@ -92,10 +93,20 @@ class CPTensor(FactorizedTensor, name="CP"):
 
     @classmethod
     def from_tensor(cls, tensor, rank="same", **kwargs):
-        _decomposition_unavailable("CPTensor.from_tensor")
+        """CP-ALS of a dense tensor in fp64, cast back (reference: factorized_tensors.py:107-116)."""
+        rank = tenalg.validate_cp_rank(tuple(tensor.shape), rank)
+        dtype = tensor.dtype
+        with torch.no_grad():
+            weights, factors = decomposition.parafac(tensor.to(torch.float64), rank, **kwargs)
+        return cls(nn.Parameter(weights.to(dtype).contiguous()), [nn.Parameter(f.to(dtype).contiguous()) for f in factors])
 
     def init_from_tensor(self, tensor, l2_reg=1e-5, **kwargs):
-        _decomposition_unavailable("CPTensor.init_from_tensor")
+        """Re-initialise the factors from a dense tensor (reference: factorized_tensors.py:118-124)."""
+        with torch.no_grad():
+            weights, factors = decomposition.parafac(tensor, self.rank, l2_reg=l2_reg, **kwargs)
+        self.weights = nn.Parameter(weights.contiguous())
+        self.factors = FactorList([nn.Parameter(f.contiguous()) for f in factors])
+        return self
 
     @property
     def decomposition(self):
@@ -171,10 +182,36 @@ class TuckerTensor(FactorizedTensor, name="Tucker"):
 
     @classmethod
     def from_tensor(cls, tensor, rank="same", fixed_rank_modes=None, **kwargs):
-        _decomposition_unavailable("TuckerTensor.from_tensor")
+        """HOSVD + HOOI of a dense tensor (reference: factorized_tensors.py:246-254)."""
+        rank = tenalg.validate_tucker_rank(tuple(tensor.shape), rank, fixed_modes=fixed_rank_modes)
+        with torch.no_grad():
+            core, factors = decomposition.tucker(tensor, rank, **kwargs)
+        return cls(nn.Parameter(core.contiguous()), [nn.Parameter(f.contiguous()) for f in factors])
 
     def init_from_tensor(self, tensor, unsqueezed_modes=None, unsqueezed_init="average", **kwargs):
-        _decomposition_unavailable("TuckerTensor.init_from_tensor")
+        """Re-initialise core and factors from a dense tensor (reference: factorized_tensors.py:256-301).  ``unsqueezed_modes``:
+        rank-1 modes of this factorization that ``tensor`` does not have; the other modes are decomposed and the extra
+        factors are filled with ``1 / size`` ('average') or the given constant."""
+        if unsqueezed_modes is not None:
+            unsqueezed_modes = sorted(unsqueezed_modes)
+            for mode in unsqueezed_modes[::-1]:
+                if self.rank[mode] != 1:
+                    raise ValueError("It is only possible to initialize by averagig over mode for which rank=1."
+                                     f"However, got unsqueezed_modes={unsqueezed_modes} but rank[{mode}]={self.rank[mode]} != 1.")
+            rank = tuple(r for i, r in enumerate(self.rank) if i not in unsqueezed_modes)
+        else:
+            rank = self.rank
+        with torch.no_grad():
+            core, factors = decomposition.tucker(tensor, rank, **kwargs)
+            if unsqueezed_modes is not None:
+                for mode in unsqueezed_modes:
+                    size = self.shape[mode]
+                    fill = 1.0 / size if unsqueezed_init == "average" else float(unsqueezed_init)
+                    factors.insert(mode, torch.full((size, 1), fill, dtype=core.dtype, device=core.device))
+                    core = core.unsqueeze(mode)
+        self.core = nn.Parameter(core.contiguous())
+        self.factors = FactorList([nn.Parameter(f.contiguous()) for f in factors])
+        return self
 
     @property
     def decomposition(self):
@@ -235,10 +272,19 @@ class TTTensor(FactorizedTensor, name="TT"):
 
     @classmethod
     def from_tensor(cls, tensor, rank="same", **kwargs):
-        _decomposition_unavailable("TTTensor.from_tensor")
+        """TT-SVD of a dense tensor (reference: factorized_tensors.py:391-400)."""
+        rank = tenalg.validate_tt_rank(tuple(tensor.shape), rank)
+        with torch.no_grad():
+            factors = decomposition.tensor_train(tensor, rank)
+        return cls([nn.Parameter(f.contiguous()) for f in factors])
 
     def init_from_tensor(self, tensor, **kwargs):
-        _decomposition_unavailable("TTTensor.init_from_tensor")
+        """Re-initialise the cores from a dense tensor (reference: factorized_tensors.py:402-409)."""
+        with torch.no_grad():
+            factors = decomposition.tensor_train(tensor, self.rank)
+        self.factors = FactorList([nn.Parameter(f.contiguous()) for f in factors])
+        self.rank = tuple([f.shape[0] for f in factors] + [1])
+        return self
 
     @property
     def decomposition(self):

@@ -16,7 +16,8 @@ from torch import nn
 from .. import tenalg, embedding_ops
 from ..ops import contract
 from ..utils import FactorList
-from .core import TensorizedTensor, flatten_tensorized_shape, _decomposition_unavailable
+from .core import TensorizedTensor, flatten_tensorized_shape
+from .. import decomposition
 from .factorized_tensors import CPTensor, TuckerTensor, DenseTensor, _is_int
 
 
@@ -90,7 +91,13 @@ class CPTensorized(CPTensor, TensorizedTensor, name="CP"):
 
     @classmethod
     def from_tensor(cls, tensor, tensorized_shape, rank="same", **kwargs):
-        _decomposition_unavailable("CPTensorized.from_tensor")
+        """CP-ALS (fp64) of the tensorized matrix (reference: tensorized_matrices.py:124-134)."""
+        rank = tenalg.validate_cp_rank(tuple(tensor.shape), rank)
+        dtype = tensor.dtype
+        with torch.no_grad():
+            weights, factors = decomposition.parafac(tensor.to(torch.float64), rank, **kwargs)
+        return cls(nn.Parameter(weights.to(dtype).contiguous()), [nn.Parameter(f.to(dtype).contiguous()) for f in factors],
+                   tensorized_shape, rank=rank)
 
     def __getitem__(self, indices):
         """Integer indices on leading plain modes (the n_layers case, reference: tensorized_matrices.py:136-193):
@@ -136,7 +143,11 @@ class TuckerTensorized(TensorizedTensor, TuckerTensor, name="Tucker"):
 
     @classmethod
     def from_tensor(cls, tensor, tensorized_shape, rank="same", fixed_rank_modes=None, **kwargs):
-        _decomposition_unavailable("TuckerTensorized.from_tensor")
+        """HOSVD + HOOI of the tensorized matrix (reference: tensorized_matrices.py:219-228)."""
+        rank = tenalg.validate_tucker_rank(tuple(tensor.shape), rank, fixed_modes=fixed_rank_modes)
+        with torch.no_grad():
+            core, factors = decomposition.tucker(tensor, rank, **kwargs)
+        return cls(nn.Parameter(core.contiguous()), [nn.Parameter(f.contiguous()) for f in factors], tensorized_shape, rank=rank)
 
     def __getitem__(self, indices):
         """Integer indices on leading plain modes (reference: tensorized_matrices.py:230-311)."""
@@ -236,10 +247,20 @@ class BlockTT(TensorizedTensor, name="BlockTT"):
 
     @classmethod
     def from_tensor(cls, tensor, tensorized_shape, rank, **kwargs):
-        _decomposition_unavailable("BlockTT.from_tensor")
+        """TT-matrix SVD of a tensor of shape (rows_1..rows_d, cols_1..cols_d) (reference: tensorized_matrices.py:516-524)."""
+        rank = validate_block_tt_rank(tensorized_shape, rank)
+        with torch.no_grad():
+            factors = decomposition.tensor_train_matrix(tensor, rank, **kwargs)
+        factors = [nn.Parameter(f.contiguous()) for f in factors]
+        return cls(factors, tensorized_shape, tuple([f.shape[0] for f in factors] + [1]))
 
     def init_from_tensor(self, tensor, **kwargs):
-        _decomposition_unavailable("BlockTT.init_from_tensor")
+        """Re-initialise the cores from a dense tensor (reference: tensorized_matrices.py:526-535)."""
+        with torch.no_grad():
+            factors = decomposition.tensor_train_matrix(tensor, self.rank, **kwargs)
+        self.factors = FactorList([nn.Parameter(f.contiguous()) for f in factors])
+        self.rank = tuple([f.shape[0] for f in factors] + [1])
+        return self
 
 
 # north_star names a "TT-matrix"/"TTMatrix" weight; the reference has no such class (SURVEY App. C.6):

@@ -370,11 +370,50 @@ def contract(spec: str, a: torch.Tensor, b: torch.Tensor, addend: Optional[torch
 
     ``spec`` is a two-operand einsum string.  Indices shared by both operands and the output are batch indices; no
     operand is ever permuted or copied -- strides go straight into the kernel descriptor."""
+    if a.is_complex() or b.is_complex() or (addend is not None and addend.is_complex()):
+        return _complex_contract(spec, a, b, addend, addend_letters, float(alpha))
     if a.dtype != b.dtype:
         raise TypeError(f"contract: operand dtypes differ ({a.dtype} vs {b.dtype})")
     if addend is not None and len(addend_letters) != addend.dim():
         raise ValueError("addend_letters must name every dim of the addend")
     return _contract_op(a, b, addend, spec, addend_letters, float(alpha))
+
+
+def _complex_contract(spec, a, b, addend, addend_letters, alpha):
+    """Complex operands (the Complex* factorized tensors, reference: complex_factorized_tensors.py): the real kernels run on the
+    real / imaginary planes -- re = ar.br - ai.bi, im = ar.bi + ai.br, the second product of each pair accumulating onto the
+    first through the kernel's addend -- and the planes are joined again.  Up to 4 launches, still no CPU path."""
+    out_letters = spec.split("->")[1]
+
+    def planes(t):
+        if t is None:
+            return None, None
+        if t.is_complex():
+            return t.real.contiguous(), t.imag.contiguous()
+        return t, None
+
+    (ar, ai), (br, bi), (dr, di) = planes(a), planes(b), planes(addend)
+    real_dtype = ar.dtype
+
+    def to_real(t):
+        return None if t is None else t.to(real_dtype)
+
+    br, bi, dr, di = to_real(br), to_real(bi), to_real(dr), to_real(di)
+
+    def acc(x, y, sign, base, base_letters):
+        if x is None or y is None:
+            return base, base_letters
+        return (_contract_op(x, y, base, spec, base_letters if base is not None else "", sign * alpha), out_letters)
+
+    re, re_l = acc(ar, br, 1.0, dr, addend_letters)
+    re, re_l = acc(ai, bi, -1.0, re, re_l)
+    im, im_l = acc(ar, bi, 1.0, di, addend_letters)
+    im, im_l = acc(ai, br, 1.0, im, im_l)
+    if im is None:
+        im = torch.zeros_like(re)
+    elif im_l != out_letters:           # only the addend had an imaginary part: broadcast it to the output's shape
+        im = im.reshape([im.shape[im_l.index(l)] if l in im_l else 1 for l in out_letters]).expand_as(re).contiguous()
+    return torch.complex(re, im)
 
 
 def reduce_to(t: torch.Tensor, letters: str, keep: str) -> torch.Tensor:

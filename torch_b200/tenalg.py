@@ -215,7 +215,8 @@ def blocktt_to_tensor(cores, tensorized_shape):
     cores = list(cores)
     n_entries = len(tensorized_shape)
     if (len(cores) == 3 and n_entries == 2 and all(c.dim() == 4 for c in cores)
-            and not any(isinstance(s, int) for s in tensorized_shape) and cores[0].shape[0] == 1 and cores[2].shape[3] == 1):
+            and not any(isinstance(s, int) for s in tensorized_shape) and cores[0].shape[0] == 1 and cores[2].shape[3] == 1
+            and not cores[0].is_complex()):
         from . import blocktt_ops
         rows, cols = [c.shape[1] for c in cores], [c.shape[2] for c in cores]
         if blocktt_ops.blocktt3_fits(rows, cols, cores[0].shape[3], cores[1].shape[3], True):

@@ -106,3 +106,23 @@ class ParameterList(_KeyedList):
 
     def _store(self, key, element):
         self.register_parameter(key, element)
+
+
+class ComplexFactorList(FactorList):
+    """FactorList of complex factors stored as real (..., 2) parameters -- optimisers and DDP see real tensors -- and handed
+    out as complex views (reference: tltorch/utils/parameter_list.py:85-107)."""
+
+    def __getitem__(self, index):
+        if isinstance(index, int):
+            value = getattr(self, self.keys[index])
+            return torch.view_as_complex(value) if torch.is_tensor(value) else value
+        return self.__class__([torch.view_as_complex(getattr(self, k)) for k in self.keys[index]])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self.keys)))
+
+    def _store(self, key, element):
+        if torch.is_tensor(element) and element.is_complex():
+            real = torch.view_as_real(element.detach() if isinstance(element, nn.Parameter) else element)
+            element = nn.Parameter(real, requires_grad=element.requires_grad) if isinstance(element, nn.Parameter) else real
+        super()._store(key, element)
