@@ -495,7 +495,13 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))   # a mismatched collective fails, not hangs
+        kw = {}
+        if args.nccl_ctas > 0:      # cap the SMs the all-reduce kernels take from the (persistent, one-CTA-per-SM) compute kernels
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = args.nccl_ctas
+            opts.config.min_ctas = 1
+            kw["pg_options"] = opts
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180), **kw)   # a mismatched collective fails, not hangs
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torch.distributed.run", file=sys.stderr)
     peaks, peak_src = _peaks()
@@ -515,7 +521,9 @@ def run_ours(args):
     x = torch.randn(B, 64, 56, 56, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     gy = torch.randn(B, 512, 7, 7, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     buckets = []
-    if world > 1:
+    if world > 1 and args.exchange == "tail":
+        buckets.append(GradientBucket(params))
+    elif world > 1:
         for g in sorted(set(STAGE_OF)):
             buckets.append(GradientBucket([p for i, c in enumerate(convs) if STAGE_OF[i] == g for p in c.parameters()]))
 
@@ -528,6 +536,12 @@ def run_ours(args):
             acts.append(c(acts[-1]))
         if world == 1:
             acts[-1].backward(gy)
+            return
+        if args.exchange == "tail":
+            # one flat bucket, all-reduced after the whole backward: the compute kernels are persistent (one CTA per SM), so an
+            # all-reduce running beside them takes SMs away and stretches every kernel it overlaps
+            acts[-1].backward(gy)
+            buckets[0].allreduce()
             return
         # backward stage by stage (last stage first); a stage's bucket is all-reduced asynchronously as soon as its gradients
         # are final, so the exchange overlaps the backward of the earlier stages (one NCCL call per stage, 4 per step)
@@ -599,7 +613,9 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "images_per_gpu": B, "global_images": B * world, "parallelism": f"dp{world}",
                        "step_mode": mode, "memory_format": "torch.channels_last (input, upstream gradient and every activation in between)", "l2": "working set per step (~2 GB of activations) >> 126 MB L2, no explicit flush",
                        "between_layers": "none (BN / ReLU / residual adds are not part of the factorized-layer path)",
-                       "exchange": "per-stage flat fp32 buckets (4), NCCL all-reduce(AVG) issued asynchronously inside the graph" if world > 1 else "none",
+                       "exchange": ("none" if world == 1 else "one flat fp32 bucket, NCCL all-reduce(AVG) after the backward pass, inside the graph" if args.exchange == "tail"
+                                    else "per-stage flat fp32 buckets (4), NCCL all-reduce(AVG) issued asynchronously inside the graph")
+                                   + (f", NCCL max_ctas {args.nccl_ctas}" if world > 1 and args.nccl_ctas > 0 else ""),
                        "cpu_affinity": f"{len(affinity)} CPUs local to the GPU (NVML)" if affinity else "unchanged"},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "roofline": roofline}
 
@@ -670,6 +686,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=IMAGES_PER_GPU, help="images per GPU of the headline workload (256 = BASELINE)")
     ap.add_argument("--configs", default="all", help="N = 1: which other BASELINE configs to time as well: all | none | 1,2,4,5")
+    ap.add_argument("--exchange", default="tail", choices=["staged", "tail"], help="N > 1: per-stage asynchronous buckets | one bucket after the backward")
+    ap.add_argument("--nccl-ctas", type=int, default=0, help="N > 1: cap on the CTAs NCCL's kernels use (0 = NCCL's default)")
     ap.add_argument("--eager", action="store_true", help="issue every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--skip-extras", action="store_true", help="profiling runs: skip the e2e, cpu_baseline and other-config legs")
     args = ap.parse_args()

@@ -899,7 +899,11 @@ def test_trl_spatial_first_plan_vs_rows_plan(B, C, hw, ranks, out, monkeypatch):
 
 
 @pytest.mark.parametrize("stride,h,w,r,batch", [(1, 28, 28, 141, 3), (1, 7, 7, 573, 5), (1, 14, 14, 285, 2), (2, 28, 28, 189, 3),
-                                                (2, 14, 14, 381, 2), (2, 56, 56, 93, 2), (1, 5, 9, 13, 3), (1, 3, 2, 8, 1)])
+                                                (2, 14, 14, 381, 2), (2, 56, 56, 93, 2), (1, 5, 9, 13, 3), (1, 3, 2, 8, 1),
+                                                # staged kernels (dwsep_staged.cu): many bands per block (both stages of the ring, several
+                                                # mbarrier phases), ragged last band / last segment, one-segment rows, wide rows
+                                                (1, 14, 14, 24, 160), (1, 7, 7, 64, 400), (1, 28, 28, 141, 48), (1, 9, 30, 40, 70),
+                                                (1, 6, 56, 72, 40), (1, 11, 3, 16, 200)])
 def test_dwsep_rows_kernels_vs_fp64(stride, h, w, r, batch):
     """tlt_dwsep_rows_fwd / _dgrad / _wgrad / _finalize (separable 3x3 depthwise sweep on channels-last rows, config 3's rank
     widths and map sizes, odd maps, a ragged channel chunk) vs fp64 autograd of the two depthwise 1-D convolutions of cp_conv

@@ -32,6 +32,8 @@ elif what.startswith("cp_conv"):
     layer.reset_parameters()
     layer = layer.to(torch.bfloat16)
     x = torch.randn(256, int(cin), int(hw), int(hw), device=dev, dtype=torch.bfloat16)
+    if what.startswith("cp_conv_cl"):          # channels-last activations: the rows route of config 3
+        x = x.contiguous(memory_format=torch.channels_last)
 elif what == "tucker_linear":
     layer = tlt.FactorizedLinear((16, 16, 16), (16, 16, 16), bias=True, factorization="tucker", rank=0.75, device=dev).to(torch.bfloat16)
     x = torch.randn(8192, 4096, device=dev, dtype=torch.bfloat16)
