@@ -384,6 +384,54 @@ int tlt_cast(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, i
 /* Writes `bytes` bytes of zeros/garbage through L2 (bench.py's L2 flush between timed iterations). */
 int tlt_l2_flush(void* scratch, size_t bytes, void* stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * tlt_cplinear_*: the CP-factorized linear layer as ONE op per direction (fp32)
+ *     y[b, o] = sum_r ( sum_i x[b, i] prod_m U_m[i_m, r] ) lambda_r prod_m V_m[o_m, r] + bias[o]
+ * Replaces: linear_cp (tltorch/functional/factorized_linear.py:23-36) -> tensor_dot_cp (factorized_tensordot.py:70-103),
+ * i.e. the n-ary tl.einsum of the activation with the CP factors, and its autograd.  The Khatri-Rao matrices are rebuilt
+ * tile by tile in shared memory, never materialised.  Factors are (d_m, R) row-major fp32, in the order of the
+ * tensorized shape (first mode slowest); x is (B, I = prod in_dims), y is (B, O = prod out_dims), I and O multiples of 4.
+ *   tlt_cplinear_workspace_size  bytes of ONE (B, round4(R)) fp32 matrix: `z` for the forward call (kept for the backward
+ *                                call), `g` (scratch) for the backward call
+ *   tlt_cplinear_fwd   y, z <- x, factors, lambda (+ bias or NULL)                                       2 launches
+ *   tlt_cplinear_bwd   dx, dU_m (d_m, R), dV_m (e_m, R), dlambda (R), dbias (O) or NULL <- x, dy, z      4 launches
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t batch, rank;
+  int32_t n_in, n_out;             /* tensorized modes per side, 1..4 */
+  int64_t in_dims[4], out_dims[4];
+} tlt_cplinear_desc;
+size_t tlt_cplinear_workspace_size(const tlt_cplinear_desc* desc);
+int tlt_cplinear_fwd(const tlt_cplinear_desc* desc, const float* x, const void* const* factors_in, const void* const* factors_out,
+                     const float* lambda, const float* bias, float* z, float* y, void* stream);
+int tlt_cplinear_bwd(const tlt_cplinear_desc* desc, const float* x, const float* dy, const float* z, const void* const* factors_in,
+                     const void* const* factors_out, const float* lambda, float* g, float* dx, void* const* d_factors_in,
+                     void* const* d_factors_out, float* dlambda, float* dbias, void* stream);
+
+/* --------------------------------------------------------------------------------------------------------------
+ * tlt_trl_tail_*: the Tucker tensor-regression layer behind its input projection (bf16), one op per direction
+ *     v[b, r] = sum_{j, c} zp[b, j, c] core[c, j, r];      y[b, o] = sum_r v[b, r] F_o[o, r] + bias[o]
+ * zp (B, J, ldz) is the projected activation, channels-last (rc valid channels per row of pitch ldz, J = product of the
+ * spatial ranks); core (rc, J, ro); F_o (out, ro), ro <= 16.  Replaces: the core expansion tenalg.multi_mode_dot(core,
+ * factors[n_input:]) and tenalg.inner(x, regression_weights) of tucker_trl (tltorch/functional/tensor_regression.py:42-49)
+ * and their autograd.  v / dv: fp32 (B, ro), v written by the forward call and read by the backward call.
+ *   tlt_trl_tail_fwd   y (B, out), v <- zp, core, F_o (+ bias or NULL)                                  1 launch
+ *   tlt_trl_tail_bwd   dzp, dcore, dF_o, dbias (or NULL), all bf16 <- zp, dy, core, F_o, v; dv scratch  2 launches
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t batch, j, rc, ldz, ro, out;
+} tlt_trl_tail_desc;
+int tlt_trl_tail_fwd(const tlt_trl_tail_desc* desc, const void* zp, const void* core, const void* f_out, const void* bias, void* y,
+                     float* v, void* stream);
+int tlt_trl_tail_bwd(const tlt_trl_tail_desc* desc, const void* zp, const void* dy, const void* core, const void* f_out, const float* v,
+                     float* dv, void* dzp, void* dcore, void* df_out, void* dbias, void* stream);
+/* Kronecker product of two small bf16 matrices A (da, pa), B (db, pb): k[(a, b), (p, q)] = A[a, p] B[b, q], and its backward
+ * (dA, dB <- dk).  Replaces: the merged spatial factor of the input projection of tucker_trl / TCL (tensor_regression.py:40,
+ * tensor_contraction_layers.py:75 contract one mode at a time; the spatial modes are applied here as ONE matrix). */
+int tlt_kron2_fwd(const void* a, const void* b, int32_t da, int32_t pa, int32_t db, int32_t pb, void* k, void* stream);
+int tlt_kron2_bwd(const void* a, const void* b, const void* dk, int32_t da, int32_t pa, int32_t db, int32_t pb, void* d_a, void* d_b,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -420,6 +420,91 @@ def emulate_kr_bwd(factors, weights, g, dfs, dw):
     LOG.append(("khatri_rao_bwd", [tuple(f.shape) for f in factors], weights is not None))
 
 
+def _kr_full(fs):
+    """(prod dims, R) Khatri-Rao matrix, first factor slowest, fp64."""
+    out = fs[0].double()
+    for f in fs[1:]:
+        out = (out[:, None, :] * f.double()[None, :, :]).reshape(-1, f.shape[1])
+    return out
+
+
+def emulate_cplinear_fwd(d, x, f_in, f_out, lam, bias, z, y):
+    """tlt_cplinear_fwd: the descriptor's dims must describe the factors it is given; z keeps round4(R) columns, pad = 0."""
+    assert [int(d.in_dims[k]) for k in range(d.n_in)] == [f.shape[0] for f in f_in]
+    assert [int(d.out_dims[k]) for k in range(d.n_out)] == [f.shape[0] for f in f_out]
+    R = int(d.rank)
+    zz = x.double() @ _kr_full(f_in)
+    z.zero_()
+    z[:, :R] = zz.to(z.dtype)
+    yy = (zz * lam.double()) @ _kr_full(f_out).t()
+    if bias is not None:
+        yy = yy + bias.double()
+    y.copy_(yy.to(y.dtype))
+    LOG.append(("cplinear_fwd", tuple(x.shape), R))
+
+
+def emulate_cplinear_bwd(d, x, gy, z, f_in, f_out, lam, g, dx, df_in, df_out, dlam, dbias):
+    R = int(d.rank)
+    kin, kout = _kr_full(f_in), _kr_full(f_out)
+    G = gy.double() @ kout
+    zz = z[:, :R].double()
+    dx.copy_(((G * lam.double()) @ kin.t()).to(dx.dtype))
+    dlam.copy_((zz * G).sum(0).to(dlam.dtype))
+    if dbias is not None:
+        dbias.copy_(gy.double().sum(0).to(dbias.dtype))
+
+    def factor_grads(dkr, fs, outs):
+        dims = [f.shape[0] for f in fs]
+        t = dkr.reshape(*dims, R)
+        letters = "abcd"[:len(fs)]
+        for k in range(len(fs)):
+            others = [fs[j].double() for j in range(len(fs)) if j != k]
+            spec = letters + "r" + "".join("," + letters[j] + "r" for j in range(len(fs)) if j != k) + "->" + letters[k] + "r"
+            outs[k].copy_((torch.einsum(spec, t, *others) if others else t).to(outs[k].dtype))
+
+    factor_grads(x.double().t() @ (G * lam.double()), f_in, df_in)
+    factor_grads(gy.double().t() @ (zz * lam.double()), f_out, df_out)
+    LOG.append(("cplinear_bwd", tuple(x.shape), R))
+
+
+def emulate_kron_fwd(a, b, k):
+    k.copy_(torch.einsum("ap,bq->abpq", a.double(), b.double()).reshape(k.shape).to(k.dtype))
+    LOG.append(("kron2_fwd", tuple(a.shape), tuple(b.shape)))
+
+
+def emulate_kron_bwd(a, b, dk, d_a, d_b):
+    g = dk.double().reshape(a.shape[0], b.shape[0], a.shape[1], b.shape[1])
+    d_a.copy_(torch.einsum("abpq,bq->ap", g, b.double()).to(d_a.dtype))
+    d_b.copy_(torch.einsum("abpq,ap->bq", g, a.double()).to(d_b.dtype))
+    LOG.append(("kron2_bwd", tuple(a.shape), tuple(b.shape)))
+
+
+def emulate_trl_tail_fwd(d, zp, core, fo, bias, y, v):
+    B, J, rc, ldz, ro, O = (int(getattr(d, k)) for k in ("batch", "j", "rc", "ldz", "ro", "out"))
+    assert tuple(zp.shape) == (B, J, ldz) and core.numel() == rc * J * ro and tuple(fo.shape) == (O, ro)
+    vv = torch.einsum("bjc,cjr->br", zp[:, :, :rc].double(), core.reshape(rc, J, ro).double())
+    v.copy_(vv.to(v.dtype))
+    yy = vv @ fo.double().t()
+    if bias is not None:
+        yy = yy + bias.double()
+    y.copy_(yy.to(y.dtype))
+    LOG.append(("trl_tail_fwd", (B, J, rc, ro, O)))
+
+
+def emulate_trl_tail_bwd(d, zp, gy, core, fo, v, dv, dzp, dcore, dfo, dbias):
+    B, J, rc, ldz, ro, O = (int(getattr(d, k)) for k in ("batch", "j", "rc", "ldz", "ro", "out"))
+    g = gy.double()
+    dvv = g @ fo.double()
+    dv.copy_(dvv.to(dv.dtype))
+    dzp.zero_()
+    dzp[:, :, :rc] = torch.einsum("br,cjr->bjc", dvv, core.reshape(rc, J, ro).double()).to(dzp.dtype)
+    dcore.copy_(torch.einsum("bjc,br->cjr", zp[:, :, :rc].double(), dvv).reshape(dcore.shape).to(dcore.dtype))
+    dfo.copy_((g.t() @ v.double()).to(dfo.dtype))
+    if dbias is not None:
+        dbias.copy_(g.sum(0).to(dbias.dtype))
+    LOG.append(("trl_tail_bwd", (B, J, rc, ro, O)))
+
+
 def emulate_scale_modes(x, masks, alpha, y):
     res = x.double() * alpha
     for k, m in enumerate(masks):
@@ -508,6 +593,13 @@ def emulated_kernels():
     from torch_b200 import kr_ops as ko
     from torch_b200 import spatial_ops as so
     from torch_b200 import cprows_ops as co
+    from torch_b200 import cplinear_ops as cl
+    from torch_b200 import trl_ops as tr
+    saved_tr = tr._execute_fwd, tr._execute_bwd, tr._execute_kron_fwd, tr._execute_kron_bwd
+    tr._execute_fwd, tr._execute_bwd, tr._execute_kron_fwd, tr._execute_kron_bwd = (
+        emulate_trl_tail_fwd, emulate_trl_tail_bwd, emulate_kron_fwd, emulate_kron_bwd)
+    saved_cl = cl._execute_fwd, cl._execute_bwd
+    cl._execute_fwd, cl._execute_bwd = emulate_cplinear_fwd, emulate_cplinear_bwd
     saved_so = so._execute_spatial_fwd, so._execute_spatial_bwd
     so._execute_spatial_fwd, so._execute_spatial_bwd = emulate_spatial_fwd, emulate_spatial_bwd
     saved_co = co._execute_pack, co._execute_fwd, co._execute_bwd, co._execute_finalize, co._ws_bytes, co._acc_bytes
@@ -541,6 +633,8 @@ def emulated_kernels():
     try:
         yield LOG
     finally:
+        cl._execute_fwd, cl._execute_bwd = saved_cl
+        tr._execute_fwd, tr._execute_bwd, tr._execute_kron_fwd, tr._execute_kron_bwd = saved_tr
         so._execute_spatial_fwd, so._execute_spatial_bwd = saved_so
         co._execute_pack, co._execute_fwd, co._execute_bwd, co._execute_finalize, co._ws_bytes, co._acc_bytes = saved_co
         ops._execute_contract, ops._execute_conv = saved

@@ -34,7 +34,10 @@ def test_descriptor_structs_match_header_layout(tmp_path):
     from torch_b200 import _cuda
     probes = [("tlt_contract_desc", _cuda.ContractDesc, ["dtype_a", "nb", "size_b", "a_b", "b_n", "c_b", "d_n", "alpha", "split_k"]),
               ("tlt_gemm_desc", _cuda.GemmDesc, ["M", "ldc", "a_major", "dtype_c", "dtype_bias", "alpha"]),
-              ("tlt_conv_desc", _cuda.ConvDesc, ["dtype", "batch", "in_size", "kernel", "dilation"])]
+              ("tlt_conv_desc", _cuda.ConvDesc, ["dtype", "batch", "in_size", "kernel", "dilation"]),
+              ("tlt_cplinear_desc", _cuda.CpLinearDesc, ["batch", "rank", "n_in", "n_out", "in_dims", "out_dims"]),
+              ("tlt_cpconv_rows_desc", _cuda.CpConvRowsDesc, ["batch", "rank", "height", "stride"]),
+              ("tlt_trl_tail_desc", _cuda.TrlTailDesc, ["batch", "j", "rc", "ldz", "ro", "out"])]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{REPO}/include/tltorch_cuda.h"', "int main(){"]
     for cname, _, fields in probes:
         lines.append(f'printf("%zu\\n", sizeof({cname}));')

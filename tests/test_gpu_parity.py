@@ -1058,3 +1058,73 @@ def test_tensor_dropout_vs_oracle_on_gpu(kind, shape, rank, proba, training, dty
     for n, a, b in zip(params, grads, go):
         errs[n] = G.rel_err(a, b)
     _report(f"dropout {kind} rank={rank} train={training} {dtype}", errs, TOL[dtype])
+
+
+@pytest.mark.parametrize("in_shape,out_shape,rank,batch,bias", [
+    ((4, 8, 16), (4, 8, 16), 2341, 128, True),     # BASELINE config 1
+    ((4, 8, 16), (4, 8, 16), 0.5, 300, False),     # several batch tiles (128-row tiles of the projection, 32-row tiles of the expansion)
+    ((2, 6), (3, 4), 9, 37, True),                 # everything ragged: 12 features, rank tile of 16 not full, rank % 4 = 1
+    ((12,), (2, 2, 5, 1), 50, 3, True),            # one mode in, four out
+    ((16, 16), (8, 64), 130, 64, True),            # rank % 4 = 2, 512 output features
+])
+def test_cp_linear_fused_vs_oracle(in_shape, out_shape, rank, batch, bias, monkeypatch):
+    """fp32 CP FactorizedLinear through the fused op (tlt_cplinear_fwd / _bwd, csrc/cplinear.cu: 2 launches forward, 4 backward, no
+    Khatri-Rao matrix materialised) vs the fp64 oracle of linear_cp -> tensor_dot_cp (functional/factorized_linear.py:23-36,
+    factorized_tensordot.py:70-103): y, dx and every parameter gradient at north_star's fp32 tolerance 1e-5."""
+    import math
+    import torch_b200 as tlt
+    from torch_b200 import _cuda
+    from oracle import reference_path as rp
+    monkeypatch.setenv("TLT_CPLINEAR_FUSED", "1")          # opt-in path (slower than the unfused chain at config 1's size)
+    torch.manual_seed(batch)
+    lin = tlt.FactorizedLinear(in_shape, out_shape, bias=bias, factorization="cp", rank=rank, implementation="factorized", device=dev(),
+                               dtype=torch.float32)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.normal_(0, 0.4)
+    x = torch.randn(batch, math.prod(in_shape), device=dev(), requires_grad=True)
+    gy = torch.randn(batch, math.prod(out_shape), device=dev())
+    n0 = _cuda.lib().tlt_launch_count()
+    y = lin(x)
+    names = [n for n, _ in lin.named_parameters()]
+    grads = torch.autograd.grad(y, [x] + list(lin.parameters()), gy)
+    assert _cuda.lib().tlt_launch_count() - n0 == 6, "the fused op is 2 + 4 launches"
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in lin.named_parameters()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(len(in_shape) + len(out_shape))]
+    yo = rp.factorized_linear(xo, "cp", (leaves["weight.weights"], fs), (out_shape, in_shape), bias=leaves.get("bias"), order="sane")
+    go = torch.autograd.grad(yo, [xo] + [leaves[n] for n in names], gy.double().cpu())
+    errs = {"y": G.rel_err(y, yo)}
+    for a, b_, n in zip(grads, go, ["x"] + names):
+        errs["d" + n] = G.rel_err(a, b_)
+    _report(_tag(), errs, 1e-5)
+
+
+@pytest.mark.parametrize("B,J,rc,ldz,ro,O,bias", [(512, 16, 64, 64, 10, 1000, True), (37, 12, 20, 24, 5, 30, True), (5, 1, 3, 8, 16, 7, False),
+                                                  (300, 6, 33, 40, 1, 513, True)])
+def test_trl_tail_op_vs_fp64(B, J, rc, ldz, ro, O, bias):
+    """tlt_trl_tail_fwd / _bwd (core contraction + output expansion + bias of tucker_trl, tensor_regression.py:42-49, one launch forward,
+    two backward) vs fp64 autograd: config 4's shape, ragged everything, the largest output rank, a batch that crosses the 256-row
+    staging chunk of the parameter-gradient kernel."""
+    from torch_b200 import trl_ops
+    torch.manual_seed(B + O)
+    zp = torch.zeros(B, J, ldz, device=dev(), dtype=torch.bfloat16)
+    zp[:, :, :rc] = (torch.randn(B, J, rc, device=dev()) * 0.5).to(torch.bfloat16)
+    zp.requires_grad_(True)
+    core = (torch.randn(rc, J, ro, device=dev()) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    fo = (torch.randn(O, ro, device=dev()) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    bv = torch.randn(O, device=dev()).to(torch.bfloat16).requires_grad_(True) if bias else None
+    y = trl_ops.trl_tail(zp, core, fo, bv)
+    gy = torch.randn_like(y)
+    leaves = [zp, core, fo] + ([bv] if bias else [])
+    grads = torch.autograd.grad(y, leaves, gy)
+    lo = [t.detach().double().cpu().requires_grad_(True) for t in leaves]
+    vo = torch.einsum("bjc,cjr->br", lo[0][:, :, :rc], lo[1])
+    yo = vo @ lo[2].t() + (lo[3] if bias else 0)
+    go = torch.autograd.grad(yo, lo, gy.double().cpu())
+    errs = {"y": G.rel_err(y, yo), "dzp": G.rel_err(grads[0][:, :, :rc], go[0][:, :, :rc]), "dcore": G.rel_err(grads[1], go[1]),
+            "dfo": G.rel_err(grads[2], go[2])}
+    if bias:
+        errs["dbias"] = G.rel_err(grads[3], go[3])
+    assert float(grads[0][:, :, rc:].abs().max()) == 0.0 if ldz > rc else True
+    _report(_tag(), errs, 1e-2)

@@ -425,3 +425,65 @@ def test_channels_last_input_takes_the_rows_route_without_transposes():
         assert G.rel_err(yc, yn.double()) < 1e-2
         for a, b in zip(gc_, gn):
             assert G.rel_err(a, b.double()) < 2e-2
+
+
+@pytest.mark.parametrize("in_shape,out_shape,rank,batch,bias", [((4, 8, 16), (4, 8, 16), 37, 5, True), ((2, 6), (3, 4), 9, 3, False),
+                                                              ((12,), (2, 2, 5, 1), 6, 4, True)])
+def test_cp_linear_fused_op_host_logic(in_shape, out_shape, rank, batch, bias, monkeypatch):
+    """fp32 CP FactorizedLinear takes the fused op (cplinear_ops: 2 + 4 launches); descriptor dims / factor order / autograd plumbing
+    checked on the emulator against the oracle of linear_cp (factorized_linear.py:23-36)."""
+    from oracle import reference_path as rp
+    import math
+    monkeypatch.setenv("TLT_CPLINEAR_FUSED", "1")
+    torch.manual_seed(rank)
+    lin = tlt.FactorizedLinear(in_shape, out_shape, bias=bias, factorization="cp", rank=rank, implementation="factorized", dtype=torch.float32)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.normal_(0, 0.5)
+    x = torch.randn(batch, math.prod(in_shape), requires_grad=True)
+    gy = torch.randn(batch, math.prod(out_shape))
+    with emulated_kernels() as log:
+        y = lin(x)
+        names = [n for n, _ in lin.named_parameters()]
+        grads = torch.autograd.grad(y, [x] + list(lin.parameters()), gy)
+    assert [e[0] for e in log] == ["cplinear_fwd", "cplinear_bwd"]
+    leaves = {n: p.detach().double().requires_grad_(True) for n, p in lin.named_parameters()}
+    xo = x.detach().double().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(len(in_shape) + len(out_shape))]
+    yo = rp.factorized_linear(xo, "cp", (leaves["weight.weights"], fs), (out_shape, in_shape), bias=leaves.get("bias"), order="sane")
+    go = torch.autograd.grad(yo, [xo] + [leaves[n] for n in names], gy.double())
+    assert G.rel_err(y, yo) < 1e-5
+    for a, b_, n in zip(grads, go, ["x"] + names):
+        assert G.rel_err(a, b_) < 1e-5, n
+
+
+def test_tucker_trl_fused_route_host_logic(monkeypatch):
+    """bf16 Tucker TRL with one output mode on a (B, C, h, w) map -> spatial_project, channel GEMM, tltorch::trl_tail (core
+    contraction + output expansion + bias as one op): routing, descriptor, autograd of x and of every parameter against the fp64
+    einsum of tucker_trl (tensor_regression.py:37-49), launch funnels emulated."""
+    from torch_b200 import spatial_ops
+    torch.manual_seed(21)
+    monkeypatch.setattr(spatial_ops, "eligible", lambda x, S, J: x.shape[1] % 128 == 0 and S <= 64 and J <= 16)
+    B, C, h, w, O = 24, 256, 7, 7, 30
+    trl_layer = tlt.TRL((C, h, w), (O,), bias=True, factorization="tucker", rank=(20, 4, 3, 5))
+    with torch.no_grad():
+        for p in trl_layer.parameters():
+            p.normal_(0, 0.3)
+    trl_layer = trl_layer.to(torch.bfloat16)
+    x = (torch.randn(B, C, h, w) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    params = dict(trl_layer.named_parameters())
+    with emulated_kernels() as log:
+        y = trl_layer(x)
+        gy = torch.randn_like(y)
+        got = torch.autograd.grad(y, [x] + list(params.values()), gy)
+    kinds = [e[0] for e in log]
+    assert "trl_tail_fwd" in kinds and "trl_tail_bwd" in kinds and "spatial_project_fwd" in kinds, kinds
+    leaves = {n: p.detach().double().requires_grad_(True) for n, p in params.items()}
+    xo = x.detach().double().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(4)]
+    Wt = torch.einsum("abcd,ia,jb,kc,ld->ijkl", leaves["weight.core"], *fs)
+    yo = torch.einsum("bijk,ijkl->bl", xo, Wt) + leaves["bias"]
+    want = torch.autograd.grad(yo, [xo] + list(leaves.values()), gy.double())
+    assert G.rel_err(y, yo) < 2e-2
+    for n, a, b in zip(["x"] + list(params), got, want):
+        assert G.rel_err(a, b) < 2e-2, n

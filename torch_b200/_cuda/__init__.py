@@ -76,6 +76,15 @@ class CpConvRowsDesc(C.Structure):
                 ("height", C.c_int64), ("width", C.c_int64), ("stride", C.c_int32)]
 
 
+class CpLinearDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("rank", C.c_int64), ("n_in", C.c_int32), ("n_out", C.c_int32),
+                ("in_dims", C.c_int64 * 4), ("out_dims", C.c_int64 * 4)]
+
+
+class TrlTailDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("j", C.c_int64), ("rc", C.c_int64), ("ldz", C.c_int64), ("ro", C.c_int64), ("out", C.c_int64)]
+
+
 # every symbol include/tltorch_cuda.h declares: (name, restype, argtypes)
 _vp = C.c_void_p
 SYMBOLS = {
@@ -131,6 +140,14 @@ SYMBOLS = {
     "tlt_cpconv_rows_fwd": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp]),
     "tlt_cpconv_rows_bwd": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_cpconv_rows_finalize": (C.c_int, [C.POINTER(CpConvRowsDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cplinear_workspace_size": (C.c_size_t, [C.POINTER(CpLinearDesc)]),
+    "tlt_cplinear_fwd": (C.c_int, [C.POINTER(CpLinearDesc), _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _vp, _vp, _vp, _vp]),
+    "tlt_cplinear_bwd": (C.c_int, [C.POINTER(CpLinearDesc), _vp, _vp, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _vp, _vp,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _vp, _vp]),
+    "tlt_trl_tail_fwd": (C.c_int, [C.POINTER(TrlTailDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_trl_tail_bwd": (C.c_int, [C.POINTER(TrlTailDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_kron2_fwd": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "tlt_kron2_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "tlt_spatial_project_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "tlt_spatial_project_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "tlt_spatial_project_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),

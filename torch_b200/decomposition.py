@@ -94,9 +94,17 @@ def _mttkrp(tensor, weights, factors, mode):
     return out * weights.unsqueeze(0)
 
 
+def _fp64(tensor):
+    """Decompositions iterate in fp64 whatever the parameter dtype (the reconstruction-error estimate ||T||^2 + ||rec||^2 - 2<T, rec>
+    cancels catastrophically in fp32 and stops ALS early); results are cast back by the callers below."""
+    wide = torch.complex128 if tensor.is_complex() else torch.float64
+    return tensor.to(wide), tensor.dtype
+
+
 def parafac(tensor, rank, n_iter_max=100, init="svd", tol=1e-8, l2_reg=0.0, normalize_factors=False, random_state=None,
             fixed_modes=None, return_errors=False, verbose=False, **unused):
     """CP decomposition by alternating least squares -> (weights (R), [factors (d_k, R)])."""
+    tensor, out_dtype = _fp64(tensor)
     rank = tenalg.validate_cp_rank(tuple(tensor.shape), rank)
     gen = None
     if random_state is not None:
@@ -140,6 +148,7 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", tol=1e-8, l2_reg=0.0, norm
                 print(f"parafac iteration {iteration}: reconstruction error {errors[-1]:.3e}")
             if iteration >= 1 and abs(errors[-2] - errors[-1]) < tol:
                 break
+    weights, factors = weights.to(out_dtype), [f.to(out_dtype) for f in factors]
     if return_errors:
         return (weights, factors), errors
     return weights, factors
@@ -199,8 +208,10 @@ def tucker(tensor, rank, fixed_factors=None, n_iter_max=100, init="svd", tol=1e-
     """Tucker decomposition -> (core (r_0..), [factors (d_k, r_k)])."""
     if fixed_factors:
         raise NotImplementedError("tucker(fixed_factors=...) is not used by the factorized layers")
+    tensor, out_dtype = _fp64(tensor)
     rank = tenalg.validate_tucker_rank(tuple(tensor.shape), rank)
     (core, factors), errors = partial_tucker(tensor, rank, None, n_iter_max, init, tol, random_state, verbose)
+    core, factors = core.to(out_dtype), [f.to(out_dtype) for f in factors]
     if return_errors:
         return (core, factors), errors
     return core, factors
@@ -211,6 +222,7 @@ def tucker(tensor, rank, fixed_factors=None, n_iter_max=100, init="svd", tol=1e-
 # =====================================================================================================================
 def tensor_train(tensor, rank, verbose=False, **unused):
     """TT-SVD -> [cores (r_k, d_k, r_{k+1})].  Ranks are clipped to what each unfolding supports."""
+    tensor, out_dtype = _fp64(tensor)
     shape = tuple(tensor.shape)
     rank = list(tenalg.validate_tt_rank(shape, rank))
     order = len(shape)
@@ -222,13 +234,13 @@ def tensor_train(tensor, rank, verbose=False, **unused):
         current = min(n_row, n_col, rank[k + 1])
         U, S, V = svd_interface(unfolding, n_eigenvecs=current)
         rank[k + 1] = current
-        cores[k] = U.reshape(rank[k], shape[k], rank[k + 1]).contiguous()
+        cores[k] = U.reshape(rank[k], shape[k], rank[k + 1]).contiguous()     # (cast back to the caller's dtype at the end)
         if verbose:
             print(f"TT factor {k} computed with shape {tuple(cores[k].shape)}")
         unfolding = S.reshape(-1, 1) * V
     prev_rank, last_dim = unfolding.shape
     cores[-1] = unfolding.reshape(prev_rank, last_dim, 1).contiguous()
-    return cores
+    return [c.to(out_dtype) for c in cores]
 
 
 def tensor_train_matrix(tensor, rank, verbose=False, **unused):

@@ -2,6 +2,7 @@
 import math
 
 from .. import tenalg
+from .. import trl_ops
 
 
 def trl(x, weight, bias=None, **kwargs):
@@ -50,6 +51,9 @@ def tucker_trl(x, weight, project_input=False, bias=None):
         cost_rec, cost_proj = _tucker_trl_cost(tuple(x.shape), weight)
         project_input = cost_proj < cost_rec
     factors = list(weight.factors)
+    if project_input and trl_ops.eligible(x, weight, bias):
+        # projection (one pass over the activation + the channel GEMM) -> ONE launch for core contraction, output expansion and bias
+        return trl_ops.tucker_trl_fused(x, weight, bias)
     if project_input:
         x = tenalg.multi_mode_dot(x, factors[:n_input], modes=range(1, n_input + 1), transpose=True)
         regression_weights = tenalg.multi_mode_dot(weight.core, factors[n_input:], modes=range(n_input, weight.order))
