@@ -368,7 +368,8 @@ def other_configs(dev):
         if dropout:
             conv.weight = tlt.tensor_dropout(conv.weight, p=0.1)
             conv.train()
-        x = torch.randn(512, 512, 7, 7, device=dev, dtype=torch.bfloat16).requires_grad_(True)
+        # channels-last activations, like the headline config (the conv follows the ResNet stage whose maps are kept in that format)
+        x = torch.randn(512, 512, 7, 7, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
 
         def cpu(sample=64):
             core = (torch.randn(388, 388, 2, 2) * 0.05).requires_grad_(True)
@@ -382,7 +383,7 @@ def other_configs(dev):
                     c, f = rp.tucker_dropout_apply(core, fs, idx, 0.1, training=True)
                 return torch.autograd.grad(rp.tucker_conv(xc, c, f, None, [1, 1], [1, 1], [1, 1]), [xc, core] + fs, gy)
             return step, sample, f"{sample} images, tucker_conv chain as shipped" + (" + TuckerDropout" if dropout else "")
-        return dict(name="4-conv: Tucker FactorizedConv 512->512 3x3 @7^2 rank 0.5 -> (388,388,2,2), batch 512, bf16" +
+        return dict(name="4-conv: Tucker FactorizedConv 512->512 3x3 @7^2 rank 0.5 -> (388,388,2,2), batch 512, bf16, channels-last" +
                          (" + tensor_dropout(p=0.1)" if dropout else ""),
                     layers=[conv], x=x, samples=512, bound="tensor", bytes=134.4e6, flops=263.8e9, dtype="bf16", cpu=cpu)
 

@@ -11,6 +11,8 @@ reconstructed kernels (:16-53).  CPU tensors raise NotImplementedError (no fallb
 import ctypes as C
 from typing import List, Optional
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -519,6 +521,18 @@ def dwsep_eligible(factors, kernel, stride, padding, dilation, spatial):
     return stride[0] == 1 or (spatial[0] % 2 == 0 and spatial[1] % 2 == 0)
 
 
+_BRANCHES = os.environ.get("TLT_CHAIN_BRANCHES", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the weight-gradient branch of the chain's backward op."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def _execute_chain_prep(c_in, c_out, rank, flip_d, f_in, f_out, kh, kw, lam, wp_in, wp_out, taps_f, taps_d):
     _cuda.require_cuda(f_in, f_out, kh, kw, lam, wp_in, wp_out, taps_f, taps_d)
     _cuda.check(_cuda.lib().tlt_cpchain_prep(c_in, c_out, rank, 1 if flip_d else 0, _cuda.ptr(f_in), _cuda.ptr(f_out), _cuda.ptr(kh),
@@ -581,17 +595,31 @@ def _chain_bwd_op(gy: torch.Tensor, xr: torch.Tensor, z1: torch.Tensor, z2: torc
     dev, bf, f32 = xr.device, torch.bfloat16, torch.float32
     p_in, p_out = xr.shape[0], gy.shape[0]
     dz2 = torch.empty((p_out, ld), dtype=bf, device=dev)                 # dz2[b, r] = sum_o gy[b, o] F_out[o, r]
-    _execute_gemm(gy, wp_out, None, dz2, M=p_out, N=ld, K=cout_p, lda=gy.stride(0), ldb=ld, a_major=0, b_major=1)
     dz1 = torch.empty((p_in, ld), dtype=bf, device=dev)
-    _execute_dwsep("dgrad", dz2, taps_d, dz1, batch, height, width, stride)
     dx = torch.empty((p_in, cin_p), dtype=bf, device=dev)                # dx[b, c] = sum_r dz1[b, r] F_in[c, r]
-    _execute_gemm(dz1, wp_in, None, dx, M=p_in, N=cin_p, K=ld, lda=ld, ldb=cin_p, a_major=0, b_major=1)
     acc = torch.empty((_dwsep_parts(), 9, ld), dtype=f32, device=dev)
-    _execute_dwsep("wgrad", z1, dz2, acc, batch, height, width, stride)
     dw_out = torch.empty((c_out, ld), dtype=f32, device=dev)             # dW_out[o, r] = sum_b gy[b, o] z2[b, r]   (split-K, fp32)
-    _execute_gemm(gy, z2, None, dw_out, M=c_out, N=ld, K=p_out, lda=gy.stride(0), ldb=ld, a_major=1, b_major=1)
     dw_in = torch.empty((c_in, ld), dtype=f32, device=dev)               # dW_in[c, r] = sum_b x[b, c] dz1[b, r]   (F_in's own layout)
+    _execute_gemm(gy, wp_out, None, dz2, M=p_out, N=ld, K=cout_p, lda=gy.stride(0), ldb=ld, a_major=0, b_major=1)
+    # two branches from here: [transposed sweep -> dx GEMM -> dW_in GEMM] on the current stream, [weight-gradient sweep -> dW_out GEMM]
+    # on a side stream (every buffer is allocated above, on the current stream, and outlives the join).  On the small maps
+    # (14^2, 7^2) each of these launches is a few waves of work: the second branch fills the tails of the first.  Captured into a
+    # CUDA graph the fork / join are plain graph edges.
+    side = _side_stream(dev) if _BRANCHES and dev.type == "cuda" else None
+    if side is not None:
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _execute_dwsep("wgrad", z1, dz2, acc, batch, height, width, stride)
+            _execute_gemm(gy, z2, None, dw_out, M=c_out, N=ld, K=p_out, lda=gy.stride(0), ldb=ld, a_major=1, b_major=1)
+    _execute_dwsep("dgrad", dz2, taps_d, dz1, batch, height, width, stride)
+    _execute_gemm(dz1, wp_in, None, dx, M=p_in, N=cin_p, K=ld, lda=ld, ldb=cin_p, a_major=0, b_major=1)
+    if side is None:
+        _execute_dwsep("wgrad", z1, dz2, acc, batch, height, width, stride)
+        _execute_gemm(gy, z2, None, dw_out, M=c_out, N=ld, K=p_out, lda=gy.stride(0), ldb=ld, a_major=1, b_major=1)
     _execute_gemm(xr, dz1, None, dw_in, M=c_in, N=ld, K=p_in, lda=xr.stride(0), ldb=ld, a_major=1, b_major=1)
+    if side is not None:
+        main.wait_stream(side)
     g_lam, g_kh, g_kw = torch.empty_like(lam), torch.empty_like(kh), torch.empty_like(kw)
     g_fout, g_fin = torch.empty((c_out, r), dtype=lam.dtype, device=dev), torch.empty((c_in, r), dtype=lam.dtype, device=dev)
     _execute_chain_post(c_in, c_out, r, dw_out, dw_in, acc, kh.contiguous(), kw.contiguous(), lam.contiguous(), g_fout, g_fin, g_kh,
