@@ -903,7 +903,9 @@ def test_trl_spatial_first_plan_vs_rows_plan(B, C, hw, ranks, out, monkeypatch):
                                                 # staged kernels (dwsep_staged.cu): many bands per block (both stages of the ring, several
                                                 # mbarrier phases), ragged last band / last segment, one-segment rows, wide rows
                                                 (1, 14, 14, 24, 160), (1, 7, 7, 64, 400), (1, 28, 28, 141, 48), (1, 9, 30, 40, 70),
-                                                (1, 6, 56, 72, 40), (1, 11, 3, 16, 200)])
+                                                (1, 6, 56, 72, 40), (1, 11, 3, 16, 200),
+                                                # stride-2 weight gradient through the staged kernel, many bands per block
+                                                (2, 28, 28, 24, 60), (2, 14, 14, 64, 150), (2, 10, 6, 16, 100), (2, 56, 56, 93, 12)])
 def test_dwsep_rows_kernels_vs_fp64(stride, h, w, r, batch):
     """tlt_dwsep_rows_fwd / _dgrad / _wgrad / _finalize (separable 3x3 depthwise sweep on channels-last rows, config 3's rank
     widths and map sizes, odd maps, a ragged channel chunk) vs fp64 autograd of the two depthwise 1-D convolutions of cp_conv

@@ -367,7 +367,7 @@ static unsigned grid_for(long long items) {
 namespace tlt {
 namespace dwst {   // dwsep_staged.cu: the same sweeps from TMA-landed bands in shared memory (stride 1); 1 launched, 0 not covered
 int staged_fwd(int batch, int H, int W, int ld, const void* z, const float* taps, void* y, cudaStream_t st);
-int staged_wgrad(int batch, int H, int W, int ld, const void* z, const void* gy, float* acc, cudaStream_t st);
+int staged_wgrad(int batch, int H, int W, int ld, int stride, const void* z, const void* gy, float* acc, cudaStream_t st);
 }  // namespace dwst
 }  // namespace tlt
 
@@ -424,7 +424,7 @@ extern "C" int tlt_dwsep_rows_wgrad(const tlt_dwsep_desc* d, const void* z, cons
   TLT_REQUIRE(smem <= 48 * 1024 && g.cpr <= 256, "tlt_dwsep_rows_wgrad: ld too large");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)tlt_dwsep_rows_wgrad_parts();
-  if (d->stride == 1 && staged_enabled() && dwst::staged_wgrad(g.batch, g.H, g.W, (int)d->ld, z, gy, acc, st) == 1)
+  if (staged_enabled() && dwst::staged_wgrad(g.batch, g.H, g.W, (int)d->ld, (int)d->stride, z, gy, acc, st) == 1)
     return check_launch("dwsep_staged_kernel<wgrad>");
   if (d->stride == 1) dwsep_wgrad_kernel<1><<<grid, 256, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);
   else dwsep_wgrad_kernel<2><<<grid, 256, smem, st>>>(g, (const uint4*)z, (const uint4*)gy, acc);

@@ -46,7 +46,9 @@ __device__ __forceinline__ uint4 pack(const f2 (&o)[4]) {
 }
 
 struct SGeom {
-  int batch, H, W, cpr;
+  int batch, H, W, cpr;           // H, W: the INPUT map (the output map is H / S x W / S; bands, rows r and segments are output rows / columns)
+  int S, Ho, Wo;                  // stride (2: weight gradient only)
+  uint32_t grow_bytes;            // bytes of a row of the second operand (Wo * ld * 2)
   int BR, SL, NSEG, bands;        // band rows, segment length, segments per row, bands per image
   int units;                      // batch * bands
   int nst;                        // stages of the band ring (2..4)
@@ -59,16 +61,17 @@ constexpr int kWgradThreads = 384, kFwdThreads = 512;
 // Lands unit u's band: input rows [h0 - 1, h0 + BR] that exist (and, for the weight gradient, the BR rows of the other operand)
 template <bool WGRAD>
 __device__ __forceinline__ void issue_unit(const SGeom& g, int u, const char* src, const char* gy, uint32_t zbuf, uint32_t gbuf, uint32_t bar) {
-  const int n = u / g.bands, h0 = (u - n * g.bands) * g.BR;
-  const int hz0 = h0 >= 1 ? h0 - 1 : 0, hz1 = min(h0 + g.BR + 1, g.H);          // input rows [hz0, hz1)
-  const int hg1 = min(h0 + g.BR, g.H);
-  const uint32_t bytes = (uint32_t)(hz1 - hz0) * g.row_bytes + (WGRAD ? (uint32_t)(hg1 - h0) * g.row_bytes : 0u);
+  const int n = u / g.bands, h0 = (u - n * g.bands) * g.BR;                      // h0: first OUTPUT row of the band
+  const int zfirst = g.S * h0 - 1;                                               // image row held by slab row 0
+  const int hz0 = zfirst >= 0 ? zfirst : 0, hz1 = min(g.S * (min(h0 + g.BR, g.Ho) - 1) + 2, g.H);   // input rows [hz0, hz1)
+  const int hg1 = min(h0 + g.BR, g.Ho);
+  const uint32_t bytes = (uint32_t)(hz1 - hz0) * g.row_bytes + (WGRAD ? (uint32_t)(hg1 - h0) * g.grow_bytes : 0u);
   mbar_expect_tx(bar, bytes);
   const char* base = src + (size_t)n * g.H * g.row_bytes;
-  for (int h = hz0; h < hz1; ++h) bulk_g2s(zbuf + (uint32_t)(h - (h0 - 1)) * g.row_bytes, base + (size_t)h * g.row_bytes, g.row_bytes, bar);
+  for (int h = hz0; h < hz1; ++h) bulk_g2s(zbuf + (uint32_t)(h - zfirst) * g.row_bytes, base + (size_t)h * g.row_bytes, g.row_bytes, bar);
   if (WGRAD) {
-    const char* gb = gy + (size_t)n * g.H * g.row_bytes;
-    for (int h = h0; h < hg1; ++h) bulk_g2s(gbuf + (uint32_t)(h - h0) * g.row_bytes, gb + (size_t)h * g.row_bytes, g.row_bytes, bar);
+    const char* gb = gy + (size_t)n * g.Ho * g.grow_bytes;
+    for (int h = h0; h < hg1; ++h) bulk_g2s(gbuf + (uint32_t)(h - h0) * g.grow_bytes, gb + (size_t)h * g.grow_bytes, g.grow_bytes, bar);
   }
 }
 
@@ -95,7 +98,7 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
   const int c = tid % g.cpr, slot = tid / g.cpr;
   const int r = slot / g.NSEG, sg = slot - r * g.NSEG;
   const bool lane_ok = slot < g.BR * g.NSEG;
-  const int w_begin = sg * g.SL, w_end = min(g.W, w_begin + g.SL);
+  const int w_begin = sg * g.SL, w_end = min(g.Wo, w_begin + g.SL);      // output columns of this thread's segment
 
   f2 k[6][4];                                                          // FWD: taps of this chunk's 8 channels
   if (!WGRAD) {
@@ -133,12 +136,12 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
     }
     mbar_wait(bar0 + 8 * st, (uint32_t)ph);
     const int n = u / g.bands, h0 = (u - n * g.bands) * g.BR;
-    const int h = h0 + r;
-    if (!lane_ok || h >= g.H) continue;
-    const bool ok0 = h >= 1, ok2 = h + 1 < g.H;
+    const int h = h0 + r;                                              // output row
+    if (!lane_ok || h >= g.Ho) continue;
+    const bool ok0 = g.S * h >= 1, ok2 = g.S * h + 1 < g.H;
     const uint32_t zbuf = sbase + (uint32_t)st * stage_bytes;
-    // slab row j holds image row h0 - 1 + j: rows h - 1, h, h + 1 are j = r, r + 1, r + 2
-    const uint32_t a0 = zbuf + (uint32_t)r * g.row_bytes + (uint32_t)c * 16, a1 = a0 + g.row_bytes, a2 = a1 + g.row_bytes;
+    // slab row j holds image row S h0 - 1 + j: input rows S h - 1, S h, S h + 1 are j = S r, S r + 1, S r + 2
+    const uint32_t a0 = zbuf + (uint32_t)(g.S * r) * g.row_bytes + (uint32_t)c * 16, a1 = a0 + g.row_bytes, a2 = a1 + g.row_bytes;
     const uint32_t colb = (uint32_t)g.cpr * 16;                        // bytes per position
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 
@@ -171,7 +174,7 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
         for (int i = 0; i < 4; ++i) { va[i] = vb[i]; vb[i] = vc[i]; }
       }
     } else {
-      const uint32_t gb = zbuf + g.z_stage + (uint32_t)r * g.row_bytes + (uint32_t)c * 16;
+      const uint32_t gb = zbuf + g.z_stage + (uint32_t)r * g.grow_bytes + (uint32_t)c * 16;
       f2 win[3][3][4];                                                 // [column slot][row][pair]
       auto col = [&](int x, f2 (&dstw)[3][4]) {
         const bool okx = x >= 0 && x < g.W;
@@ -179,6 +182,27 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
         unpack(okx ? lds16(a1 + (uint32_t)x * colb) : zero, dstw[1]);
         unpack(okx && ok2 ? lds16(a2 + (uint32_t)x * colb) : zero, dstw[2]);
       };
+      if (g.S == 2) {
+        // stride 2: centre w reads input columns 2 w - 1, 2 w, 2 w + 1; the last one is the next centre's first
+        col(2 * w_begin - 1, win[0]);
+        for (int w = w_begin; w < w_end; ++w) {
+          col(2 * w, win[1]);
+          col(2 * w + 1, win[2]);
+          f2 d[4];
+          unpack(lds16(gb + (uint32_t)w * colb), d);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dT[3 * rr + j][i] = fma2(d[i], win[j][rr][i], dT[3 * rr + j][i]);
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) win[0][rr][i] = win[2][rr][i];
+        }
+        continue;
+      }
       col(w_begin - 1, win[0]);
       col(w_begin, win[1]);
       for (int w0 = w_begin; w0 < w_end; w0 += 3) {
@@ -218,33 +242,35 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
 }
 
 // Band / thread geometry; false when the shape does not fit (the caller keeps the walking kernels of dwsep_rows.cu)
-static bool plan(int batch, int H, int W, int ld, bool wgrad, SGeom* g, int* threads, size_t* smem) {
+static bool plan(int batch, int H, int W, int ld, int S, bool wgrad, SGeom* g, int* threads, size_t* smem) {
   const int cpr = ld / 8;
   const int cap = wgrad ? kWgradThreads : kFwdThreads;
-  const long long row_bytes = (long long)W * ld * 2;
-  if (cpr > cap || row_bytes > 64 * 1024 || row_bytes % 16) return false;
+  const int Ho = H / S, Wo = W / S;
+  const long long row_bytes = (long long)W * ld * 2, grow_bytes = (long long)Wo * ld * 2;
+  if (cpr > cap || row_bytes > 64 * 1024 || row_bytes % 16 || grow_bytes % 16 || (S != 1 && !wgrad)) return false;
   const long long budget = 200 * 1024 - (wgrad ? 9LL * ld * 4 : 0) - 64;
   // deepest ring first (4 stages, then 3, then 2), the tallest band that allows it
   int BR = 0, nst = 0;
   for (int want = 4; want >= 2 && !BR; --want)
     for (int br = 4; br >= 1; --br) {
-      const long long stage = (br + 2) * row_bytes + (wgrad ? br * row_bytes : 0);
+      const long long stage = (S * (br - 1) + 3) * row_bytes + (wgrad ? br * grow_bytes : 0);
       if (want * stage <= budget && cpr * br <= cap) { BR = br; nst = want; break; }
     }
   if (!BR) return false;
   // segments: as many threads as the cap allows, at least 3 columns per segment (two columns of every segment are recomputed halo)
   const int max_seg = cap / (cpr * BR);
-  int SL = (W + max_seg - 1) / max_seg;
-  if (SL < 3) SL = W < 3 ? W : 3;
-  const int nseg = (W + SL - 1) / SL;
+  int SL = (Wo + max_seg - 1) / max_seg;
+  if (SL < 3) SL = Wo < 3 ? Wo : 3;
+  const int nseg = (Wo + SL - 1) / SL;
   g->batch = batch; g->H = H; g->W = W; g->cpr = cpr;
+  g->S = S; g->Ho = Ho; g->Wo = Wo; g->grow_bytes = (uint32_t)grow_bytes;
   g->BR = BR; g->NSEG = nseg; g->SL = SL; g->nst = nst;
-  g->bands = (H + BR - 1) / BR;
+  g->bands = (Ho + BR - 1) / BR;
   if ((long long)batch * g->bands > 0x7fffffffLL) return false;
   g->units = batch * g->bands;
   g->row_bytes = (uint32_t)row_bytes;
-  g->z_stage = (uint32_t)((BR + 2) * row_bytes);
-  g->g_stage = (uint32_t)(BR * row_bytes);
+  g->z_stage = (uint32_t)((S * (BR - 1) + 3) * row_bytes);
+  g->g_stage = (uint32_t)(BR * grow_bytes);
   *threads = (cpr * BR * nseg + 31) / 32 * 32;
   *smem = (size_t)nst * ((size_t)g->z_stage + (wgrad ? g->g_stage : 0)) + 32 + (wgrad ? (size_t)9 * ld * 4 : 0);
   return true;
@@ -253,16 +279,16 @@ static bool plan(int batch, int H, int W, int ld, bool wgrad, SGeom* g, int* thr
 // -> 1 launched, 0 shape not covered (caller falls back), < 0 error
 int staged_fwd(int batch, int H, int W, int ld, const void* z, const float* taps, void* y, cudaStream_t st) {
   SGeom g; int threads; size_t smem;
-  if (!plan(batch, H, W, ld, false, &g, &threads, &smem)) return 0;
+  if (!plan(batch, H, W, ld, 1, false, &g, &threads, &smem)) return 0;
   if (ensure_smem((const void*)dwsep_staged_kernel<false>, smem) != TLT_OK) return 0;
   const int resident = (smem * 2 + 2048 <= 227 * 1024 ? 2 : 1) * device_sms();     // two blocks per SM when their slabs fit side by side
   const int grid = g.units < resident ? g.units : resident;
   dwsep_staged_kernel<false><<<grid, threads, smem, st>>>(g, (const char*)z, nullptr, taps, (uint4*)y, nullptr);
   return 1;
 }
-int staged_wgrad(int batch, int H, int W, int ld, const void* z, const void* gy, float* acc, cudaStream_t st) {
+int staged_wgrad(int batch, int H, int W, int ld, int stride, const void* z, const void* gy, float* acc, cudaStream_t st) {
   SGeom g; int threads; size_t smem;
-  if (!plan(batch, H, W, ld, true, &g, &threads, &smem)) return 0;
+  if (!plan(batch, H, W, ld, stride, true, &g, &threads, &smem)) return 0;
   if (ensure_smem((const void*)dwsep_staged_kernel<true>, smem) != TLT_OK) return 0;
   dwsep_staged_kernel<true><<<device_sms(), threads, smem, st>>>(g, (const char*)z, (const char*)gy, nullptr, nullptr, acc);
   return 1;
