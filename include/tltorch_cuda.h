@@ -288,6 +288,23 @@ int tlt_khatri_rao_fwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R,
                        void* out, void* stream);
 int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
                        const void* g, float* const* dF, float* dweights, void* stream);
+/* same, with g at a leading dimension ldg >= R (e.g. the fp32 output of a GEMM with rows padded to a 16-byte pitch) */
+int tlt_khatri_rao_bwd_ld(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
+                          const void* g, int64_t ldg, float* const* dF, float* dweights, void* stream);
+/* all factor gradients (and the weight gradient) of one Khatri-Rao product in ONE launch; dF[k] may be NULL */
+int tlt_khatri_rao_bwd_all(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
+                           const void* g, int64_t ldg, float* const* dF, float* dweights, void* stream);
+/* fp32 factors -> the (weighted) Khatri-Rao matrix written directly as 3-way bf16 split operands (layouts / patterns of
+ * tlt_split3_bf16 below), no fp32 matrix in between */
+int tlt_khatri_rao_split3(int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
+                          int32_t pattern_cols, void* out_cols, int32_t pattern_rows, void* out_rows, void* stream);
+/* fp32 -> 3-way bf16 split operand (hi / mid / lo pieces repeated over six reduction blocks: pattern 0 = A side, 1 = B side) so that
+ * an fp32 product runs as ONE tlt_gemm_bf16_tc launch with K six blocks long, fp32 accumulation (~1e-6 relative error).  out_cols:
+ * (rows, 6 * round8(cols)) for a K-major operand, out_rows: (6 * rows, round8(cols)) for an MN-major operand; either may be NULL.
+ * Replaces: the fp32 torch.einsum / matmul products of linear_cp (tltorch/functional/factorized_linear.py:23-36,
+ * factorized_tensordot.py:70-103) at BASELINE config 1, whose 1e-5 tolerance rules plain bf16 / TF32 products out. */
+int tlt_split3_bf16(const float* src, int64_t rows, int64_t cols, int64_t ld, int32_t pattern_cols, void* out_cols,
+                    int32_t pattern_rows, void* out_rows, void* stream);
 
 /* --------------------------------------------------------------------------------------------------------------
  * Separable 3x3 depthwise convolution on channels-last rows (bf16, padding 1, stride 1 or 2): rows (B H W, ld), ld = round8(R),

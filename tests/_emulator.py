@@ -467,6 +467,36 @@ def emulate_cplinear_bwd(d, x, gy, z, f_in, f_out, lam, g, dx, df_in, df_out, dl
     LOG.append(("cplinear_bwd", tuple(x.shape), R))
 
 
+def emulate_split3(src, rows, cols, ld, pat_cols, out_cols, pat_rows, out_rows):
+    """tlt_split3_bf16: hi / mid / lo bf16 pieces in the six-block patterns (A: h h m h m l, B: h m h l m h), pad columns zero."""
+    x = torch.as_strided(src, (rows, cols), (ld, 1)).float()
+    hi = x.to(torch.bfloat16); r = x - hi.float()
+    mid = r.to(torch.bfloat16); r = r - mid.float()
+    lo = r.to(torch.bfloat16)
+    pieces = [hi, mid, lo]
+    pats = {0: [0, 0, 1, 0, 1, 2], 1: [0, 1, 0, 2, 1, 0]}
+    cp = (cols + 7) // 8 * 8
+    if out_cols is not None:
+        out_cols.zero_()
+        for b, q in enumerate(pats[pat_cols]):
+            out_cols[:, b * cp:b * cp + cols] = pieces[q]
+    if out_rows is not None:
+        out_rows.zero_()
+        for b, q in enumerate(pats[pat_rows]):
+            out_rows[b * rows:(b + 1) * rows, :cols] = pieces[q]
+    LOG.append(("split3", rows, cols))
+
+
+def emulate_kr_split(factors, weights, pat_cols, out_cols, pat_rows, out_rows):
+    kr = _kr_ref(factors, weights).float().contiguous()
+    emulate_split3(kr, kr.shape[0], kr.shape[1], kr.shape[1], pat_cols, out_cols, pat_rows, out_rows)
+
+
+def emulate_kr_bwd_ld(factors, weights, g, ldg, dfs, dw):
+    R = factors[0].shape[1]
+    emulate_kr_bwd(factors, weights, torch.as_strided(g, (g.shape[0], R), (ldg, 1)).contiguous(), dfs, dw)
+
+
 def emulate_kron_fwd(a, b, k):
     k.copy_(torch.einsum("ap,bq->abpq", a.double(), b.double()).reshape(k.shape).to(k.dtype))
     LOG.append(("kron2_fwd", tuple(a.shape), tuple(b.shape)))
@@ -594,6 +624,9 @@ def emulated_kernels():
     from torch_b200 import spatial_ops as so
     from torch_b200 import cprows_ops as co
     from torch_b200 import cplinear_ops as cl
+    from torch_b200 import cplinear_tc_ops as ct
+    saved_ct = ct._execute_split, ct._execute_kr_bwd_ld, ct._execute_kr_split
+    ct._execute_split, ct._execute_kr_bwd_ld, ct._execute_kr_split = emulate_split3, emulate_kr_bwd_ld, emulate_kr_split
     from torch_b200 import trl_ops as tr
     saved_tr = tr._execute_fwd, tr._execute_bwd, tr._execute_kron_fwd, tr._execute_kron_bwd
     tr._execute_fwd, tr._execute_bwd, tr._execute_kron_fwd, tr._execute_kron_bwd = (
@@ -634,6 +667,7 @@ def emulated_kernels():
         yield LOG
     finally:
         cl._execute_fwd, cl._execute_bwd = saved_cl
+        ct._execute_split, ct._execute_kr_bwd_ld, ct._execute_kr_split = saved_ct
         tr._execute_fwd, tr._execute_bwd, tr._execute_kron_fwd, tr._execute_kron_bwd = saved_tr
         so._execute_spatial_fwd, so._execute_spatial_bwd = saved_so
         co._execute_pack, co._execute_fwd, co._execute_bwd, co._execute_finalize, co._ws_bytes, co._acc_bytes = saved_co

@@ -1078,6 +1078,7 @@ def test_cp_linear_fused_vs_oracle(in_shape, out_shape, rank, batch, bias, monke
     from torch_b200 import _cuda
     from oracle import reference_path as rp
     monkeypatch.setenv("TLT_CPLINEAR_FUSED", "1")          # opt-in path (slower than the unfused chain at config 1's size)
+    monkeypatch.setenv("TLT_CPLINEAR_TC", "0")             # (the tensor-core route would take the layer first)
     torch.manual_seed(batch)
     lin = tlt.FactorizedLinear(in_shape, out_shape, bias=bias, factorization="cp", rank=rank, implementation="factorized", device=dev(),
                                dtype=torch.float32)
@@ -1130,3 +1131,41 @@ def test_trl_tail_op_vs_fp64(B, J, rc, ldz, ro, O, bias):
         errs["dbias"] = G.rel_err(grads[3], go[3])
     assert float(grads[0][:, :, rc:].abs().max()) == 0.0 if ldz > rc else True
     _report(_tag(), errs, 1e-2)
+
+
+@pytest.mark.parametrize("in_shape,out_shape,rank,batch,bias", [
+    ((4, 8, 16), (4, 8, 16), 2341, 128, True),     # BASELINE config 1
+    ((4, 8, 16), (4, 8, 16), 0.5, 300, False),     # batch not a multiple of any tile
+    ((2, 8), (4, 4), 67, 16, True),                # smallest eligible layer: 16 features, rank % 8 = 3
+    ((16, 16), (8, 64), 130, 64, True),
+])
+def test_cp_linear_tensor_core_vs_oracle(in_shape, out_shape, rank, batch, bias):
+    """fp32 CP FactorizedLinear with every product on tcgen05 through 3-way bf16-split operands (cplinear_tc_ops, csrc/split3.cu) vs the
+    fp64 oracle of linear_cp -> tensor_dot_cp (functional/factorized_linear.py:23-36, factorized_tensordot.py:70-103): y, dx and every
+    parameter gradient at north_star's fp32 tolerance 1e-5 (a plain bf16 product would sit at ~3e-3)."""
+    import math
+    import torch_b200 as tlt
+    from oracle import reference_path as rp
+    torch.manual_seed(batch)
+    lin = tlt.FactorizedLinear(in_shape, out_shape, bias=bias, factorization="cp", rank=rank, implementation="factorized", device=dev(),
+                               dtype=torch.float32)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.normal_(0, 0.4)
+    x = torch.randn(batch, math.prod(in_shape), device=dev(), requires_grad=True)
+    gy = torch.randn(batch, math.prod(out_shape), device=dev())
+    from torch_b200 import cplinear_tc_ops
+    assert cplinear_tc_ops.eligible(x, lin.weight.weights, list(lin.weight.factors)[:len(out_shape)], list(lin.weight.factors)[len(out_shape):],
+                                    lin.bias)
+    y = lin(x)
+    names = [n for n, _ in lin.named_parameters()]
+    grads = torch.autograd.grad(y, [x] + list(lin.parameters()), gy)
+    leaves = {n: p.detach().double().cpu().requires_grad_(True) for n, p in lin.named_parameters()}
+    xo = x.detach().double().cpu().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(len(in_shape) + len(out_shape))]
+    yo = rp.factorized_linear(xo, "cp", (leaves["weight.weights"], fs), (out_shape, in_shape), bias=leaves.get("bias"), order="sane")
+    go = torch.autograd.grad(yo, [xo] + [leaves[n] for n in names], gy.double().cpu())
+    errs = {"y": G.rel_err(y, yo)}
+    for a, b_, n in zip(grads, go, ["x"] + names):
+        errs["d" + n] = G.rel_err(a, b_)
+    _report(_tag(), errs, 1e-5)

@@ -435,6 +435,7 @@ def test_cp_linear_fused_op_host_logic(in_shape, out_shape, rank, batch, bias, m
     from oracle import reference_path as rp
     import math
     monkeypatch.setenv("TLT_CPLINEAR_FUSED", "1")
+    monkeypatch.setenv("TLT_CPLINEAR_TC", "0")
     torch.manual_seed(rank)
     lin = tlt.FactorizedLinear(in_shape, out_shape, bias=bias, factorization="cp", rank=rank, implementation="factorized", dtype=torch.float32)
     with torch.no_grad():
@@ -487,3 +488,34 @@ def test_tucker_trl_fused_route_host_logic(monkeypatch):
     assert G.rel_err(y, yo) < 2e-2
     for n, a, b in zip(["x"] + list(params), got, want):
         assert G.rel_err(a, b) < 2e-2, n
+
+
+@pytest.mark.parametrize("in_shape,out_shape,rank,batch,bias", [((4, 8, 16), (4, 8, 16), 70, 24, True), ((2, 8), (4, 4), 67, 16, False)])
+def test_cp_linear_tc_route_host_logic(in_shape, out_shape, rank, batch, bias, monkeypatch):
+    """fp32 CP FactorizedLinear on the tensor cores (cplinear_tc_ops: Khatri-Rao operands, 3-way bf16 split in the six-block patterns,
+    one GEMM per product, Khatri-Rao backward at a padded leading dimension): operand layouts, paddings and autograd plumbing on
+    the emulator against the oracle of linear_cp (factorized_linear.py:23-36).  The emulated split keeps the real bf16 pieces, so
+    the 1e-5 agreement also checks that the six blocks pair up as hi.hi + hi.mid + mid.hi + hi.lo + mid.mid + lo.hi."""
+    from oracle import reference_path as rp
+    import math
+    torch.manual_seed(rank)
+    lin = tlt.FactorizedLinear(in_shape, out_shape, bias=bias, factorization="cp", rank=rank, implementation="factorized", dtype=torch.float32)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.normal_(0, 0.5)
+    x = torch.randn(batch, math.prod(in_shape), requires_grad=True)
+    gy = torch.randn(batch, math.prod(out_shape))
+    with emulated_kernels() as log:
+        y = lin(x)
+        names = [n for n, _ in lin.named_parameters()]
+        grads = torch.autograd.grad(y, [x] + list(lin.parameters()), gy)
+    kinds = [e[0] for e in log]
+    assert kinds.count("gemm") == 6 and "split3" in kinds, kinds
+    leaves = {n: p.detach().double().requires_grad_(True) for n, p in lin.named_parameters()}
+    xo = x.detach().double().requires_grad_(True)
+    fs = [leaves[f"weight.factors.factor_{i}"] for i in range(len(in_shape) + len(out_shape))]
+    yo = rp.factorized_linear(xo, "cp", (leaves["weight.weights"], fs), (out_shape, in_shape), bias=leaves.get("bias"), order="sane")
+    go = torch.autograd.grad(yo, [xo] + [leaves[n] for n in names], gy.double())
+    assert G.rel_err(y, yo) < 1e-5
+    for a, b_, n in zip(grads, go, ["x"] + names):
+        assert G.rel_err(a, b_) < 1e-5, n

@@ -148,6 +148,13 @@ SYMBOLS = {
     "tlt_trl_tail_bwd": (C.c_int, [C.POINTER(TrlTailDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_kron2_fwd": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "tlt_kron2_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "tlt_khatri_rao_bwd_ld": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, C.c_int64,
+                                        C.POINTER(C.c_void_p), _vp, _vp]),
+    "tlt_khatri_rao_bwd_all": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, C.c_int64,
+                                         C.POINTER(C.c_void_p), _vp, _vp]),
+    "tlt_khatri_rao_split3": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, C.c_int32, _vp, C.c_int32,
+                                        _vp, _vp]),
+    "tlt_split3_bf16": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, _vp]),
     "tlt_spatial_project_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "tlt_spatial_project_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "tlt_spatial_project_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),

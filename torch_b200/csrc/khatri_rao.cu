@@ -20,6 +20,7 @@ struct KrParams {
   const void* f[4];
   const void* w;
   long long rows;
+  long long ldg;            // backward: leading dimension of g (R when dense)
 };
 
 template <typename T>
@@ -70,17 +71,101 @@ __global__ void __launch_bounds__(128) khatri_rao_bwd_kernel(const KrParams p, i
         mul *= p.dims[j];
       }
     }
-    acc = fmaf(to_f32<T>(g[(long long)row * p.R + r]), v, acc);
+    acc = fmaf(to_f32<T>(g[(long long)row * p.ldg + r]), v, acc);
   }
   const float wr = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
   atomicAdd(dF + (long long)ik * p.R + r, wr * acc);
   if (k == 0 && dw != nullptr) atomicAdd(dw + r, acc * to_f32<T>(static_cast<const T*>(p.f[0])[(long long)ik * p.R + r]));
 }
 
+// All factor gradients of one Khatri-Rao product in ONE launch: blockIdx.y walks the rows of every factor in turn (the launch per
+// factor re-read g once each: 3 launches of ~12 us per side at BASELINE config 1).  dF[k] zeroed by the caller.
+struct KrGrads { float* dF[4]; };
+template <typename T>
+__global__ void __launch_bounds__(128) khatri_rao_bwd_all_kernel(const KrParams p, const T* __restrict__ g, const KrGrads out,
+                                                                 float* __restrict__ dw) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int ik = blockIdx.y, k = 0;
+  while (k < p.n - 1 && ik >= p.dims[k]) { ik -= p.dims[k]; ++k; }
+  if (r >= p.R || out.dF[k] == nullptr) return;
+  const int others = (int)(p.rows / p.dims[k]);
+  const int per_split = (others + gridDim.z - 1) / gridDim.z;
+  const int o0 = blockIdx.z * per_split, o1 = min(others, o0 + per_split);
+  if (o0 >= o1) return;
+  float acc = 0.f;
+  for (int o = o0; o < o1; ++o) {
+    int rem = o, row = 0, mul = 1;
+    float v = 1.f;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      if (j < p.n) {
+        int i;
+        if (j == k) i = ik;
+        else {
+          const int q = rem / p.dims[j];
+          i = rem - q * p.dims[j];
+          rem = q;
+          v *= to_f32<T>(static_cast<const T*>(p.f[j])[(long long)i * p.R + r]);
+        }
+        row += i * mul;
+        mul *= p.dims[j];
+      }
+    }
+    acc = fmaf(to_f32<T>(g[(long long)row * p.ldg + r]), v, acc);
+  }
+  const float wr = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
+  atomicAdd(out.dF[k] + (long long)ik * p.R + r, wr * acc);
+  if (k == 0 && dw != nullptr) atomicAdd(dw + r, acc * to_f32<T>(static_cast<const T*>(p.f[0])[(long long)ik * p.R + r]));
+}
+
+// Khatri-Rao product written directly as 3-way bf16 split operands (see split3.cu): no fp32 matrix in between.
+__device__ __forceinline__ void kr_split3(float x, __nv_bfloat16 (&pz)[3]) {
+  pz[0] = __float2bfloat16_rn(x);
+  float r = x - __bfloat162float(pz[0]);
+  pz[1] = __float2bfloat16_rn(r);
+  r -= __bfloat162float(pz[1]);
+  pz[2] = __float2bfloat16_rn(r);
+}
+__global__ void __launch_bounds__(256) khatri_rao_split3_kernel(const KrParams p, int colsP, int pat_cols, __nv_bfloat162* __restrict__ out_cols,
+                                                                int pat_rows, __nv_bfloat162* __restrict__ out_rows) {
+  const int half = colsP / 2;
+  const long long total = p.rows * half;
+  const int pa = (0) | (0 << 2) | (1 << 4) | (0 << 6) | (1 << 8) | (2 << 10), pb = (0) | (1 << 2) | (0 << 4) | (2 << 6) | (1 << 8) | (0 << 10);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long row = e / half;
+    const int c = (int)(e - row * half) * 2;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < p.R) {
+      const bool two = c + 1 < p.R;
+      v0 = p.w ? static_cast<const float*>(p.w)[c] : 1.f;
+      v1 = two ? (p.w ? static_cast<const float*>(p.w)[c + 1] : 1.f) : 0.f;
+      long long rem = row;
+#pragma unroll
+      for (int k = 3; k >= 0; --k) {
+        if (k < p.n) {
+          const int i = (int)(rem % p.dims[k]);
+          rem /= p.dims[k];
+          const float* f = static_cast<const float*>(p.f[k]) + (long long)i * p.R + c;
+          v0 *= f[0];
+          if (two) v1 *= f[1];
+        }
+      }
+    }
+    __nv_bfloat16 p0[3], p1[3];
+    kr_split3(v0, p0);
+    kr_split3(v1, p1);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      if (out_cols) { const int q = ((pat_cols ? pb : pa) >> (2 * b)) & 3; out_cols[(row * 6 * colsP + (long long)b * colsP + c) / 2] = __halves2bfloat162(p0[q], p1[q]); }
+      if (out_rows) { const int q = ((pat_rows ? pb : pa) >> (2 * b)) & 3; out_rows[(((long long)b * p.rows + row) * colsP + c) / 2] = __halves2bfloat162(p0[q], p1[q]); }
+    }
+  }
+}
+
 static int fill_kr(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* w, KrParams* p) {
   TLT_REQUIRE(dtype == TLT_F32 || dtype == TLT_BF16, "khatri_rao: dtype must be f32 or bf16");
   TLT_REQUIRE(n >= 1 && n <= 4 && dims && factors && R >= 1 && R < (1LL << 31), "khatri_rao: 1..4 factors");
-  p->n = n; p->R = (int)R; p->w = w; p->rows = 1;
+  p->n = n; p->R = (int)R; p->w = w; p->rows = 1; p->ldg = R;
   for (int k = 0; k < 4; ++k) { p->dims[k] = 1; p->f[k] = nullptr; }
   for (int k = 0; k < n; ++k) {
     TLT_REQUIRE(dims[k] >= 1 && dims[k] <= 65535 && factors[k], "khatri_rao: bad factor");
@@ -110,10 +195,17 @@ extern "C" int tlt_khatri_rao_fwd(int32_t dtype, int32_t n, const int64_t* dims,
 
 extern "C" int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors,
                                   const void* weights, const void* g, float* const* dF, float* dweights, void* stream) {
+  return tlt_khatri_rao_bwd_ld(dtype, n, dims, R, factors, weights, g, R, dF, dweights, stream);
+}
+
+// same with g given at a leading dimension ldg >= R (the fp32 output of a GEMM whose rows are padded to a 16-byte pitch)
+extern "C" int tlt_khatri_rao_bwd_ld(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors,
+                                     const void* weights, const void* g, int64_t ldg, float* const* dF, float* dweights, void* stream) {
   KrParams p;
   int rc = fill_kr(dtype, n, dims, R, factors, weights, &p);
   if (rc) return rc;
-  TLT_REQUIRE(g && dF, "tlt_khatri_rao_bwd: null argument");
+  TLT_REQUIRE(g && dF && ldg >= R, "tlt_khatri_rao_bwd: null argument");
+  p.ldg = ldg;
   cudaStream_t st = (cudaStream_t)stream;
   for (int k = 0; k < n; ++k) {
     if (dF[k] == nullptr && !(k == 0 && dweights)) continue;
@@ -135,4 +227,53 @@ extern "C" int tlt_khatri_rao_bwd(int32_t dtype, int32_t n, const int64_t* dims,
     if (rc) return rc;
   }
   return TLT_OK;
+}
+
+// fp32 factors -> the (weighted) Khatri-Rao matrix as 3-way bf16 split operands: out_cols (rows, 6 round8(R)) and / or out_rows
+// (6 rows, round8(R)), patterns as in tlt_split3_bf16
+extern "C" int tlt_khatri_rao_split3(int32_t n, const int64_t* dims, int64_t R, const void* const* factors, const void* weights,
+                                     int32_t pattern_cols, void* out_cols, int32_t pattern_rows, void* out_rows, void* stream) {
+  KrParams p;
+  int rc = fill_kr(TLT_F32, n, dims, R, factors, weights, &p);
+  if (rc) return rc;
+  TLT_REQUIRE((out_cols || out_rows) && (pattern_cols == 0 || pattern_cols == 1) && (pattern_rows == 0 || pattern_rows == 1) &&
+              p.rows < (1LL << 31), "tlt_khatri_rao_split3: bad arguments");
+  const int colsP = (int)((R + 7) & ~(int64_t)7);
+  const long long total = p.rows * (colsP / 2), blocks = (total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+  khatri_rao_split3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, colsP, pattern_cols, (__nv_bfloat162*)out_cols, pattern_rows,
+                                                                  (__nv_bfloat162*)out_rows);
+  return check_launch("khatri_rao_split3_kernel");
+}
+
+// every factor gradient (and the weight gradient) in one launch; dF[k] may be NULL to skip a factor (dF[0] is needed for dweights)
+extern "C" int tlt_khatri_rao_bwd_all(int32_t dtype, int32_t n, const int64_t* dims, int64_t R, const void* const* factors,
+                                      const void* weights, const void* g, int64_t ldg, float* const* dF, float* dweights, void* stream) {
+  KrParams p;
+  int rc = fill_kr(dtype, n, dims, R, factors, weights, &p);
+  if (rc) return rc;
+  TLT_REQUIRE(g && dF && ldg >= R && p.rows < (1LL << 31), "tlt_khatri_rao_bwd_all: bad arguments");
+  TLT_REQUIRE(!dweights || dF[0], "tlt_khatri_rao_bwd_all: the weight gradient needs dF[0]");
+  p.ldg = ldg;
+  cudaStream_t st = (cudaStream_t)stream;
+  KrGrads out;
+  long long ysum = 0, min_others = p.rows;
+  for (int k = 0; k < 4; ++k) {
+    out.dF[k] = k < n ? dF[k] : nullptr;
+    if (k < n) {
+      ysum += p.dims[k];
+      if (p.rows / p.dims[k] < min_others) min_others = p.rows / p.dims[k];
+      if (dF[k]) TLT_CHECK_CUDA(cudaMemsetAsync(dF[k], 0, (size_t)p.dims[k] * p.R * sizeof(float), st));
+    }
+  }
+  TLT_REQUIRE(ysum <= 65535, "tlt_khatri_rao_bwd_all: too many factor rows");
+  const long long bx = (p.R + 127) / 128;
+  long long splits = (148LL * 16 + bx * ysum - 1) / (bx * ysum);                      // ~16 blocks of 128 threads per SM
+  if (splits > min_others) splits = min_others;
+  if (splits > 65535) splits = 65535;
+  if (splits < 1) splits = 1;
+  dim3 grid((unsigned)bx, (unsigned)ysum, (unsigned)splits);
+  if (dtype == TLT_BF16) khatri_rao_bwd_all_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(p, (const __nv_bfloat16*)g, out, dweights);
+  else khatri_rao_bwd_all_kernel<float><<<grid, 128, 0, st>>>(p, (const float*)g, out, dweights);
+  return check_launch("khatri_rao_bwd_all_kernel");
 }

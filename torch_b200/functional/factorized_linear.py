@@ -6,6 +6,7 @@ from .. import tenalg
 from .. import blocktt_ops
 from .. import tucker_ops
 from .. import cplinear_ops
+from .. import cplinear_tc_ops
 from .factorized_tensordot import tensor_dot_tucker, tensor_dot_cp
 
 _L = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
@@ -44,6 +45,10 @@ def linear_cp(tensor, cp_matrix, transpose=True, bias=None):
     f_in = [factors[m] for m in modes_cp]
     f_out = [f for m, f in enumerate(factors) if m not in modes_cp]
     x2 = tensor.reshape(-1, math.prod(in_shape))
+    if f_out and cplinear_tc_ops.eligible(x2, cp_matrix.weights, f_out, f_in, bias):
+        # every product of the layer as one tcgen05 GEMM on 3-way bf16-split operands (fp32-class accuracy, csrc/split3.cu)
+        y = cplinear_tc_ops.cp_linear_tc(x2, cp_matrix.weights, f_out, f_in, bias)
+        return y.reshape(-1, *[f.shape[0] for f in f_out])
     if f_out and cplinear_ops.eligible(x2, cp_matrix.weights, f_out, f_in, bias):
         # the whole chain in 2 launches forward / 4 backward, Khatri-Rao tiles rebuilt in shared memory (csrc/cplinear.cu)
         y = cplinear_ops.cp_linear_fused(x2, cp_matrix.weights, f_out, f_in, bias)
