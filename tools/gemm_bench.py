@@ -1,8 +1,7 @@
 """Micro-benchmark of tlt_gemm_bf16_tc on the hot-path GEMM shapes, beside torch.matmul (cuBLAS) on the same box.
 
 Development aid (run on the GPU box):  python tools/gemm_bench.py [--quick]
-Prints one line per (shape, variant): time, TFLOP/s, max relative error vs cuBLAS.  TLT_GEMM_IMPL=2 selects the
-previous kernel for A/B comparison.
+Prints one line per (shape, variant): time, TFLOP/s, max relative error vs cuBLAS.
 """
 import ctypes as C
 import os
@@ -78,7 +77,7 @@ def run(M, N, K, a_mn, b_mn, out_dtype, split, iters=20):
 
 
 if __name__ == "__main__":
-    print("TLT_GEMM_IMPL =", os.environ.get("TLT_GEMM_IMPL", "(default 3)"), flush=True)
+    
     shapes = SHAPES[:3] if "--quick" in sys.argv else SHAPES
     if "--chain" in sys.argv:      # the six GEMMs of every unfused CP-conv rows chain layer of config 3 (256 images)
         shapes = []

@@ -1,5 +1,5 @@
-"""Time tlt_pointwise_tc alone (CUDA events) on config 3's 56^2 / 28^2 1x1 shapes; TLT_PW_DBG=1|2 (development switches that drop the
-epilogue's stores) separates the load + MMA side from the epilogue."""
+"""Time tlt_pointwise_tc alone (CUDA events) on config 3's 56^2 / 28^2 1x1 shapes (NCHW activations); TLT_PW_T=on|off forces the
+transposed-role kernel."""
 import json
 import os
 import sys
@@ -32,5 +32,5 @@ for (B, K, N, S) in [(256, 64, 69, 3136), (256, 69, 64, 3136), (256, 128, 141, 7
     y = torch.empty(B, N, S, device=dev, dtype=torch.bfloat16)
     ms = timed(lambda: pointwise_ops._execute_pointwise(x, w, None, y))
     byts = (x.numel() + y.numel()) * 2
-    print(json.dumps({"case": f"pointwise_tc B={B} K={K} N={N} S={S} dbg={os.environ.get('TLT_PW_DBG', '0')} T={os.environ.get('TLT_PW_T', 'off')}",
+    print(json.dumps({"case": f"pointwise_tc B={B} K={K} N={N} S={S} T={os.environ.get('TLT_PW_T', 'off')}",
                       "ms": ms, "GBps": byts / ms / 1e6}), flush=True)

@@ -28,217 +28,18 @@ struct GemmParams {
 };
 
 
-// one 32-column chunk of one accumulator row -> alpha / bias / cast -> global
-__device__ __forceinline__ void store_chunk32(const GemmParams& p, const uint32_t* v, const float* bv, void* Cout, int row, int col0) {
-  float f[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = p.alpha * __uint_as_float(v[i]);
-  if (p.has_bias) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] += bv[i];
-  }
-  if (p.c_f32) {
-    float* dst = (float*)Cout + (long long)row * p.ldc + col0;
-    if (col0 + 32 <= p.N) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 o = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-        if (p.accumulate) { float4 q = *(float4*)(dst + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-        *(float4*)(dst + i) = o;
-      }
-    } else {
-      for (int i = 0; i < 32 && col0 + i < p.N; ++i) dst[i] = p.accumulate ? dst[i] + f[i] : f[i];
-    }
-  } else {
-    __nv_bfloat16* dst = (__nv_bfloat16*)Cout + (long long)row * p.ldc + col0;
-    if (col0 + 32 <= p.N) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 o;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[i], f[i + 1]), h1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]), h3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
-        o.x = *(uint32_t*)&h0; o.y = *(uint32_t*)&h1; o.z = *(uint32_t*)&h2; o.w = *(uint32_t*)&h3;
-        *(uint4*)(dst + i) = o;
-      }
-    } else {
-      for (int i = 0; i < 32 && col0 + i < p.N; ++i) dst[i] = __float2bfloat16_rn(f[i]);
-    }
-  }
-}
-
 // =====================================================================================================================
-// v2: CTA-pair kernel.  A cluster of two CTAs (one TPC) owns a 256 x BN output tile: CTA r stages rows [128r, 128r+128) of
+// CTA-pair kernel.  A cluster of two CTAs (one TPC) owns a 256 x BN output tile: CTA r stages rows [128r, 128r+128) of
 // A and columns [BN/2 r, BN/2 (r+1)) of B, the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both
 // CTAs' shared memory, and each CTA's TMEM receives its own 128 accumulator rows.  Per FLOP this halves the shared-memory
-// traffic of the single-CTA kernel (which saturates the 128 B/clk smem port at ~2/3 of tensor peak).
+// traffic of a single-CTA kernel (which saturates the 128 B/clk smem port at ~2/3 of tensor peak).
 //   warp 0: TMA producer   warp 1: MMA issuer (leader CTA only)   warp 2: TMEM alloc   warps 4-11: epilogue
 // =====================================================================================================================
 constexpr int kGemm2Threads = 384;
-
-template <int BN, int kStages>
-struct SmemLayout2 {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB: this CTA's 128 rows
-  static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;       // this CTA's half of the N extent
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = kStages * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
-};
-
-template <int BN, int kStages>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
-gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                     const GemmParams p, const void* __restrict__ bias, void* __restrict__ Cout) {
-  using L = SmemLayout2<BN, kStages>;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
-  constexpr int HALF_N = BN / 2;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = cluster_ctarank();
-  const bool leader = cta_rank == 0;
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
-    tmem_relinquish_2sm();
-  }
-  tc_fence_before();
-  cluster_sync_all();          // barriers of BOTH CTAs are initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    // ===================================== TMA producer (both CTAs) =====================================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / p.tiles_n) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
-        const int n0 = (tile % p.tiles_n) * BN + (int)cta_rank * HALF_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-          // Bytes of BOTH CTAs complete_tx on the leader's barrier; the leader's single arrive.expect_tx covers them all
-          // (the tx-count may go transiently negative if the peer's bytes land first -- the phase cannot complete until
-          // the leader's arrival).  No remote arrive on this path: a cluster-scope release would cost a MEMBAR per stage.
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
-          const int k0 = kb * BLOCK_K;
-          if (!p.a_mn) {
-            tma_load_2d_2sm(sa, &map_a, full_bar(stage), k0, m0);
-          } else {
-#pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              tma_load_2d_2sm(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d_2sm(sb, &map_b, full_bar(stage), k0, n0);
-          } else {
-#pragma unroll
-            for (int c = 0; c < HALF_N / 64; ++c)
-              tma_load_2d_2sm(sb + c * (BLOCK_K * 128), &map_b, full_bar(stage), n0 + 64 * c, k0);
-          }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===================================== MMA issuer (leader CTA) ======================================
-    if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc(2 * BLOCK_M, BN, p.a_mn, p.b_mn);
-      const uint32_t a_lbo = p.a_mn ? BLOCK_K * 128 : 16, b_lbo = p.b_mn ? BLOCK_K * 128 : 16;
-      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);
-      const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * L::STAGE_BYTES, sb = sa + L::A_BYTES;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit_2sm(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ===================================== epilogue (both CTAs, 8 warps) ================================
-    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32)
-    const int col_half = (warp - 4) >> 2;          // columns [HALF_N*col_half, +HALF_N)
-    const uint32_t leader_tempty0 = mapa_u32(tempty_bar(0), 0);
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile / p.tiles_n) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
-      const int n0 = (tile % p.tiles_n) * BN + col_half * HALF_N;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_half * HALF_N);
-#pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
-        uint32_t v[32];
-        float bv[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        const int col0 = n0 + c * 32;
-        if (p.has_bias && col0 < p.N) load_bias32(bias, p.bias_bf16, col0, p.N, bv);
-        tmem_ld_wait();
-        if (row < p.M && col0 < p.N) store_chunk32(p, v, bv, Cout, row, col0);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();          // both CTAs are done with TMEM and with each other's shared memory
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
-  }
-}
-
-
-// =====================================================================================================================
-// v3: the CTA-pair mainloop of v2 with (a) a shared-memory-staged epilogue -- TMEM -> registers -> SWIZZLE_128B smem
-// -> cp.async.bulk.tensor store (full 128-byte lines, OOB rows/columns clipped by the TMA unit) instead of per-thread
-// 16-byte global stores, which kept l1tex 72 % busy and the tensor pipe 44 % active on the N=3072 / K=768 launches
-// (profiles/r01_gemm_tc2_full.md) -- and (b) split-K work units whose fp32 partials meet in C through
-// cp.reduce.async.bulk.tensor (.add), so the K = tokens weight-gradient GEMMs (36 output tiles) fill all 74 SM pairs.
-//   warp 0: TMA producer   warp 1: MMA issuer (leader CTA only)   warp 2: TMEM alloc   warps 4-11: epilogue
-// =====================================================================================================================
+// Epilogue: shared-memory staged -- TMEM -> registers -> SWIZZLE_128B smem -> cp.async.bulk.tensor store (full 128-byte lines, OOB
+// rows / columns clipped by the TMA unit); per-thread 16-byte global stores kept l1tex 72 % busy and the tensor pipe 44 % active on
+// the N = 3072 / K = 768 launches (profiles/r01_gemm_tc2_full.md: the kernel version this one replaced).  Split-K work units meet
+// in C through cp.reduce.async.bulk.tensor (.add), so the K = tokens weight-gradient GEMMs (36 output tiles) fill all 74 SM pairs.
 constexpr int kEpiWarps = 8;
 constexpr int kEpiBufBytes = 4096;          // 32 rows x 128 bytes per epilogue warp
 
@@ -447,32 +248,6 @@ gemm_bf16_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // Host side
 // ------------------------------------------------------------------------------------------------------------
 template <int BN, int kStages>
-static int launch_gemm2(const tlt_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, cudaStream_t st) {
-  using L = SmemLayout2<BN, kStages>;
-  CUtensorMap ma, mb;
-  int rc;
-  if (!d->a_major) rc = make_map(&ma, A, d->K, d->M, d->lda, BLOCK_K, BLOCK_M);
-  else rc = make_map(&ma, A, d->M, d->K, d->lda, 64, BLOCK_K);
-  if (rc) return rc;
-  if (!d->b_major) rc = make_map(&mb, B, d->K, d->N, d->ldb, BLOCK_K, BN / 2);
-  else rc = make_map(&mb, B, d->N, d->K, d->ldb, 64, BLOCK_K);
-  if (rc) return rc;
-  GemmParams p;
-  p.M = (int)d->M; p.N = (int)d->N; p.K = (int)d->K; p.ldc = d->ldc;
-  p.a_mn = d->a_major; p.b_mn = d->b_major;
-  p.c_f32 = d->dtype_c == TLT_F32; p.accumulate = d->accumulate; p.has_bias = bias != nullptr; p.bias_bf16 = d->dtype_bias == TLT_BF16;
-  p.alpha = d->alpha;
-  p.tiles_m = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  p.tiles_n = (p.N + BN - 1) / BN;
-  TLT_ENSURE_SMEM((gemm_bf16_tc2_kernel<BN, kStages>), L::TOTAL);
-  int tiles = p.tiles_m * p.tiles_n;
-  int pairs = num_sms() / 2;
-  int clusters = tiles < pairs ? tiles : pairs;
-  gemm_bf16_tc2_kernel<BN, kStages><<<2 * clusters, kGemm2Threads, L::TOTAL, st>>>(ma, mb, p, bias, C);
-  return check_launch("gemm_bf16_tc2_kernel");
-}
-
-template <int BN, int kStages>
 static int launch_gemm3(const tlt_gemm_desc* d, int splits, const void* A, const void* B, const void* bias, void* C, cudaStream_t st) {
   using L = SmemLayout3<BN, kStages>;
   CUtensorMap ma, mb, mc;
@@ -507,15 +282,6 @@ static int launch_gemm3(const tlt_gemm_desc* d, int splits, const void* A, const
   int clusters = units < pairs ? units : pairs;
   gemm_bf16_tc3_kernel<BN, kStages><<<2 * clusters, kGemm2Threads, L::TOTAL, st>>>(ma, mb, mc, p, bias);
   return check_launch("gemm_bf16_tc3_kernel");
-}
-
-static int gemm_impl() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TLT_GEMM_IMPL");
-    v = (e && e[0] == '2') ? 2 : 3;
-  }
-  return v;
 }
 
 // Tile width and split-K factor by a small cost model: units are dealt round-robin to the 74 SM pairs; a unit costs its
@@ -571,16 +337,6 @@ extern "C" int tlt_gemm_bf16_tc(const tlt_gemm_desc* d, const void* A, const voi
   TLT_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0,
               "tlt_gemm_bf16_tc: operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (gemm_impl() == 2) {
-    // previous CTA-pair kernel (per-thread global stores in the epilogue), kept for A/B comparison: TLT_GEMM_IMPL=2
-    int pairs = num_sms() / 2;
-    long long tm = (d->M + 255) / 256;
-    long long t256 = tm * ((d->N + 255) / 256), t128 = tm * ((d->N + 127) / 128);
-    auto eff = [&](long long tiles) { long long w = (tiles + pairs - 1) / pairs; return (double)tiles / (double)(w * pairs); };
-    bool n256 = d->N > 128 && eff(t256) >= 0.75 * eff(t128);
-    if (n256) return launch_gemm2<256, 6>(d, A, B, bias, C, st);
-    return launch_gemm2<128, 8>(d, A, B, bias, C, st);
-  }
   int bn, splits;
   choose_tiling(d, &bn, &splits);
   if (d->split_k > 0) splits = d->dtype_c == TLT_F32 ? d->split_k : 1;

@@ -36,7 +36,7 @@ struct PwParams {
   int c_reduce;
   int w_res, nst;                // forward: weight tile resident in the memory of the last ring stages; ring stages in use
   int tail16;                    // forward: k16 steps of the LAST k block (4 = a full block)
-  int dbg;                       // development only (TLT_PW_DBG): 1 = epilogue drains TMEM but stores nothing, 2 = no TMA store
+  int dbg;                       // development only: 1 = epilogue drains TMEM but stores nothing, 2 = no TMA store (always 0 in the product)
 };
 
 template <int BN, int kStages>
@@ -647,192 +647,6 @@ static int w1_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
   return check_launch("pointwise_wgrad1_kernel");
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Single-CTA forward / data-gradient kernel: the pair kernel's math (positions on the TMEM lanes, MN-major activation operand,
-// transposing epilogue) as one cta_group::1 MMA per SM with a plain TMA ring -- the structure that lets the single-CTA weight
-// gradient above stream at 5.5 TB/s.  Unit = (image, 128 positions, channel tile of BN); K loop over 64-channel blocks with the
-// ragged tail as {64 s, 16 k} boxes; TMEM double-buffered (2 x BN columns).
-// ---------------------------------------------------------------------------------------------------------------------
-template <int BN> struct F1Smem {
-  static constexpr int kStages = BN == 128 ? 5 : 4;
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;      // X^T: 2 chunks {64 s, 64 k}
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;           // Wt {64 k, BN n}
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int EPI_OFFSET = kStages * STAGE;
-  static constexpr int BAR_OFFSET = EPI_OFFSET + kPwEpiWarps * kPwEpiBuf;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(kPwThreads, 1)
-pointwise_fwd1_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_at, const PwParams p,
-                      const void* __restrict__ bias) {
-  using L = F1Smem<BN>;
-  constexpr int kStages = L::kStages;
-  constexpr int HALF_N = BN / 2;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  volatile uint32_t* tmem_slot_gen = (volatile uint32_t*)(smem_gen + L::BAR_OFFSET + 8 * (2 * kStages + 4));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_units = p.batch * p.tiles_m * p.tiles_n;
-  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
-  auto decode = [&](int u, int& z, int& tm, int& tn) {
-    tn = u % p.tiles_n;
-    const int r = u / p.tiles_n;
-    tm = r % p.tiles_m; z = r / p.tiles_m;
-  };
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); tma_prefetch_desc(&map_c); tma_prefetch_desc(&map_at); }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kPwEpiWarps); }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        int z, tm, tn;
-        decode(u, z, tm, tn);
-        const int m0 = tm * BLOCK_M;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * L::STAGE, sb = sa + L::A_BYTES;
-          const int n16 = kb == kb_total - 1 ? p.tail16 : BLOCK_K / UMMA_K;
-          mbar_expect_tx(full_bar(stage), (BLOCK_M / 64) * n16 * (UMMA_K * 128) + L::B_BYTES);
-          const int k0 = kb * BLOCK_K;
-          if (n16 == BLOCK_K / UMMA_K) {
-#pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_3d(sa + c * (BLOCK_K * 128), &map_a, full_bar(stage), m0 + 64 * c, k0, z);
-          } else {
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              for (int j = 0; j < n16; ++j)
-                tma_load_3d(sa + c * (BLOCK_K * 128) + j * (UMMA_K * 128), &map_at, full_bar(stage), m0 + 64 * c, k0 + UMMA_K * j, z);
-          }
-          tma_load_2d(sb, &map_b, full_bar(stage), k0, tn * BN);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_M, BN, 1, 0);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * L::STAGE, sb = sa + L::A_BYTES;
-          const int n16 = kb == kb_total - 1 ? p.tail16 : BLOCK_K / UMMA_K;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if (k < n16) {
-              const uint64_t da = make_smem_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024);
-              const uint64_t db = make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-              umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k != 0) ? 1u : 0u);
-            }
-          }
-          umma_commit(empty_bar(stage));
-          if (kb == kb_total - 1) umma_commit(tfull_bar(acc));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 4) {
-    const int quarter = warp & 3;
-    const int col_half = (warp - 4) >> 2;
-    const uint32_t ebuf = smem_base + L::EPI_OFFSET + (warp - 4) * kPwEpiBuf;
-    constexpr int n_chunks = HALF_N / 32;
-    int acc = 0; uint32_t acc_phase = 0;
-    uint32_t ehalf = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      int z, tm, tn;
-      decode(u, z, tm, tn);
-      const int m0 = tm * BLOCK_M + quarter * 32;
-      const int n0 = tn * BN + col_half * HALF_N;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_half * HALF_N);
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        const int col0 = n0 + c * 32;
-        const bool live = m0 < p.S && col0 < p.N;                // warp-uniform
-        uint32_t v[32];
-        if (live) {
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-        }
-        if (c == n_chunks - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        if (!live) continue;
-        if (lane == 0) bulk_wait_read1();
-        __syncwarp();
-        float bv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) bv[i] = 0.f;
-        if (p.has_bias) load_bias32(bias, p.bias_bf16, col0, p.N, bv);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(v[i]) + bv[i]);
-          st_shared_b16(ebuf + ehalf + i * 64 + lane * 2, *(const uint16_t*)&h);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&map_c, ebuf + ehalf, m0, col0, z);
-          bulk_commit();
-        }
-        ehalf ^= 2048u;
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (lane == 0) bulk_wait_read0();
-    __syncwarp();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
-template <int BN>
-static int f1_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mat, const PwParams& p,
-                     const void* bias, long long units, cudaStream_t st) {
-  using L = F1Smem<BN>;
-  TLT_ENSURE_SMEM((pointwise_fwd1_kernel<BN>), L::TOTAL);
-  const int sms = num_sms();
-  pointwise_fwd1_kernel<BN><<<(unsigned)(units < sms ? units : sms), kPwThreads, L::TOTAL, st>>>(ma, mb, mc, mat, p, bias);
-  return check_launch("pointwise_fwd1_kernel");
-}
-
 template <int BN, int kStages, bool WGRAD>
 static int pw_launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mat, const PwParams& p,
                      const void* bias, int units, cudaStream_t st) {
@@ -916,7 +730,7 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
   p.tiles_m = (int)((S + 2 * BLOCK_M - 1) / (2 * BLOCK_M));
   p.tiles_n = (int)((N + (wide ? 256 : 128) - 1) / (wide ? 256 : 128));
   p.has_bias = bias != nullptr; p.bias_bf16 = d->dtype_bias == TLT_BF16;
-  { const char* e = getenv("TLT_PW_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = 0;
   const long long units = (long long)p.batch * p.tiles_m * p.tiles_n;
   TLT_REQUIRE(units < (1LL << 31), "tlt_pointwise_tc: too many tiles");
   cudaStream_t st = (cudaStream_t)stream;
@@ -960,20 +774,6 @@ extern "C" int tlt_pointwise_tc(const tlt_pointwise_desc* d, const void* x, cons
       const int sms = num_sms();
       pointwise_tct_kernel<<<(unsigned)(un < sms ? un : sms), kPwThreads, kTctSmem, st>>>(ma, mw, mc64, mat, p, bias);
       return check_launch("pointwise_tct_kernel");
-    }
-  }
-  {
-    const char* env = getenv("TLT_PW_F1");
-    if (env && env[0] == 'o' && env[1] == 'n' && N <= 256) {
-      // single-CTA variant (see pointwise_fwd1_kernel)
-      CUtensorMap mb1;
-      const int bn = N <= 128 ? 128 : 256;
-      if ((rc = make_map(&mb1, wt, K, N, d->w_ld, BLOCK_K, bn))) return rc;                     // Wt {64 k, BN n}
-      p.tiles_m = (int)((S + BLOCK_M - 1) / BLOCK_M);
-      p.tiles_n = 1;
-      const long long u1 = (long long)p.batch * p.tiles_m;
-      TLT_REQUIRE(u1 < (1LL << 31), "tlt_pointwise_tc: too many tiles");
-      return bn == 128 ? f1_launch<128>(ma, mb1, mc, mat, p, bias, u1, st) : f1_launch<256>(ma, mb1, mc, mat, p, bias, u1, st);
     }
   }
   if (wide) return pw_launch<256, 5, false>(ma, mb, mc, mat, p, bias, (int)units, st);
