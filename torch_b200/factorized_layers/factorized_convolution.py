@@ -3,6 +3,7 @@ tltorch/factorized_layers/factorized_convolution.py:109-457, forward dispatch :1
 import warnings
 
 import numpy as np
+from ..utils.nvtx import annotate
 import torch
 import torch.nn as nn
 
@@ -115,6 +116,7 @@ class FactorizedConv(nn.Module):
         self.kernel_shape = kernel_shape
         self.forward_fun = _get_factorized_conv(self.weight, self.implementation)
 
+    @annotate(lambda m: f"tltorch.FactorizedConv[{m.factorization}] {m.in_channels}->{m.out_channels}")
     def forward(self, x, indices=0):
         if self.n_layers == 1:
             if indices != 0:

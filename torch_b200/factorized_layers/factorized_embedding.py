@@ -2,6 +2,7 @@
 factorized form and looked up WITHOUT being rebuilt (reference: tltorch/factorized_layers/factorized_embedding.py:10-236,
 forward :96-117).  The lookup indexes the weight in factorized form (``weight[rows, :]``, torch_b200/embedding_ops.py)."""
 import numpy as np
+from ..utils.nvtx import annotate
 import torch
 from torch import nn
 
@@ -50,6 +51,7 @@ class FactorizedEmbedding(nn.Module):
         with torch.no_grad():
             tensor_init(self.weight, std=target_stddev)
 
+    @annotate(lambda m: "tltorch.FactorizedEmbedding")
     def forward(self, input, indices=0):
         output_shape = (*input.shape, self.embedding_dim)
         flattened_input = input.reshape(-1)

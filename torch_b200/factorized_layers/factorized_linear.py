@@ -3,6 +3,7 @@ tltorch/factorized_layers/factorized_linear.py:15-280, forward dispatch :96-123)
 import math
 
 import numpy as np
+from ..utils.nvtx import annotate
 import torch
 from torch import nn
 from torch.utils import checkpoint
@@ -65,6 +66,7 @@ class FactorizedLinear(nn.Module):
                 bound = 1 / math.sqrt(self.in_features)
                 torch.nn.init.uniform_(self.bias, -bound, bound)
 
+    @annotate(lambda m: f"tltorch.FactorizedLinear[{m.factorization}] {m.in_features}->{m.out_features}")
     def forward(self, x, indices=0):
         if self.n_layers == 1:
             if indices != 0:

@@ -1,6 +1,7 @@
 """Tensor Contraction Layer (reference: tltorch/factorized_layers/tensor_contraction_layers.py:19-94)."""
 import math
 
+from ..utils.nvtx import annotate
 import torch
 import torch.nn as nn
 from torch.nn import init
@@ -34,6 +35,7 @@ class TCL(nn.Module):
     def factors(self):
         return [getattr(self, f"factor_{i}") for i in range(self.order)]
 
+    @annotate(lambda m: "tltorch.TCL")
     def forward(self, x):
         # one fused launch when a sample fits shared memory (bias added in the same kernel), else a per-mode chain
         return tenalg.multi_mode_dot(x, self.factors, modes=self.contraction_modes, addend=self.bias)

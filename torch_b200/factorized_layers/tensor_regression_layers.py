@@ -1,4 +1,5 @@
 """Tensor Regression Layer (reference: tltorch/factorized_layers/tensor_regression_layers.py:16-132)."""
+from ..utils.nvtx import annotate
 import torch
 import torch.nn as nn
 
@@ -39,6 +40,7 @@ class TRL(nn.Module):
             self.init_from_random()
         self.factorization = self.weight.name
 
+    @annotate(lambda m: "tltorch.TRL")
     def forward(self, x):
         # NB: like the reference (:75-77) the weight MODULE is passed, not weight(): hooks registered on a TRL weight
         # (tensor dropout / lasso) therefore do not fire here.  Call functional.tensor_regression.trl
