@@ -116,7 +116,7 @@ class FactorizedConv(nn.Module):
         self.kernel_shape = kernel_shape
         self.forward_fun = _get_factorized_conv(self.weight, self.implementation)
 
-    @annotate(lambda m: f"tltorch.FactorizedConv[{m.factorization}] {m.in_channels}->{m.out_channels}")
+    @annotate(lambda m: f"tltorch.FactorizedConv[{type(m.weight).__name__}] {m.in_channels}->{m.out_channels}")
     def forward(self, x, indices=0):
         if self.n_layers == 1:
             if indices != 0:

@@ -66,7 +66,7 @@ class FactorizedLinear(nn.Module):
                 bound = 1 / math.sqrt(self.in_features)
                 torch.nn.init.uniform_(self.bias, -bound, bound)
 
-    @annotate(lambda m: f"tltorch.FactorizedLinear[{m.factorization}] {m.in_features}->{m.out_features}")
+    @annotate(lambda m: f"tltorch.FactorizedLinear[{type(m.weight).__name__}] {m.in_features}->{m.out_features}")
     def forward(self, x, indices=0):
         if self.n_layers == 1:
             if indices != 0:
