@@ -434,14 +434,15 @@ int tlt_cplinear_bwd(const tlt_cplinear_desc* desc, const float* x, const float*
  * and their autograd.  v / dv: fp32 (B, ro), v written by the forward call and read by the backward call.
  *   tlt_trl_tail_fwd   y (B, out), v <- zp, core, F_o (+ bias or NULL)                                  1 launch
  *   tlt_trl_tail_bwd   dzp, dcore, dF_o, dbias (or NULL), all bf16 <- zp, dy, core, F_o, v; dv scratch  2 launches
+ *                      (phases: 1 = dv / dzp, 2 = parameter gradients, 3 = both -- the two launches may go to different streams)
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct {
   int64_t batch, j, rc, ldz, ro, out;
 } tlt_trl_tail_desc;
 int tlt_trl_tail_fwd(const tlt_trl_tail_desc* desc, const void* zp, const void* core, const void* f_out, const void* bias, void* y,
                      float* v, void* stream);
-int tlt_trl_tail_bwd(const tlt_trl_tail_desc* desc, const void* zp, const void* dy, const void* core, const void* f_out, const float* v,
-                     float* dv, void* dzp, void* dcore, void* df_out, void* dbias, void* stream);
+int tlt_trl_tail_bwd(const tlt_trl_tail_desc* desc, int32_t phases, const void* zp, const void* dy, const void* core, const void* f_out,
+                     const float* v, float* dv, void* dzp, void* dcore, void* df_out, void* dbias, void* stream);
 /* Kronecker product of two small bf16 matrices A (da, pa), B (db, pb): k[(a, b), (p, q)] = A[a, p] B[b, q], and its backward
  * (dA, dB <- dk).  Replaces: the merged spatial factor of the input projection of tucker_trl / TCL (tensor_regression.py:40,
  * tensor_contraction_layers.py:75 contract one mode at a time; the spatial modes are applied here as ONE matrix). */

@@ -521,18 +521,21 @@ def emulate_trl_tail_fwd(d, zp, core, fo, bias, y, v):
     LOG.append(("trl_tail_fwd", (B, J, rc, ro, O)))
 
 
-def emulate_trl_tail_bwd(d, zp, gy, core, fo, v, dv, dzp, dcore, dfo, dbias):
+def emulate_trl_tail_bwd(d, zp, gy, core, fo, v, dv, dzp, dcore, dfo, dbias, phases=3):
     B, J, rc, ldz, ro, O = (int(getattr(d, k)) for k in ("batch", "j", "rc", "ldz", "ro", "out"))
     g = gy.double()
-    dvv = g @ fo.double()
-    dv.copy_(dvv.to(dv.dtype))
-    dzp.zero_()
-    dzp[:, :, :rc] = torch.einsum("br,cjr->bjc", dvv, core.reshape(rc, J, ro).double()).to(dzp.dtype)
-    dcore.copy_(torch.einsum("bjc,br->cjr", zp[:, :, :rc].double(), dvv).reshape(dcore.shape).to(dcore.dtype))
-    dfo.copy_((g.t() @ v.double()).to(dfo.dtype))
-    if dbias is not None:
-        dbias.copy_(g.sum(0).to(dbias.dtype))
-    LOG.append(("trl_tail_bwd", (B, J, rc, ro, O)))
+    if phases & 1:
+        dvv = g @ fo.double()
+        dv.copy_(dvv.to(dv.dtype))
+        dzp.zero_()
+        dzp[:, :, :rc] = torch.einsum("br,cjr->bjc", dvv, core.reshape(rc, J, ro).double()).to(dzp.dtype)
+    if phases & 2:                                   # reads the dv the first phase wrote (fp32), like the kernel
+        dvv = dv.double()
+        dcore.copy_(torch.einsum("bjc,br->cjr", zp[:, :, :rc].double(), dvv).reshape(dcore.shape).to(dcore.dtype))
+        dfo.copy_((g.t() @ v.double()).to(dfo.dtype))
+        if dbias is not None:
+            dbias.copy_(g.sum(0).to(dbias.dtype))
+    LOG.append(("trl_tail_bwd", (B, J, rc, ro, O), phases))
 
 
 def emulate_scale_modes(x, masks, alpha, y):

@@ -145,7 +145,7 @@ SYMBOLS = {
     "tlt_cplinear_bwd": (C.c_int, [C.POINTER(CpLinearDesc), _vp, _vp, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _vp, _vp,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _vp, _vp, _vp]),
     "tlt_trl_tail_fwd": (C.c_int, [C.POINTER(TrlTailDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tlt_trl_tail_bwd": (C.c_int, [C.POINTER(TrlTailDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_trl_tail_bwd": (C.c_int, [C.POINTER(TrlTailDesc), C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tlt_kron2_fwd": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "tlt_kron2_bwd": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "tlt_khatri_rao_bwd_ld": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, _vp, C.c_int64,

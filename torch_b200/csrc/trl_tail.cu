@@ -281,17 +281,24 @@ extern "C" int tlt_trl_tail_fwd(const tlt_trl_tail_desc* d, const void* zp, cons
   return check_launch("trl_tail_fwd_kernel");
 }
 
-extern "C" int tlt_trl_tail_bwd(const tlt_trl_tail_desc* d, const void* zp, const void* gy, const void* core, const void* fo, const float* v,
-                                float* dv, void* dzp, void* dcore, void* dfo, void* dbias, void* stream) {
+// phases: 1 = the per-row launch (dv, dzp), 2 = the parameter-gradient launch (dcore, dF_o, dbias; reads dv), 3 = both.  A caller that
+// overlaps the parameter gradients with the rest of its backward pass issues the two phases on different streams.
+extern "C" int tlt_trl_tail_bwd(const tlt_trl_tail_desc* d, int32_t phases, const void* zp, const void* gy, const void* core, const void* fo,
+                                const float* v, float* dv, void* dzp, void* dcore, void* dfo, void* dbias, void* stream) {
   Geom g;
   int rc = fill(d, &g);
   if (rc) return rc;
-  TLT_REQUIRE(zp && gy && core && fo && v && dv && dzp && dcore && dfo, "tlt_trl_tail_bwd: null pointer");
+  TLT_REQUIRE(phases >= 1 && phases <= 3 && zp && gy && core && fo && v && dv, "tlt_trl_tail_bwd: bad arguments");
+  TLT_REQUIRE(!(phases & 1) || dzp, "tlt_trl_tail_bwd: phase 1 needs dzp");
+  TLT_REQUIRE(!(phases & 2) || (dcore && dfo), "tlt_trl_tail_bwd: phase 2 needs dcore and df_out");
   cudaStream_t st = (cudaStream_t)stream;
-  trl_tail_bwd_rows<<<(g.B + TB - 1) / TB, 256, 0, st>>>(g, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)core, (const __nv_bfloat16*)fo, dv,
-                                                        (__nv_bfloat16*)dzp);
-  rc = check_launch("trl_tail_bwd_rows");
-  if (rc) return rc;
+  if (phases & 1) {
+    trl_tail_bwd_rows<<<(g.B + TB - 1) / TB, 256, 0, st>>>(g, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)core, (const __nv_bfloat16*)fo, dv,
+                                                          (__nv_bfloat16*)dzp);
+    rc = check_launch("trl_tail_bwd_rows");
+    if (rc) return rc;
+  }
+  if (!(phases & 2)) return TLT_OK;
   const int blocks = (g.O + PC - 1) / PC + (g.P + PC - 1) / PC;
   trl_tail_bwd_params<<<blocks, 256, 0, st>>>(g, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)zp, v, dv, (__nv_bfloat16*)dfo,
                                               (__nv_bfloat16*)dbias, (__nv_bfloat16*)dcore);

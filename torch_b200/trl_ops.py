@@ -9,6 +9,7 @@ tensor_regression.py:37-49).  CPU tensors raise NotImplementedError (no fallback
 """
 import ctypes as C
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -30,9 +31,10 @@ def _execute_fwd(d, zp, core, fo, bias, y, v):
                                              _cuda.ptr(v), _cuda.stream_ptr(zp)), "tlt_trl_tail_fwd")
 
 
-def _execute_bwd(d, zp, gy, core, fo, v, dv, dzp, dcore, dfo, dbias):
+def _execute_bwd(d, zp, gy, core, fo, v, dv, dzp, dcore, dfo, dbias, phases=3):
+    """phases: 1 = dv / dzp, 2 = dcore / dF_o / dbias (reads dv), 3 = both launches"""
     _cuda.require_cuda(zp, gy, core, fo, v, dv, dzp, dcore, dfo, dbias)
-    _cuda.check(_cuda.lib().tlt_trl_tail_bwd(C.byref(d), _cuda.ptr(zp), _cuda.ptr(gy), _cuda.ptr(core), _cuda.ptr(fo), _cuda.ptr(v),
+    _cuda.check(_cuda.lib().tlt_trl_tail_bwd(C.byref(d), phases, _cuda.ptr(zp), _cuda.ptr(gy), _cuda.ptr(core), _cuda.ptr(fo), _cuda.ptr(v),
                                              _cuda.ptr(dv), _cuda.ptr(dzp), _cuda.ptr(dcore), _cuda.ptr(dfo), _cuda.ptr(dbias),
                                              _cuda.stream_ptr(zp)), "tlt_trl_tail_bwd")
 
@@ -120,7 +122,7 @@ def _tail_bwd_op(zp: torch.Tensor, gy: torch.Tensor, core: torch.Tensor, f_out: 
     dzp, dcore, dfo = torch.empty_like(zp), torch.empty_like(core), torch.empty_like(f_out)
     dbias = torch.empty(f_out.shape[0], dtype=zp.dtype, device=zp.device) if need_bias else None
     dv = torch.empty_like(v)
-    _execute_bwd(_geom(zp, core, f_out), zp, gy, core, f_out, v, dv, dzp, dcore, dfo, dbias)
+    _execute_bwd(_geom(zp, core, f_out), zp, gy, core, f_out, v, dv, dzp, dcore, dfo, dbias, phases=3)
     return [dzp, dcore, dfo, dbias if need_bias else zp.new_empty(0)]
 
 
@@ -170,17 +172,171 @@ def eligible(x, weight, bias):
     return spatial_ops.eligible(x, S, J)
 
 
-def tucker_trl_fused(x, weight, bias=None):
-    """x (B, C, s_1..) bf16, weight a TuckerTensor of shape (C, s_1.., O) -> (B, O); differentiable in everything."""
+# =====================================================================================================================
+# the whole fused route as ONE op per direction: every launch is issued here, so the backward pass can put the parameter gradients
+# (tail parameters, channel factor) on a side stream beside dt -> spatial backward -> Kronecker backward
+# =====================================================================================================================
+_SIDE = {}
+
+
+def _fork(dev):
+    if dev.type != "cuda" or os.environ.get("TLT_TRL_BRANCHES", "1") == "0":
+        return None, None
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    _SIDE[key].wait_stream(main)
+    return _SIDE[key], main
+
+
+def _r8(v):
+    return (v + 7) // 8 * 8
+
+
+def _kron_chain(spatial_factors):
+    """Kronecker product of the spatial factors, left to right; returns (k, intermediates) for the backward pass."""
+    k, chain = spatial_factors[0], []
+    for m in spatial_factors[1:]:
+        out = torch.empty((k.shape[0] * m.shape[0], k.shape[1] * m.shape[1]), dtype=k.dtype, device=k.device)
+        _execute_kron_fwd(k, m, out)
+        chain.append((k, m))
+        k = out
+    return k, chain
+
+
+@torch.library.custom_op("tltorch::tucker_trl_fwd", mutates_args=())
+def _trl_fwd_op(x: torch.Tensor, core: torch.Tensor, factors: List[torch.Tensor], bias: Optional[torch.Tensor]) -> List[torch.Tensor]:
+    """-> [y (B, O), t (B, J, C), zp (B, J, ldz), wp (ldz, round8(C)), v (B, ro) fp32, k (S, J)]"""
     from . import spatial_ops
-    from .tucker_ops import padded_linear
-    factors = list(weight.factors)
+    from .blocktt_ops import _execute_gemm
+    from .tucker_ops import _execute_pack_kmajor
+    x, core = x.contiguous(), core.contiguous()
+    fs = [f.contiguous() for f in factors]
     b, c = x.shape[0], x.shape[1]
     S = math.prod(x.shape[2:])
-    k = factors[1]                                                   # (s_1, q_1) ... Kronecker product of the spatial factors
-    for m in factors[2:-1]:
-        k = kron2(k, m)
-    t = spatial_ops.spatial_project(x.reshape(b, c, S), k)          # (B, J, C)
-    J = k.shape[1]
-    z = padded_linear(t.reshape(b * J, c), factors[0].t(), None, True)   # (B J, round8(rc)), pad columns zero
-    return trl_tail(z.reshape(b, J, z.shape[1]), weight.core, factors[-1], bias)
+    dev, bf = x.device, x.dtype
+    k, _ = _kron_chain(fs[1:-1])
+    J, rc = k.shape[1], fs[0].shape[1]
+    t = torch.empty((b, J, c), dtype=bf, device=dev)
+    spatial_ops._execute_spatial_fwd(x.reshape(b, c, S), k, t)
+    ldz, cp = _r8(rc), _r8(c)
+    wp = torch.empty((ldz, cp), dtype=bf, device=dev)                 # F_c^T re-pitched K-major, pad rows zero
+    _execute_pack_kmajor(fs[0].t(), wp[:rc])
+    if ldz != rc:
+        wp[rc:].zero_()
+    zp = torch.empty((b * J, ldz), dtype=bf, device=dev)
+    _execute_gemm(t.reshape(b * J, c), wp, None, zp, M=b * J, N=ldz, K=cp if cp == c else c, lda=c, ldb=cp, a_major=0, b_major=0)
+    fo = fs[-1]
+    y = torch.empty((b, fo.shape[0]), dtype=bf, device=dev)
+    v = torch.empty((b, core.shape[-1]), dtype=torch.float32, device=dev)
+    zp3 = zp.reshape(b, J, ldz)
+    _execute_fwd(_geom(zp3, core, fo), zp3, core, fo, None if bias is None else bias.contiguous(), y, v)
+    return [y, t, zp3, wp, v, k]
+
+
+@_trl_fwd_op.register_fake
+def _(x, core, factors, bias):
+    b, c = x.shape[0], x.shape[1]
+    J = math.prod(f.shape[1] for f in factors[1:-1])
+    S = math.prod(f.shape[0] for f in factors[1:-1])
+    ldz = _r8(factors[0].shape[1])
+    return [x.new_empty((b, factors[-1].shape[0])), x.new_empty((b, J, c)), x.new_empty((b, J, ldz)), x.new_empty((ldz, _r8(c))),
+            x.new_empty((b, core.shape[-1]), dtype=torch.float32), x.new_empty((S, J))]
+
+
+@torch.library.custom_op("tltorch::tucker_trl_bwd", mutates_args=())
+def _trl_bwd_op(gy: torch.Tensor, x: torch.Tensor, t: torch.Tensor, zp: torch.Tensor, wp: torch.Tensor, v: torch.Tensor, k: torch.Tensor,
+                core: torch.Tensor, factors: List[torch.Tensor], need_bias: bool) -> List[torch.Tensor]:
+    """-> [dx, dcore, dbias | empty, dF_c, dF_s1.., dF_o]"""
+    from . import spatial_ops
+    from .blocktt_ops import _execute_gemm
+    gy, x, core = gy.contiguous(), x.contiguous(), core.contiguous()
+    fs = [f.contiguous() for f in factors]
+    b, c = x.shape[0], x.shape[1]
+    S, J = k.shape
+    rc, ldz, cp = fs[0].shape[1], zp.shape[2], wp.shape[1]
+    dev, bf, f32 = x.device, x.dtype, torch.float32
+    fo = fs[-1]
+    d = _geom(zp, core, fo)
+    dv = torch.empty_like(v)
+    dzp = torch.empty_like(zp)
+    dcore, dfo = torch.empty_like(core), torch.empty_like(fo)
+    dbias = torch.empty(fo.shape[0], dtype=bf, device=dev) if need_bias else None
+    dt = torch.empty((b * J, c), dtype=bf, device=dev)
+    dwp = torch.empty((rc, cp), dtype=f32, device=dev)               # dF_c^T: fp32 so that the GEMM may split the B J reduction
+    dfc = torch.empty_like(fs[0])
+    dx = torch.empty_like(x)
+    dk32 = torch.zeros((S, J), dtype=f32, device=dev)
+    _execute_bwd(d, zp, gy, core, fo, v, dv, dzp, None, None, None, phases=1)          # dv, dzp
+    side, main = _fork(dev)
+
+    def params():
+        _execute_bwd(d, zp, gy, core, fo, v, dv, None, dcore, dfo, dbias, phases=2)    # dcore, dF_o, dbias
+        _execute_gemm(dzp.reshape(b * J, ldz), t.reshape(b * J, c), None, dwp, M=rc, N=c, K=b * J, lda=ldz, ldb=c, a_major=1, b_major=1)
+        dfc.copy_(dwp[:, :c].t())                                                      # (C, rc) bf16 <- (rc, C) fp32
+
+    if side is not None:
+        with torch.cuda.stream(side):
+            params()
+    # dt[b j, c] = sum_r dzp[b j, r] F_c[c, r]:  B operand (n = c, k = r) at wp[r * ld + c] -> MN-major
+    _execute_gemm(dzp.reshape(b * J, ldz), wp, None, dt, M=b * J, N=c, K=ldz, lda=ldz, ldb=cp, a_major=0, b_major=1)
+    spatial_ops._execute_spatial_bwd(x.reshape(b, c, S), k, dt.reshape(b, J, c), dx.reshape(b, c, S), dk32)
+    # Kronecker chain backward, right to left
+    spatial = fs[1:-1]
+    chain, acc = [], spatial[0]                                      # (left operand, factor) of every product; the left operands
+    for idx, m in enumerate(spatial[1:]):                            # beyond the first are intermediates, recomputed here
+        chain.append((acc, m))
+        if idx + 2 < len(spatial):
+            nxt = torch.empty((acc.shape[0] * m.shape[0], acc.shape[1] * m.shape[1]), dtype=bf, device=dev)
+            _execute_kron_fwd(acc, m, nxt)
+            acc = nxt
+    dk = dk32.to(bf)
+    grads_s = [None] * len(spatial)
+    for idx in range(len(chain) - 1, -1, -1):
+        a, m = chain[idx]
+        d_a, d_m = torch.empty_like(a), torch.empty_like(m)
+        _execute_kron_bwd(a, m, dk, d_a, d_m)
+        grads_s[idx + 1] = d_m
+        dk = d_a
+    grads_s[0] = dk
+    if side is None:
+        params()
+    else:
+        main.wait_stream(side)
+    return [dx, dcore, dbias if need_bias else x.new_empty(0), dfc] + grads_s + [dfo]
+
+
+@_trl_bwd_op.register_fake
+def _(gy, x, t, zp, wp, v, k, core, factors, need_bias):
+    return ([torch.empty_like(x), torch.empty_like(core), x.new_empty(factors[-1].shape[0] if need_bias else 0)]
+            + [torch.empty_like(f) for f in factors])
+
+
+def _trl_setup(ctx, inputs, output):
+    x, core, factors, bias = inputs
+    ctx.n = len(factors)
+    ctx.has_bias = bias is not None
+    ctx.save_for_backward(x, output[1], output[2], output[3], output[4], output[5], core, *factors)
+    ctx.set_materialize_grads(False)
+
+
+def _trl_backward(ctx, grads):
+    if grads[0] is None:
+        return None, None, None, None
+    saved = list(ctx.saved_tensors)
+    x, t, zp, wp, v, k, core = saved[:7]
+    factors = saved[7:]
+    need_bias = ctx.has_bias and ctx.needs_input_grad[3]
+    outs = _trl_bwd_op(grads[0], x, t, zp, wp, v, k, core, factors, need_bias)
+    return outs[0], outs[1], list(outs[3:3 + ctx.n]), (outs[2] if need_bias else None)
+
+
+_trl_fwd_op.register_autograd(_trl_backward, setup_context=_trl_setup)
+
+
+def tucker_trl_fused(x, weight, bias=None):
+    """x (B, C, s_1..) bf16, weight a TuckerTensor of shape (C, s_1.., O) -> (B, O); differentiable in everything.  One op per
+    direction: Kronecker product of the spatial factors -> spatial projection (one pass over the activation) -> channel-mode GEMM
+    -> tail (core contraction + output expansion + bias); the backward pass runs the parameter gradients on a side stream."""
+    return _trl_fwd_op(x, weight.core, list(weight.factors), bias)[0]
