@@ -20,11 +20,13 @@ if what == "trl":
             p.mul_(0.05)
     layer = layer.to(torch.bfloat16)
     x = torch.randn(512, 2048, 7, 7, device=dev, dtype=torch.bfloat16)
-elif what == "tucker_conv":
+elif what in ("tucker_conv", "tucker_conv_cl"):
     layer = tlt.FactorizedConv(512, 512, 3, order=2, padding=1, factorization="tucker", rank=0.5, bias=True, device=dev)
     layer.reset_parameters()
     layer = layer.to(torch.bfloat16)
     x = torch.randn(512, 512, 7, 7, device=dev, dtype=torch.bfloat16)
+    if what.endswith("_cl"):
+        x = x.contiguous(memory_format=torch.channels_last)
 elif what.startswith("cp_conv"):
     _, cin, cout, hw, stride = what.split(":")
     layer = tlt.FactorizedConv(int(cin), int(cout), 3, order=2, padding=1, stride=int(stride), factorization="cp", rank=0.25, bias=False,

@@ -301,7 +301,11 @@ def expand_core(core, kernel_factors):
         return None
     kron = kernel_factors[0]
     for f in kernel_factors[1:]:                                             # (K, Q) (x) (k, q) -> (K k, Q q), tiny
-        kron = ops.contract("ac,bd->abcd", kron, f).reshape(kron.shape[0] * f.shape[0], kron.shape[1] * f.shape[1])
+        if kron.dtype == torch.bfloat16 and f.dtype == torch.bfloat16:
+            from .trl_ops import kron2                                      # two-kernel Kronecker op (csrc/trl_tail.cu)
+            kron = kron2(kron, f)
+        else:
+            kron = ops.contract("ac,bd->abcd", kron, f).reshape(kron.shape[0] * f.shape[0], kron.shape[1] * f.shape[1])
     r0, r1 = core.shape[0], core.shape[1]
     return _skinny_op(core.reshape(r0 * r1, _prod(q)), kron).reshape(r0, r1, *k)
 

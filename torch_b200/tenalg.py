@@ -114,7 +114,8 @@ def _trailing_modes_first(tensor, pairs, transpose):
         # mode as a K-major tcgen05 GEMM on the S / J times smaller, channels-last t
         k = oriented[0]
         for m in oriented[1:]:
-            k = contract("ap,bq->abpq", k, m).reshape(k.shape[0] * m.shape[0], k.shape[1] * m.shape[1])
+            from .trl_ops import kron2                                           # bf16 here: the two-kernel Kronecker op
+            k = kron2(k, m)
         t = spatial_ops.spatial_project(tensor.reshape(b, c, S), k)              # (B, J, C)
         z = padded_linear(t.reshape(b * J, c), m0, None, True)                   # (B J, round8(r_0)), pad columns zero
         z = z.reshape(b, *[m.shape[1] for m in oriented], z.shape[1])
