@@ -229,20 +229,31 @@ def profile_entry_points(step, reps=2):
     """Eager pass with a CUDA-event pair around every launcher call of libtltorch_cuda.so (torch_b200._cuda.PROFILE)."""
     import torch
     from torch_b200 import _cuda
+    from torch_b200 import ops, rows_ops
     step()
     torch.cuda.synchronize()
-    _cuda.PROFILE = []
+    _cuda.PROFILE, ops.PROFILE = [], []      # ops.PROFILE: the GEMM funnel also records each launch's algorithmic FLOPs and bytes
+    branches, rows_ops._BRANCHES = rows_ops._BRANCHES, False     # per-launch times: no second branch running beside the timed launch
     for _ in range(reps):
         step()
     torch.cuda.synchronize()
+    rows_ops._BRANCHES = branches
     prof, _cuda.PROFILE = _cuda.PROFILE, None
+    gemms, ops.PROFILE = ops.PROFILE, None
     table = {}
     for name, a, b in prof:
         t = table.setdefault(name, [0.0, 0])
         t[0] += a.elapsed_time(b)
         t[1] += 1
-    return {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[1] / reps} for k, v in
-            sorted(table.items(), key=lambda kv: -kv[1][0])}
+    out = {k: {"ms_per_step": v[0] / reps, "launches_per_step": v[1] / reps} for k, v in
+           sorted(table.items(), key=lambda kv: -kv[1][0])}
+    if gemms and "tlt_gemm_bf16_tc" in out:
+        # time: the innermost event pair (around the C call itself); eager launches of ~20 us kernels are host-bound, so the pair
+        # also spans part of the launch latency -- durations here are upper bounds (ncu: profiles/r02_launches_config3.md)
+        out["tlt_gemm_bf16_tc"].update({"algorithmic_flops_per_step": sum(g[3] for g in gemms) / reps,
+                                        "algorithmic_bytes_per_step": sum(g[4] for g in gemms) / reps,
+                                        "event_ms_per_step": out["tlt_gemm_bf16_tc"]["ms_per_step"]})
+    return out
 
 
 def time_e2e(dev_inputs, run, outputs, steps, world, dist):
@@ -604,6 +615,17 @@ def run_ours(args):
         roofline["kernels"] = {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"]}
                                for k, v in list(table.items())[:8]}
         roofline["dominant_entry_point"] = top[0]
+        if "algorithmic_bytes_per_step" in top[1]:
+            # the dominant kernel family on its own: algorithmic operand + result bytes (and FLOPs) of its launches over their
+            # CUDA-event time in this eager pass -- the per-kernel figure next to the whole-step one above
+            n = top[1]["launches_per_step"]
+            gbs = top[1]["algorithmic_bytes_per_step"] / (top[1]["event_ms_per_step"] / 1e3) / 1e9
+            roofline["dominant_kernel"] = {"entry_point": top[0], "launches_per_step": n, "bound": "hbm",
+                                           "algorithmic_bytes_per_launch": top[1]["algorithmic_bytes_per_step"] / n,
+                                           "avg_launch_us": top[1]["event_ms_per_step"] * 1e3 / n, "achieved": gbs, "unit": "GB/s",
+                                           "peak": roofline["peak"], "frac": gbs / roofline["peak"],
+                                           "note": "CUDA-event time of the eager pass (an upper bound for ~20 us launches); ncu launch list: profiles/r02_launches_config3.md",
+                                           "tflops": top[1]["algorithmic_flops_per_step"] / (top[1]["event_ms_per_step"] / 1e3) / 1e12}
         roofline["dominant_share_of_kernel_time"] = top[1]["ms_per_step"] / total if total else None
         roofline["kernel_time_ms_per_step"] = total
         roofline["kernel_share_of_step"] = total / ms
