@@ -366,7 +366,7 @@ static unsigned grid_for(long long items) {
 
 namespace tlt {
 namespace dwst {   // dwsep_staged.cu: the same sweeps from TMA-landed bands in shared memory (stride 1); 1 launched, 0 not covered
-int staged_fwd(int batch, int H, int W, int ld, const void* z, const float* taps, void* y, cudaStream_t st);
+int staged_fwd(int batch, int H, int W, int ld, int stride, const void* z, const float* taps, void* y, cudaStream_t st);
 int staged_wgrad(int batch, int H, int W, int ld, int stride, const void* z, const void* gy, float* acc, cudaStream_t st);
 }  // namespace dwst
 }  // namespace tlt
@@ -392,7 +392,7 @@ extern "C" int tlt_dwsep_rows_fwd(const tlt_dwsep_desc* d, const void* z, const 
   int rc = fill(d, &g, false);
   if (rc) return rc;
   TLT_REQUIRE(z && taps && y && ((uintptr_t)z % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)taps % 16) == 0, "tlt_dwsep_rows_fwd: 16-byte aligned tensors");
-  if (d->stride == 1 && staged_enabled() && dwst::staged_fwd(g.batch, g.H, g.W, (int)d->ld, z, taps, y, (cudaStream_t)stream) == 1)
+  if (staged_enabled() && dwst::staged_fwd(g.batch, g.H, g.W, (int)d->ld, (int)d->stride, z, taps, y, (cudaStream_t)stream) == 1)
     return check_launch("dwsep_staged_kernel<fwd>");
   if (d->stride == 1) dwsep_fwd_kernel<1><<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, taps, (uint4*)y);
   else dwsep_fwd_kernel<2><<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)z, taps, (uint4*)y);
@@ -405,7 +405,7 @@ extern "C" int tlt_dwsep_rows_dgrad(const tlt_dwsep_desc* d, const void* gy, con
   int rc = fill(d, &g, true);
   if (rc) return rc;
   TLT_REQUIRE(gy && taps && dz && ((uintptr_t)gy % 16) == 0 && ((uintptr_t)dz % 16) == 0 && ((uintptr_t)taps % 16) == 0, "tlt_dwsep_rows_dgrad: 16-byte aligned tensors");
-  if (d->stride == 1 && staged_enabled() && dwst::staged_fwd(g.batch, g.H, g.W, (int)d->ld, gy, taps, dz, (cudaStream_t)stream) == 1)
+  if (d->stride == 1 && staged_enabled() && dwst::staged_fwd(g.batch, g.H, g.W, (int)d->ld, 1, gy, taps, dz, (cudaStream_t)stream) == 1)
     return check_launch("dwsep_staged_kernel<dgrad>");
   if (d->stride == 1) dwsep_fwd_kernel<1><<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, taps, (uint4*)dz);
   else dwsep_dgrad2_kernel<<<grid_for(g.items), 128, 0, (cudaStream_t)stream>>>(g, (const uint4*)gy, taps, (uint4*)dz);

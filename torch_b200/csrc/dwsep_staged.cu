@@ -160,9 +160,24 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
         for (int i = 0; i < 4; ++i) v[i] = fma2(k[2][i], d[i], fma2(k[1][i], b[i], mul2(k[0][i], a[i])));
       };
       f2 va[4], vb[4], vc[4];
+      uint4* out = dst + ((size_t)(n * g.Ho + h) * g.Wo) * g.cpr + c;
+      if (g.S == 2) {
+        // stride 2: output column w reads v at input columns 2 w - 1, 2 w, 2 w + 1; the last one is the next output's first
+        hpass(2 * w_begin - 1, va);
+        for (int w = w_begin; w < w_end; ++w) {
+          hpass(2 * w, vb);
+          hpass(2 * w + 1, vc);
+          f2 o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = fma2(k[5][i], vc[i], fma2(k[4][i], vb[i], mul2(k[3][i], va[i])));
+          out[(size_t)w * g.cpr] = pack(o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) va[i] = vc[i];
+        }
+        continue;
+      }
       hpass(w_begin - 1, va);
       hpass(w_begin, vb);
-      uint4* out = dst + ((size_t)(n * g.H + h) * g.W) * g.cpr + c;
 #pragma unroll 2
       for (int w = w_begin; w < w_end; ++w) {
         hpass(w + 1, vc);
@@ -247,7 +262,7 @@ static bool plan(int batch, int H, int W, int ld, int S, bool wgrad, SGeom* g, i
   const int cap = wgrad ? kWgradThreads : kFwdThreads;
   const int Ho = H / S, Wo = W / S;
   const long long row_bytes = (long long)W * ld * 2, grow_bytes = (long long)Wo * ld * 2;
-  if (cpr > cap || row_bytes > 64 * 1024 || row_bytes % 16 || grow_bytes % 16 || (S != 1 && !wgrad)) return false;
+  if (cpr > cap || row_bytes > 64 * 1024 || row_bytes % 16 || grow_bytes % 16) return false;
   const long long budget = 200 * 1024 - (wgrad ? 9LL * ld * 4 : 0) - 64;
   // deepest ring first (4 stages, then 3, then 2), the tallest band that allows it
   int BR = 0, nst = 0;
@@ -277,9 +292,9 @@ static bool plan(int batch, int H, int W, int ld, int S, bool wgrad, SGeom* g, i
 }
 
 // -> 1 launched, 0 shape not covered (caller falls back), < 0 error
-int staged_fwd(int batch, int H, int W, int ld, const void* z, const float* taps, void* y, cudaStream_t st) {
+int staged_fwd(int batch, int H, int W, int ld, int stride, const void* z, const float* taps, void* y, cudaStream_t st) {
   SGeom g; int threads; size_t smem;
-  if (!plan(batch, H, W, ld, 1, false, &g, &threads, &smem)) return 0;
+  if (!plan(batch, H, W, ld, stride, false, &g, &threads, &smem)) return 0;
   if (ensure_smem((const void*)dwsep_staged_kernel<false>, smem) != TLT_OK) return 0;
   const int resident = (smem * 2 + 2048 <= 227 * 1024 ? 2 : 1) * device_sms();     // two blocks per SM when their slabs fit side by side
   const int grid = g.units < resident ? g.units : resident;
