@@ -450,6 +450,46 @@ int tlt_kron2_fwd(const void* a, const void* b, int32_t da, int32_t pa, int32_t 
 int tlt_kron2_bwd(const void* a, const void* b, const void* dk, int32_t da, int32_t pa, int32_t db, int32_t pb, void* d_a, void* d_b,
                   void* stream);
 
+/* --------------------------------------------------------------------------------------------------------------
+ * Op-level entry points (a whole layer per call; csrc/op_level.cu).  They sequence the same launches as the Python ops on the
+ * caller's stream; every intermediate lives in caller-allocated workspaces (`ws`: written by fwd, read by bwd; `gws`: scratch of bwd).
+ *
+ * tlt_blocktt3_linear_*: FactorizedLinear with a 3-core BlockTT weight (bf16), dense plan: W rebuilt from the cores, one GEMM (+ bias);
+ *   backward: dx, the three core gradients (through an fp32 split-K dW) and the bias gradient.  transpose = 1: y = x W^T (the layer's
+ *   orientation, x has prod(cols) features), 0: y = x W.  Replaces: linear_blocktt (tltorch/functional/factorized_linear.py:39-60)
+ *   and its autograd.
+ * tlt_tucker_trl_*: Tucker tensor-regression layer with one output mode on (B, C, s_1..s_n) bf16 maps (n = 1..3; shapes accepted by
+ *   tlt_spatial_project_supported).  factors = [F_c (C, rc), F_s1 (s_1, q_1) .. F_sn, F_o (out, ro)], core (rc, q_1..q_n, ro).
+ *   Replaces: tucker_trl (tltorch/functional/tensor_regression.py:37-49) and its autograd.  side_stream (or NULL): a second stream
+ *   for the parameter-gradient branch of the backward pass.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+  tlt_blocktt3_desc tt;
+  int64_t batch;
+  int32_t transpose;
+  int32_t dtype_bias;              /* tlt_dtype of bias / dbias (ignored when NULL) */
+} tlt_blocktt3_linear_desc;
+size_t tlt_blocktt3_linear_workspace_size(const tlt_blocktt3_linear_desc* desc);
+size_t tlt_blocktt3_linear_grad_workspace_size(const tlt_blocktt3_linear_desc* desc);
+int tlt_blocktt3_linear_fwd(const tlt_blocktt3_linear_desc* desc, const void* x, const void* c1, const void* c2, const void* c3,
+                            const void* bias, void* ws, void* y, void* stream);
+int tlt_blocktt3_linear_bwd(const tlt_blocktt3_linear_desc* desc, const void* x, const void* dy, const void* ws, const void* c1,
+                            const void* c2, const void* c3, void* gws, void* dx, void* d1, void* d2, void* d3, void* dbias, void* stream);
+
+typedef struct {
+  int64_t batch, channels;
+  int32_t n_spatial;
+  int64_t spatial[3], spatial_rank[3];
+  int64_t rc, ro, out;             /* channel rank, output rank (<= 16), output features */
+} tlt_tucker_trl_desc;
+size_t tlt_tucker_trl_workspace_size(const tlt_tucker_trl_desc* desc);
+size_t tlt_tucker_trl_grad_workspace_size(const tlt_tucker_trl_desc* desc);
+int tlt_tucker_trl_fwd(const tlt_tucker_trl_desc* desc, const void* x, const void* core, const void* const* factors, const void* bias,
+                       void* ws, void* y, void* stream);
+int tlt_tucker_trl_bwd(const tlt_tucker_trl_desc* desc, const void* x, const void* dy, const void* core, const void* const* factors,
+                       const void* ws, void* gws, void* dx, void* dcore, void* const* d_factors, void* dbias, void* stream,
+                       void* side_stream);
+
 #ifdef __cplusplus
 }
 #endif

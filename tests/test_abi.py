@@ -37,7 +37,9 @@ def test_descriptor_structs_match_header_layout(tmp_path):
               ("tlt_conv_desc", _cuda.ConvDesc, ["dtype", "batch", "in_size", "kernel", "dilation"]),
               ("tlt_cplinear_desc", _cuda.CpLinearDesc, ["batch", "rank", "n_in", "n_out", "in_dims", "out_dims"]),
               ("tlt_cpconv_rows_desc", _cuda.CpConvRowsDesc, ["batch", "rank", "height", "stride"]),
-              ("tlt_trl_tail_desc", _cuda.TrlTailDesc, ["batch", "j", "rc", "ldz", "ro", "out"])]
+              ("tlt_trl_tail_desc", _cuda.TrlTailDesc, ["batch", "j", "rc", "ldz", "ro", "out"]),
+              ("tlt_blocktt3_linear_desc", _cuda.BlockTT3LinearDesc, ["tt", "batch", "transpose", "dtype_bias"]),
+              ("tlt_tucker_trl_desc", _cuda.TuckerTrlDesc, ["batch", "channels", "n_spatial", "spatial", "spatial_rank", "rc", "ro", "out"])]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{REPO}/include/tltorch_cuda.h"', "int main(){"]
     for cname, _, fields in probes:
         lines.append(f'printf("%zu\\n", sizeof({cname}));')

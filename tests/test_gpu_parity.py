@@ -1169,3 +1169,97 @@ def test_cp_linear_tensor_core_vs_oracle(in_shape, out_shape, rank, batch, bias)
     for a, b_, n in zip(grads, go, ["x"] + names):
         errs["d" + n] = G.rel_err(a, b_)
     _report(_tag(), errs, 1e-5)
+
+
+def _ws(nbytes):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev())
+
+
+@pytest.mark.parametrize("transpose,bias", [(True, True), (False, False)])
+def test_op_level_blocktt3_linear_matches_python_op(transpose, bias):
+    """tlt_blocktt3_linear_fwd / _bwd (one C call per direction, caller-owned workspaces: the entry points a non-Python host binds,
+    SURVEY 8(b)) give the same y / dx / core gradients / bias gradient as the torch_b200 op on BASELINE config 2's `up` layer shape
+    (reduced batch), i.e. as linear_blocktt (functional/factorized_linear.py:39-60) within the bf16 tolerance."""
+    import ctypes as C
+    from torch_b200 import _cuda, blocktt_ops
+    torch.manual_seed(3)
+    rows, cols, r = (8, 12, 32), (8, 8, 12), 16
+    c1 = (torch.randn(1, rows[0], cols[0], r, device=dev()) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    c2 = (torch.randn(r, rows[1], cols[1], r, device=dev()) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    c3 = (torch.randn(r, rows[2], cols[2], 1, device=dev()) * 0.3).to(torch.bfloat16).requires_grad_(True)
+    R, Cn = 8 * 12 * 32, 8 * 8 * 12
+    fin, fout = (Cn, R) if transpose else (R, Cn)
+    B = 384
+    x = torch.randn(B, fin, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    bv = torch.randn(fout, device=dev(), dtype=torch.bfloat16, requires_grad=True) if bias else None
+    y_ref = blocktt_ops.blocktt3_linear(x, c1, c2, c3, bv, transpose)
+    gy = torch.randn_like(y_ref)
+    g_ref = torch.autograd.grad(y_ref, [x, c1, c2, c3] + ([bv] if bias else []), gy)
+    d = _cuda.BlockTT3LinearDesc()
+    d.tt.dtype = _cuda.dtype_code(torch.bfloat16)
+    for k in range(3):
+        d.tt.rows[k], d.tt.cols[k] = rows[k], cols[k]
+    d.tt.rank1 = d.tt.rank2 = r
+    d.batch, d.transpose, d.dtype_bias = B, int(transpose), _cuda.dtype_code(torch.bfloat16)
+    lib = _cuda.lib()
+    ws, gws = _ws(lib.tlt_blocktt3_linear_workspace_size(C.byref(d))), _ws(lib.tlt_blocktt3_linear_grad_workspace_size(C.byref(d)))
+    y = torch.empty_like(y_ref)
+    st = _cuda.stream_ptr(x)
+    _cuda.check(lib.tlt_blocktt3_linear_fwd(C.byref(d), _cuda.ptr(x), _cuda.ptr(c1), _cuda.ptr(c2), _cuda.ptr(c3), _cuda.ptr(bv), _cuda.ptr(ws),
+                                            _cuda.ptr(y), st), "fwd")
+    dx, d1, d2, d3 = torch.empty_like(x), torch.empty_like(c1), torch.empty_like(c2), torch.empty_like(c3)
+    db = torch.empty(fout, device=dev(), dtype=torch.bfloat16) if bias else None
+    _cuda.check(lib.tlt_blocktt3_linear_bwd(C.byref(d), _cuda.ptr(x), _cuda.ptr(gy), _cuda.ptr(ws), _cuda.ptr(c1), _cuda.ptr(c2), _cuda.ptr(c3),
+                                            _cuda.ptr(gws), _cuda.ptr(dx), _cuda.ptr(d1), _cuda.ptr(d2), _cuda.ptr(d3), _cuda.ptr(db), st), "bwd")
+    torch.cuda.synchronize()
+    errs = {"y": G.rel_err(y, y_ref.double().cpu()), "dx": G.rel_err(dx, g_ref[0].double().cpu()), "d1": G.rel_err(d1, g_ref[1].double().cpu()),
+            "d2": G.rel_err(d2, g_ref[2].double().cpu()), "d3": G.rel_err(d3, g_ref[3].double().cpu())}
+    if bias:
+        errs["dbias"] = G.rel_err(db, g_ref[4].double().cpu())
+    _report(_tag(), errs, 1e-2)
+
+
+@pytest.mark.parametrize("spatial,sranks,side", [((7, 7), (4, 4), True), ((7, 7), (4, 3), False), ((4, 3, 2), (2, 2, 2), True), ((49,), (12,), False)])
+def test_op_level_tucker_trl_matches_python_op(spatial, sranks, side):
+    """tlt_tucker_trl_fwd / _bwd (a whole Tucker TRL per C call, optional second stream for the parameter-gradient branch) vs the
+    torch_b200 layer (tucker_trl, functional/tensor_regression.py:37-49): y, dx and every parameter gradient; 1, 2 and 3 spatial modes."""
+    import ctypes as C
+    import torch_b200 as tlt
+    from torch_b200 import _cuda
+    torch.manual_seed(len(spatial))
+    B, Cc, rc, ro, O = 64, 256, 24, 5, 40
+    layer = tlt.TRL((Cc,) + tuple(spatial), (O,), bias=True, factorization="tucker", rank=(rc,) + tuple(sranks) + (ro,), device=dev())
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.normal_(0, 0.3)
+    layer = layer.to(torch.bfloat16)
+    x = torch.randn(B, Cc, *spatial, device=dev(), dtype=torch.bfloat16, requires_grad=True)
+    y_ref = layer(x)
+    gy = torch.randn_like(y_ref)
+    names = [n for n, _ in layer.named_parameters()]
+    g_ref = dict(zip(["x"] + names, torch.autograd.grad(y_ref, [x] + list(layer.parameters()), gy)))
+    core, factors, bv = layer.weight.core.detach(), [f.detach().contiguous() for f in layer.weight.factors], layer.bias.detach()
+    d = _cuda.TuckerTrlDesc()
+    d.batch, d.channels, d.n_spatial, d.rc, d.ro, d.out = B, Cc, len(spatial), rc, ro, O
+    for k in range(len(spatial)):
+        d.spatial[k], d.spatial_rank[k] = spatial[k], sranks[k]
+    lib = _cuda.lib()
+    nws = lib.tlt_tucker_trl_workspace_size(C.byref(d))
+    assert nws > 0, "shape refused by the op-level entry point"
+    ws, gws = _ws(nws), _ws(lib.tlt_tucker_trl_grad_workspace_size(C.byref(d)))
+    fptr = (C.c_void_p * len(factors))(*[f.data_ptr() for f in factors])
+    y = torch.empty_like(y_ref)
+    st = _cuda.stream_ptr(x)
+    _cuda.check(lib.tlt_tucker_trl_fwd(C.byref(d), _cuda.ptr(x), _cuda.ptr(core), fptr, _cuda.ptr(bv), _cuda.ptr(ws), _cuda.ptr(y), st), "fwd")
+    dx, dcore, db = torch.empty_like(x), torch.empty_like(core), torch.empty_like(bv)
+    dfs = [torch.empty_like(f) for f in factors]
+    dptr = (C.c_void_p * len(dfs))(*[f.data_ptr() for f in dfs])
+    s2 = torch.cuda.Stream() if side else None
+    _cuda.check(lib.tlt_tucker_trl_bwd(C.byref(d), _cuda.ptr(x), _cuda.ptr(gy), _cuda.ptr(core), fptr, _cuda.ptr(ws), _cuda.ptr(gws), _cuda.ptr(dx),
+                                       _cuda.ptr(dcore), dptr, _cuda.ptr(db), st, C.c_void_p(s2.cuda_stream) if side else None), "bwd")
+    torch.cuda.synchronize()
+    errs = {"y": G.rel_err(y, y_ref.double().cpu()), "dx": G.rel_err(dx, g_ref["x"].double().cpu()),
+            "dcore": G.rel_err(dcore, g_ref["weight.core"].double().cpu()), "dbias": G.rel_err(db, g_ref["bias"].double().cpu())}
+    for k, f in enumerate(dfs):
+        errs[f"dfactor_{k}"] = G.rel_err(f, g_ref[f"weight.factors.factor_{k}"].double().cpu())
+    _report(_tag(), errs, 1e-2)

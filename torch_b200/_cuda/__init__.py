@@ -81,6 +81,15 @@ class CpLinearDesc(C.Structure):
                 ("in_dims", C.c_int64 * 4), ("out_dims", C.c_int64 * 4)]
 
 
+class BlockTT3LinearDesc(C.Structure):
+    _fields_ = [("tt", BlockTT3Desc), ("batch", C.c_int64), ("transpose", C.c_int32), ("dtype_bias", C.c_int32)]
+
+
+class TuckerTrlDesc(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("channels", C.c_int64), ("n_spatial", C.c_int32), ("spatial", C.c_int64 * 3),
+                ("spatial_rank", C.c_int64 * 3), ("rc", C.c_int64), ("ro", C.c_int64), ("out", C.c_int64)]
+
+
 class TrlTailDesc(C.Structure):
     _fields_ = [("batch", C.c_int64), ("j", C.c_int64), ("rc", C.c_int64), ("ldz", C.c_int64), ("ro", C.c_int64), ("out", C.c_int64)]
 
@@ -155,6 +164,15 @@ SYMBOLS = {
     "tlt_khatri_rao_split3": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_void_p), _vp, C.c_int32, _vp, C.c_int32,
                                         _vp, _vp]),
     "tlt_split3_bf16": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, _vp]),
+    "tlt_blocktt3_linear_workspace_size": (C.c_size_t, [C.POINTER(BlockTT3LinearDesc)]),
+    "tlt_blocktt3_linear_grad_workspace_size": (C.c_size_t, [C.POINTER(BlockTT3LinearDesc)]),
+    "tlt_blocktt3_linear_fwd": (C.c_int, [C.POINTER(BlockTT3LinearDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_blocktt3_linear_bwd": (C.c_int, [C.POINTER(BlockTT3LinearDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tlt_tucker_trl_workspace_size": (C.c_size_t, [C.POINTER(TuckerTrlDesc)]),
+    "tlt_tucker_trl_grad_workspace_size": (C.c_size_t, [C.POINTER(TuckerTrlDesc)]),
+    "tlt_tucker_trl_fwd": (C.c_int, [C.POINTER(TuckerTrlDesc), _vp, _vp, C.POINTER(C.c_void_p), _vp, _vp, _vp, _vp]),
+    "tlt_tucker_trl_bwd": (C.c_int, [C.POINTER(TuckerTrlDesc), _vp, _vp, _vp, C.POINTER(C.c_void_p), _vp, _vp, _vp, _vp,
+                                     C.POINTER(C.c_void_p), _vp, _vp, _vp]),
     "tlt_spatial_project_supported": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "tlt_spatial_project_fwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     "tlt_spatial_project_bwd": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.abspath(os.path.join(HERE, "..", "_cuda"))
 LIB = os.path.join(OUT_DIR, "libtltorch_cuda.so")
-SOURCES = ["api.cu", "contract.cu", "conv.cu", "gemm_tc.cu", "blocktt.cu", "dwconv.cu", "pointwise_tc.cu", "modedot.cu", "mmd16.cu", "rows.cu", "skinny.cu", "dwconv_rows.cu", "dwconv_tma.cu", "khatri_rao.cu", "dwsep_rows.cu", "dwsep_staged.cu", "cpchain.cu", "cplinear.cu", "trl_tail.cu", "split3.cu", "cpconv_rows.cu", "cpconv_rows2.cu", "spatial_project.cu"]
+SOURCES = ["api.cu", "contract.cu", "conv.cu", "gemm_tc.cu", "blocktt.cu", "dwconv.cu", "pointwise_tc.cu", "modedot.cu", "mmd16.cu", "rows.cu", "skinny.cu", "dwconv_rows.cu", "dwconv_tma.cu", "khatri_rao.cu", "dwsep_rows.cu", "dwsep_staged.cu", "cpchain.cu", "cplinear.cu", "trl_tail.cu", "split3.cu", "op_level.cu", "cpconv_rows.cu", "cpconv_rows2.cu", "spatial_project.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

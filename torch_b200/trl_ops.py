@@ -217,6 +217,8 @@ def _trl_fwd_op(x: torch.Tensor, core: torch.Tensor, factors: List[torch.Tensor]
     S = math.prod(x.shape[2:])
     dev, bf = x.device, x.dtype
     k, _ = _kron_chain(fs[1:-1])
+    if len(fs) == 3:
+        k = k.clone()                                                 # one spatial mode: k IS a factor; an op may not return an input
     J, rc = k.shape[1], fs[0].shape[1]
     t = torch.empty((b, J, c), dtype=bf, device=dev)
     spatial_ops._execute_spatial_fwd(x.reshape(b, c, S), k, t)
