@@ -19,6 +19,7 @@ import torch
 
 from . import _cuda
 from . import kr_ops
+from . import streams
 
 __all__ = ["cp_linear_tc", "eligible"]
 
@@ -74,24 +75,11 @@ def _kr_split(factors, weights, rows, R):
     return oc, orr
 
 
-_SIDE = {}
-
-
 def _fork(dev):
-    """(side stream waiting on the current stream, current stream) -- or (None, None) off the GPU / when branches are disabled"""
-    if dev.type != "cuda" or os.environ.get("TLT_CPLINEAR_BRANCHES", "1") == "0":
-        return None, None
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    _SIDE[key].wait_stream(main)
-    return _SIDE[key], main
+    return streams.fork(dev, "TLT_CPLINEAR_BRANCHES")
 
 
-def _join(side, main):
-    if side is not None:
-        main.wait_stream(side)
+_join = streams.join
 
 
 def _split(src, cols=False, rows=False, pat_cols=0, pat_rows=0):

@@ -2,6 +2,7 @@
 // cpconv_rows2.cu: the first separable pass folded into the stage-1 MMA).  sm_100a only.
 #pragma once
 #include "tc_common.cuh"
+#include "f32x2.cuh"
 
 namespace tlt {
 namespace cpr {
@@ -99,13 +100,7 @@ __device__ __forceinline__ void z_store8(uint32_t zbuf, int m, int r, const floa
 // ---- packed fp32 pairs -------------------------------------------------------------------------------------------------------
 // A three-register FFMA issues every other cycle per SM sub-partition on this part; fma.rn.f32x2 does two FMAs in the same slot.
 // Adjacent TMEM columns land in adjacent registers (tcgen05.ld .x8), so a pair of columns IS an aligned 64-bit register pair.
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f2 pku(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+using namespace tlt::f32x2;
 
 
 }  // namespace cpr

@@ -14,17 +14,12 @@
 //   unpacked columns rotating through an unrolled loop), shared-memory then global fp32 reductions; tlt_dwsep_rows_finalize
 //   turns dT into the gradients of kh, kw and lambda.
 #include "common.cuh"
+#include "f32x2.cuh"
 
 namespace tlt {
 namespace dws {
 
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f2 pku(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+using namespace tlt::f32x2;
 
 struct Geom {
   int batch, H, W, Ho, Wo, cpr;      // cpr = ld / 8 chunks per row

@@ -12,17 +12,12 @@
 //   thread = (16-byte channel chunk c, row r of the band, segment of SL columns): it keeps c for the whole kernel, so the nine
 //   weight-gradient sums of its 8 channels stay in registers across all bands of the block.
 #include "tc_common.cuh"
+#include "f32x2.cuh"
 
 namespace tlt {
 namespace dwst {
 
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f2 pku(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ float lo_of(f2 v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float hi_of(f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+using namespace tlt::f32x2;
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

@@ -526,15 +526,10 @@ def dwsep_eligible(factors, kernel, stride, padding, dilation, spatial):
 
 
 _BRANCHES = os.environ.get("TLT_CHAIN_BRANCHES", "1") != "0"
-_SIDE_STREAMS = {}
-
-
 def _side_stream(dev):
-    """One side stream per device for the weight-gradient branch of the chain's backward op."""
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
-    return _SIDE_STREAMS[key]
+    """The side stream of the weight-gradient branch of the chain's backward op (torch_b200/streams.py)."""
+    from . import streams
+    return streams.side_stream(dev)
 
 
 def _execute_chain_prep(c_in, c_out, rank, flip_d, f_in, f_out, kh, kw, lam, wp_in, wp_out, taps_f, taps_d):

@@ -15,6 +15,7 @@ from typing import List, Optional
 import torch
 
 from . import _cuda
+from . import streams
 
 __all__ = ["tucker_trl_fused", "eligible", "trl_tail"]
 
@@ -176,18 +177,8 @@ def eligible(x, weight, bias):
 # the whole fused route as ONE op per direction: every launch is issued here, so the backward pass can put the parameter gradients
 # (tail parameters, channel factor) on a side stream beside dt -> spatial backward -> Kronecker backward
 # =====================================================================================================================
-_SIDE = {}
-
-
 def _fork(dev):
-    if dev.type != "cuda" or os.environ.get("TLT_TRL_BRANCHES", "1") == "0":
-        return None, None
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    _SIDE[key].wait_stream(main)
-    return _SIDE[key], main
+    return streams.fork(dev, "TLT_TRL_BRANCHES")
 
 
 def _r8(v):
