@@ -55,10 +55,20 @@ __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ dw_
   float t[9];
 #pragma unroll
   for (int a = 0; a < 9; ++a) t[a] = 0.f;
+  // 5 x 9 independent loads in flight per thread (148 slabs = one trip): walked one slab at a time the block spent ~1 us of L2 latency
+  // per trip and the launch took 11 us inside the graph (gpurun_out/r4b/timeline.json)
   if (r < R)
-    for (int p = pl; p < parts; p += 32)
+    for (int p0 = pl; p0 < parts; p0 += 32 * 5) {
+      float v[5][9];
 #pragma unroll
-      for (int a = 0; a < 9; ++a) t[a] += dT[((size_t)p * 9 + a) * ld + r];
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int a = 0; a < 9; ++a) v[i][a] = p0 + 32 * i < parts ? __ldg(dT + ((size_t)(p0 + 32 * i) * 9 + a) * ld + r) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int a = 0; a < 9; ++a) t[a] += v[i][a];
+    }
 #pragma unroll
   for (int a = 0; a < 9; ++a) red[a][pl][ch] = t[a];
   __syncthreads();
@@ -118,7 +128,7 @@ extern "C" int tlt_cpchain_post(int64_t c_in, int64_t c_out, int64_t rank, const
   const int cin_p = r8(c_in), ld = r8(rank);
   const int tap_blocks = (int)((rank + 7) / 8);
   const long long elems = (long long)(c_in + c_out) * rank;
-  const int ew_blocks = (int)((elems + 255) / 256 < 592 ? (elems + 255) / 256 : 592);
+  const int ew_blocks = (int)((elems + 255) / 256 < 4736 ? (elems + 255) / 256 : 4736);     // one element per thread up to 1.2 M elements
   cpc::post_kernel<<<tap_blocks + ew_blocks, 256, 0, (cudaStream_t)stream>>>(dw_out, dw_in, acc, parts, (const __nv_bfloat16*)kh,
                                                                             (const __nv_bfloat16*)kw, (const __nv_bfloat16*)lam, (int)c_in,
                                                                             (int)c_out, (int)rank, cin_p, ld, tap_blocks,

@@ -308,10 +308,19 @@ __global__ void __launch_bounds__(256) dwsep_finalize_kernel(const float* __rest
   float t[9];
 #pragma unroll
   for (int a = 0; a < 9; ++a) t[a] = 0.f;
+  // 5 x 9 independent loads in flight per thread (see cpc::post_kernel)
   if (r < R)
-    for (int p = pl; p < parts; p += 32)
+    for (int p0 = pl; p0 < parts; p0 += 32 * 5) {
+      float v[5][9];
 #pragma unroll
-      for (int a = 0; a < 9; ++a) t[a] += dT[((size_t)p * 9 + a) * ld + r];
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int a = 0; a < 9; ++a) v[i][a] = p0 + 32 * i < parts ? __ldg(dT + ((size_t)(p0 + 32 * i) * 9 + a) * ld + r) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int a = 0; a < 9; ++a) t[a] += v[i][a];
+    }
 #pragma unroll
   for (int a = 0; a < 9; ++a) red[a][pl][ch] = t[a];
   __syncthreads();

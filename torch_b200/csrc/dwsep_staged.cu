@@ -13,6 +13,8 @@
 //   weight-gradient sums of its 8 channels stay in registers across all bands of the block.
 #include "tc_common.cuh"
 #include "f32x2.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace tlt {
 namespace dwst {
@@ -259,18 +261,34 @@ static bool plan(int batch, int H, int W, int ld, int S, bool wgrad, SGeom* g, i
   const long long row_bytes = (long long)W * ld * 2, grow_bytes = (long long)Wo * ld * 2;
   if (cpr > cap || row_bytes > 64 * 1024 || row_bytes % 16 || grow_bytes % 16) return false;
   const long long budget = 200 * 1024 - (wgrad ? 9LL * ld * 4 : 0) - 64;
-  // deepest ring first (4 stages, then 3, then 2), the tallest band that allows it
+  // The tallest band with at least two ring stages wins, measured over config 3's shapes (tools/sweep_bench.py, gpurun_out/r4c, r4d):
+  // a taller band re-reads fewer halo rows ((S (BR - 1) + 3) input rows per S BR), gives every thread a longer run of columns (two
+  // columns of a segment are recomputed halo) and keeps the block at the thread cap on narrow maps -- a 1-row band of a stride-2
+  // sweep ran 120 threads per SM (75 us at 56^2 against 41 us with 4-row bands).  Ragged last bands idle their threads, so bands that
+  // divide the map are preferred (7 rows at 28^2 / 14^2 / 7^2).  Then the deepest ring that still fits (2..4 stages).
   int BR = 0, nst = 0;
-  for (int want = 4; want >= 2 && !BR; --want)
-    for (int br = 4; br >= 1; --br) {
-      const long long stage = (S * (br - 1) + 3) * row_bytes + (wgrad ? br * grow_bytes : 0);
-      if (want * stage <= budget && cpr * br <= cap) { BR = br; nst = want; break; }
-    }
+  double best = 1e30;
+  for (int br = Ho < 8 ? Ho : 8; br >= 1; --br) {
+    const long long stage = (S * (br - 1) + 3) * row_bytes + (wgrad ? br * grow_bytes : 0);
+    if (2 * stage > budget || cpr * br > cap) continue;
+    const int nb = (Ho + br - 1) / br;
+    const double score = (double)(nb * br) / Ho * (double)(S * (br - 1) + 3) / (S * br);
+    if (score < best - 1e-9) { best = score; BR = br; nst = (int)(budget / stage < 4 ? budget / stage : 4); }
+  }
   if (!BR) return false;
+  // development switches (tools/sweep_bench.py): band height / ring depth / minimum segment length of the plan
+  int min_sl = 3;
+  if (const char* e = getenv("TLT_DWST_PLAN")) {
+    int br = 0, ns = 0, sl = 0;
+    if (sscanf(e, "%d,%d,%d", &br, &ns, &sl) == 3 && br >= 1 && ns >= 2 && ns <= 4 && sl >= 1 && cpr * br <= cap &&
+        (long long)ns * ((S * (br - 1) + 3) * row_bytes + (wgrad ? br * grow_bytes : 0)) <= budget) {
+      BR = br; nst = ns; min_sl = sl;
+    }
+  }
   // segments: as many threads as the cap allows, at least 3 columns per segment (two columns of every segment are recomputed halo)
   const int max_seg = cap / (cpr * BR);
   int SL = (Wo + max_seg - 1) / max_seg;
-  if (SL < 3) SL = Wo < 3 ? Wo : 3;
+  if (SL < min_sl) SL = Wo < min_sl ? Wo : min_sl;
   const int nseg = (Wo + SL - 1) / SL;
   g->batch = batch; g->H = H; g->W = W; g->cpr = cpr;
   g->S = S; g->Ho = Ho; g->Wo = Wo; g->grow_bytes = (uint32_t)grow_bytes;
