@@ -37,7 +37,10 @@ def main():
         calls = {"fwd": lambda: rows_ops._execute_dwsep("fwd", z, taps, y, B, hw, hw, s),
                  "dgrad": lambda: rows_ops._execute_dwsep("dgrad", g, taps, dz, B, hw, hw, s),
                  "wgrad": lambda: rows_ops._execute_dwsep("wgrad", z, g, acc, B, hw, hw, s)}
-        mb = {"fwd": (z.numel() + g.numel()) * 2 / 1e6, "dgrad": (z.numel() + g.numel()) * 2 / 1e6, "wgrad": (z.numel() + g.numel()) * 2 / 1e6}
+        dw = torch.zeros(9, ld, device=dev, dtype=torch.float32)
+        calls["tile_wgrad"] = lambda: rows_ops._execute_dwconv_rows("wgrad", z, g, dw, B, [hw, hw], [ho, ho], [3, 3], [s, s], [1, 1], [1, 1])
+        calls["tile_fwd"] = lambda: rows_ops._execute_dwconv_rows("fwd", z, torch.randn(9, ld, device=dev, dtype=torch.bfloat16), y, B, [hw, hw], [ho, ho], [3, 3], [s, s], [1, 1], [1, 1])
+        mb = {"tile_wgrad": (z.numel() + g.numel()) * 2 / 1e6, "tile_fwd": (z.numel() + g.numel()) * 2 / 1e6, "fwd": (z.numel() + g.numel()) * 2 / 1e6, "dgrad": (z.numel() + g.numel()) * 2 / 1e6, "wgrad": (z.numel() + g.numel()) * 2 / 1e6}
         ref = {}
         for plan in [""] + args.plans:
             if plan:
@@ -61,6 +64,9 @@ def main():
                 us = t / args.reps * 1e3
                 out[kind + "_us"] = round(us, 1)
                 out[kind + "_gbs"] = round(mb[kind] / us * 1e3)
+                if kind == "tile_wgrad":
+                    dw.zero_(); fn(); torch.cuda.synchronize()
+                    out["tile_wgrad_maxdiff_vs_staged"] = float((dw - ref["wgrad"]).abs().max() / ref["wgrad"].abs().max()) if "wgrad" in ref else None
                 if kind == "wgrad":
                     if not plan:
                         ref["wgrad"] = acc.sum(0).clone()
