@@ -20,8 +20,13 @@ import bench
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=256)
+    ap.add_argument("--config", default="3", help="3 (headline) or a key of bench.other_configs: 1, 2, 4-conv, 4-conv+dropout, 4-TRL, 5-tucker, 5-blocktt")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    if args.config != "3":
+        c = bench.other_configs(dev)[args.config]()
+        step = bench._fwd_bwd_step(c["layers"], c["x"])[0]
+        return timeline(step)
     torch.manual_seed(1234)
     convs = []
     for cin, cout, hw, s in bench.RESNET18:
@@ -42,6 +47,10 @@ def main():
             a = c(a)
         a.backward(gy)
 
+    timeline(step)
+
+
+def timeline(step):
     run, mode, launches, graphed = bench.time_graph(step, 5, 3)
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
