@@ -43,10 +43,21 @@ __global__ void __launch_bounds__(256) post_kernel(const float* __restrict__ dw_
                                                    __nv_bfloat16* __restrict__ g_lam) {
   __shared__ float red[9][32][8];
   if ((int)blockIdx.x >= tap_blocks) {
-    const int n_out = c_out * R, n_in = c_in * R;
-    for (int i = (blockIdx.x - tap_blocks) * blockDim.x + threadIdx.x; i < n_out + n_in; i += (gridDim.x - tap_blocks) * blockDim.x) {
-      if (i < n_out) { const int c = i / R, r = i - c * R; g_fout[i] = __float2bfloat16_rn(dw_out[(size_t)c * ld + r]); }
-      else { const int j = i - n_out, c = j / R, r = j - c * R; g_fin[j] = __float2bfloat16_rn(dw_in[(size_t)c * ld + r]); }
+    // a thread converts 8 consecutive rank entries of one row: two 16-byte loads, eight 2-byte stores (rows of the (C, R) gradients
+    // start at odd element offsets when R is odd); neighbouring threads cover neighbouring 16-byte spans
+    const int cpr = ld >> 3, total = (c_out + c_in) * cpr;
+    for (int i = (blockIdx.x - tap_blocks) * blockDim.x + threadIdx.x; i < total; i += (gridDim.x - tap_blocks) * blockDim.x) {
+      int row = i / cpr;
+      const int r0 = (i - row * cpr) * 8;
+      const float* src;
+      __nv_bfloat16* dst;
+      if (row < c_out) { src = dw_out + (size_t)row * ld + r0; dst = g_fout + (size_t)row * R + r0; }
+      else { row -= c_out; src = dw_in + (size_t)row * ld + r0; dst = g_fin + (size_t)row * R + r0; }
+      const float4 a = __ldg((const float4*)src), b = __ldg((const float4*)src + 1);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (r0 + e < R) dst[e] = __float2bfloat16_rn(v[e]);
     }
     return;
   }
@@ -127,8 +138,8 @@ extern "C" int tlt_cpchain_post(int64_t c_in, int64_t c_out, int64_t rank, const
               g_kw && g_lam, "tlt_cpchain_post: bad arguments");
   const int cin_p = r8(c_in), ld = r8(rank);
   const int tap_blocks = (int)((rank + 7) / 8);
-  const long long elems = (long long)(c_in + c_out) * rank;
-  const int ew_blocks = (int)((elems + 255) / 256 < 4736 ? (elems + 255) / 256 : 4736);     // one element per thread up to 1.2 M elements
+  const long long vecs = (long long)(c_in + c_out) * (ld / 8);
+  const int ew_blocks = (int)((vecs + 255) / 256 < 592 ? (vecs + 255) / 256 : 592);
   cpc::post_kernel<<<tap_blocks + ew_blocks, 256, 0, (cudaStream_t)stream>>>(dw_out, dw_in, acc, parts, (const __nv_bfloat16*)kh,
                                                                             (const __nv_bfloat16*)kw, (const __nv_bfloat16*)lam, (int)c_in,
                                                                             (int)c_out, (int)rank, cin_p, ld, tap_blocks,
