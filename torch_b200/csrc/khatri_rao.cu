@@ -92,30 +92,117 @@ __global__ void __launch_bounds__(128) khatri_rao_bwd_all_kernel(const KrParams 
   const int per_split = (others + gridDim.z - 1) / gridDim.z;
   const int o0 = blockIdx.z * per_split, o1 = min(others, o0 + per_split);
   if (o0 >= o1) return;
-  float acc = 0.f;
-  for (int o = o0; o < o1; ++o) {
-    int rem = o, row = 0, mul = 1;
-    float v = 1.f;
+  // the other indices of row o0 are decoded once and then counted up (last factor fastest); a factor entry is re-read only when
+  // its index moves.  Decoding every row with two runtime divisions made this launch 30 us at BASELINE config 1 (3.6 M terms).
+  int idx[4], mul[4];
+  float fv[4];
+  {
+    int rem = o0, m = 1;
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
+      idx[j] = 0; mul[j] = 0; fv[j] = 1.f;
       if (j < p.n) {
-        int i;
-        if (j == k) i = ik;
+        mul[j] = m;
+        m *= p.dims[j];
+        if (j == k) idx[j] = ik;
         else {
           const int q = rem / p.dims[j];
-          i = rem - q * p.dims[j];
+          idx[j] = rem - q * p.dims[j];
           rem = q;
-          v *= to_f32<T>(static_cast<const T*>(p.f[j])[(long long)i * p.R + r]);
+          fv[j] = to_f32<T>(static_cast<const T*>(p.f[j])[(long long)idx[j] * p.R + r]);
         }
-        row += i * mul;
-        mul *= p.dims[j];
       }
     }
-    acc = fmaf(to_f32<T>(g[(long long)row * p.ldg + r]), v, acc);
+  }
+  float acc = 0.f;
+  for (int o = o0; o < o1; ++o) {
+    const int row = idx[0] * mul[0] + idx[1] * mul[1] + idx[2] * mul[2] + idx[3] * mul[3];
+    acc = fmaf(to_f32<T>(g[(long long)row * p.ldg + r]), (fv[0] * fv[1]) * (fv[2] * fv[3]), acc);
+    bool carry = true;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      if (j < p.n && j != k && carry) {
+        if (++idx[j] == p.dims[j]) idx[j] = 0; else carry = false;
+        fv[j] = to_f32<T>(static_cast<const T*>(p.f[j])[(long long)idx[j] * p.R + r]);
+      }
+    }
   }
   const float wr = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
   atomicAdd(out.dF[k] + (long long)ik * p.R + r, wr * acc);
   if (k == 0 && dw != nullptr) atomicAdd(dw + r, acc * to_f32<T>(static_cast<const T*>(p.f[0])[(long long)ik * p.R + r]));
+}
+
+// The same gradients in ONE pass over g: a thread owns a rank column r and a run of PREFIXES (the index tuple of all factors but the
+// last); per prefix it loads the d_last entries of g that share it (independent loads, all in flight), keeps the last factor's
+// column and its gradient in registers, and carries one running sum per earlier factor that is flushed (one atomic) when that
+// factor's index moves.  g is read once instead of once per factor, and nothing is decoded by division inside the loop: 30 -> ~5 us
+// per launch at BASELINE config 1 (dims (4, 8, 16), R = 2341).  Last dimensions above MAXD keep the kernel above.
+template <typename T, int MAXD>
+__global__ void __launch_bounds__(128) khatri_rao_bwd_fused_kernel(const KrParams p, const T* __restrict__ g, const KrGrads out,
+                                                                   float* __restrict__ dw, int prefixes, int per_split) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.R) return;
+  const int n = p.n, dl = p.dims[n - 1];
+  const int o0 = blockIdx.y * per_split, o1 = min(prefixes, o0 + per_split);
+  if (o0 >= o1) return;
+  const float wr = p.w ? to_f32<T>(static_cast<const T*>(p.w)[r]) : 1.f;
+  const T* fl_ptr = static_cast<const T*>(p.f[n - 1]) + r;
+  float fl[MAXD], dlast[MAXD];
+#pragma unroll
+  for (int i = 0; i < MAXD; ++i) { fl[i] = i < dl ? to_f32<T>(fl_ptr[(long long)i * p.R]) : 0.f; dlast[i] = 0.f; }
+  int idx[3] = {0, 0, 0};
+  float fv[3] = {1.f, 1.f, 1.f}, acc[3] = {0.f, 0.f, 0.f};
+  {
+    int rem = o0;
+#pragma unroll
+    for (int j = 2; j >= 0; --j)
+      if (j < n - 1) {
+        const int q = rem / p.dims[j];
+        idx[j] = rem - q * p.dims[j];
+        rem = q;
+        fv[j] = to_f32<T>(static_cast<const T*>(p.f[j])[(long long)idx[j] * p.R + r]);
+      }
+  }
+  auto flush = [&](int j) {
+    if (out.dF[j]) atomicAdd(out.dF[j] + (long long)idx[j] * p.R + r, wr * acc[j]);
+    if (j == 0 && dw) atomicAdd(dw + r, acc[0] * fv[0]);
+    acc[j] = 0.f;
+  };
+  for (int o = o0; o < o1; ++o) {
+    const T* gp = g + (long long)o * dl * p.ldg + r;
+    float gv[MAXD];
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) gv[i] = i < dl ? to_f32<T>(gp[(long long)i * p.ldg]) : 0.f;
+    const float pre = fv[0] * fv[1] * fv[2];
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) { t = fmaf(gv[i], fl[i], t); dlast[i] = fmaf(gv[i], pre, dlast[i]); }
+    acc[0] = fmaf(t, fv[1] * fv[2], acc[0]);
+    acc[1] = fmaf(t, fv[0] * fv[2], acc[1]);
+    acc[2] = fmaf(t, fv[0] * fv[1], acc[2]);
+    const bool last = o + 1 == o1;
+    bool carry = true;
+#pragma unroll
+    for (int j = 2; j >= 0; --j)
+      if (j < n - 1 && (carry || last)) {
+        flush(j);
+        if (carry) {
+          if (++idx[j] == p.dims[j]) idx[j] = 0; else carry = false;
+          if (!last) fv[j] = to_f32<T>(static_cast<const T*>(p.f[j])[(long long)idx[j] * p.R + r]);
+        }
+      }
+  }
+  if (out.dF[n - 1]) {
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i)
+      if (i < dl) atomicAdd(out.dF[n - 1] + (long long)i * p.R + r, wr * dlast[i]);
+  }
+  if (n == 1 && dw) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXD; ++i) sacc = fmaf(dlast[i], fl[i], sacc);
+    atomicAdd(dw + r, sacc);
+  }
 }
 
 // Khatri-Rao product written directly as 3-way bf16 split operands (see split3.cu): no fp32 matrix in between.
@@ -265,6 +352,24 @@ extern "C" int tlt_khatri_rao_bwd_all(int32_t dtype, int32_t n, const int64_t* d
       if (p.rows / p.dims[k] < min_others) min_others = p.rows / p.dims[k];
       if (dF[k]) TLT_CHECK_CUDA(cudaMemsetAsync(dF[k], 0, (size_t)p.dims[k] * p.R * sizeof(float), st));
     }
+  }
+  const long long bxf = (p.R + 127) / 128;
+  if (p.dims[n - 1] <= 32) {      // one pass over g (khatri_rao_bwd_fused_kernel)
+    const long long prefixes = p.rows / p.dims[n - 1];
+    long long fs = 148 / bxf;                                          // about one 128-thread block per SM: runs of prefixes stay
+    if (fs < 1) fs = 1;                                               // long, so the atomics per loaded entry stay few
+    if (fs > prefixes) fs = prefixes;
+    const int per_split = (int)((prefixes + fs - 1) / fs);
+    dim3 gridf((unsigned)bxf, (unsigned)((prefixes + per_split - 1) / per_split));
+    const bool small = p.dims[n - 1] <= 16;
+    if (dtype == TLT_BF16) {
+      if (small) khatri_rao_bwd_fused_kernel<__nv_bfloat16, 16><<<gridf, 128, 0, st>>>(p, (const __nv_bfloat16*)g, out, dweights, (int)prefixes, per_split);
+      else khatri_rao_bwd_fused_kernel<__nv_bfloat16, 32><<<gridf, 128, 0, st>>>(p, (const __nv_bfloat16*)g, out, dweights, (int)prefixes, per_split);
+    } else {
+      if (small) khatri_rao_bwd_fused_kernel<float, 16><<<gridf, 128, 0, st>>>(p, (const float*)g, out, dweights, (int)prefixes, per_split);
+      else khatri_rao_bwd_fused_kernel<float, 32><<<gridf, 128, 0, st>>>(p, (const float*)g, out, dweights, (int)prefixes, per_split);
+    }
+    return check_launch("khatri_rao_bwd_fused_kernel");
   }
   TLT_REQUIRE(ysum <= 65535, "tlt_khatri_rao_bwd_all: too many factor rows");
   const long long bx = (p.R + 127) / 128;
