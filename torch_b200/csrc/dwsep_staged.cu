@@ -49,6 +49,7 @@ struct SGeom {
   int BR, SL, NSEG, bands;        // band rows, segment length, segments per row, bands per image
   int units;                      // batch * bands
   int nst;                        // stages of the band ring (2..4)
+  int red;                        // weight gradient: the ring is large enough for the [slots][9][ld] block reduction
   uint32_t row_bytes;             // W * ld * 2
   uint32_t z_stage, g_stage;      // bytes of one stage of the input slab ((BR + 2) rows) / of the second operand's slab (BR rows)
 };
@@ -238,18 +239,42 @@ dwsep_staged_kernel(const SGeom g, const char* __restrict__ src, const char* __r
     }
   }
   if (WGRAD) {
-    if (lane_ok) {
-#pragma unroll
-      for (int a = 0; a < 9; ++a)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          atomicAdd(sacc + a * ld + c * 8 + 2 * i, lo_of(dT[a][i]));
-          atomicAdd(sacc + a * ld + c * 8 + 2 * i + 1, hi_of(dT[a][i]));
-        }
-    }
-    __syncthreads();
     float* out = part + (size_t)blockIdx.x * 9 * ld;
-    for (int i = tid; i < 9 * ld; i += blockDim.x) out[i] = sacc[i];
+    if (g.red) {
+      // block reduction through the (now idle) band ring: every thread stores its 72 sums as plain 16-byte stores, [slot][9][ld], then
+      // thread i adds the slots of entry i.  The 72 fp32 shared-memory atomics per thread this replaces are compare-and-swap loops:
+      // they were most of the ~17 us this launch cost at ANY batch size (tools/sweep_bench.py --batch 32 .. 512)
+      __syncthreads();                                                 // the last band has been consumed by everybody
+      float4* red = reinterpret_cast<float4*>(smem);
+      if (lane_ok) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          float4* dst = red + ((size_t)(slot * 9 + a) * ld + c * 8) / 4;
+          dst[0] = make_float4(lo_of(dT[a][0]), hi_of(dT[a][0]), lo_of(dT[a][1]), hi_of(dT[a][1]));
+          dst[1] = make_float4(lo_of(dT[a][2]), hi_of(dT[a][2]), lo_of(dT[a][3]), hi_of(dT[a][3]));
+        }
+      }
+      __syncthreads();
+      const float* rf = reinterpret_cast<const float*>(smem);
+      const int slots = g.BR * g.NSEG, n = 9 * ld;
+      for (int i = tid; i < n; i += blockDim.x) {
+        float sum = 0.f;
+        for (int sl = 0; sl < slots; ++sl) sum += rf[(size_t)sl * n + i];
+        out[i] = sum;
+      }
+    } else {
+      if (lane_ok) {
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            atomicAdd(sacc + a * ld + c * 8 + 2 * i, lo_of(dT[a][i]));
+            atomicAdd(sacc + a * ld + c * 8 + 2 * i + 1, hi_of(dT[a][i]));
+          }
+      }
+      __syncthreads();
+      for (int i = tid; i < 9 * ld; i += blockDim.x) out[i] = sacc[i];
+    }
   }
 }
 
@@ -299,6 +324,7 @@ static bool plan(int batch, int H, int W, int ld, int S, bool wgrad, SGeom* g, i
   g->row_bytes = (uint32_t)row_bytes;
   g->z_stage = (uint32_t)((S * (BR - 1) + 3) * row_bytes);
   g->g_stage = (uint32_t)(BR * grow_bytes);
+  g->red = wgrad && (long long)BR * nseg * 9 * ld * 4 <= (long long)nst * ((long long)g->z_stage + g->g_stage) ? 1 : 0;
   *threads = (cpr * BR * nseg + 31) / 32 * 32;
   *smem = (size_t)nst * ((size_t)g->z_stage + (wgrad ? g->g_stage : 0)) + 32 + (wgrad ? (size_t)9 * ld * 4 : 0);
   return true;
