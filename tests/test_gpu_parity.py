@@ -1007,6 +1007,39 @@ def test_khatri_rao_kernels_vs_fp64(dims, R, with_w, dtype):
         assert G.rel_err(a, b) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dims,R,with_w,pad", [((4, 8, 16), 2341, True, 3), ((4, 8, 16), 2341, False, 0), ((5,), 130, True, 0), ((3, 20), 77, True, 1),
+                                               ((2, 3, 4, 5), 17, True, 0), ((6, 40), 65, True, 0), ((7, 3, 32), 200, False, 8)])
+def test_khatri_rao_all_gradients_one_launch_vs_fp64(dims, R, with_w, pad, dtype):
+    """tlt_khatri_rao_bwd_all: every factor gradient and the weight gradient of one Khatri-Rao product in one launch, g at a
+    leading dimension >= R -- the one-pass kernel (last dimension <= 16 / <= 32: register tiles of 16 / 32) and the per-factor kernel
+    behind it (last dimension 40), against fp64 autograd of the einsum (factorized_tensordot.py:70-103 evaluates exactly this product)."""
+    from torch_b200 import cplinear_tc_ops as ct
+    torch.manual_seed(R + len(dims))
+    fs = [(torch.randn(d, R, device=dev()) * 0.7).to(dtype) for d in dims]
+    w = torch.rand(R, device=dev()).add(0.5).to(dtype) if with_w else None
+    rows = 1
+    for d in dims:
+        rows *= d
+    ldg = R + pad
+    g = torch.randn(rows, ldg, device=dev()).to(dtype)
+    dfs = [torch.full((d, R), 7.0, device=dev()) for d in dims]          # the call zeroes them itself
+    dw = torch.zeros(R, device=dev()) if with_w else None
+    ct._execute_kr_bwd_ld(fs, w, g, ldg, dfs, dw)
+    fo = [f.double().cpu().requires_grad_(True) for f in fs]
+    wo = w.double().cpu().requires_grad_(True) if with_w else None
+    L = "abcd"[:len(dims)]
+    ref = torch.einsum(",".join(l + "r" for l in L) + "->" + L + "r", *fo)
+    if with_w:
+        ref = ref * wo
+    go = torch.autograd.grad(ref.reshape(rows, R), fo + ([wo] if with_w else []), g[:, :R].double().cpu())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    errs = {f"dF{k}": G.rel_err(a, b) for k, (a, b) in enumerate(zip(dfs, go))}
+    if with_w:
+        errs["dw"] = G.rel_err(dw, go[-1])
+    _report(_tag(), errs, tol)
+
+
 # ------------------------------------------------------------------------------------------------- CP / TT tensor dropout on the GPU
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("training", [True, False])
