@@ -200,8 +200,9 @@ def bind_to_gpu_numa_node(index):
 # =====================================================================================================================
 # generic timing helpers
 # =====================================================================================================================
-def time_graph(step, steps, warmup, eager=False):
-    """(ms per step, mode, runner, launches per step): warm-up, capture into a CUDA graph, CUDA-event timing of `steps` replays."""
+def time_graph(step, steps, warmup, eager=False, results=None):
+    """(runner, mode, launches per step, graph): warm-up, capture into a CUDA graph.  `results`: see GraphedStep (the graph's own
+    result buffers, snapshotted at capture time -> graph.results)."""
     import torch
     from torch_b200 import ops
     for _ in range(max(warmup, 3)):
@@ -214,7 +215,7 @@ def time_graph(step, steps, warmup, eager=False):
     if not eager:
         try:
             from torch_b200.graphs import GraphedStep
-            graphed = GraphedStep(step)
+            graphed = GraphedStep(step, results=results)
             run, mode = graphed.replay, "cuda_graph"
         except Exception as exc:
             print(f"bench.py: CUDA-graph capture failed ({exc!r}); running eagerly", file=sys.stderr)
@@ -256,8 +257,38 @@ def profile_entry_points(step, reps=2):
     return out
 
 
-def time_e2e(dev_inputs, run, outputs, steps, world, dist):
-    """Host (pinned) buffers in and out through torch_b200.pipeline.HostPipelinedStep; every copy inside the timed region."""
+def graph_outputs(graphed):
+    """-> outputs() for a captured step: [input gradient, every parameter gradient flattened into ONE persistent buffer], read from the
+    graph's own result buffers (graphed.results = [x.grad, p.grad ...] at capture time)."""
+    import torch
+    res = graphed.results
+    flat = torch.cat([g.reshape(-1) for g in res[1:]])
+
+    def outputs():
+        torch.cat([g.reshape(-1) for g in res[1:]], out=flat)
+        return [res[0], flat]
+    return outputs
+
+
+def second_replica(make_step, inputs, params):
+    """The same step captured a second time on clones of its static inputs: with two copies the host pipeline needs no staging passes
+    (HostPipelinedStep(replicas=...)).  -> (inputs, replay, outputs) or None when the capture fails."""
+    import torch
+    from torch_b200.graphs import GraphedStep
+    try:
+        x2 = inputs[0].detach().clone().requires_grad_(True)
+        rest = [t.detach().clone() for t in inputs[1:]]
+        g2 = GraphedStep(make_step(x2, *rest), results=lambda: [x2.grad] + [p.grad for p in params])
+        return ([x2] + rest, g2.replay, graph_outputs(g2), g2)
+    except Exception as exc:
+        print(f"bench.py: second graph replica failed ({exc!r}); e2e keeps the staging copies", file=sys.stderr)
+        torch.cuda.synchronize()
+        return None
+
+
+def time_e2e(dev_inputs, run, outputs, steps, world, dist, replicas=None):
+    """Host (pinned) buffers in and out through torch_b200.pipeline.HostPipelinedStep; every copy inside the timed region.
+    replicas: [(static inputs, replay, outputs), ...] -- one captured copy of the step per pipeline slot (no staging copies)."""
     import torch
     from torch_b200.pipeline import HostPipelinedStep
     def pinned_like(t, fill):           # same strides as the device tensor (channels-last stays channels-last): plain byte copies
@@ -266,7 +297,7 @@ def time_e2e(dev_inputs, run, outputs, steps, world, dist):
     host_in = [pinned_like(t, True) for t in dev_inputs]
     outs = outputs()
     host_out = [pinned_like(o, False) for o in outs]
-    pipe = HostPipelinedStep(dev_inputs, run, outputs)
+    pipe = HostPipelinedStep(dev_inputs, run, outputs, replicas=replicas)
     for _ in range(3):
         pipe.submit(host_in, host_out)
     pipe.drain()
@@ -306,10 +337,10 @@ def roofline_of(bound, alg_bytes, alg_flops, ms, peaks, peak_src, timed_alone=Fa
 # =====================================================================================================================
 # the other BASELINE configs (N = 1 only): name, builder -> (layers, x, samples, bound, bytes, flops, cpu maker)
 # =====================================================================================================================
-def _fwd_bwd_step(layers, x):
+def _fwd_bwd_step(layers, x, gy=None):
     import torch
     params = [p for l in layers for p in l.parameters()]
-    holder = {}
+    holder = {} if gy is None else {"gy": gy}
 
     def step():
         x.grad = None
@@ -458,8 +489,10 @@ def run_other_configs(args, dev, peaks, peak_src, which):
         t_start = time.time()
         try:
             c = make()
-            step, outputs, holder, _ = _fwd_bwd_step(c["layers"], c["x"])
-            run, mode, launches, graphed = time_graph(step, args.steps, args.warmup, args.eager)
+            step, outputs, holder, cparams = _fwd_bwd_step(c["layers"], c["x"])
+            cx = c["x"]
+            run, mode, launches, graphed = time_graph(step, args.steps, args.warmup, args.eager,
+                                                      results=lambda: [cx.grad] + [p.grad for p in cparams])
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.steps):
@@ -472,8 +505,17 @@ def run_other_configs(args, dev, peaks, peak_src, which):
                      "roofline": roofline_of(c["bound"], c["bytes"], c["flops"], ms, peaks, peak_src),
                      "l2": "working set per step > 126 MB L2" if c["bytes"] > 2.5e8 else "working set fits L2: warm-L2 number (as in training)"}
             if not args.skip_extras:
-                e2e_ms, h2d, d2h = time_e2e([c["x"], holder["gy"]], run, outputs, max(5, min(args.steps, 15)), 1, None)
-                entry["e2e"] = {"value": c["samples"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+                replicas, second = None, None
+                if graphed is not None:      # two captured copies of the step: host copies land in / leave from a copy's own buffers
+                    outputs = graph_outputs(graphed)
+                    layers = c["layers"]
+                    second = second_replica(lambda x2, gy2: _fwd_bwd_step(layers, x2, gy2)[0], [c["x"], holder["gy"]], cparams)
+                    if second is not None:
+                        replicas = [([c["x"], holder["gy"]], run, outputs), second[:3]]
+                e2e_ms, h2d, d2h = time_e2e([c["x"], holder["gy"]], run, outputs, max(5, min(args.steps, 15)), 1, None, replicas)
+                entry["e2e"] = {"value": c["samples"] / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                "staging_copies": replicas is None}
+                del replicas, second
                 entry["cpu_baseline"] = cpu_baseline(c["cpu"])
             out.append(entry)
             del c, step, outputs, holder, run, graphed
@@ -539,38 +581,42 @@ def run_ours(args):
         for g in sorted(set(STAGE_OF)):
             buckets.append(GradientBucket([p for i, c in enumerate(convs) if STAGE_OF[i] == g for p in c.parameters()]))
 
-    def step():
-        x.grad = None
-        for p in params:
-            p.grad = None
-        acts = [x]
-        for c in convs:
-            acts.append(c(acts[-1]))
-        if world == 1:
-            acts[-1].backward(gy)
-            return
-        if args.exchange == "tail":
-            # one flat bucket, all-reduced after the whole backward: the compute kernels are persistent (one CTA per SM), so an
-            # all-reduce running beside them takes SMs away and stretches every kernel it overlaps
-            acts[-1].backward(gy)
-            buckets[0].allreduce()
-            return
-        # backward stage by stage (last stage first); a stage's bucket is all-reduced asynchronously as soon as its gradients
-        # are final, so the exchange overlaps the backward of the earlier stages (one NCCL call per stage, 4 per step)
-        g_out, works = gy, []
-        for grp in sorted(set(STAGE_OF), reverse=True):
-            first = STAGE_OF.index(grp)
-            last = len(STAGE_OF) - 1 - STAGE_OF[::-1].index(grp)
-            inp = acts[first]
-            stage_params = [p for i in range(first, last + 1) for p in convs[i].parameters()]
-            grads = torch.autograd.grad(acts[last + 1], [inp] + stage_params, g_out, retain_graph=False)
-            for p, g in zip(stage_params, grads[1:]):
-                p.grad = g
-            g_out = grads[0]
-            works.append((buckets[grp], buckets[grp].allreduce_async()))
-        x.grad = g_out
-        for b, w in works:
-            b.finish(w)
+    def make_step(x, gy):          # the step as a closure over ITS static inputs (a second copy is captured for the e2e pipeline)
+        def step():
+            x.grad = None
+            for p in params:
+                p.grad = None
+            acts = [x]
+            for c in convs:
+                acts.append(c(acts[-1]))
+            if world == 1:
+                acts[-1].backward(gy)
+                return
+            if args.exchange == "tail":
+                # one flat bucket, all-reduced after the whole backward: the compute kernels are persistent (one CTA per SM), so an
+                # all-reduce running beside them takes SMs away and stretches every kernel it overlaps
+                acts[-1].backward(gy)
+                buckets[0].allreduce()
+                return
+            # backward stage by stage (last stage first); a stage's bucket is all-reduced asynchronously as soon as its gradients
+            # are final, so the exchange overlaps the backward of the earlier stages (one NCCL call per stage, 4 per step)
+            g_out, works = gy, []
+            for grp in sorted(set(STAGE_OF), reverse=True):
+                first = STAGE_OF.index(grp)
+                last = len(STAGE_OF) - 1 - STAGE_OF[::-1].index(grp)
+                inp = acts[first]
+                stage_params = [p for i in range(first, last + 1) for p in convs[i].parameters()]
+                grads = torch.autograd.grad(acts[last + 1], [inp] + stage_params, g_out, retain_graph=False)
+                for p, g in zip(stage_params, grads[1:]):
+                    p.grad = g
+                g_out = grads[0]
+                works.append((buckets[grp], buckets[grp].allreduce_async()))
+            x.grad = g_out
+            for b, w in works:
+                b.finish(w)
+        return step
+
+    step = make_step(x, gy)
 
     def barrier():
         torch.cuda.synchronize()
@@ -578,7 +624,8 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    run_step, mode, launches_per_step, graphed = time_graph(step, args.steps, args.warmup, args.eager)
+    run_step, mode, launches_per_step, graphed = time_graph(step, args.steps, args.warmup, args.eager,
+                                                            results=lambda: [x.grad] + [p.grad for p in params])
     barrier()
 
     # ------------------------------------------------------------------ timed region (device-resident inputs)
@@ -642,11 +689,18 @@ def run_ours(args):
                        "cpu_affinity": f"{len(affinity)} CPUs local to the GPU (NVML)" if affinity else "unchanged"},
             "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "roofline": roofline}
 
+    replicas, second = None, None
     if not args.skip_extras:
         def outputs():
             return [x.grad, torch.cat([p.grad.reshape(-1) for p in params])]
+        if graphed is not None:
+            outputs = graph_outputs(graphed)      # the graph's own result buffers (the eager profiling pass above rebound the .grad attributes)
+            if world == 1:                        # N = 1: a second captured copy of the step, no staging copies (N > 1 is bound by the host link)
+                second = second_replica(make_step, [x, gy], params)
+                if second is not None:
+                    replicas = [([x, gy], run_step, outputs), second[:3]]
         e2e_steps = max(5, min(args.steps, 20))
-        e2e_ms, h2d, d2h = time_e2e([x, gy], run_step, outputs, e2e_steps, world, dist if world > 1 else None)
+        e2e_ms, h2d, d2h = time_e2e([x, gy], run_step, outputs, e2e_steps, world, dist if world > 1 else None, replicas)
         t = torch.tensor([e2e_ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -654,11 +708,14 @@ def run_ours(args):
         line["e2e"] = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "steps": e2e_steps, "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "h2d_gbs_per_gpu": h2d / (e2e_ms / 1e3) / 1e9, "d2h_gbs_per_gpu": d2h / (e2e_ms / 1e3) / 1e9,
-                       "pipeline": "3 streams: H2D(i+1) | kernels(i) | D2H(i-1); pinned host buffers on the GPU's NUMA node; in: input "
+                       "staging_copies": replicas is None,
+                       "pipeline": "3 streams: H2D(i+1) | kernels(i) | D2H(i-1)" + ("; the step is captured twice and the host copies land in / leave from "
+                                   "a copy's own static buffers (no staging passes)" if replicas is not None else "; device staging buffers on both sides") +
+                                   "; pinned host buffers on the GPU's NUMA node; in: input "
                                    "feature map + upstream gradient; out: input gradient + all factor gradients (the forward output "
                                    "stays on the device: it is consumed by the backward pass of the same step)"}
     # release the captured graph (it holds NCCL kernels) BEFORE the other configs and before tearing the communicator down
-    del run_step, graphed
+    del run_step, graphed, replicas, second
     gc.collect()
     torch.cuda.synchronize()
 

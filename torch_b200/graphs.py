@@ -20,7 +20,10 @@ class GraphedStep:
     >>> g = GraphedStep(step); g.replay()        # x.grad / p.grad hold the results after each replay
     """
 
-    def __init__(self, fn, warmup=3):
+    def __init__(self, fn, warmup=3, results=None):
+        """``results``: optional callable evaluated right after the capture -- it returns the step's result tensors (``x.grad``,
+        ``p.grad`` ...), which at that moment are the graph's own static buffers.  Keep ``self.results`` instead of re-reading the
+        ``.grad`` attributes later: any eager step run afterwards rebinds them to fresh tensors the graph never writes."""
         self.fn = fn
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -32,6 +35,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             fn()
+        self.results = results() if results is not None else None
 
     def replay(self):
         self.graph.replay()
